@@ -1,0 +1,74 @@
+// tests/host_harness.cpp -- TEST-ONLY host build of the thread-serial device
+// primitives (csrc/bp_*.cuh are __host__ __device__).  It lets the CPU test
+// suite check the exact code that runs inside the kernels against the oracle
+// without a GPU.  It is NOT part of the product: boundplanner_b200/ never
+// loads it and libbpgeo.so has no CPU path.
+#include "../boundplanner_b200/csrc/bp_math.cuh"
+#include "../boundplanner_b200/csrc/bp_mvie.cuh"
+#include "../boundplanner_b200/csrc/bp_lp.cuh"
+#include "../boundplanner_b200/csrc/bp_fk.cuh"
+
+struct HostRows {
+  const double* A;   // [m,3]
+  const double* B;   // [m]
+  double a(int i, int k) const { return A[3 * i + k]; }
+  double b(int i) const { return B[i]; }
+};
+
+extern "C" {
+
+int hh_mvie(const double* A, const double* b, int m, int free_centre, const double* c0, double* E, double* Q,
+            double* centre, int* iters) {
+  HostRows rows{A, b};
+  double L[6], d[3];
+  int st = free_centre ? bp_mvie_solve<9>(rows, m, c0, L, d, iters) : bp_mvie_solve<6>(rows, m, c0, L, d, iters);
+  double det;
+  bp_shape_from_L(L, E, Q, &det);
+  centre[0] = d[0]; centre[1] = d[1]; centre[2] = d[2];
+  return st;
+}
+
+// closest points of n boxes to p in the metric of E (q_inv): y[n,3], dist[n]
+void hh_box_qp(const double* E, const double* p, const double* lb, const double* ub, int n, double* y,
+               double* dist) {
+  double Q[9], M[9];
+  bp_inv3(E, Q);
+  bp_mat3_ata(Q, M);
+  BpMetric mt;
+  bp_metric_init(M, &mt);
+  for (int j = 0; j < n; ++j) {
+    double lo[3], hi[3], z[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = lb[3 * j + k] - p[k]; hi[k] = ub[3 * j + k] - p[k]; }
+    int mask = bp_box_qp(mt, lo, hi, z);
+    bp_box_point(p, lb + 3 * j, ub + 3 * j, z, mask, y + 3 * j);
+    double zz[3] = {y[3 * j] - p[0], y[3 * j + 1] - p[1], y[3 * j + 2] - p[2]};
+    double w[3];
+    bp_mat3_vec(Q, zz, w);
+    dist[j] = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  }
+}
+
+void hh_seg_box(const double* p0, const double* p1, const double* lb, const double* ub, int n, double* x,
+                double* phi) {
+  double d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+  for (int j = 0; j < n; ++j) {
+    double d2;
+    phi[j] = bp_seg_box(p0, d, lb + 3 * j, ub + 3 * j, x + 3 * j, &d2);
+  }
+}
+
+int hh_pair_lp(const double* A1, const double* b1, int m1, const double* A2, const double* b2, int m2, double tol,
+               double* xout, int* iters) {
+  HostRows r1{A1, b1}, r2{A2, b2};
+  return bp_pair_feasible(r1, m1, r2, m2, tol, xout, iters);
+}
+
+void hh_fk(const double* q, int n, double* p_ee, double* p_col, double* T_ee, double* jac) {
+  for (int i = 0; i < n; ++i)
+    bp_fk_iiwa14(q + 7 * i, p_ee + 3 * i, p_col + 21 * i, T_ee ? T_ee + 16 * i : nullptr,
+                 jac ? jac + 42 * i : nullptr);
+}
+
+double hh_min_eig(const double* A) { return bp_sym3_min_eig(A); }
+
+}  // extern "C"
