@@ -283,7 +283,7 @@ BP_HD double bp_seg_box(const double* p0, const double* d, const double* lb, con
       double e = pk < lb[k] ? lb[k] - pk : (pk > ub[k] ? pk - ub[k] : 0.0);
       g += e * e;
     }
-    if (g < best * (1.0 - 1e-12) - 1e-300 || (i == 0 && g < best)) {
+    if (i == 0 || g < best * (1.0 - 1e-12) - 1e-24) {
       best = g;
       bphi = phi;
     }

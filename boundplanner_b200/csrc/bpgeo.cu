@@ -1,0 +1,873 @@
+// bpgeo.cu -- sm_100a kernels and the C ABI of libbpgeo.so (see include/bpgeo.h).
+//
+// Kernel map (reference sites in the per-kernel comments):
+//   k_closest_points        K1  compute_set_projs          ConvexSetFinder.py:465-489
+//   k_closest_points_line   K2  compute_set_projs_line     ConvexSetFinder.py:491-510
+//   k_poly_point            K3  compute_polyhedron         ConvexSetFinder.py:423-463
+//   k_poly_line             K3' greedy loop of find_set_collision_avoidance :309-375
+//   k_mvie                  K4  mvie_socp / mvie_socp_fixed_mid  :512-562
+//   (k_poly_point, k_mvie) x max_iter + k_mvie(final) = K5 find_set_around_point :190-240
+//   k_pair_feasible         K6  set_intersection           BoundPlanner.py:774-798
+//   k_fk                    K7  RobotModel.fk_pos/_col/hom_transform/jacobian :146-231
+//
+// Layout in HBM: the scene is six SoA columns (lbx,lby,lbz,ubx,uby,ubz) of N
+// doubles, already inflated; a convex set is m rows (a0,a1,a2 | b) in
+// A[S,m_max,3], b[S,m_max]; per-seed loop state lives in a SeedState array in
+// the caller-provided workspace.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bpgeo.h"
+#include "bp_math.cuh"
+#include "bp_mvie.cuh"
+#include "bp_lp.cuh"
+#include "bp_fk.cuh"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int bp_fail(const char* what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess)
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  else
+    snprintf(g_err, sizeof(g_err), "%s", what);
+  return 1;
+}
+#define BP_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return bp_fail(#call, e_);   \
+  } while (0)
+
+struct bp_scene {
+  double* cols;   // device, 6 * cap doubles: lbx | lby | lbz | ubx | uby | ubz (stride cap)
+  int n;
+  int cap;
+  double inflate;
+};
+
+struct SceneView {
+  const double* lb[3];
+  const double* ub[3];
+  int n;
+};
+
+static SceneView view_of(const bp_scene* s) {
+  SceneView v;
+  for (int k = 0; k < 3; ++k) {
+    v.lb[k] = s->cols + (size_t)k * s->cap;
+    v.ub[k] = s->cols + (size_t)(3 + k) * s->cap;
+  }
+  v.n = s->n;
+  return v;
+}
+
+// Per-seed state of the IRIS loop (find_set_around_point, :190-240)
+struct SeedState {
+  double Q[9];      // q_ellipse
+  double p[3];      // p_seed (moves when the centre is free)
+  double det, det_old;
+  int k;            // loop counter
+  int active;       // still inside the while loop
+  int status;
+  int pad;
+};
+
+struct Vec3 { double v[3]; };
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_box(const SceneView& sc, int j, double* lb, double* ub) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    lb[k] = __ldg(sc.lb[k] + j);
+    ub[k] = __ldg(sc.ub[k] + j);
+  }
+}
+
+// (value, index) argmin across the block; ties -> smallest index (np.argmin, quirk Q11).
+// Every thread returns the block result.  red_* are [2][32] ping-pong buffers.
+__device__ __forceinline__ void block_argmin(double& val, int& idx, double (*red_val)[32], int (*red_idx)[32],
+                                             int& buf) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double ov = __shfl_xor_sync(full, val, off);
+    int oi = __shfl_xor_sync(full, idx, off);
+    if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red_val[buf][warp] = val; red_idx[buf][warp] = idx; }
+  __syncthreads();
+  double bv = red_val[buf][0];
+  int bi = red_idx[buf][0];
+  for (int w = 1; w < nw; ++w) {
+    double ov = red_val[buf][w];
+    int oi = red_idx[buf][w];
+    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  val = bv; idx = bi;
+  buf ^= 1;
+}
+
+struct PassMetric {
+  double Q[9];
+  double G[9];       // Q Q^T (normals, :440)
+  BpMetric mt;       // M = Q^T Q (QP objective == squared dist, :429)
+};
+
+__device__ __forceinline__ void pass_metric_init(const double* Q, PassMetric* pm) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) pm->Q[k] = Q[k];
+  double M[9];
+  bp_mat3_ata(Q, M);
+  bp_mat3_mul_bt(Q, Q, pm->G);
+  bp_metric_init(M, &pm->mt);
+}
+
+// closest point of box j to p in the pass metric; returns dist (:429)
+__device__ __forceinline__ double closest_on_box(const PassMetric& pm, const double* p, const double* lb,
+                                                 const double* ub, double* y) {
+  double lo[3], hi[3], z[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { lo[k] = lb[k] - p[k]; hi[k] = ub[k] - p[k]; }
+  int mask = bp_box_qp(pm.mt, lo, hi, z);
+  bp_box_point(p, lb, ub, z, mask, y);
+  double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
+  double w[3];
+  bp_mat3_vec(pm.Q, zz, w);
+  return sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+}
+
+// ---------------------------------------------------------------------------
+// K1 test hook / batched compute_set_projs
+// ---------------------------------------------------------------------------
+__global__ void k_closest_points(SceneView sc, const double* __restrict__ seeds, const double* __restrict__ q_inv,
+                                 double* __restrict__ y_out, double* __restrict__ dist_out) {
+  const int s = blockIdx.y;
+  double E[9], Q[9], p[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) E[k] = q_inv[(size_t)s * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = seeds[(size_t)s * 3 + k];
+  bp_inv3(E, Q);
+  PassMetric pm;
+  pass_metric_init(Q, &pm);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < sc.n; j += gridDim.x * blockDim.x) {
+    double lb[3], ub[3], y[3];
+    load_box(sc, j, lb, ub);
+    double d = closest_on_box(pm, p, lb, ub, y);
+    size_t o = (size_t)s * sc.n + j;
+    y_out[3 * o] = y[0]; y_out[3 * o + 1] = y[1]; y_out[3 * o + 2] = y[2];
+    dist_out[o] = d;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2 test hook / batched compute_set_projs_line
+// ---------------------------------------------------------------------------
+__global__ void k_closest_points_line(SceneView sc, const double* __restrict__ p0s, const double* __restrict__ p1s,
+                                      double* __restrict__ x_out, double* __restrict__ phi_out) {
+  const int s = blockIdx.y;
+  double p0[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { p0[k] = p0s[(size_t)s * 3 + k]; d[k] = p1s[(size_t)s * 3 + k] - p0[k]; }
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < sc.n; j += gridDim.x * blockDim.x) {
+    double lb[3], ub[3], x[3], d2;
+    load_box(sc, j, lb, ub);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lb[k] += 0.001; ub[k] -= 0.001; }   // b - 0.001 (:496)
+    double phi = bp_seg_box(p0, d, lb, ub, x, &d2);
+    size_t o = (size_t)s * sc.n + j;
+    x_out[3 * o] = x[0]; x_out[3 * o + 1] = x[1]; x_out[3 * o + 2] = x[2];
+    phi_out[o] = phi;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: one compute_polyhedron pass, one CTA per seed (ConvexSetFinder.py:423-463)
+//   phase 1: every thread solves the box QP of its obstacles (j = tid + k*T)
+//            and keeps dist[j] in shared memory (dead obstacles: +inf);
+//   phase 2: greedy loop -- block argmin, halfspace from the winner (its QP is
+//            re-solved redundantly by every thread instead of storing y[N,3]),
+//            vertex test over the surviving obstacles.  One barrier per pick.
+// mode 0: standalone pass (bp_polyhedron); mode 1: inside the IRIS loop (checks
+// and updates the SeedState loop control, :203-207).
+// ---------------------------------------------------------------------------
+struct PolyParams {
+  const double* seeds;       // [S,3]      (mode 0)
+  const double* q_ellipse;   // [S,9]      (mode 0)
+  const double* init_rows;   // [S,6,4]    (mode 0)
+  SeedState* state;          // [S]        (mode 1)
+  double ws_rows[6];         // b of the 6 workspace rows: ub0,-lb0,ub1,-lb1,ub2,-lb2 (mode 1)
+  double* A;
+  double* b;
+  int* m;
+  int* status;
+  int m_max;
+  int mode;
+  int max_iter;
+};
+
+__global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr) {
+  extern __shared__ double s_dist[];
+  __shared__ double red_val[2][32];
+  __shared__ int red_idx[2][32];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double p[3];
+  PassMetric pm;
+  double* Arow = pr.A + (size_t)s * pr.m_max * 3;
+  double* brow = pr.b + (size_t)s * pr.m_max;
+  if (pr.mode == 1) {
+    SeedState* st = pr.state + s;
+    if (!st->active || st->status != BP_OK) return;
+    // while |det - det_old| / det_old > 0.01: k += 1; if k > max_iter: break   (:203-207)
+    double det = st->det, det_old = st->det_old;
+    int k = st->k;
+    bool go = fabs(det - det_old) / det_old > 0.01;
+    if (go) go = (k + 1 <= pr.max_iter);
+    __syncthreads();                       // everybody has read the state
+    if (!go) {
+      if (tid == 0) { st->active = 0; if (fabs(det - det_old) / det_old > 0.01) st->k = k + 1; }
+      return;
+    }
+    if (tid == 0) st->k = k + 1;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) p[q] = st->p[q];
+    pass_metric_init(st->Q, &pm);
+    if (tid < 6) {
+      int ax = tid >> 1;
+      double sgn = (tid & 1) ? -1.0 : 1.0;
+      Arow[3 * tid + 0] = ax == 0 ? sgn : 0.0;
+      Arow[3 * tid + 1] = ax == 1 ? sgn : 0.0;
+      Arow[3 * tid + 2] = ax == 2 ? sgn : 0.0;
+      brow[tid] = pr.ws_rows[tid];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) p[q] = pr.seeds[(size_t)s * 3 + q];
+    double Q[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Q[q] = pr.q_ellipse[(size_t)s * 9 + q];
+    pass_metric_init(Q, &pm);
+    if (tid < 6) {
+      const double* r = pr.init_rows + ((size_t)s * 6 + tid) * 4;
+      Arow[3 * tid + 0] = r[0]; Arow[3 * tid + 1] = r[1]; Arow[3 * tid + 2] = r[2];
+      brow[tid] = r[3];
+    }
+  }
+
+  // phase 1: closest points and distances
+  double lmin = BP_INF;
+  int lidx = 0x7fffffff;
+  for (int j = tid; j < sc.n; j += T) {
+    double lb[3], ub[3], y[3];
+    load_box(sc, j, lb, ub);
+    double d = closest_on_box(pm, p, lb, ub, y);
+    s_dist[j] = d;
+    if (d < lmin) { lmin = d; lidx = j; }
+  }
+
+  // phase 2: greedy halfspaces
+  int m_cur = 6;
+  int status = BP_OK;
+  int buf = 0;
+  while (true) {
+    double val = lmin;
+    int idx = lidx;
+    block_argmin(val, idx, red_val, red_idx, buf);
+    if (!(val < BP_INF)) break;                      // no obstacle left
+    if (val < 0.99) { status = BP_ELLIPSE_VIOLATION; break; }   // :433-438
+    double lb[3], ub[3], y[3];
+    load_box(sc, idx, lb, ub);
+    closest_on_box(pm, p, lb, ub, y);
+    double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
+    double a[3];
+    bp_mat3_vec(pm.G, zz, a);
+    a[0] *= 2.0; a[1] *= 2.0; a[2] *= 2.0;           // 2 (Q Q^T)(cp - p)   (:440)
+    double bh = a[0] * y[0] + a[1] * y[1] + a[2] * y[2];
+    double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    a[0] /= nrm; a[1] /= nrm; a[2] /= nrm; bh /= nrm;
+    if (tid == 0 && m_cur < pr.m_max) {
+      Arow[3 * m_cur + 0] = a[0]; Arow[3 * m_cur + 1] = a[1]; Arow[3 * m_cur + 2] = a[2];
+      brow[m_cur] = bh;
+    }
+    ++m_cur;
+    // delete the winner and every obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458)
+    lmin = BP_INF;
+    lidx = 0x7fffffff;
+    for (int j = tid; j < sc.n; j += T) {
+      double d = s_dist[j];
+      if (!(d < BP_INF)) continue;
+      double l2[3], u2[3];
+      load_box(sc, j, l2, u2);
+      if (j == idx || bp_box_min_halfspace(a, bh, l2, u2) >= -1e-4) {
+        s_dist[j] = BP_INF;
+      } else if (d < lmin) {
+        lmin = d; lidx = j;
+      }
+    }
+  }
+  if (status == BP_OK && m_cur > pr.m_max) status = BP_ROW_OVERFLOW;
+  if (tid == 0) {
+    pr.m[s] = m_cur < pr.m_max ? m_cur : pr.m_max;
+    if (pr.mode == 1) {
+      if (status != BP_OK) { pr.state[s].status = status; pr.state[s].active = 0; }
+    } else {
+      pr.status[s] = status;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3': greedy loop of find_set_collision_avoidance (ConvexSetFinder.py:309-375)
+// ---------------------------------------------------------------------------
+struct LineParams {
+  const double* p0;          // [S,3]
+  const double* p1;          // [S,3]
+  double ws_rows[6];
+  int limit_space;
+  double e_max;
+  double* A;
+  double* b;
+  int* m;
+  int* status;
+  int* collision;
+  int m_max;
+};
+
+__device__ __forceinline__ double seg_closest(const double* p0, const double* d, const double* lb,
+                                              const double* ub, double* x, double* pc) {
+  double l2[3], u2[3], d2;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { l2[k] = lb[k] + 0.001; u2[k] = ub[k] - 0.001; }     // b - 0.001 (:496)
+  double phi = bp_seg_box(p0, d, l2, u2, x, &d2);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pc[k] = p0[k] + phi * d[k];                             // :326
+  double e0 = x[0] - pc[0], e1 = x[1] - pc[1], e2 = x[2] - pc[2];
+  return sqrt(e0 * e0 + e1 * e1 + e2 * e2);                                           // :327
+}
+
+__global__ void __launch_bounds__(512) k_poly_line(SceneView sc, LineParams pr) {
+  extern __shared__ double s_dist[];
+  __shared__ double red_val[2][32];
+  __shared__ int red_idx[2][32];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double p0[3], p1[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p0[k] = pr.p0[(size_t)s * 3 + k];
+    p1[k] = pr.p1[(size_t)s * 3 + k];
+    d[k] = p1[k] - p0[k];
+  }
+  double* Arow = pr.A + (size_t)s * pr.m_max * 3;
+  double* brow = pr.b + (size_t)s * pr.m_max;
+  if (tid < 6) {
+    int ax = tid >> 1;
+    double sgn = (tid & 1) ? -1.0 : 1.0;
+    Arow[3 * tid + 0] = ax == 0 ? sgn : 0.0;
+    Arow[3 * tid + 1] = ax == 1 ? sgn : 0.0;
+    Arow[3 * tid + 2] = ax == 2 ? sgn : 0.0;
+    // init_halfspaces_point: b = p[i] + e_max / -p[i] + e_max (:400-421)
+    brow[tid] = pr.limit_space ? (sgn * p0[ax] + pr.e_max) : pr.ws_rows[tid];
+  }
+  double lmin = BP_INF;
+  int lidx = 0x7fffffff;
+  for (int j = tid; j < sc.n; j += T) {
+    double lb[3], ub[3], x[3], pc[3];
+    load_box(sc, j, lb, ub);
+    double dd = seg_closest(p0, d, lb, ub, x, pc);
+    s_dist[j] = dd;
+    if (dd < lmin) { lmin = dd; lidx = j; }
+  }
+  int m_cur = 6, buf = 0, collision = 0;
+  while (true) {
+    double val = lmin;
+    int idx = lidx;
+    block_argmin(val, idx, red_val, red_idx, buf);
+    if (!(val < BP_INF)) break;
+    double lb[3], ub[3], x[3], pc[3];
+    load_box(sc, idx, lb, ub);
+    seg_closest(p0, d, lb, ub, x, pc);
+    double a[3] = {x[0] - pc[0], x[1] - pc[1], x[2] - pc[2]};
+    double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (nrm < 1e-6) {                                  // line touches an obstacle (:336-345)
+      collision = 1;
+      a[0] = x[0] - p0[0]; a[1] = x[1] - p0[1]; a[2] = x[2] - p0[2];
+      nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      if (nrm < 1e-6) {
+        a[0] = d[0]; a[1] = d[1]; a[2] = d[2];
+        nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      }
+    }
+    a[0] /= nrm; a[1] /= nrm; a[2] /= nrm;
+    double bh = (a[0] * x[0] + a[1] * x[1] + a[2] * x[2]) - 0.001;    // :347
+    if (tid == 0 && m_cur < pr.m_max) {
+      Arow[3 * m_cur + 0] = a[0]; Arow[3 * m_cur + 1] = a[1]; Arow[3 * m_cur + 2] = a[2];
+      brow[m_cur] = bh;
+    }
+    ++m_cur;
+    lmin = BP_INF;
+    lidx = 0x7fffffff;
+    for (int j = tid; j < sc.n; j += T) {
+      double dd = s_dist[j];
+      if (!(dd < BP_INF)) continue;
+      double l2[3], u2[3];
+      load_box(sc, j, l2, u2);
+      if (j == idx || bp_box_min_halfspace(a, bh, l2, u2) >= -1e-4) {   // unshrunk vertices (:352-357)
+        s_dist[j] = BP_INF;
+      } else if (dd < lmin) {
+        lmin = dd; lidx = j;
+      }
+    }
+  }
+  if (tid == 0) {
+    pr.m[s] = m_cur < pr.m_max ? m_cur : pr.m_max;
+    pr.status[s] = m_cur > pr.m_max ? BP_ROW_OVERFLOW : BP_OK;
+    pr.collision[s] = collision;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: MVIE, one thread per set, 32 sets per CTA; rows staged in shared memory
+// as [coef][row][lane] so that every lane reads its own bank.
+// mode 0: loop step with fixed centre   (mvie_socp_fixed_mid, :220-221)
+// mode 1: loop step with free centre    (mvie_socp, :222-223)
+// mode 2: final free-centre solve after the loop (:235-238), no loop control
+// mode 3: standalone (bp_mvie), centre/hint from `centre`, free_centre flag
+// ---------------------------------------------------------------------------
+struct SmemRows {
+  const double* base;   // shared
+  int lane;
+  __device__ __forceinline__ double a(int i, int k) const { return base[(k * BP_MAX_ROWS + i) * 32 + lane]; }
+  __device__ __forceinline__ double b(int i) const { return base[(3 * BP_MAX_ROWS + i) * 32 + lane]; }
+};
+
+struct MvieParams {
+  const double* A;
+  const double* b;
+  const int* m;
+  int S;
+  int m_max;
+  int mode;
+  int free_centre;            // mode 3
+  SeedState* state;           // modes 0-2
+  const double* centre;       // mode 3 [S,3]
+  const double* hint;         // mode 2 optional [S,3] hint (line sets: p0)
+  double* q_inv_out;          // mode 3
+  double* q_ellipse_out;      // mode 3, and export target of modes 0-2 when non-null
+  double* centre_out;
+  int* status_out;
+  int* iters_out;             // newton iterations (mode 3) or NULL
+};
+
+__global__ void __launch_bounds__(32) k_mvie(MvieParams pr) {
+  extern __shared__ double s_rows[];
+  const int lane = threadIdx.x;
+  const int s = blockIdx.x * 32 + lane;
+  const bool valid = s < pr.S;
+  bool run = valid;
+  SeedState* st = nullptr;
+  double c0[3] = {0.0, 0.0, 0.0};
+  if (valid) {
+    if (pr.mode <= 2) {
+      st = pr.state + s;
+      run = (st->status == BP_OK) && (pr.mode == 2 || st->active);
+      c0[0] = st->p[0]; c0[1] = st->p[1]; c0[2] = st->p[2];
+      if (pr.mode == 2 && pr.hint) { c0[0] = pr.hint[3 * s]; c0[1] = pr.hint[3 * s + 1]; c0[2] = pr.hint[3 * s + 2]; }
+    } else {
+      c0[0] = pr.centre[3 * s]; c0[1] = pr.centre[3 * s + 1]; c0[2] = pr.centre[3 * s + 2];
+    }
+  }
+  int m = 0;
+  if (run) {
+    m = pr.m[s];
+    const double* A = pr.A + (size_t)s * pr.m_max * 3;
+    const double* b = pr.b + (size_t)s * pr.m_max;
+    for (int i = 0; i < m; ++i) {
+      s_rows[(0 * BP_MAX_ROWS + i) * 32 + lane] = A[3 * i + 0];
+      s_rows[(1 * BP_MAX_ROWS + i) * 32 + lane] = A[3 * i + 1];
+      s_rows[(2 * BP_MAX_ROWS + i) * 32 + lane] = A[3 * i + 2];
+      s_rows[(3 * BP_MAX_ROWS + i) * 32 + lane] = b[i];
+    }
+  }
+  if (!run) return;
+  SmemRows rows{s_rows, lane};
+  double L[6], d[3];
+  int iters = 0;
+  const bool free_c = (pr.mode == 1 || pr.mode == 2 || (pr.mode == 3 && pr.free_centre));
+  int status = free_c ? bp_mvie_solve<9>(rows, m, c0, L, d, &iters) : bp_mvie_solve<6>(rows, m, c0, L, d, &iters);
+  double E[9], Q[9], detQ;
+  bp_shape_from_L(L, E, Q, &detQ);
+  if (pr.mode <= 2) {
+    if (status != BP_OK) { st->status = status; st->active = 0; return; }
+    if (pr.mode < 2) st->det_old = st->det;             // :217
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st->Q[k] = Q[k];
+    st->p[0] = d[0]; st->p[1] = d[1]; st->p[2] = d[2];
+    if (pr.mode < 2) {
+      st->det = detQ;                                    // :229
+      if (bp_sym3_min_eig(E) < 1e-3) st->active = 0;     // :232-233
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { pr.q_inv_out[(size_t)s * 9 + k] = E[k]; pr.q_ellipse_out[(size_t)s * 9 + k] = Q[k]; }
+    pr.centre_out[3 * s] = d[0]; pr.centre_out[3 * s + 1] = d[1]; pr.centre_out[3 * s + 2] = d[2];
+    pr.status_out[s] = status;
+    if (pr.iters_out) pr.iters_out[s] = iters;
+  }
+}
+
+__global__ void k_state_init(SeedState* st, const double* __restrict__ seeds, int S) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  SeedState v;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) v.Q[k] = 0.0;
+  v.Q[0] = v.Q[4] = v.Q[8] = 1.0 / 1e-4;                 // q_ellipse = diag(1/a) (:192-194)
+  v.p[0] = seeds[3 * s]; v.p[1] = seeds[3 * s + 1]; v.p[2] = seeds[3 * s + 2];
+  v.det = 100.0; v.det_old = 1.0;                        // :200-201
+  v.k = 0; v.active = 1; v.status = BP_OK; v.pad = 0;
+  st[s] = v;
+}
+
+__global__ void k_state_export(const SeedState* st, int S, int max_iter, double* __restrict__ q_ellipse,
+                               double* __restrict__ p_mid, int* __restrict__ status, int* __restrict__ iters) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  if (q_ellipse) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q_ellipse[(size_t)s * 9 + k] = st[s].Q[k];
+  }
+  if (p_mid) { p_mid[3 * s] = st[s].p[0]; p_mid[3 * s + 1] = st[s].p[1]; p_mid[3 * s + 2] = st[s].p[2]; }
+  if (status) status[s] = st[s].status;
+  if (iters) {
+    // the reference's while test runs once more after the last pass and bumps k
+    // before breaking on k > max_iter (:203-207)
+    int k = st[s].k;
+    if (st[s].active && st[s].status == BP_OK && k >= max_iter &&
+        fabs(st[s].det - st[s].det_old) / st[s].det_old > 0.01) ++k;
+    iters[s] = k;
+  }
+}
+
+// line sets: seed the state for the trailing free-centre MVIE (:370-374)
+__global__ void k_state_init_line(SeedState* st, const double* __restrict__ p0, const int* __restrict__ status, int S) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  SeedState v;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) v.Q[k] = 0.0;
+  v.p[0] = p0[3 * s]; v.p[1] = p0[3 * s + 1]; v.p[2] = p0[3 * s + 2];
+  v.det = 100.0; v.det_old = 1.0;
+  v.k = 0; v.active = 0; v.status = status[s]; v.pad = 0;
+  st[s] = v;
+}
+
+// ---------------------------------------------------------------------------
+// K6: pairwise feasibility.  Block = 8 rows i x 32 columns j; a warp holds one i
+// and 32 consecutive j, so its ballot is one word of the adjacency bit-matrix.
+// ---------------------------------------------------------------------------
+struct GlobalRows {
+  const double* A;
+  const double* B;
+  __device__ __forceinline__ double a(int i, int k) const { return __ldg(A + 3 * i + k); }
+  __device__ __forceinline__ double b(int i) const { return __ldg(B + i); }
+};
+
+__global__ void __launch_bounds__(256) k_pair_feasible(const double* __restrict__ A, const double* __restrict__ b,
+                                                       const int* __restrict__ m, int S, int m_max, double tol,
+                                                       int row_begin, int row_end, unsigned int* __restrict__ adj) {
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int i = row_begin + blockIdx.y * 8 + wy;
+  const int j = blockIdx.x * 32 + lane;
+  const int words = (S + 31) >> 5;
+  if (i >= row_end) return;
+  int res = 0;
+  if (j < S && j > i) {
+    GlobalRows r1{A + (size_t)i * m_max * 3, b + (size_t)i * m_max};
+    GlobalRows r2{A + (size_t)j * m_max * 3, b + (size_t)j * m_max};
+    res = bp_pair_feasible(r1, m[i], r2, m[j], tol, (double*)nullptr, (int*)nullptr);
+  }
+  unsigned int word = __ballot_sync(0xffffffffu, res != 0);
+  if (lane == 0) adj[(size_t)(i - row_begin) * words + blockIdx.x] = word;
+}
+
+// ---------------------------------------------------------------------------
+// K7: FK, one thread per configuration.  q and the outputs are staged through
+// shared memory so that global traffic is fully coalesced 16-byte accesses.
+// ---------------------------------------------------------------------------
+#define FK_T 128
+__device__ __forceinline__ void block_copy_out(double* __restrict__ dst, const double* src_smem, int count) {
+  // dst is 16-byte aligned when the tile start is (tile * FK_T * width doubles, width*FK_T even)
+  for (int e = threadIdx.x; e < count; e += FK_T) dst[e] = src_smem[e];
+}
+
+__global__ void __launch_bounds__(FK_T) k_fk(const double* __restrict__ q, int B, double* __restrict__ p_ee,
+                                             double* __restrict__ p_col, double* __restrict__ T_ee,
+                                             double* __restrict__ jac) {
+  __shared__ double s_q[FK_T * 7];
+  __shared__ double s_pe[FK_T * 3];
+  __shared__ double s_pc[FK_T * 21];
+  extern __shared__ double s_T[];          // FK_T*16 when T_ee requested
+  const int base = blockIdx.x * FK_T;
+  const int nb = min(FK_T, B - base);
+  for (int e = threadIdx.x; e < nb * 7; e += FK_T) s_q[e] = q[(size_t)base * 7 + e];
+  __syncthreads();
+  if (threadIdx.x < nb) {
+    double qq[7], pe[3], pc[21], T[16], J[42];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) qq[k] = s_q[threadIdx.x * 7 + k];
+    bp_fk_iiwa14(qq, pe, pc, T_ee ? T : nullptr, jac ? J : nullptr);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_pe[threadIdx.x * 3 + k] = pe[k];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) s_pc[threadIdx.x * 21 + k] = pc[k];
+    if (T_ee) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s_T[threadIdx.x * 16 + k] = T[k];
+    }
+    if (jac) {
+      double* jo = jac + (size_t)(base + threadIdx.x) * 42;
+#pragma unroll
+      for (int k = 0; k < 42; ++k) jo[k] = J[k];
+    }
+  }
+  __syncthreads();
+  block_copy_out(p_ee + (size_t)base * 3, s_pe, nb * 3);
+  block_copy_out(p_col + (size_t)base * 21, s_pc, nb * 21);
+  if (T_ee) block_copy_out(T_ee + (size_t)base * 16, s_T, nb * 16);
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+static int poly_threads(int n) { return n <= 256 ? 128 : (n <= 4096 ? 256 : 512); }
+
+static int set_dyn_smem(const void* fn, size_t bytes) {
+  if (bytes > 227 * 1024) return bp_fail("scene too large for the shared-memory distance table (N > 29056)");
+  if (bytes > 48 * 1024) BP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+extern "C" {
+
+int bpgeo_abi_version(void) { return BPGEO_ABI_VERSION; }
+const char* bp_last_error_string(void) { return g_err; }
+
+static int scene_upload(bp_scene* sc, const double* boxes_host, int n, double inflate, cudaStream_t stream) {
+  if (n > sc->cap) {
+    if (sc->cols) BP_CUDA(cudaFree(sc->cols));
+    sc->cols = nullptr;
+    sc->cap = ((n + 31) / 32) * 32;
+    BP_CUDA(cudaMalloc(&sc->cols, sizeof(double) * 6 * (size_t)sc->cap));
+  }
+  sc->n = n;
+  sc->inflate = inflate;
+  if (n == 0) return 0;
+  double* tmp = (double*)malloc(sizeof(double) * 6 * (size_t)sc->cap);
+  if (!tmp) return bp_fail("out of host memory");
+  memset(tmp, 0, sizeof(double) * 6 * (size_t)sc->cap);
+  for (int j = 0; j < n; ++j)
+    for (int k = 0; k < 3; ++k) {
+      tmp[(size_t)k * sc->cap + j] = boxes_host[6 * j + k] - inflate;          // -lb + inflate  (:141)
+      tmp[(size_t)(3 + k) * sc->cap + j] = boxes_host[6 * j + 3 + k] + inflate;
+    }
+  cudaError_t e = cudaMemcpyAsync(sc->cols, tmp, sizeof(double) * 6 * (size_t)sc->cap, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  free(tmp);
+  if (e != cudaSuccess) return bp_fail("scene upload", e);
+  return 0;
+}
+
+int bp_scene_create(const double* boxes_host, int n, double inflate, bp_scene** out) {
+  if (!out || n < 0 || (n > 0 && !boxes_host)) return bp_fail("bp_scene_create: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return bp_fail("bp_scene_create: no CUDA device (libbpgeo has no CPU fallback)", e);
+  bp_scene* sc = (bp_scene*)calloc(1, sizeof(bp_scene));
+  if (!sc) return bp_fail("out of host memory");
+  int rc = scene_upload(sc, boxes_host, n, inflate, 0);
+  if (rc) { free(sc); return rc; }
+  *out = sc;
+  return 0;
+}
+
+int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream) {
+  if (!scene || n < 0 || (n > 0 && !boxes_host)) return bp_fail("bp_scene_update: bad arguments");
+  return scene_upload(scene, boxes_host, n, inflate, (cudaStream_t)stream);
+}
+
+int bp_scene_destroy(bp_scene* scene) {
+  if (!scene) return 0;
+  if (scene->cols) cudaFree(scene->cols);
+  free(scene);
+  return 0;
+}
+
+int bp_scene_size(const bp_scene* scene) { return scene ? scene->n : -1; }
+
+int bp_closest_points(const bp_scene* scene, const double* seeds_dev, const double* q_inv_dev, int S,
+                      double* y_out_dev, double* dist_out_dev, void* stream) {
+  if (!scene || S < 0) return bp_fail("bp_closest_points: bad arguments");
+  if (S == 0 || scene->n == 0) return 0;
+  dim3 grid((scene->n + 255) / 256, S);
+  k_closest_points<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(scene), seeds_dev, q_inv_dev, y_out_dev, dist_out_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_closest_points_line(const bp_scene* scene, const double* p0_dev, const double* p1_dev, int S,
+                           double* x_out_dev, double* phi_out_dev, void* stream) {
+  if (!scene || S < 0) return bp_fail("bp_closest_points_line: bad arguments");
+  if (S == 0 || scene->n == 0) return 0;
+  dim3 grid((scene->n + 255) / 256, S);
+  k_closest_points_line<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(scene), p0_dev, p1_dev, x_out_dev, phi_out_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* q_inv_dev, const double* q_ellipse_dev,
+                  const double* init_rows_dev, int S, int m_max, double* A_dev, double* b_dev, int* m_dev,
+                  int* status_dev, void* stream) {
+  (void)q_inv_dev;   // the pass metric is derived from q_ellipse (= q_inv^-1, :227-228)
+  if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS) return bp_fail("bp_polyhedron: bad arguments");
+  if (S == 0) return 0;
+  PolyParams pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.seeds = seeds_dev; pr.q_ellipse = q_ellipse_dev; pr.init_rows = init_rows_dev;
+  pr.A = A_dev; pr.b = b_dev; pr.m = m_dev; pr.status = status_dev; pr.m_max = m_max; pr.mode = 0;
+  size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
+  if (set_dyn_smem((const void*)k_poly_point, smem)) return 1;
+  k_poly_point<<<S, poly_threads(scene->n), smem, (cudaStream_t)stream>>>(view_of(scene), pr);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_mvie(const MvieParams& pr, cudaStream_t stream) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(double) * 4 * BP_MAX_ROWS * 32;
+  if (!attr_set) {
+    BP_CUDA(cudaFuncSetAttribute((const void*)k_mvie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_mvie<<<(pr.S + 31) / 32, 32, smem, stream>>>(pr);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_mvie(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, int free_centre,
+            const double* centre_dev, double* q_inv_out_dev, double* q_ellipse_out_dev, double* centre_out_dev,
+            int* status_dev, int* newton_iters_dev, void* stream) {
+  if (S < 0 || m_max < 1 || m_max > BP_MAX_ROWS) return bp_fail("bp_mvie: bad arguments");
+  if (S == 0) return 0;
+  MvieParams pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.A = A_dev; pr.b = b_dev; pr.m = m_dev; pr.S = S; pr.m_max = m_max; pr.mode = 3; pr.free_centre = free_centre;
+  pr.centre = centre_dev; pr.q_inv_out = q_inv_out_dev; pr.q_ellipse_out = q_ellipse_out_dev;
+  pr.centre_out = centre_out_dev; pr.status_out = status_dev; pr.iters_out = newton_iters_dev;
+  return launch_mvie(pr, (cudaStream_t)stream);
+}
+
+size_t bp_build_sets_workspace_bytes(int S) { return sizeof(SeedState) * (size_t)(S > 0 ? S : 1); }
+
+int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, const double* ws_min_host,
+                        const double* ws_max_host, int fixed_mid, int optimize, int max_iter, int m_max,
+                        double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev, double* p_mid_dev,
+                        int* status_dev, int* iters_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || max_iter < 1 || !ws_min_host || !ws_max_host)
+    return bp_fail("bp_build_sets_point: bad arguments");
+  if (S == 0) return 0;
+  if (workspace_bytes < bp_build_sets_workspace_bytes(S)) return bp_fail("bp_build_sets_point: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SeedState* st = (SeedState*)workspace_dev;
+  k_state_init<<<(S + 127) / 128, 128, 0, stream>>>(st, seeds_dev, S);
+  PolyParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.state = st; pp.A = A_dev; pp.b = b_dev; pp.m = m_dev; pp.status = status_dev; pp.m_max = m_max;
+  pp.mode = 1; pp.max_iter = max_iter;
+  for (int i = 0; i < 3; ++i) { pp.ws_rows[2 * i] = ws_max_host[i]; pp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
+  MvieParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st;
+  size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
+  if (set_dyn_smem((const void*)k_poly_point, smem)) return 1;
+  const int T = poly_threads(scene->n);
+  const int passes = optimize ? max_iter : 1;
+  for (int it = 0; it < passes; ++it) {
+    k_poly_point<<<S, T, smem, stream>>>(view_of(scene), pp);
+    if (!optimize) break;                                 // :214-215
+    mp.mode = fixed_mid ? 0 : 1;
+    if (launch_mvie(mp, stream)) return 1;
+  }
+  if (optimize && fixed_mid) {                            // :235-238
+    mp.mode = 2;
+    if (launch_mvie(mp, stream)) return 1;
+  }
+  k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, optimize ? max_iter : 1 << 30, q_ellipse_dev, p_mid_dev, status_dev, iters_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double* p1_dev, int S,
+                       const double* ws_min_host, const double* ws_max_host, int limit_space, double e_max,
+                       int compute_ellipsoid, int m_max, double* A_dev, double* b_dev, int* m_dev,
+                       double* q_ellipse_dev, double* p_mid_dev, int* collision_dev, int* status_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || !ws_min_host || !ws_max_host)
+    return bp_fail("bp_build_sets_line: bad arguments");
+  if (S == 0) return 0;
+  if (compute_ellipsoid && workspace_bytes < bp_build_sets_workspace_bytes(S))
+    return bp_fail("bp_build_sets_line: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LineParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.p0 = p0_dev; lp.p1 = p1_dev; lp.limit_space = limit_space; lp.e_max = e_max;
+  for (int i = 0; i < 3; ++i) { lp.ws_rows[2 * i] = ws_max_host[i]; lp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
+  lp.A = A_dev; lp.b = b_dev; lp.m = m_dev; lp.status = status_dev; lp.collision = collision_dev; lp.m_max = m_max;
+  size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
+  if (set_dyn_smem((const void*)k_poly_line, smem)) return 1;
+  k_poly_line<<<S, poly_threads(scene->n), smem, stream>>>(view_of(scene), lp);
+  if (compute_ellipsoid) {
+    SeedState* st = (SeedState*)workspace_dev;
+    k_state_init_line<<<(S + 127) / 128, 128, 0, stream>>>(st, p0_dev, status_dev, S);
+    MvieParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st; mp.mode = 2;
+    if (launch_mvie(mp, stream)) return 1;
+    k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, 0, q_ellipse_dev, p_mid_dev, status_dev, nullptr);
+  }
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                     int row_begin, int row_end, unsigned int* adj_bits_dev, void* stream) {
+  if (S < 0 || row_begin < 0 || row_end > S || row_begin > row_end || m_max < 1)
+    return bp_fail("bp_pair_feasible: bad arguments");
+  if (row_end == row_begin) return 0;
+  dim3 grid((S + 31) / 32, (row_end - row_begin + 7) / 8);
+  k_pair_feasible<<<grid, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, row_end,
+                                                           adj_bits_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev, double* T_ee_dev, double* jac_dev,
+                 void* stream) {
+  if (B < 0 || !p_ee_dev || !p_col_dev) return bp_fail("bp_fk_iiwa14: bad arguments");
+  if (B == 0) return 0;
+  size_t smem = T_ee_dev ? sizeof(double) * FK_T * 16 : 0;
+  k_fk<<<(B + FK_T - 1) / FK_T, FK_T, smem, (cudaStream_t)stream>>>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

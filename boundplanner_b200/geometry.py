@@ -1,0 +1,248 @@
+"""Batched device-side API over libbpgeo.so.
+
+PyTorch is plumbing only (device memory, streams); every compute call goes
+through the C ABI in include/bpgeo.h with raw device pointers.  All tensors are
+float64 / int32 CUDA tensors.  Reference sites are cited per function.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BP_MAX_ROWS, check
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.BpGeoError("boundplanner_b200 needs a CUDA device (no CPU fallback)")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _host3(v):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(3))
+    return a, a.ctypes.data_as(_dp)
+
+
+def _dev(x, dtype=torch.float64):
+    """Host array / tensor -> contiguous CUDA tensor (H2D copy when needed)."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda", dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).cuda()
+
+
+class Scene:
+    """Obstacle boxes resident in HBM (SoA, inflated).
+
+    Replaces BoundPlanner.make_box / add_obstacle_reps (BoundPlanner.py:126-152).
+    ``boxes``: [N,6] rows (lb, ub) on the host; ``inflate`` = obs_size_increase."""
+
+    def __init__(self, boxes, inflate=0.0):
+        _require_cuda()
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p(0)
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 6))
+        torch.cuda.current_device()        # make sure a context exists on the current device
+        check(self._lib.bp_scene_create(boxes.ctypes.data_as(_dp), boxes.shape[0], float(inflate),
+                                        ctypes.byref(self._h)))
+        self.n = boxes.shape[0]
+        self.inflate = float(inflate)
+
+    def update(self, boxes, inflate=None):
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 6))
+        if inflate is None:
+            inflate = self.inflate
+        check(self._lib.bp_scene_update(self._h, boxes.ctypes.data_as(_dp), boxes.shape[0], float(inflate), _stream()))
+        self.n = boxes.shape[0]
+        self.inflate = float(inflate)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.bp_scene_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class SetBatch:
+    """S convex sets {x : A[s,:m[s]] x <= b[s,:m[s]]} plus their ellipsoids."""
+
+    A: torch.Tensor            # [S,m_max,3]
+    b: torch.Tensor            # [S,m_max]
+    m: torch.Tensor            # [S] int32
+    q_ellipse: torch.Tensor    # [S,3,3]
+    p_mid: torch.Tensor        # [S,3]
+    status: torch.Tensor       # [S] int32
+    iters: torch.Tensor | None = None      # [S] int32 (k of the IRIS loop)
+    collision: torch.Tensor | None = None  # [S] int32 (line sets)
+
+    def to_sets(self):
+        """Host list of [A (m,3), b (m,)] like the reference's set representation."""
+        A, b, m = self.A.cpu().numpy(), self.b.cpu().numpy(), self.m.cpu().numpy()
+        return [[A[s, : m[s]].copy(), b[s, : m[s]].copy()] for s in range(A.shape[0])]
+
+
+def _alloc_sets(S, m_max):
+    dev = "cuda"
+    # padded rows follow normalize_set_size: A = 0, b = 10 (util_functions.py:121-122)
+    A = torch.zeros((S, m_max, 3), dtype=torch.float64, device=dev)
+    b = torch.full((S, m_max), 10.0, dtype=torch.float64, device=dev)
+    m = torch.zeros((S,), dtype=torch.int32, device=dev)
+    return A, b, m
+
+
+def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS):
+    """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds."""
+    lib = _lib.load()
+    seeds = _dev(seeds).reshape(-1, 3)
+    S = seeds.shape[0]
+    A, b, m = _alloc_sets(S, m_max)
+    q = torch.zeros((S, 3, 3), dtype=torch.float64, device="cuda")
+    p = torch.zeros((S, 3), dtype=torch.float64, device="cuda")
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    iters = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    wbytes = lib.bp_build_sets_workspace_bytes(S)
+    work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
+    amin, pmin = _host3(ws_min)      # host arrays must outlive the call
+    amax, pmax = _host3(ws_max)
+    check(lib.bp_build_sets_point(scene._h, _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)), int(bool(optimize)),
+                                  int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m), _ptr(q), _ptr(p),
+                                  _ptr(status), _ptr(iters), _ptr(work), wbytes, _stream()))
+    del amin, amax
+    return SetBatch(A, b, m, q, p, status, iters=iters)
+
+
+def build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False, limit_space=False, e_max=0.3,
+                    m_max=BP_MAX_ROWS):
+    """ConvexSetFinder.find_set_collision_avoidance (ConvexSetFinder.py:309-375) for S segments."""
+    lib = _lib.load()
+    p0 = _dev(p0).reshape(-1, 3)
+    p1 = _dev(p1).reshape(-1, 3)
+    S = p0.shape[0]
+    A, b, m = _alloc_sets(S, m_max)
+    q = torch.zeros((S, 3, 3), dtype=torch.float64, device="cuda")
+    p = torch.zeros((S, 3), dtype=torch.float64, device="cuda")
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    coll = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    wbytes = lib.bp_build_sets_workspace_bytes(S)
+    work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
+    amin, pmin = _host3(ws_min)      # host arrays must outlive the call
+    amax, pmax = _host3(ws_max)
+    check(lib.bp_build_sets_line(scene._h, _ptr(p0), _ptr(p1), S, pmin, pmax, int(bool(limit_space)), float(e_max),
+                                 int(bool(compute_ellipsoid)), int(m_max), _ptr(A), _ptr(b), _ptr(m), _ptr(q),
+                                 _ptr(p), _ptr(coll), _ptr(status), _ptr(work), wbytes, _stream()))
+    del amin, amax
+    return SetBatch(A, b, m, q, p, status, collision=coll)
+
+
+def closest_points(scene, seeds, q_inv):
+    """ConvexSetFinder.compute_set_projs (:465-489) + dists (:429): y [S,N,3], dist [S,N]."""
+    lib = _lib.load()
+    seeds = _dev(seeds).reshape(-1, 3)
+    q_inv = _dev(q_inv).reshape(-1, 3, 3)
+    S = seeds.shape[0]
+    y = torch.empty((S, scene.n, 3), dtype=torch.float64, device="cuda")
+    dist = torch.empty((S, scene.n), dtype=torch.float64, device="cuda")
+    check(lib.bp_closest_points(scene._h, _ptr(seeds), _ptr(q_inv), S, _ptr(y), _ptr(dist), _stream()))
+    return y, dist
+
+
+def closest_points_line(scene, p0, p1):
+    """ConvexSetFinder.compute_set_projs_line (:491-510): x [S,N,3], phi [S,N]."""
+    lib = _lib.load()
+    p0 = _dev(p0).reshape(-1, 3)
+    p1 = _dev(p1).reshape(-1, 3)
+    S = p0.shape[0]
+    x = torch.empty((S, scene.n, 3), dtype=torch.float64, device="cuda")
+    phi = torch.empty((S, scene.n), dtype=torch.float64, device="cuda")
+    check(lib.bp_closest_points_line(scene._h, _ptr(p0), _ptr(p1), S, _ptr(x), _ptr(phi), _stream()))
+    return x, phi
+
+
+def polyhedron(scene, seeds, q_inv, q_ellipse, init_rows, m_max=BP_MAX_ROWS):
+    """ConvexSetFinder.compute_polyhedron (:423-463): one greedy pass for S seeds.
+    init_rows: [S,6,4] (a | b)."""
+    lib = _lib.load()
+    seeds = _dev(seeds).reshape(-1, 3)
+    S = seeds.shape[0]
+    q_inv = _dev(q_inv).reshape(S, 3, 3)
+    q_ellipse = _dev(q_ellipse).reshape(S, 3, 3)
+    init_rows = _dev(init_rows).reshape(S, 6, 4)
+    A, b, m = _alloc_sets(S, m_max)
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    check(lib.bp_polyhedron(scene._h, _ptr(seeds), _ptr(q_inv), _ptr(q_ellipse), _ptr(init_rows), S, int(m_max),
+                            _ptr(A), _ptr(b), _ptr(m), _ptr(status), _stream()))
+    return A, b, m, status
+
+
+def mvie(A, b, m, centre, free_centre):
+    """mvie_socp (free_centre=True, :512-537) / mvie_socp_fixed_mid (:539-562) for S sets.
+    Returns q_inv (= L L^T), q_ellipse (= q_inv^-1), centre, status, newton_iters."""
+    lib = _lib.load()
+    A = _dev(A)
+    S, m_max = A.shape[0], A.shape[1]
+    b = _dev(b).reshape(S, m_max)
+    m = _dev(m, torch.int32).reshape(S)
+    centre = _dev(centre).reshape(S, 3)
+    q_inv = torch.empty((S, 3, 3), dtype=torch.float64, device="cuda")
+    q_ell = torch.empty((S, 3, 3), dtype=torch.float64, device="cuda")
+    c_out = torch.empty((S, 3), dtype=torch.float64, device="cuda")
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    its = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    check(lib.bp_mvie(_ptr(A), _ptr(b), _ptr(m), S, m_max, int(bool(free_centre)), _ptr(centre), _ptr(q_inv),
+                      _ptr(q_ell), _ptr(c_out), _ptr(status), _ptr(its), _stream()))
+    return q_inv, q_ell, c_out, status, its
+
+
+def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None):
+    """BoundPlanner.set_intersection (BoundPlanner.py:774-787, tol from :797) for all
+    pairs (i, j>i), i in [row_begin,row_end).  Returns uint32-packed bits as an
+    int32 tensor [rows, ceil(S/32)]."""
+    lib = _lib.load()
+    S, m_max = A.shape[0], A.shape[1]
+    if row_end is None:
+        row_end = S
+    words = (S + 31) // 32
+    bits = torch.zeros((row_end - row_begin, words), dtype=torch.int32, device="cuda")
+    check(lib.bp_pair_feasible(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), int(row_begin), int(row_end),
+                               _ptr(bits), _stream()))
+    return bits
+
+
+def unpack_adjacency(bits, S, row_begin=0):
+    """int32 words [rows, words] -> bool [rows, S]."""
+    shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+    b = ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
+    return b.reshape(bits.shape[0], -1)[:, :S]
+
+
+def fk_iiwa14(q, want_pose=False, want_jacobian=False):
+    """RobotModel.fk_pos / fk_pos_col / hom_transform_endeffector / jacobian_fk
+    (RobotModel.py:146-231) for B configurations.  Returns (p_ee [B,3],
+    p_col [B,7,3], T_ee [B,4,4] | None, jac [B,6,7] | None)."""
+    lib = _lib.load()
+    q = _dev(q).reshape(-1, 7)
+    B = q.shape[0]
+    p_ee = torch.empty((B, 3), dtype=torch.float64, device="cuda")
+    p_col = torch.empty((B, 7, 3), dtype=torch.float64, device="cuda")
+    T = torch.empty((B, 4, 4), dtype=torch.float64, device="cuda") if want_pose else None
+    J = torch.empty((B, 6, 7), dtype=torch.float64, device="cuda") if want_jacobian else None
+    check(lib.bp_fk_iiwa14(_ptr(q), B, _ptr(p_ee), _ptr(p_col), _ptr(T), _ptr(J), _stream()))
+    return p_ee, p_col, T, J

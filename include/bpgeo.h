@@ -1,0 +1,126 @@
+/* bpgeo.h -- C ABI of libbpgeo.so, the B200-native geometry core for BoundPlanner.
+ *
+ * The reference (Thieso/BoundPlanner) is pure Python and has no FFI of its own:
+ * the seam is the Python object boundary between the planner / BoundMPC and
+ *   - ConvexSetFinder            bound_planner/BoundPlanner/ConvexSetFinder.py:102-766
+ *   - BoundPlanner.set_intersection / add_edges
+ *                                bound_planner/BoundPlanner/BoundPlanner.py:774-798
+ *   - RobotModel.fk*             bound_planner/RobotModel/RobotModel.py:146-231
+ * Every entry point below names the reference call it replaces.  The Python
+ * stubs that bind it are in boundplanner_b200/_lib.py; the one-line changes a
+ * reference maintainer would make are in INTEGRATION.md.
+ *
+ * Conventions
+ *   - fp64 everywhere, row-major.
+ *   - "dev" pointers are CUDA device pointers owned by the caller; "host"
+ *     pointers are ordinary host memory.  The library owns only bp_scene.
+ *   - All kernels are enqueued on `stream` (a cudaStream_t passed as void*);
+ *     no hidden synchronisation, no hidden allocation: scratch comes from the
+ *     caller through (workspace, workspace_bytes), sized by the *_workspace_bytes
+ *     query.
+ *   - Return value: 0 on success, non-zero on error; bp_last_error_string()
+ *     describes the last error of the calling thread.
+ *   - Per-item status codes (int32, one per seed / segment):
+ *       BP_OK 0, BP_ELLIPSE_VIOLATION 1 (ConvexSetFinder.py:433-438 RuntimeError),
+ *       BP_ROW_OVERFLOW 2 (more than m_max rows), BP_MVIE_NO_INTERIOR 3,
+ *       BP_MVIE_NOT_CONVERGED 4.
+ *   - There is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef BPGEO_H
+#define BPGEO_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPGEO_ABI_VERSION 1
+#define BP_MAX_ROWS 48 /* hard cap on rows per convex set (reference MVIE cap: 20, quirk Q5) */
+
+typedef struct bp_scene bp_scene;
+
+int bpgeo_abi_version(void);
+const char* bp_last_error_string(void);
+
+/* ---- obstacle scene ---------------------------------------------------------
+ * Replaces BoundPlanner.make_box / add_obstacle_reps (BoundPlanner.py:126-152):
+ * box k = [lbx,lby,lbz,ubx,uby,ubz]; the library stores lb - inflate, ub + inflate
+ * (b += obs_size_increase, :141) as SoA columns in HBM.  boxes_host: [n,6]. */
+int bp_scene_create(const double* boxes_host, int n, double inflate, bp_scene** out);
+int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream);
+int bp_scene_destroy(bp_scene* scene);
+int bp_scene_size(const bp_scene* scene);
+
+/* ---- K1: closest points in the ellipsoid metric -----------------------------
+ * Replaces ConvexSetFinder.compute_set_projs (:465-489; OSQP QP :10-49) for
+ * S (p0, q_inv) pairs at once.  y_out[S,N,3] = E x* + p0, dist_out[S,N] =
+ * || q_inv^-1 (y - p0) ||  (the `dists` of compute_polyhedron, :429). */
+int bp_closest_points(const bp_scene* scene, const double* seeds_dev /*[S,3]*/, const double* q_inv_dev /*[S,3,3]*/,
+                      int S, double* y_out_dev, double* dist_out_dev, void* stream);
+
+/* ---- K2: closest points to a segment ----------------------------------------
+ * Replaces ConvexSetFinder.compute_set_projs_line (:491-510; qpOASES QP :52-99).
+ * x_out[S,N,3], phi_out[S,N]; obstacles are shrunk by 0.001 as at :496. */
+int bp_closest_points_line(const bp_scene* scene, const double* p0_dev /*[S,3]*/, const double* p1_dev /*[S,3]*/,
+                           int S, double* x_out_dev, double* phi_out_dev, void* stream);
+
+/* ---- K3: one greedy separating-halfspace pass --------------------------------
+ * Replaces ConvexSetFinder.compute_polyhedron (:423-463) for S seeds.
+ * init_rows_dev: [S,6,4] rows (a0,a1,a2,b) that start every set (init_halfspaces).
+ * Output rows A[S,m_max,3], b[S,m_max], m[S], status[S]. */
+int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* q_inv_dev, const double* q_ellipse_dev,
+                  const double* init_rows_dev, int S, int m_max, double* A_dev, double* b_dev, int* m_dev,
+                  int* status_dev, void* stream);
+
+/* ---- K4: maximum-volume inscribed ellipsoid -----------------------------------
+ * Replaces ConvexSetFinder.mvie_socp (:512-537, free_centre=1; centre_dev is an
+ * interior start hint) and mvie_socp_fixed_mid (:539-562, free_centre=0;
+ * centre_dev is the fixed centre).  q_inv_out = L L^T [S,3,3], q_ellipse_out =
+ * its inverse [S,3,3], centre_out [S,3]. */
+int bp_mvie(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*[S,m_max]*/, const int* m_dev /*[S]*/, int S,
+            int m_max, int free_centre, const double* centre_dev /*[S,3]*/, double* q_inv_out_dev,
+            double* q_ellipse_out_dev, double* centre_out_dev, int* status_dev, int* newton_iters_dev /*or NULL*/,
+            void* stream);
+
+/* ---- K5: the whole IRIS loop ---------------------------------------------------
+ * Replaces ConvexSetFinder.find_set_around_point (:190-240) for S seeds.
+ * ws_min/ws_max (host, 3 each) are the workspace box of init_halfspaces (:377-398).
+ * Outputs: A[S,m_max,3], b[S,m_max], m[S] (6 + picked rows, NOT reduced),
+ * q_ellipse[S,3,3], p_mid[S,3], status[S], iters[S] (k of the while loop). */
+size_t bp_build_sets_workspace_bytes(int S);
+int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, const double* ws_min_host,
+                        const double* ws_max_host, int fixed_mid, int optimize, int max_iter, int m_max,
+                        double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev, double* p_mid_dev,
+                        int* status_dev, int* iters_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces ConvexSetFinder.find_set_collision_avoidance (:309-375) for S segments.
+ * limit_space selects init_halfspaces_point(p0, e_max) (:400-421).  collision[S]
+ * is the reference's `collision` flag (:336-345).  q_ellipse / p_mid are written
+ * only when compute_ellipsoid != 0. */
+int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double* p1_dev, int S,
+                       const double* ws_min_host, const double* ws_max_host, int limit_space, double e_max,
+                       int compute_ellipsoid, int m_max, double* A_dev, double* b_dev, int* m_dev,
+                       double* q_ellipse_dev, double* p_mid_dev, int* collision_dev, int* status_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- K6: pairwise set-intersection test -----------------------------------------
+ * Replaces BoundPlanner.set_intersection (BoundPlanner.py:774-787) as called by
+ * add_edges with tol = 0.01 (:796-798), for every pair (i, j), i in
+ * [row_begin,row_end), j in (i, S).  adj_bits_dev: [(row_end-row_begin), words]
+ * uint32 words, words = (S+31)/32; bit j of row i is 1 iff sets i and j intersect.
+ * Bits with j <= i are 0. */
+int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*[S,m_max]*/, const int* m_dev /*[S]*/,
+                     int S, int m_max, double tol, int row_begin, int row_end, unsigned int* adj_bits_dev,
+                     void* stream);
+
+/* ---- K7: iiwa14 forward kinematics -----------------------------------------------
+ * Replaces the numeric branch of RobotModel.fk_pos (RobotModel.py:146-160),
+ * fk_pos_col (:162-181), hom_transform_endeffector (:197-211), jacobian_fk
+ * (:213-231).  q[B,7]; p_ee[B,3]; p_col[B,7,3] (joint_3..7, link4_col, ee_col);
+ * T_ee[B,4,4] or NULL; jac[B,6,7] or NULL. */
+int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev, double* T_ee_dev, double* jac_dev,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPGEO_H */

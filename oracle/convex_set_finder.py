@@ -109,7 +109,7 @@ def closest_points_segment_boxes(lb, ub, p0, p1):
     # among (numerically) equal minimisers take the smallest phi (quirk Q9)
     phi_out = np.full(N, np.inf)
     x_out = np.zeros((N, 3))
-    thr = best * (1.0 + 1e-12) + 1e-300
+    thr = best * (1.0 + 1e-12) + 1e-24
     for obj, phi, x in cands:
         sel = (obj <= thr) & (phi < phi_out)
         phi_out[sel] = phi[sel]
