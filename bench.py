@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the BoundPlanner geometry core on B200.
+
+Workload (BASELINE.json configs[1], "C2"): synthetic 1k random box obstacles,
+256 seeds per GPU, set inflation (find_set_around_point, fixed_mid=True,
+optimize=True) + all-pairs set-graph build (tol 0.01).  One "step" = one pass of
+that hot path over the seed batch.  Metric: convex sets built per second
+(whole job), with set-pair checks/s alongside.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): every rank builds its
+own 256 seeds over the replicated scene (weak scaling), the halfspace tensors
+are all-gathered and the pair matrix is split in balanced row blocks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_OBS = 1000
+N_SEEDS = 256           # per GPU
+TOL = 0.01
+METRIC = "convex_sets_built_per_sec"
+UNIT = "sets/s"
+WORKLOAD = "C2: 1000 random box obstacles (edge U[0.02,0.08], inflate 0.01), 256 seeds/GPU, IRIS loop fixed_mid + all-pairs set graph tol 0.01"
+
+
+# ----------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's Python path
+# ----------------------------------------------------------------------------
+def _oracle_worker(args):
+    boxes, inflate, ws_min, ws_max, seeds = args
+    from oracle.convex_set_finder import ConvexSetFinder
+    from oracle.obstacles import obstacle_reps
+
+    obs_sets, pts, _ = obstacle_reps(boxes, inflate)
+    f = ConvexSetFinder(obs_sets, pts, ws_max, ws_min, max_rows=None)
+    sets = []
+    for p in seeds:
+        try:
+            A, b, _, _ = f.find_set_around_point(p, fixed_mid=True, optimize=True)
+            sets.append([A, b])
+        except RuntimeError:
+            pass
+    return sets
+
+
+def cpu_sample(boxes, inflate, ws_min, ws_max, seeds, cores):
+    """Build len(seeds) sets with the oracle on `cores` processes and test all their
+    pairs with the reference's linprog call; returns (seconds, n_sets, n_pairs)."""
+    from oracle.set_graph import set_intersection
+
+    t0 = time.perf_counter()
+    if cores == 1:
+        sets = _oracle_worker((boxes, inflate, ws_min, ws_max, seeds))
+    else:
+        import multiprocessing as mp
+
+        chunks = [seeds[i::cores] for i in range(cores)]
+        with mp.get_context("fork").Pool(cores) as pool:
+            parts = pool.map(_oracle_worker, [(boxes, inflate, ws_min, ws_max, c) for c in chunks if len(c)])
+        sets = [s for p in parts for s in p]
+    npairs = 0
+    for i in range(len(sets)):
+        for j in range(i):
+            set_intersection(sets[i], sets[j], TOL)
+            npairs += 1
+    return time.perf_counter() - t0, len(seeds), npairs
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The true
+    reference cannot run here (casadi/cvxpy/cdd absent, no network), so this is
+    the oracle port (kind "port"), split over all host cores, on a bounded sample
+    of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from boundplanner_b200 import scenes
+
+    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(N_OBS, N_SEEDS)
+    cores = os.cpu_count() or 1
+    cores = min(cores, 32)
+    per_step = max(cores * 2, 8)
+    for _ in range(args.warmup):
+        cpu_sample(boxes, inflate, ws_min, ws_max, seeds[: max(2, cores)], cores)
+    tot_t, tot_sets, tot_pairs = 0.0, 0, 0
+    for k in range(args.steps):
+        sel = seeds[(k * per_step) % N_SEEDS: (k * per_step) % N_SEEDS + per_step]
+        t, ns, npairs = cpu_sample(boxes, inflate, ws_min, ws_max, sel, cores)
+        tot_t += t
+        tot_sets += ns
+        tot_pairs += npairs
+    value = tot_sets / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{per_step} seeds + their pair checks per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} of the {N_SEEDS} C2 seeds per step, vectorised NumPy oracle "
+                                   f"(oracle/convex_set_finder.py) over {cores} processes + scipy linprog per pair"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pair_checks_per_sec": tot_pairs / tot_t,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from boundplanner_b200 import _lib, distributed as bpd, geometry as geo, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.load()
+
+    # same scene on every rank, per-rank seeds (weak scaling: 256 seeds per GPU)
+    boxes, inflate, seeds0, ws_min, ws_max = scenes.config_c2(N_OBS, N_SEEDS)
+    if rank == 0:
+        seeds = seeds0
+    else:
+        seeds = scenes.free_points(N_SEEDS, boxes, inflate, np.random.default_rng(100 + rank), ws_min, ws_max)
+    scene = geo.Scene(boxes, inflate)
+    seeds_host = torch.as_tensor(seeds).pin_memory()
+    seeds_dev = seeds_host.cuda()
+    S_total = N_SEEDS * world
+
+    def pair_fn(A, b, m, tol, r0, r1):
+        return geo.pair_feasible(A, b, m, tol, r0, r1)
+
+    def step_device(seeds_d):
+        out = geo.build_sets_point(scene, seeds_d, ws_min, ws_max, fixed_mid=True, optimize=True)
+        bits, _ = bpd.sharded_adjacency(out.A, out.b, out.m, pair_fn, TOL)
+        return out, bits
+
+    def step_e2e():
+        sd = seeds_host.cuda(non_blocking=True)                      # H2D of the step's inputs
+        out, bits = step_device(sd)
+        res = [t.cpu() for t in (out.A, out.b, out.m, out.q_ellipse, out.p_mid, out.status, bits)]   # D2H
+        return res
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out, bits = step_device(seeds_dev)
+    barrier()
+
+    # ---- timed region: K steps, device-resident inputs, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        ev[k][0].record()
+        out, bits = step_device(seeds_dev)
+        ev[k][1].record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        res = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = seeds_host.numel() * 8
+    d2h = sum(t.numel() * t.element_size() for t in res)
+
+    # ---- per-kernel timing of the dominant kernels (roofline), CUDA events on the launch stream
+    prof = kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch)
+
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = tt[0].item(), tt[1].item()
+    status = out.status.cpu().numpy()
+    mrows = out.m.cpu().numpy()
+    n_pairs = S_total * (S_total - 1) // 2
+    value = S_total * args.steps / (dev_ms * 1e-3)
+    launches_per_step = 1 + 5 * 2 + 1 + 1 + 1      # state_init, 5x(poly,mvie), final mvie, export, pair
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_obstacles": N_OBS, "seeds_per_gpu": N_SEEDS, "pairs": n_pairs,
+                       "l2": "flushed between timed steps (256 MiB fill)",
+                       "frac_sets_over_20_rows": float((mrows > 20).mean()),
+                       "frac_status_ok": float((status == 0).mean())},
+            "pair_checks_per_sec": n_pairs * args.steps / (dev_ms * 1e-3),
+            "e2e": {"value": S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": prof["roofline"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),
+            "kernels": prof["kernels"],
+        }
+        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            n_cpu = 24
+            t, ns, npairs = cpu_sample(boxes, inflate, ws_min, ws_max, seeds0[:n_cpu], 1)
+            line["cpu_baseline"] = {
+                "value": ns / t, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"first {n_cpu} of the {N_SEEDS} C2 seeds + their {npairs} pair checks, vectorised NumPy "
+                          "oracle (stronger than the reference's per-obstacle solver loop), 1 core"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
+    """Time the kernels of one step in isolation (CUDA events on the launch
+    stream, L2-cold) and build the roofline entry of the dominant one."""
+    import statistics
+
+    def timeit(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    S = seeds_dev.shape[0]
+    N = scene.n
+    # one polyhedron pass (K3) with the initial sphere, one fixed-mid and one free MVIE (K4) on the built rows
+    q0 = torch.eye(3, dtype=torch.float64, device="cuda").repeat(S, 1, 1)
+    init_rows = torch.zeros((S, 6, 4), dtype=torch.float64, device="cuda")
+    for i in range(3):
+        init_rows[:, 2 * i, i] = 1.0
+        init_rows[:, 2 * i, 3] = float(ws_max[i])
+        init_rows[:, 2 * i + 1, i] = -1.0
+        init_rows[:, 2 * i + 1, 3] = -float(ws_min[i])
+    t_poly = timeit(lambda: geo.polyhedron(scene, seeds_dev, q0 * 1e-4, q0 * 1e4, init_rows))
+    t_mvie_fm = timeit(lambda: geo.mvie(out.A, out.b, out.m, seeds_dev, False))
+    res = geo.mvie(out.A, out.b, out.m, seeds_dev, True)
+    t_mvie_free = timeit(lambda: geo.mvie(out.A, out.b, out.m, seeds_dev, True))
+    newton_free = float(res[4].double().mean().item())
+    newton_fm = float(geo.mvie(out.A, out.b, out.m, seeds_dev, False)[4].double().mean().item())
+    t_pair = timeit(lambda: geo.pair_feasible(out.A, out.b, out.m, TOL))
+    m_mean = float(out.m.double().mean().item())
+    kernels = {
+        "k_poly_point_ms": t_poly, "k_mvie_fixed_mid_ms": t_mvie_fm, "k_mvie_free_ms": t_mvie_free,
+        "k_pair_feasible_ms": t_pair, "newton_iters_fixed_mid": newton_fm, "newton_iters_free": newton_free,
+        "mean_rows": m_mean,
+    }
+
+    def roofline(hbm_peak, which):
+        # dominant kernel of the step: k_mvie (5 fixed-mid + 1 free per seed) vs 5 x k_poly_point
+        t_m = 5 * t_mvie_fm + t_mvie_free
+        t_p = 5 * t_poly
+        if t_m >= t_p:
+            # algorithmic bytes per launch: rows in (m*32 B) + shape/centre out (9+9+3)*8 B per set
+            bytes_alg = S * (m_mean * 32 + 21 * 8)
+            dur = t_mvie_free
+            name = "k_mvie(free centre)"
+            flops = S * newton_free * (m_mean * 200.0 + 250.0)
+        else:
+            # scene read once per CTA (N*48 B) + rows out per set
+            bytes_alg = S * (N * 48 + m_mean * 32)
+            dur = t_poly
+            name = "k_poly_point"
+            flops = S * N * (1100.0 + 64.0 * (m_mean - 6))
+        ach = bytes_alg / (dur * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": which,
+                "note": "fp64-latency-bound kernel: operands are L2/shared-memory resident, HBM traffic is "
+                        "compulsory input/output only; see fp64_gflops",
+                "fp64_gflops": flops / (dur * 1e-3) / 1e9}
+
+    return {"kernels": kernels, "roofline": roofline}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

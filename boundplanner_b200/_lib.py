@@ -44,6 +44,7 @@ SIGNATURES = {
                                 _vp, _sz, _vp]),
     "bp_pair_feasible": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp]),
     "bp_fk_iiwa14": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "bp_probe_fp64": (_i, [_i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,301 @@
+// bp_mvie_warp.cuh -- K4, warp-cooperative: ONE WARP solves one MVIE.
+//
+// Same algorithm, same constants and the same summation order over rows as the
+// thread-serial specification in bp_mvie.cuh (which the host harness tests
+// against the oracle); only the work distribution differs:
+//   * lanes own rows (row = lane, lane + 32): slack / cone residual / barrier
+//     gradient pieces are evaluated one row per lane;
+//   * the Hessian, gradient and second-moment sums are "dots of two feature
+//     columns over the rows": every lane owns up to two of the NH + NV + 6
+//     outputs and walks the rows in shared memory in ascending order;
+//   * the NV x NV LDL^T solve is done redundantly by every lane in registers,
+//     so all control flow (Newton / line-search / path-following decisions) is
+//     warp-uniform -- no divergence, no votes needed except feasibility.
+// The thread-per-set version ran at 2.1 active threads per warp (ncu,
+// profiles/r01_baseline_mvie_pair_summary.txt); this one keeps 32 lanes busy
+// on the row work and removes the serialisation.
+#pragma once
+#include "bp_mvie.cuh"
+
+// feature columns: rr[NV], tw*a[3], a[3], one; the row stride is kept odd so that
+// the per-lane row writes spread over the shared-memory banks
+#define BP_MVIE_W(NV) ((((NV) + 7) & 1) ? ((NV) + 7) : ((NV) + 8))
+#define BP_MVIE_SCRATCH_DOUBLES (BP_MAX_ROWS * 17 + 64)
+
+template <int NV>
+__device__ __forceinline__ void bp_mvie_decode_output(int e, int* cx, int* cy) {
+  constexpr int NH = NV * (NV + 1) / 2;
+  if (e < NH) {
+    int j = 0;
+    while ((j + 1) * (j + 2) / 2 <= e) ++j;
+    *cx = j;
+    *cy = e - j * (j + 1) / 2;
+  } else if (e < NH + NV) {
+    *cx = e - NH;
+    *cy = NV + 6;                                 // "one" column: plain sum
+  } else if (e < NH + NV + 6) {
+    const int w = e - NH - NV;                    // (p,q) in 00,01,02,11,12,22
+    const int p = w < 3 ? 0 : (w < 5 ? 1 : 2);
+    const int q = w < 3 ? w : (w < 5 ? w - 2 : 2);
+    *cx = NV + p;                                 // tw * a_p
+    *cy = NV + 3 + q;                             // a_q
+  } else {
+    *cx = -1;
+    *cy = -1;
+  }
+}
+
+__device__ __forceinline__ double bp_warp_min(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+__device__ __forceinline__ double bp_warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ double bp_warp_prod(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// A, b: global rows of this set; scratch: BP_MVIE_SCRATCH_DOUBLES doubles of shared memory private to the warp.
+template <int NV>
+__device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restrict__ b, int m, const double* c0,
+                            double* scratch, double* Lout, double* dout, int* iters_out) {
+  constexpr int NH = NV * (NV + 1) / 2;
+  constexpr int W = BP_MVIE_W(NV);
+  constexpr int NOUT = NH + NV + 6;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double* F = scratch;                          // [m][W]
+  double* OUT = scratch + BP_MAX_ROWS * 17;     // [64]
+
+  // rows owned by this lane
+  double ra[2][3], rb[2];
+  bool rv[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = lane + 32 * q;
+    rv[q] = i < m;
+    ra[q][0] = ra[q][1] = ra[q][2] = 0.0;
+    rb[q] = 1.0;
+    if (rv[q]) {
+      ra[q][0] = A[3 * i]; ra[q][1] = A[3 * i + 1]; ra[q][2] = A[3 * i + 2];
+      rb[q] = b[i];
+      F[i * W + NV + 3] = ra[q][0]; F[i * W + NV + 4] = ra[q][1]; F[i * W + NV + 5] = ra[q][2];
+      F[i * W + NV + 6] = 1.0;
+    }
+  }
+  int cx[2], cy[2];
+  bp_mvie_decode_output<NV>(lane, &cx[0], &cy[0]);
+  bp_mvie_decode_output<NV>(lane + 32, &cx[1], &cy[1]);
+
+  // strictly feasible start: ball of half the inradius around c0
+  double r = BP_INF;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (rv[q]) {
+      double s = rb[q] - (ra[q][0] * c0[0] + ra[q][1] * c0[1] + ra[q][2] * c0[2]);
+      double nrm = sqrt(ra[q][0] * ra[q][0] + ra[q][1] * ra[q][1] + ra[q][2] * ra[q][2]);
+      if (nrm > 0.0) r = fmin(r, s / nrm);
+      else if (!(s > 0.0)) r = -1.0;
+    }
+  }
+  r = bp_warp_min(r);
+  if (!(r > 0.0) || !(r < BP_INF)) return BP_MVIE_NO_INTERIOR;
+  r *= 0.5;
+  double x[NV];
+  x[0] = r; x[1] = 0.0; x[2] = r; x[3] = 0.0; x[4] = 0.0; x[5] = r;
+  if (NV == 9) { x[6] = c0[0]; x[7] = c0[1]; x[8] = c0[2]; }
+  double cen[3] = {c0[0], c0[1], c0[2]};
+
+  const double nu = 2.0 * m + 4.0;
+  const double t_final = nu / BP_MVIE_GAP_TOL;
+  double t = 1.0;
+  int iters = 0;
+  int status = BP_OK;
+  double xc_prev[NV];
+  double t_prev = 0.0;
+  for (int outer = 0; outer < BP_MVIE_OUTER_MAX; ++outer) {
+    const bool last = (t >= t_final);
+    const double inner_tol = last ? 1e-13 : BP_MVIE_INNER_TOL;
+    double lam2_prev = BP_INF;
+    bool centred = false;
+    for (int inner = 0; inner < BP_MVIE_INNER_MAX; ++inner) {
+      ++iters;
+      if (NV == 9) { cen[0] = x[6]; cen[1] = x[7]; cen[2] = x[8]; }
+      // ---- per-row barrier pieces -> feature rows
+      double rs[2], ru[2][3], rpsi[2], rtw[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double a0 = ra[q][0], a1 = ra[q][1], a2 = ra[q][2];
+        const double s = rb[q] - (a0 * cen[0] + a1 * cen[1] + a2 * cen[2]);
+        const double u0 = x[0] * a0 + x[1] * a1 + x[3] * a2;
+        const double u1 = x[2] * a1 + x[4] * a2;
+        const double u2 = x[5] * a2;
+        const double psi = s * s - (u0 * u0 + u1 * u1 + u2 * u2);
+        rs[q] = s; ru[q][0] = u0; ru[q][1] = u1; ru[q][2] = u2; rpsi[q] = psi;
+        rtw[q] = 0.0;
+        if (rv[q]) {
+          const double tw = 2.0 * (1.0 / psi);
+          rtw[q] = tw;
+          double* f = F + (lane + 32 * q) * W;
+          f[0] = -u0 * a0 * tw; f[1] = -u0 * a1 * tw; f[2] = -u1 * a1 * tw;
+          f[3] = -u0 * a2 * tw; f[4] = -u1 * a2 * tw; f[5] = -u2 * a2 * tw;
+          if (NV == 9) { f[6] = -s * a0 * tw; f[7] = -s * a1 * tw; f[8] = -s * a2 * tw; }
+          f[NV] = tw * a0; f[NV + 1] = tw * a1; f[NV + 2] = tw * a2;
+        }
+      }
+      __syncwarp();
+      // ---- column dots over the rows (ascending row order, like the serial code).
+      // Control flow is kept warp-uniform: with more than 32 outputs every lane
+      // walks two column pairs (lanes without a second output walk a dummy).
+      {
+        double acc0 = 0.0, acc1 = 0.0;
+        const int ax0 = cx[0], ay0 = cy[0];
+        if (NOUT > 40) {
+          const int ax1 = cx[1] >= 0 ? cx[1] : 0, ay1 = cx[1] >= 0 ? cy[1] : 0;
+          for (int i = 0; i < m; ++i) {
+            const double* f = F + i * W;
+            acc0 += f[ax0] * f[ay0];
+            acc1 += f[ax1] * f[ay1];
+          }
+          if (cx[1] >= 0) OUT[lane + 32] = acc1;
+        } else {
+          for (int i = 0; i < m; ++i) {
+            const double* f = F + i * W;
+            acc0 += f[ax0] * f[ay0];
+          }
+          // NV == 6: 33 outputs; the last one (W22) comes from a butterfly sum
+          const double w22 = bp_warp_sum(rtw[0] * ra[0][2] * ra[0][2] + rtw[1] * ra[1][2] * ra[1][2]);
+          if (lane == 0) OUT[32] = w22;
+        }
+        OUT[lane] = acc0;
+      }
+      __syncwarp();
+      double g[NV], H[NH];
+#pragma unroll
+      for (int k = 0; k < NH; ++k) H[k] = OUT[k];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) g[k] = -OUT[NH + k];
+      {
+        const double w00 = OUT[NH + NV], w01 = OUT[NH + NV + 1], w02 = OUT[NH + NV + 2];
+        const double w11 = OUT[NH + NV + 3], w12 = OUT[NH + NV + 4], w22 = OUT[NH + NV + 5];
+        H[0] += w00; H[1] += w01; H[2] += w11; H[6] += w02; H[7] += w12; H[9] += w22;
+        H[5] += w11; H[12] += w12; H[14] += w22; H[20] += w22;
+        if (NV == 9) { H[27] -= w00; H[34] -= w01; H[35] -= w11; H[42] -= w02; H[43] -= w12; H[44] -= w22; }
+        const double i0 = 1.0 / x[0], i2 = 1.0 / x[2], i5 = 1.0 / x[5];
+        g[0] -= t * i0; g[2] -= 2.0 * t * i2; g[5] -= t * i5;
+        H[0] += t * i0 * i0; H[5] += 2.0 * t * i2 * i2; H[20] += t * i5 * i5;
+      }
+      __syncwarp();                      // OUT is rewritten next iteration
+      double dx[NV];
+      if (!bp_ldl_solve<NV>(H, g, dx)) {
+        status = (t > 1e8) ? BP_OK : BP_MVIE_NOT_CONVERGED;
+        goto done;
+      }
+      double lam2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) lam2 -= g[k] * dx[k];
+      if (!(lam2 > 0.0)) { centred = true; break; }
+      // ---- line search: psi(x + alpha dx) = psi + alpha B1 + alpha^2 A2 per row
+      double dcn[3] = {0.0, 0.0, 0.0};
+      if (NV == 9) { dcn[0] = dx[6]; dcn[1] = dx[7]; dcn[2] = dx[8]; }
+      double rds[2], rB1[2], rA2[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double a0 = ra[q][0], a1 = ra[q][1], a2 = ra[q][2];
+        const double ds = -(a0 * dcn[0] + a1 * dcn[1] + a2 * dcn[2]);
+        const double e0 = dx[0] * a0 + dx[1] * a1 + dx[3] * a2;
+        const double e1 = dx[2] * a1 + dx[4] * a2;
+        const double e2 = dx[5] * a2;
+        rds[q] = ds;
+        rB1[q] = 2.0 * (rs[q] * ds - (ru[q][0] * e0 + ru[q][1] * e1 + ru[q][2] * e2));
+        rA2[q] = ds * ds - (e0 * e0 + e1 * e1 + e2 * e2);
+      }
+      double alpha = 1.0;
+      bool accepted = false;
+      for (int bt = 0; bt < 60; ++bt) {
+        bool ok = (x[0] + alpha * dx[0] > 0.0) && (x[2] + alpha * dx[2] > 0.0) && (x[5] + alpha * dx[5] > 0.0);
+        double prod = 1.0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (rv[q]) {
+            const double rel = alpha * (rB1[q] + alpha * rA2[q]) / rpsi[q];
+            if (!(rs[q] + alpha * rds[q] > 0.0) || !(rel > -1.0)) ok = false;
+            prod *= 1.0 + rel;
+          }
+        }
+        ok = __all_sync(full, ok);
+        if (ok) {
+          if (lam2 < 0.01) accepted = true;
+          else {
+            const double logsum = log(bp_warp_prod(prod));
+            const double dF = -t * (log1p(alpha * dx[0] / x[0]) + 2.0 * log1p(alpha * dx[2] / x[2]) +
+                                    log1p(alpha * dx[5] / x[5])) - logsum;
+            if (dF <= -0.25 * alpha * lam2) accepted = true;
+          }
+          if (accepted) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) x[k] += alpha * dx[k];
+            break;
+          }
+        }
+        alpha *= 0.5;
+      }
+      if (!accepted) { centred = lam2 < 1e-2; break; }
+      if (lam2 < inner_tol) { centred = true; break; }
+      if (lam2 < 1e-3 && lam2 > 0.1 * lam2_prev) { centred = true; break; }
+      lam2_prev = lam2;
+    }
+    if (last) {
+      if (!centred) status = BP_MVIE_NOT_CONVERGED;
+      break;
+    }
+    // ---- next barrier parameter + secant predictor in tau = 1/t
+    double t_next = t * BP_MVIE_T_MULT;
+    if (t_next > t_final) t_next = t_final;
+    if (t_prev > 0.0 && t >= BP_MVIE_PRED_FROM) {
+      double w = (1.0 / t_next - 1.0 / t) / (1.0 / t - 1.0 / t_prev);
+      double xp[NV];
+      bool ok = false;
+      for (int tr = 0; tr < 4 && !ok; ++tr) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) xp[k] = x[k] + w * (x[k] - xc_prev[k]);
+        ok = (xp[0] > 0.0) && (xp[2] > 0.0) && (xp[5] > 0.0);
+        double cp[3] = {cen[0], cen[1], cen[2]};
+        if (NV == 9) { cp[0] = xp[6]; cp[1] = xp[7]; cp[2] = xp[8]; }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (rv[q]) {
+            const double a0 = ra[q][0], a1 = ra[q][1], a2 = ra[q][2];
+            const double s = rb[q] - (a0 * cp[0] + a1 * cp[1] + a2 * cp[2]);
+            const double u0 = xp[0] * a0 + xp[1] * a1 + xp[3] * a2;
+            const double u1 = xp[2] * a1 + xp[4] * a2;
+            const double u2 = xp[5] * a2;
+            if (!(s > 0.0) || !(s * s - (u0 * u0 + u1 * u1 + u2 * u2) > 0.0)) ok = false;
+          }
+        }
+        ok = __all_sync(full, ok);
+        w *= 0.5;
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { xc_prev[k] = x[k]; if (ok) x[k] = xp[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) xc_prev[k] = x[k];
+    }
+    t_prev = t;
+    t = t_next;
+  }
+done:
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Lout[k] = x[k];
+  if (NV == 9) { dout[0] = x[6]; dout[1] = x[7]; dout[2] = x[8]; }
+  else { dout[0] = c0[0]; dout[1] = c0[1]; dout[2] = c0[2]; }
+  if (iters_out) *iters_out = iters;
+  return status;
+}

@@ -22,6 +22,7 @@
 #include "../../include/bpgeo.h"
 #include "bp_math.cuh"
 #include "bp_mvie.cuh"
+#include "bp_mvie_warp.cuh"
 #include "bp_lp.cuh"
 #include "bp_fk.cuh"
 
@@ -436,20 +437,12 @@ __global__ void __launch_bounds__(512) k_poly_line(SceneView sc, LineParams pr) 
 }
 
 // ---------------------------------------------------------------------------
-// K4: MVIE, one thread per set, 32 sets per CTA; rows staged in shared memory
-// as [coef][row][lane] so that every lane reads its own bank.
+// K4: MVIE, one warp (one 32-thread CTA) per set -- see bp_mvie_warp.cuh.
 // mode 0: loop step with fixed centre   (mvie_socp_fixed_mid, :220-221)
 // mode 1: loop step with free centre    (mvie_socp, :222-223)
 // mode 2: final free-centre solve after the loop (:235-238), no loop control
 // mode 3: standalone (bp_mvie), centre/hint from `centre`, free_centre flag
 // ---------------------------------------------------------------------------
-struct SmemRows {
-  const double* base;   // shared
-  int lane;
-  __device__ __forceinline__ double a(int i, int k) const { return base[(k * BP_MAX_ROWS + i) * 32 + lane]; }
-  __device__ __forceinline__ double b(int i) const { return base[(3 * BP_MAX_ROWS + i) * 32 + lane]; }
-};
-
 struct MvieParams {
   const double* A;
   const double* b;
@@ -469,41 +462,29 @@ struct MvieParams {
 };
 
 __global__ void __launch_bounds__(32) k_mvie(MvieParams pr) {
-  extern __shared__ double s_rows[];
+  __shared__ double scratch[BP_MVIE_SCRATCH_DOUBLES];
   const int lane = threadIdx.x;
-  const int s = blockIdx.x * 32 + lane;
-  const bool valid = s < pr.S;
-  bool run = valid;
+  const int s = blockIdx.x;                 // one warp (= one CTA) per set: everything below is warp-uniform
   SeedState* st = nullptr;
-  double c0[3] = {0.0, 0.0, 0.0};
-  if (valid) {
-    if (pr.mode <= 2) {
-      st = pr.state + s;
-      run = (st->status == BP_OK) && (pr.mode == 2 || st->active);
-      c0[0] = st->p[0]; c0[1] = st->p[1]; c0[2] = st->p[2];
-      if (pr.mode == 2 && pr.hint) { c0[0] = pr.hint[3 * s]; c0[1] = pr.hint[3 * s + 1]; c0[2] = pr.hint[3 * s + 2]; }
-    } else {
-      c0[0] = pr.centre[3 * s]; c0[1] = pr.centre[3 * s + 1]; c0[2] = pr.centre[3 * s + 2];
-    }
+  double c0[3];
+  if (pr.mode <= 2) {
+    st = pr.state + s;
+    const bool run = (st->status == BP_OK) && (pr.mode == 2 || st->active);
+    if (!run) return;
+    c0[0] = st->p[0]; c0[1] = st->p[1]; c0[2] = st->p[2];
+    if (pr.mode == 2 && pr.hint) { c0[0] = pr.hint[3 * s]; c0[1] = pr.hint[3 * s + 1]; c0[2] = pr.hint[3 * s + 2]; }
+  } else {
+    c0[0] = pr.centre[3 * s]; c0[1] = pr.centre[3 * s + 1]; c0[2] = pr.centre[3 * s + 2];
   }
-  int m = 0;
-  if (run) {
-    m = pr.m[s];
-    const double* A = pr.A + (size_t)s * pr.m_max * 3;
-    const double* b = pr.b + (size_t)s * pr.m_max;
-    for (int i = 0; i < m; ++i) {
-      s_rows[(0 * BP_MAX_ROWS + i) * 32 + lane] = A[3 * i + 0];
-      s_rows[(1 * BP_MAX_ROWS + i) * 32 + lane] = A[3 * i + 1];
-      s_rows[(2 * BP_MAX_ROWS + i) * 32 + lane] = A[3 * i + 2];
-      s_rows[(3 * BP_MAX_ROWS + i) * 32 + lane] = b[i];
-    }
-  }
-  if (!run) return;
-  SmemRows rows{s_rows, lane};
+  const int m = pr.m[s];
+  const double* A = pr.A + (size_t)s * pr.m_max * 3;
+  const double* b = pr.b + (size_t)s * pr.m_max;
   double L[6], d[3];
   int iters = 0;
   const bool free_c = (pr.mode == 1 || pr.mode == 2 || (pr.mode == 3 && pr.free_centre));
-  int status = free_c ? bp_mvie_solve<9>(rows, m, c0, L, d, &iters) : bp_mvie_solve<6>(rows, m, c0, L, d, &iters);
+  const int status = free_c ? bp_mvie_warp<9>(A, b, m, c0, scratch, L, d, &iters)
+                            : bp_mvie_warp<6>(A, b, m, c0, scratch, L, d, &iters);
+  if (lane != 0) return;
   double E[9], Q[9], detQ;
   bp_shape_from_L(L, E, Q, &detQ);
   if (pr.mode <= 2) {
@@ -590,12 +571,11 @@ __global__ void __launch_bounds__(256) k_pair_feasible(const double* __restrict_
   const int j = blockIdx.x * 32 + lane;
   const int words = (S + 31) >> 5;
   if (i >= row_end) return;
-  int res = 0;
-  if (j < S && j > i) {
-    GlobalRows r1{A + (size_t)i * m_max * 3, b + (size_t)i * m_max};
-    GlobalRows r2{A + (size_t)j * m_max * 3, b + (size_t)j * m_max};
-    res = bp_pair_feasible(r1, m[i], r2, m[j], tol, (double*)nullptr, (int*)nullptr);
-  }
+  const bool active = (j < S && j > i);
+  const int jj = active ? j : i;                  // inactive lanes only take part in the warp votes
+  GlobalRows r1{A + (size_t)i * m_max * 3, b + (size_t)i * m_max};
+  GlobalRows r2{A + (size_t)jj * m_max * 3, b + (size_t)jj * m_max};
+  const int res = bp_pair_feasible(r1, m[i], r2, m[jj], tol, (double*)nullptr, (int*)nullptr, active);
   unsigned int word = __ballot_sync(0xffffffffu, res != 0);
   if (lane == 0) adj[(size_t)(i - row_begin) * words + blockIdx.x] = word;
 }
@@ -752,13 +732,7 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
 }
 
 static int launch_mvie(const MvieParams& pr, cudaStream_t stream) {
-  static bool attr_set = false;
-  const size_t smem = sizeof(double) * 4 * BP_MAX_ROWS * 32;
-  if (!attr_set) {
-    BP_CUDA(cudaFuncSetAttribute((const void*)k_mvie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  k_mvie<<<(pr.S + 31) / 32, 32, smem, stream>>>(pr);
+  k_mvie<<<pr.S, 32, 0, stream>>>(pr);
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -871,3 +845,32 @@ int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Diagnostics: FP64 pipe probe used by bench.py for the roofline denominator.
+// chains independent DFMA chains per thread, iters steps each.
+// ---------------------------------------------------------------------------
+template <int CHAINS>
+__global__ void k_probe_fp64(double* out, int iters, double a, double b) {
+  double x[CHAINS];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) x[c] = 1.0 + 1e-3 * (threadIdx.x + c);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) s += x[c];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int bp_probe_fp64(int chains, int blocks, int threads, int iters, double* out_dev, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (chains == 1) k_probe_fp64<1><<<blocks, threads, 0, st>>>(out_dev, iters, 0.999999, 1e-9);
+  else if (chains == 4) k_probe_fp64<4><<<blocks, threads, 0, st>>>(out_dev, iters, 0.999999, 1e-9);
+  else if (chains == 8) k_probe_fp64<8><<<blocks, threads, 0, st>>>(out_dev, iters, 0.999999, 1e-9);
+  else return bp_fail("bp_probe_fp64: chains must be 1, 4 or 8");
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}

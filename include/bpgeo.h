@@ -120,6 +120,11 @@ int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*
 int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev, double* T_ee_dev, double* jac_dev,
                  void* stream);
 
+/* ---- diagnostics: FP64 pipe probe (roofline denominator in bench.py) ------------
+ * Launches blocks x threads threads, each running `chains` (1, 4 or 8)
+ * independent chains of `iters` dependent DFMAs; out_dev: [blocks*threads]. */
+int bp_probe_fp64(int chains, int blocks, int threads, int iters, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
