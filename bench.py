@@ -265,7 +265,7 @@ def run_gpu(args):
     mrows = out.m.cpu().numpy()
     n_pairs = S_total * (S_total - 1) // 2
     value = S_total * args.steps / (dev_ms * 1e-3)
-    launches_per_step = 1 + 5 * 2 + 1 + 1 + 1      # state_init, 5x(poly,mvie), final mvie, export, pair
+    launches_per_step = 1 + 5 * 2 + 1 + 1 + 3      # state_init, 5x(poly,mvie), final mvie, export, aabb+filter+lp
     if rank == 0:
         peaks = {}
         try:
@@ -280,7 +280,8 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "n_obstacles": N_OBS, "seeds_per_gpu": N_SEEDS, "pairs": n_pairs,
                        "l2": "flushed between timed steps (256 MiB fill)",
                        "frac_sets_over_20_rows": float((mrows > 20).mean()),
-                       "frac_status_ok": float((status == 0).mean())},
+                       "frac_status_ok": float((status == 0).mean()),
+                       "adjacency_density": float(geo.unpack_adjacency(bits, S_total).sum().item()) / max(n_pairs, 1)},
             "pair_checks_per_sec": n_pairs * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},

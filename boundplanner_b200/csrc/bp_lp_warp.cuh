@@ -1,0 +1,171 @@
+// bp_lp_warp.cuh -- K6, warp-cooperative: ONE WARP decides one set pair.
+//
+// Same algorithm and constants as the thread-serial specification in bp_lp.cuh
+// (host-tested against scipy/HiGHS); only the work distribution differs: lanes
+// own rows of the stacked system (row = lane, lane+32, lane+64), the 4x4
+// Newton system is assembled by column dots through shared memory and solved
+// redundantly by every lane, so all control flow is warp-uniform.
+// After the bounding-box filter only a few thousand pairs survive on the C2
+// workload; one thread per pair left ~125 warps each walking 40 rows serially
+// (2 ms, latency-bound); one warp per pair finishes in tens of microseconds.
+#pragma once
+#include "bp_lp.cuh"
+#include "bp_mvie_warp.cuh"   // bp_warp_min / bp_warp_prod
+
+#define BP_LP_SLOTS 3                                   // rows per lane: m1 + m2 <= 96
+#define BP_LP_SCRATCH_DOUBLES (96 * 5 + 16)
+
+__device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double* __restrict__ b1, int m1,
+                                     const double* __restrict__ A2, const double* __restrict__ b2, int m2,
+                                     double tol, double* scratch, int* iters_out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int m = m1 + m2;
+  double* F = scratch;              // [m][5]: v0 v1 v2 v3 (stride 5: conflict-free row writes)
+  double* OUT = scratch + 96 * 5;   // [16]
+  double ra[BP_LP_SLOTS][3], rc[BP_LP_SLOTS];
+  bool rv[BP_LP_SLOTS];
+  int mm = 0;
+  bool empty = false;
+#pragma unroll
+  for (int q = 0; q < BP_LP_SLOTS; ++q) {
+    const int i = lane + 32 * q;
+    ra[q][0] = ra[q][1] = ra[q][2] = 0.0;
+    rc[q] = 1.0;
+    rv[q] = false;
+    if (i < m) {
+      const double* A = i < m1 ? A1 + 3 * i : A2 + 3 * (i - m1);
+      const double bb = i < m1 ? b1[i] : b2[i - m1];
+      ra[q][0] = A[0]; ra[q][1] = A[1]; ra[q][2] = A[2];
+      rc[q] = bb - tol;
+      rv[q] = (ra[q][0] != 0.0 || ra[q][1] != 0.0 || ra[q][2] != 0.0);
+      if (!rv[q] && rc[q] < 0.0) empty = true;        // 0 <= c violated
+    }
+  }
+  empty = __any_sync(full, empty);
+  {
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < BP_LP_SLOTS; ++q) cnt += rv[q] ? 1 : 0;
+    mm = __reduce_add_sync(full, cnt);
+  }
+  if (iters_out) *iters_out = 0;
+  if (empty) return 0;
+  if (mm == 0) return 1;
+  double x[4] = {0.0, 0.0, 0.0, 0.0};
+  {
+    double smax = -BP_INF;
+#pragma unroll
+    for (int q = 0; q < BP_LP_SLOTS; ++q)
+      if (rv[q]) smax = fmax(smax, -rc[q]);            // a.x - c at x = 0
+    smax = -bp_warp_min(-smax);
+    if (smax <= 0.0) return 1;
+    x[3] = smax + 1.0;
+  }
+  // output owned by this lane: e = lane & 15 -> H (10) or g (4); lanes >= 16 sum the odd rows
+  const int e = lane & 15, half = lane >> 4;
+  int cx = 0, cy = -1;                                  // cy = -1: plain sum of column cx
+  if (e < 10) {
+    int j = 0;
+    while ((j + 1) * (j + 2) / 2 <= e) ++j;
+    cx = j; cy = e - j * (j + 1) / 2;
+  } else if (e < 14) {
+    cx = e - 10;
+  }
+  double t = 1.0;
+  int iters = 0, result = 0;
+  for (int outer = 0; outer < BP_LP_OUTER_MAX; ++outer) {
+    for (int inner = 0; inner < BP_LP_INNER_MAX; ++inner) {
+      ++iters;
+      double rslack[BP_LP_SLOTS];
+      double minq = BP_INF;
+#pragma unroll
+      for (int q = 0; q < BP_LP_SLOTS; ++q) {
+        const double slack = rc[q] - (ra[q][0] * x[0] + ra[q][1] * x[1] + ra[q][2] * x[2]) + x[3];
+        rslack[q] = slack;
+        if (lane + 32 * q < m) {
+          double* f = F + (lane + 32 * q) * 5;
+          if (rv[q]) {
+            const double r = 1.0 / slack;
+            minq = fmin(minq, slack);
+            f[0] = ra[q][0] * r; f[1] = ra[q][1] * r; f[2] = ra[q][2] * r; f[3] = -r;
+          } else {
+            f[0] = 0.0; f[1] = 0.0; f[2] = 0.0; f[3] = 0.0;
+          }
+        }
+      }
+      minq = bp_warp_min(minq);
+      __syncwarp();
+      {
+        double acc = 0.0;
+        if (e < 14) {
+          if (cy >= 0) { for (int i = half; i < m; i += 2) acc += F[i * 5 + cx] * F[i * 5 + cy]; }
+          else { for (int i = half; i < m; i += 2) acc += F[i * 5 + cx]; }
+        }
+        acc += __shfl_xor_sync(full, acc, 16);
+        if (lane < 14) OUT[lane] = acc;
+      }
+      __syncwarp();
+      double H[10], g[4];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) H[k] = OUT[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] = OUT[10 + k];
+      __syncwarp();
+      const double rn = -g[3];                          // sum r_i
+      g[3] += t;
+      // exits
+      if (x[3] - minq <= 0.0) { result = 1; goto done; }
+      {
+        const double irn = 1.0 / rn;
+        const double rho0 = g[0] * irn, rho1 = g[1] * irn, rho2 = g[2] * irn;
+        const double lb = x[3] - mm * irn - sqrt(rho0 * rho0 + rho1 * rho1 + rho2 * rho2) * BP_LP_DIAMETER;
+        if (lb > 0.0) { result = 0; goto done; }
+      }
+      double dx[4];
+      if (!bp_ldl_solve<4>(H, g, dx)) { result = 0; goto done; }
+      const double lam2 = -(g[0] * dx[0] + g[1] * dx[1] + g[2] * dx[2] + g[3] * dx[3]);
+      if (!(lam2 > 0.0)) break;
+      double rdsl[BP_LP_SLOTS];
+#pragma unroll
+      for (int q = 0; q < BP_LP_SLOTS; ++q)
+        rdsl[q] = -(ra[q][0] * dx[0] + ra[q][1] * dx[1] + ra[q][2] * dx[2]) + dx[3];
+      const bool want_armijo = lam2 >= 0.01;
+      double alpha = 1.0;
+      bool accepted = false;
+      for (int bt = 0; bt < 60; ++bt) {
+        bool ok = true;
+        double prod = 1.0;
+#pragma unroll
+        for (int q = 0; q < BP_LP_SLOTS; ++q) {
+          if (rv[q]) {
+            if (!(rslack[q] + alpha * rdsl[q] > 0.0)) ok = false;
+            if (want_armijo) prod *= 1.0 + alpha * rdsl[q] / rslack[q];
+          }
+        }
+        ok = __all_sync(full, ok);
+        if (ok) {
+          if (!want_armijo) accepted = true;
+          else {
+            const double dF = t * alpha * dx[3] - log(bp_warp_prod(prod));
+            if (dF <= -0.25 * alpha * lam2) accepted = true;
+          }
+          if (accepted) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] += alpha * dx[k];
+            break;
+          }
+        }
+        alpha *= 0.5;
+      }
+      if (!accepted) break;
+      if (lam2 < 1e-4) break;
+    }
+    if (mm / t < BP_LP_GAP_TOL) break;
+    t *= BP_LP_T_MULT;
+  }
+  result = 0;       // |s*| below the resolvable gap: not strictly feasible
+done:
+  if (iters_out) *iters_out = iters;
+  return result;
+}

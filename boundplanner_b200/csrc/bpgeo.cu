@@ -24,6 +24,7 @@
 #include "bp_mvie.cuh"
 #include "bp_mvie_warp.cuh"
 #include "bp_lp.cuh"
+#include "bp_lp_warp.cuh"
 #include "bp_fk.cuh"
 
 // ---------------------------------------------------------------------------
@@ -553,8 +554,19 @@ __global__ void k_state_init_line(SeedState* st, const double* __restrict__ p0, 
 }
 
 // ---------------------------------------------------------------------------
-// K6: pairwise feasibility.  Block = 8 rows i x 32 columns j; a warp holds one i
-// and 32 consecutive j, so its ballot is one word of the adjacency bit-matrix.
+// K6: pairwise feasibility (BoundPlanner.set_intersection, BoundPlanner.py:774-798).
+// Three kernels per call:
+//   k_set_aabb      one warp per set: exact axis-aligned bounding box of the
+//                   polytope by vertex enumeration (all row triples);
+//   k_pair_filter   every pair (i, j>i) of the row block: pairs whose boxes are
+//                   disjoint cannot intersect (the tol-shrunk sets lie inside
+//                   the unshrunk boxes) -> bit stays 0; the others are appended
+//                   to a compact work list (warp-aggregated atomics);
+//   k_pair_lp       persistent grid over the work list, one WARP per surviving
+//                   pair (bp_lp_warp.cuh: rows across lanes, warp-uniform
+//                   phase-I Newton), result bits set with atomicOr.
+// The filter only decides WHO runs the LP; every answer that is 1 comes from
+// the LP, every 0 from the LP or from a rigorous box separation.
 // ---------------------------------------------------------------------------
 struct GlobalRows {
   const double* A;
@@ -563,21 +575,116 @@ struct GlobalRows {
   __device__ __forceinline__ double b(int i) const { return __ldg(B + i); }
 };
 
-__global__ void __launch_bounds__(256) k_pair_feasible(const double* __restrict__ A, const double* __restrict__ b,
-                                                       const int* __restrict__ m, int S, int m_max, double tol,
-                                                       int row_begin, int row_end, unsigned int* __restrict__ adj) {
+#define BP_AABB_EPS 1e-9
+
+__global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, const double* __restrict__ b,
+                                                  const int* __restrict__ m, int S, int m_max,
+                                                  double* __restrict__ aabb) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const double* As = A + (size_t)s * m_max * 3;
+  const double* bs = b + (size_t)s * m_max;
+  const int ms = m[s];
+  double lo[3] = {BP_INF, BP_INF, BP_INF}, hi[3] = {-BP_INF, -BP_INF, -BP_INF};
+  const int npairs = ms * (ms - 1) / 2;
+  for (int pidx = lane; pidx < npairs; pidx += 32) {
+    // unrank pidx -> (i < j)
+    int i = 0, rem = pidx;
+    while (rem >= ms - 1 - i) { rem -= ms - 1 - i; ++i; }
+    const int j = i + 1 + rem;
+    const double a0 = __ldg(As + 3 * i), a1 = __ldg(As + 3 * i + 1), a2 = __ldg(As + 3 * i + 2), ab = __ldg(bs + i);
+    const double c0 = __ldg(As + 3 * j), c1 = __ldg(As + 3 * j + 1), c2 = __ldg(As + 3 * j + 2), cb = __ldg(bs + j);
+    // n = a x c
+    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;
+    for (int k = j + 1; k < ms; ++k) {
+      const double d0 = __ldg(As + 3 * k), d1 = __ldg(As + 3 * k + 1), d2 = __ldg(As + 3 * k + 2), db = __ldg(bs + k);
+      const double det = n0 * d0 + n1 * d1 + n2 * d2;
+      const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
+      if (!(fabs(det) > 1e-12 * scale)) continue;
+      // v = (ab (c x d) + cb (d x a) + db (a x c)) / det
+      const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
+      const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
+      const double id = 1.0 / det;
+      const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
+      const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
+      const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
+      bool inside = true;
+      for (int r = 0; r < ms && inside; ++r) {
+        const double q0 = __ldg(As + 3 * r), q1 = __ldg(As + 3 * r + 1), q2 = __ldg(As + 3 * r + 2);
+        const double viol = q0 * v0 + q1 * v1 + q2 * v2 - __ldg(bs + r);
+        if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
+      }
+      if (inside) {
+        lo[0] = fmin(lo[0], v0); hi[0] = fmax(hi[0], v0);
+        lo[1] = fmin(lo[1], v1); hi[1] = fmax(hi[1], v1);
+        lo[2] = fmin(lo[2], v2); hi[2] = fmax(hi[2], v2);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+    }
+  }
+  if (lane == 0) {
+    // no vertex found (unbounded or empty description): never reject on this set
+    const bool none = !(lo[0] <= hi[0]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      aabb[(size_t)s * 6 + k] = none ? -BP_INF : lo[k];
+      aabb[(size_t)s * 6 + 3 + k] = none ? BP_INF : hi[k];
+    }
+  }
+}
+
+// Block = 8 rows i x 32 columns j.
+__global__ void __launch_bounds__(256) k_pair_filter(const double* __restrict__ aabb, int S, int row_begin, int row_end,
+                                                     int2* __restrict__ list, unsigned int* __restrict__ count) {
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int i = row_begin + blockIdx.y * 8 + wy;
   const int j = blockIdx.x * 32 + lane;
-  const int words = (S + 31) >> 5;
   if (i >= row_end) return;
-  const bool active = (j < S && j > i);
-  const int jj = active ? j : i;                  // inactive lanes only take part in the warp votes
-  GlobalRows r1{A + (size_t)i * m_max * 3, b + (size_t)i * m_max};
-  GlobalRows r2{A + (size_t)jj * m_max * 3, b + (size_t)jj * m_max};
-  const int res = bp_pair_feasible(r1, m[i], r2, m[jj], tol, (double*)nullptr, (int*)nullptr, active);
-  unsigned int word = __ballot_sync(0xffffffffu, res != 0);
-  if (lane == 0) adj[(size_t)(i - row_begin) * words + blockIdx.x] = word;
+  bool keep = false;
+  if (j < S && j > i) {
+    keep = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double loi = __ldg(aabb + (size_t)i * 6 + k), hii = __ldg(aabb + (size_t)i * 6 + 3 + k);
+      const double loj = __ldg(aabb + (size_t)j * 6 + k), hij = __ldg(aabb + (size_t)j * 6 + 3 + k);
+      if (loi > hij + BP_AABB_EPS || loj > hii + BP_AABB_EPS) keep = false;
+    }
+  }
+  const unsigned int mask = __ballot_sync(0xffffffffu, keep);
+  if (mask == 0) return;
+  unsigned int base = 0;
+  if (lane == 0) base = atomicAdd(count, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (keep) list[base + __popc(mask & ((1u << lane) - 1u))] = make_int2(i, j);
+}
+
+__global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
+                                                 const int* __restrict__ m, int S, int m_max, double tol,
+                                                 int row_begin, const int2* __restrict__ list,
+                                                 const unsigned int* __restrict__ count,
+                                                 unsigned int* __restrict__ adj) {
+  __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int words = (S + 31) >> 5;
+  const unsigned int n = *count;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int p = warp; p < n; p += nwarps) {       // one warp per surviving pair
+    const int2 pr = list[p];
+    const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
+                                          A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
+                                          scratch[wib], nullptr);
+    if (lane == 0 && res) atomicOr(adj + (size_t)(pr.x - row_begin) * words + (pr.y >> 5), 1u << (pr.y & 31));
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -822,14 +929,41 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
   return 0;
 }
 
+size_t bp_pair_workspace_bytes(int S, int rows) {
+  if (S < 0) S = 0;
+  if (rows < 0) rows = 0;
+  // aabb [S,6] doubles | counter (16 B) | pair list: at most rows * S entries of int2
+  return sizeof(double) * 6 * (size_t)S + 16 + sizeof(int2) * (size_t)rows * (size_t)S;
+}
+
 int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
-                     int row_begin, int row_end, unsigned int* adj_bits_dev, void* stream) {
+                     int row_begin, int row_end, unsigned int* adj_bits_dev, void* workspace_dev,
+                     size_t workspace_bytes, void* stream_) {
   if (S < 0 || row_begin < 0 || row_end > S || row_begin > row_end || m_max < 1)
     return bp_fail("bp_pair_feasible: bad arguments");
   if (row_end == row_begin) return 0;
-  dim3 grid((S + 31) / 32, (row_end - row_begin + 7) / 8);
-  k_pair_feasible<<<grid, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, row_end,
-                                                           adj_bits_dev);
+  const int rows = row_end - row_begin;
+  if (workspace_bytes < bp_pair_workspace_bytes(S, rows)) return bp_fail("bp_pair_feasible: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  double* aabb = (double*)workspace_dev;
+  unsigned int* count = (unsigned int*)(aabb + 6 * (size_t)S);
+  int2* list = (int2*)((char*)count + 16);
+  const int words = (S + 31) / 32;
+  BP_CUDA(cudaMemsetAsync(adj_bits_dev, 0, sizeof(unsigned int) * (size_t)rows * words, stream));
+  BP_CUDA(cudaMemsetAsync(count, 0, 16, stream));
+  k_set_aabb<<<(S + 3) / 4, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
+  dim3 grid((S + 31) / 32, (rows + 7) / 8);
+  k_pair_filter<<<grid, 256, 0, stream>>>(aabb, S, row_begin, row_end, list, count);
+  int nsm = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const long long max_pairs = (long long)rows * S;
+  long long ctas = (max_pairs + 7) / 8;              // 8 warps per CTA, one pair per warp per trip
+  if (ctas > (long long)nsm * 8) ctas = (long long)nsm * 8;
+  if (ctas < 1) ctas = 1;
+  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, list, count, adj_bits_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -220,9 +220,11 @@ def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None):
     if row_end is None:
         row_end = S
     words = (S + 31) // 32
-    bits = torch.zeros((row_end - row_begin, words), dtype=torch.int32, device="cuda")
+    bits = torch.empty((row_end - row_begin, words), dtype=torch.int32, device="cuda")
+    wbytes = lib.bp_pair_workspace_bytes(S, row_end - row_begin)
+    work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
     check(lib.bp_pair_feasible(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), int(row_begin), int(row_end),
-                               _ptr(bits), _stream()))
+                               _ptr(bits), _ptr(work), wbytes, _stream()))
     return bits
 
 

@@ -108,9 +108,10 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
  * [row_begin,row_end), j in (i, S).  adj_bits_dev: [(row_end-row_begin), words]
  * uint32 words, words = (S+31)/32; bit j of row i is 1 iff sets i and j intersect.
  * Bits with j <= i are 0. */
+size_t bp_pair_workspace_bytes(int S, int rows /* row_end - row_begin */);
 int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*[S,m_max]*/, const int* m_dev /*[S]*/,
                      int S, int m_max, double tol, int row_begin, int row_end, unsigned int* adj_bits_dev,
-                     void* stream);
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- K7: iiwa14 forward kinematics -----------------------------------------------
  * Replaces the numeric branch of RobotModel.fk_pos (RobotModel.py:146-160),
