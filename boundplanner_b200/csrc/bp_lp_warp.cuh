@@ -17,7 +17,7 @@
 
 __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double* __restrict__ b1, int m1,
                                      const double* __restrict__ A2, const double* __restrict__ b2, int m2,
-                                     double tol, double* scratch, int* iters_out) {
+                                     double tol, double* scratch, int* iters_out, double* xout = nullptr) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int m = m1 + m2;
@@ -59,6 +59,7 @@ __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double
     for (int q = 0; q < BP_LP_SLOTS; ++q)
       if (rv[q]) smax = fmax(smax, -rc[q]);            // a.x - c at x = 0
     smax = -bp_warp_min(-smax);
+    if (xout) { xout[0] = 0.0; xout[1] = 0.0; xout[2] = 0.0; }
     if (smax <= 0.0) return 1;
     x[3] = smax + 1.0;
   }
@@ -167,5 +168,6 @@ __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double
   result = 0;       // |s*| below the resolvable gap: not strictly feasible
 done:
   if (iters_out) *iters_out = iters;
+  if (xout) { xout[0] = x[0]; xout[1] = x[1]; xout[2] = x[2]; }   // last iterate: strictly inside when result == 1
   return result;
 }

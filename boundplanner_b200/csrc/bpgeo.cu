@@ -483,8 +483,18 @@ __global__ void __launch_bounds__(32) k_mvie(MvieParams pr) {
   double L[6], d[3];
   int iters = 0;
   const bool free_c = (pr.mode == 1 || pr.mode == 2 || (pr.mode == 3 && pr.free_centre));
-  const int status = free_c ? bp_mvie_warp<9>(A, b, m, c0, scratch, L, d, &iters)
-                            : bp_mvie_warp<6>(A, b, m, c0, scratch, L, d, &iters);
+  int status = free_c ? bp_mvie_warp<9>(A, b, m, c0, scratch, L, d, &iters)
+                      : bp_mvie_warp<6>(A, b, m, c0, scratch, L, d, &iters);
+  if (status == BP_MVIE_NO_INTERIOR && free_c) {
+    // the hint is not strictly inside (e.g. mvie_socp called without one): find an
+    // interior point with the phase-I LP of K6 on the set's own rows, then retry
+    __syncwarp();
+    double xi[3];
+    if (bp_pair_feasible_warp(A, b, m, A, b, 0, 1e-9, scratch, nullptr, xi)) {
+      __syncwarp();
+      status = bp_mvie_warp<9>(A, b, m, xi, scratch, L, d, &iters);
+    }
+  }
   if (lane != 0) return;
   double E[9], Q[9], detQ;
   bp_shape_from_L(L, E, Q, &detQ);
@@ -670,7 +680,7 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
                                                  const int* __restrict__ m, int S, int m_max, double tol,
                                                  int row_begin, const int2* __restrict__ list,
                                                  const unsigned int* __restrict__ count,
-                                                 unsigned int* __restrict__ adj) {
+                                                 unsigned int* __restrict__ adj, double* __restrict__ x_feas) {
   __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int words = (S + 31) >> 5;
@@ -679,10 +689,17 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
   const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int p = warp; p < n; p += nwarps) {       // one warp per surviving pair
     const int2 pr = list[p];
+    double xi[3];
     const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                           A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
-                                          scratch[wib], nullptr);
-    if (lane == 0 && res) atomicOr(adj + (size_t)(pr.x - row_begin) * words + (pr.y >> 5), 1u << (pr.y & 31));
+                                          scratch[wib], nullptr, xi);
+    if (lane == 0 && res) {
+      atomicOr(adj + (size_t)(pr.x - row_begin) * words + (pr.y >> 5), 1u << (pr.y & 31));
+      if (x_feas) {
+        double* xo = x_feas + ((size_t)(pr.x - row_begin) * S + pr.y) * 3;
+        xo[0] = xi[0]; xo[1] = xi[1]; xo[2] = xi[2];
+      }
+    }
     __syncwarp();
   }
 }
@@ -937,9 +954,9 @@ size_t bp_pair_workspace_bytes(int S, int rows) {
 }
 
 int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
-                     int row_begin, int row_end, unsigned int* adj_bits_dev, void* workspace_dev,
-                     size_t workspace_bytes, void* stream_) {
-  if (S < 0 || row_begin < 0 || row_end > S || row_begin > row_end || m_max < 1)
+                     int row_begin, int row_end, unsigned int* adj_bits_dev, double* x_feas_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (S < 0 || row_begin < 0 || row_end > S || row_begin > row_end || m_max < 1 || m_max > BP_MAX_ROWS)
     return bp_fail("bp_pair_feasible: bad arguments");
   if (row_end == row_begin) return 0;
   const int rows = row_end - row_begin;
@@ -963,7 +980,8 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   long long ctas = (max_pairs + 7) / 8;              // 8 warps per CTA, one pair per warp per trip
   if (ctas > (long long)nsm * 8) ctas = (long long)nsm * 8;
   if (ctas < 1) ctas = 1;
-  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, list, count, adj_bits_dev);
+  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, list, count, adj_bits_dev,
+                                                       x_feas_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -211,10 +211,11 @@ def mvie(A, b, m, centre, free_centre):
     return q_inv, q_ell, c_out, status, its
 
 
-def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None):
+def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=False):
     """BoundPlanner.set_intersection (BoundPlanner.py:774-787, tol from :797) for all
     pairs (i, j>i), i in [row_begin,row_end).  Returns uint32-packed bits as an
-    int32 tensor [rows, ceil(S/32)]."""
+    int32 tensor [rows, ceil(S/32)]; with want_points also x [rows,S,3], a point of
+    each non-empty intersection (the reference's sol_lin.x)."""
     lib = _lib.load()
     S, m_max = A.shape[0], A.shape[1]
     if row_end is None:
@@ -223,8 +224,11 @@ def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None):
     bits = torch.empty((row_end - row_begin, words), dtype=torch.int32, device="cuda")
     wbytes = lib.bp_pair_workspace_bytes(S, row_end - row_begin)
     work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
+    x = torch.zeros((row_end - row_begin, S, 3), dtype=torch.float64, device="cuda") if want_points else None
     check(lib.bp_pair_feasible(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), int(row_begin), int(row_end),
-                               _ptr(bits), _ptr(work), wbytes, _stream()))
+                               _ptr(bits), _ptr(x), _ptr(work), wbytes, _stream()))
+    if want_points:
+        return bits, x
     return bits
 
 

@@ -111,6 +111,8 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
 size_t bp_pair_workspace_bytes(int S, int rows /* row_end - row_begin */);
 int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*[S,m_max]*/, const int* m_dev /*[S]*/,
                      int S, int m_max, double tol, int row_begin, int row_end, unsigned int* adj_bits_dev,
+                     double* x_feas_dev /* NULL or [rows,S,3]: a point of the intersection where the bit is 1
+                                           (the reference's sol_lin.x, BoundPlanner.py:785) */,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- K7: iiwa14 forward kinematics -----------------------------------------------

@@ -1,0 +1,167 @@
+"""GPU: the reference-facing drop-in classes behave like the reference's (as
+restated by the oracle) on the C1 example scene (boundplanner_example.py:19-92)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import RTOL, assert_rows_close  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def c1():
+    import torch
+
+    assert torch.cuda.is_available()
+    import boundplanner_b200 as bp
+    from boundplanner_b200 import scenes
+    from oracle.convex_set_finder import ConvexSetFinder as OracleFinder
+    from oracle.obstacles import obstacle_reps
+
+    boxes, ws_min, ws_max, inflate = scenes.example_scene()
+    obs_sets, pts, _ = obstacle_reps(boxes, inflate)          # what BoundPlanner.add_obstacle_reps builds
+    gpu = bp.ConvexSetFinder(obs_sets, pts, list(ws_max), list(ws_min))
+    ora = OracleFinder(obs_sets, pts, list(ws_max), list(ws_min))
+    return gpu, ora, obs_sets, pts
+
+
+def test_attributes_match_reference_surface(c1):
+    gpu, ora, obs_sets, pts = c1
+    for name in ("obs_sets", "obs_points_sets", "e_max", "e_min", "max_iter", "proj_time", "ell_time",
+                 "set_line_time", "rng", "find_set_around_point", "find_set_collision_avoidance",
+                 "compute_polyhedron", "compute_set_projs", "compute_set_projs_line", "mvie_socp",
+                 "mvie_socp_fixed_mid", "mvie_socp_fixed_r", "init_halfspaces", "init_halfspaces_point"):
+        assert hasattr(gpu, name), name
+    assert gpu.max_iter == 5 and len(gpu.obs_sets) == 12
+
+
+def test_example_start_set_and_end_set(c1):
+    """The two calls plan_convex_set_path makes first (BoundPlanner.py:278-294, :381-389)."""
+    gpu, ora, *_ = c1
+    p0 = np.array([0.3, 0.0, 0.7])
+    p1 = np.array([0.45, -0.5, 0.2])
+    A, b, Q, p = gpu.find_set_around_point(p0, fixed_mid=True)
+    Ao, bo, Qo, po = ora.find_set_around_point(p0, fixed_mid=True)
+    assert_rows_close(A, b, Ao, bo, "start set")
+    assert np.abs(Q - Qo).max() <= 1e-5 * np.abs(Qo).max() and np.abs(p - po).max() <= RTOL
+    assert A.dtype == np.float64 and A.flags.writeable          # callers mutate the arrays in place
+    l_ee = np.array([0.0, 0.0, 0.05])                            # R_y(90) @ [-0.05, 0, 0]
+    out = gpu.find_set_collision_avoidance(p1, p1 + l_ee, True)
+    outo = ora.find_set_collision_avoidance(p1, p1 + l_ee, True)
+    assert len(out) == 5 and out[4] == outo[4]
+    assert_rows_close(out[0], out[1], outo[0], outo[1], "end set")
+    assert np.abs(out[2] - outo[2]).max() <= 1e-5 * np.abs(outo[2]).max()
+    assert np.abs(out[3] - outo[3]).max() <= RTOL
+
+
+def test_mpc_call_site(c1):
+    """BoundMPC.py:486-488: find_set_collision_avoidance(pl, pf, limit_space=True, e_max=0.7)."""
+    gpu, ora, *_ = c1
+    rng = np.random.default_rng(2)
+    for _ in range(6):
+        pl = np.array([0.3, 0.0, 0.7]) + rng.normal(size=3) * 0.05
+        pf = pl + rng.normal(size=3) * 0.05
+        A, b, coll = gpu.find_set_collision_avoidance(pl, pf, limit_space=True, e_max=0.7)
+        Ao, bo, collo = ora.find_set_collision_avoidance(pl, pf, limit_space=True, e_max=0.7)
+        assert coll == collo
+        assert_rows_close(A, b, Ao, bo, "mpc line set")
+
+
+def test_component_methods(c1):
+    gpu, ora, *_ = c1
+    p = np.array([0.3, 0.0, 0.7])
+    q_inv = np.diag([1e-4] * 3)
+    q_ell = np.diag([1e4] * 3)
+    y = gpu.compute_set_projs(gpu.obs_sets, p, q_inv)
+    yo = ora.compute_set_projs(ora.obs_sets, p, q_inv)
+    assert np.abs(y - yo).max() < 1e-9
+    a0, b0 = gpu.init_halfspaces()
+    a_set, b_set = gpu.compute_polyhedron(q_inv, q_ell, p, a0, b0)
+    ao, bo = ora.compute_polyhedron(q_inv, q_ell, p, *ora.init_halfspaces())
+    assert isinstance(a_set, list) and isinstance(b_set, list)
+    assert_rows_close(np.array(a_set), np.array(b_set), np.array(ao), np.array(bo), "polyhedron")
+    A, b = np.array(a_set), np.array(b_set)
+    q1, c1_ = gpu.mvie_socp_fixed_mid(A, b, p)
+    q1o, _ = ora.mvie_socp_fixed_mid(A, b, p)
+    assert c1_ is p and np.abs(q1 - q1o).max() <= RTOL * np.abs(q1o).max()
+    q2, c2 = gpu.mvie_socp(A, b)                                 # no hint, like the reference signature
+    q2o, c2o = ora.mvie_socp(A, b)
+    assert np.abs(q2 - q2o).max() <= RTOL * np.abs(q2o).max() and np.abs(c2 - c2o).max() <= RTOL
+    x, phi = gpu.compute_set_projs_line(gpu.obs_sets, p, p + np.array([0.1, -0.2, 0.05]))
+    xo, phio = ora.compute_set_projs_line(ora.obs_sets, p, p + np.array([0.1, -0.2, 0.05]))
+    assert np.abs(x - xo).max() < 1e-9 and np.abs(phi - phio).max() < 1e-9
+
+
+def test_error_behaviour(c1):
+    gpu, ora, obs_sets, pts = c1
+    # a seed inside an (inflated) obstacle: the reference raises RuntimeError("Ellipse violates constraints")
+    inside = np.array([0.6, 0.0, -0.05])
+    with pytest.raises(RuntimeError, match="Ellipse violates constraints"):
+        gpu.find_set_around_point(inside, fixed_mid=True)
+    with pytest.raises(RuntimeError, match="Ellipse violates constraints"):
+        ora.find_set_around_point(inside, fixed_mid=True)
+    # more than 20 rows: the reference's MVIE buffers overflow with a ValueError (quirk Q5)
+    A = np.vstack([np.eye(3), -np.eye(3)] * 4)
+    b = np.ones(24)
+    with pytest.raises(ValueError):
+        gpu.mvie_socp_fixed_mid(A, b, np.zeros(3))
+    # non-box obstacles are refused loudly
+    import boundplanner_b200 as bp
+
+    bad = [[np.vstack((np.eye(3), -np.eye(3), np.ones((1, 3)))), np.ones(7)]]
+    with pytest.raises(NotImplementedError):
+        bp.ConvexSetFinder(bad, [np.zeros((8, 3))], [1, 1, 1], [-1, -1, 0])
+
+
+def test_scene_update_through_attribute_assignment(c1):
+    """add_obstacle_reps(update=True) assigns set_finder.obs_sets (BoundPlanner.py:150-152)."""
+    import boundplanner_b200 as bp
+    from boundplanner_b200 import scenes
+    from oracle.convex_set_finder import ConvexSetFinder as OracleFinder
+    from oracle.obstacles import obstacle_reps
+
+    boxes, ws_min, ws_max, inflate = scenes.example_scene()
+    obs_sets, pts, _ = obstacle_reps(boxes[:6], inflate)
+    gpu = bp.ConvexSetFinder(obs_sets, pts, list(ws_max), list(ws_min))
+    obs2, pts2, _ = obstacle_reps(boxes, inflate)
+    gpu.obs_sets = obs2.copy()
+    gpu.obs_points_sets = pts2.copy()
+    ora = OracleFinder(obs2, pts2, list(ws_max), list(ws_min))
+    p0 = np.array([0.3, 0.0, 0.7])
+    A, b, _, _ = gpu.find_set_around_point(p0, fixed_mid=True)
+    Ao, bo, _, _ = ora.find_set_around_point(p0, fixed_mid=True)
+    assert_rows_close(A, b, Ao, bo, "after update")
+
+
+def test_set_intersection_dropin():
+    import boundplanner_b200 as bp
+    from oracle.set_graph import set_intersection as ref_intersection
+
+    box = np.vstack((np.eye(3), -np.eye(3)))
+    s1 = [box, np.array([1, 1, 1, 0, 0, 0.0])]
+    s2 = [box, np.array([1.5, 1.5, 1.5, -0.5, -0.5, -0.5])]
+    s3 = [box, np.array([3, 3, 3, -2, -2, -2.0])]
+    x, inter, ok = bp.set_intersection(s1, s2, tol=0.01)
+    xr, interr, okr = ref_intersection(s1, s2, tol=0.01)
+    assert ok and okr and np.array_equal(inter[0], interr[0]) and np.array_equal(inter[1], interr[1])
+    assert np.max(inter[0] @ x - (inter[1] - 0.01)) <= 1e-9        # the returned point is inside the shrunk sets
+    x, _, ok = bp.set_intersection(s1, s3, tol=0.01)
+    assert not ok and x is None and not ref_intersection(s1, s3, tol=0.01)[2]
+    adj = bp.adjacency([s1, s2, s3], tol=0.01)
+    assert adj.tolist() == [[False, True, False], [True, False, False], [False, False, False]]
+
+
+def test_robot_model_dropin():
+    import boundplanner_b200 as bp
+    from oracle import fk_iiwa14 as ofk
+
+    model = bp.RobotModel()
+    q = np.array([0.1, -0.2, 0.3, -0.4, 0.5, -0.6, 0.7])
+    assert np.abs(model.fk_pos(q) - ofk.fk_pos(q)).max() < 1e-12
+    for i in range(7):
+        assert np.abs(model.fk_pos_col(q, i) - ofk.fk_pos_col(q, i)).max() < 1e-12
+    assert np.abs(model.hom_transform_endeffector(q) - ofk.hom_transform_endeffector(q)).max() < 1e-12
+    assert np.abs(model.fk(q) - ofk.fk(q)).max() < 1e-10
+    assert np.abs(model.jacobian_fk(q) - ofk.jacobian_fk(q)).max() < 1e-12
+    with pytest.raises(NotImplementedError):
+        model.fk_pos([0.0] * 7)                                  # non-ndarray = symbolic branch of the reference

@@ -1,0 +1,134 @@
+"""CPU: the thread-serial device primitives (csrc/bp_*.cuh), compiled for the host by
+tests/host_harness.cpp, against the oracle.  This is the exact code the kernels run
+(the warp-cooperative kernels follow the same algorithm, constants and row order)."""
+import ctypes
+
+import numpy as np
+
+from oracle import fk_iiwa14 as ofk
+from oracle import mvie as omvie
+from oracle.convex_set_finder import closest_points_segment_boxes, min_norm_point_polytopes
+from oracle.set_graph import intersection_margin, set_intersection
+
+P = ctypes.POINTER(ctypes.c_double)
+BOX = np.vstack((np.eye(3), -np.eye(3)))
+
+
+def dp(a):
+    return a.ctypes.data_as(P)
+
+
+def test_mvie_primitive(host_harness):
+    rng = np.random.default_rng(3)
+    worst, iters = 0.0, []
+    for _ in range(25):
+        k = rng.integers(3, 20)
+        c = rng.uniform(-0.5, 0.5, 3)
+        c[2] += 0.6
+        An = rng.normal(size=(k, 3))
+        An /= np.linalg.norm(An, axis=1)[:, None]
+        A = np.ascontiguousarray(np.vstack((BOX, An)))
+        b = np.concatenate((np.array([1, 1, 1.2, 1, 1, 0.0]), An @ c + rng.uniform(0.005, 0.4, k)))
+        if np.min(b - A @ c) <= 1e-3:
+            continue
+        for free in (0, 1):
+            E, Q, cen, it = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), ctypes.c_int()
+            st = host_harness.hh_mvie(dp(A), dp(b), A.shape[0], free, dp(c), dp(E), dp(Q), dp(cen), ctypes.byref(it))
+            Eo, co = omvie.mvie_free(A, b, p_hint=c) if free else omvie.mvie_fixed_mid(A, b, c)
+            assert st == 0
+            worst = max(worst, np.abs(E - Eo).max() / np.abs(Eo).max(), np.abs(cen - co).max())
+            assert np.abs(Q @ E - np.eye(3)).max() < 1e-9
+            iters.append(it.value)
+    assert worst < 1e-9
+    assert np.mean(iters) < 45          # path-following with the secant predictor
+
+
+def test_mvie_primitive_rejects_exterior_centre(host_harness):
+    b = np.array([1, 1, 1, 1, 1, 1.0])
+    E, Q, cen, it = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), ctypes.c_int()
+    st = host_harness.hh_mvie(dp(BOX.copy()), dp(b), 6, 0, dp(np.array([2.0, 0, 0])), dp(E), dp(Q), dp(cen),
+                              ctypes.byref(it))
+    assert st == 3                      # BP_MVIE_NO_INTERIOR
+
+
+def test_box_qp_primitive(host_harness):
+    rng = np.random.default_rng(4)
+    N = 300
+    lb = np.ascontiguousarray(rng.uniform(-1, 1, (N, 3)))
+    ub = np.ascontiguousarray(lb + rng.uniform(0.02, 0.3, (N, 3)))
+    for trial in range(4):
+        p = rng.uniform(-1, 1, 3)
+        L = np.tril(rng.normal(size=(3, 3))) * 0.2
+        L[np.diag_indices(3)] = rng.uniform(0.05, 0.5, 3)
+        E = np.ascontiguousarray(L @ L.T if trial else np.diag([1e-4] * 3))
+        y, dist = np.zeros((N, 3)), np.zeros(N)
+        host_harness.hh_box_qp(dp(E), dp(p), dp(lb), dp(ub), N, dp(y), dp(dist))
+        A = np.broadcast_to(BOX, (N, 6, 3))
+        x = min_norm_point_polytopes(A @ E, np.hstack((ub, -lb)) - A @ p)
+        yo = x @ E.T + p
+        do = np.linalg.norm(np.linalg.inv(E) @ (yo - p).T, axis=0)
+        assert np.abs(y - yo).max() < 1e-7
+        assert np.abs(dist - do).max() < 1e-7 * do.max()
+
+
+def test_seg_box_primitive(host_harness):
+    rng = np.random.default_rng(5)
+    N = 300
+    lb = np.ascontiguousarray(rng.uniform(-1, 1, (N, 3)))
+    ub = np.ascontiguousarray(lb + rng.uniform(0.02, 0.3, (N, 3)))
+    for trial in range(5):
+        p0 = rng.uniform(-1, 1, 3)
+        p1 = p0 + (np.array([0.4, 0, 0]) if trial == 3 else rng.normal(size=3) * 0.3)
+        x, phi = np.zeros((N, 3)), np.zeros(N)
+        host_harness.hh_seg_box(dp(p0), dp(p1), dp(lb), dp(ub), N, dp(x), dp(phi))
+        xo, phio = closest_points_segment_boxes(lb, ub, p0, p1)
+        assert np.abs(x - xo).max() < 1e-12 and np.abs(phi - phio).max() < 1e-12
+
+
+def test_pair_lp_primitive_vs_highs(host_harness):
+    rng = np.random.default_rng(6)
+    sets = []
+    for _ in range(45):
+        k = rng.integers(4, 14)
+        c = rng.uniform(-0.6, 0.6, 3)
+        An = rng.normal(size=(k, 3))
+        An /= np.linalg.norm(An, axis=1)[:, None]
+        sets.append([np.ascontiguousarray(np.vstack((BOX, An))),
+                     np.concatenate((np.array([1, 1, 1.2, 1, 1, 0.0]), An @ c + rng.uniform(0.05, 0.5, k)))])
+    n_yes = 0
+    for i in range(45):
+        for j in range(i):
+            xo, it = np.zeros(3), ctypes.c_int()
+            r = host_harness.hh_pair_lp(dp(sets[i][0]), dp(sets[i][1]), sets[i][0].shape[0], dp(sets[j][0]),
+                                        dp(sets[j][1]), sets[j][0].shape[0], ctypes.c_double(0.01), dp(xo),
+                                        ctypes.byref(it))
+            ok = bool(set_intersection(sets[i], sets[j], 0.01)[2])
+            if bool(r) != ok:
+                assert abs(intersection_margin(sets[i], sets[j], 0.01)) < 1e-6
+            n_yes += r
+            if r:       # the returned iterate is a point of the shrunk intersection
+                assert np.max(sets[i][0] @ xo - sets[i][1]) <= -0.01 + 1e-12
+                assert np.max(sets[j][0] @ xo - sets[j][1]) <= -0.01 + 1e-12
+    assert 50 < n_yes < 900
+
+
+def test_fk_primitive(host_harness):
+    rng = np.random.default_rng(7)
+    n = 100
+    q = np.ascontiguousarray(rng.uniform(ofk.Q_LOWER, ofk.Q_UPPER, (n, 7)))
+    pe, pc, T, J = np.zeros((n, 3)), np.zeros((n, 7, 3)), np.zeros((n, 4, 4)), np.zeros((n, 6, 7))
+    host_harness.hh_fk(dp(q), n, dp(pe), dp(pc), dp(T), dp(J))
+    for i in range(n):
+        assert np.abs(pe[i] - ofk.fk_pos(q[i])).max() < 1e-12
+        assert np.abs(pc[i] - ofk.fk_pos_col_all(q[i])).max() < 1e-12
+        assert np.abs(T[i] - ofk.hom_transform_endeffector(q[i])).max() < 1e-12
+        assert np.abs(J[i] - ofk.jacobian_fk(q[i])).max() < 1e-12
+
+
+def test_min_eig_primitive(host_harness):
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        L = np.tril(rng.normal(size=(3, 3)))
+        L[np.diag_indices(3)] = rng.uniform(1e-3, 1, 3)
+        E = np.ascontiguousarray(L @ L.T)
+        assert abs(host_harness.hh_min_eig(dp(E)) - np.linalg.svd(E)[1].min()) < 1e-13 * max(1.0, np.abs(E).max())
