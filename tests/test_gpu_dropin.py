@@ -165,3 +165,25 @@ def test_robot_model_dropin():
     assert np.abs(model.jacobian_fk(q) - ofk.jacobian_fk(q)).max() < 1e-12
     with pytest.raises(NotImplementedError):
         model.fk_pos([0.0] * 7)                                  # non-ndarray = symbolic branch of the reference
+
+
+def test_against_committed_golden_fixtures(c1):
+    """Kernels vs tests/golden/*.npz (generated by tests/golden/make_golden.py)."""
+    import os
+
+    import boundplanner_b200 as bp
+
+    gpu = c1[0]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_sets_golden.npz"))
+    A, b, Q, p = gpu.find_set_around_point(g["p0"], fixed_mid=True)
+    assert_rows_close(A, b, g["A0"], g["b0"], "golden start set")
+    assert np.abs(Q - g["Q0"]).max() <= 1e-5 * np.abs(g["Q0"]).max() and np.abs(p - g["c0"]).max() <= RTOL
+    A, b, Q, p, coll = gpu.find_set_collision_avoidance(g["p1"], g["p1"] + g["l_ee"], True)
+    assert_rows_close(A, b, g["A1"], g["b1"], "golden end set")
+    assert np.abs(Q - g["Q1"]).max() <= 1e-5 * np.abs(g["Q1"]).max() and bool(coll) == bool(g["collision1"])
+    fk = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_golden.npz"))
+    p_ee, p_col, T, J = bp.RobotModel.fk_batch(fk["q"], want_pose=True, want_jacobian=True)
+    assert np.abs(p_ee.cpu().numpy() - fk["p_ee"]).max() < 1e-12
+    assert np.abs(p_col.cpu().numpy() - fk["p_col"]).max() < 1e-12
+    assert np.abs(T.cpu().numpy() - fk["T_ee"]).max() < 1e-12
+    assert np.abs(J.cpu().numpy() - fk["jac"]).max() < 1e-12
