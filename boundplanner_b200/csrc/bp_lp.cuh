@@ -45,7 +45,7 @@
 // xout (optional): start point in, last iterate out.  Returns 1 = intersects.
 template <class ROWS>
 BP_HD int bp_pair_feasible(const ROWS& r1, int m1, const ROWS& r2, int m2, double tol, double* xout,
-                           int* iters_out, bool active = true) {
+                           int* iters_out, bool active = true, double t0_scale = 0.0) {
   if (!active) { m1 = 0; m2 = 0; }
   const int m = m1 + m2;
   const int mw = BP_WARP_MAX_INT(m);             // warp-uniform row-loop trip count
@@ -80,7 +80,10 @@ BP_HD int bp_pair_feasible(const ROWS& r1, int m1, const ROWS& r2, int m2, doubl
       x[3] = smax + 1.0;
     }
   }
+  // barrier parameter at entry: 1, or (rows / initial violation) * t0_scale so that the first
+  // centering already resolves margins of the size of the initial violation
   double t = 1.0;
+  if (t0_scale > 0.0 && !done) { t = t0_scale * mm / (x[3] - 1.0); if (!(t > 1.0)) t = 1.0; }
   int iters = 0, inner = 0, outer = 0;
   while (BP_WARP_ANY(!done)) {                    // one Newton iteration per trip
     if (!done) ++iters;

@@ -17,7 +17,8 @@
 
 __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double* __restrict__ b1, int m1,
                                      const double* __restrict__ A2, const double* __restrict__ b2, int m2,
-                                     double tol, double* scratch, int* iters_out, double* xout = nullptr) {
+                                     double tol, double* scratch, int* iters_out, double* xout = nullptr,
+                                     const double* x0 = nullptr, double t0_scale = 0.0) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int m = m1 + m2;
@@ -53,15 +54,19 @@ __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double
   if (empty) return 0;
   if (mm == 0) return 1;
   double x[4] = {0.0, 0.0, 0.0, 0.0};
+  if (x0) { x[0] = x0[0]; x[1] = x0[1]; x[2] = x0[2]; }
+  double t = 1.0;
   {
     double smax = -BP_INF;
 #pragma unroll
     for (int q = 0; q < BP_LP_SLOTS; ++q)
-      if (rv[q]) smax = fmax(smax, -rc[q]);            // a.x - c at x = 0
+      if (rv[q]) smax = fmax(smax, ra[q][0] * x[0] + ra[q][1] * x[1] + ra[q][2] * x[2] - rc[q]);
     smax = -bp_warp_min(-smax);
-    if (xout) { xout[0] = 0.0; xout[1] = 0.0; xout[2] = 0.0; }
+    if (xout) { xout[0] = x[0]; xout[1] = x[1]; xout[2] = x[2]; }
     if (smax <= 0.0) return 1;
     x[3] = smax + 1.0;
+    // entry barrier parameter (see bp_lp.cuh): resolves margins of the size of the initial violation
+    if (t0_scale > 0.0) { t = t0_scale * mm / smax; if (!(t > 1.0)) t = 1.0; }
   }
   // output owned by this lane: e = lane & 15 -> H (10) or g (4); lanes >= 16 sum the odd rows
   const int e = lane & 15, half = lane >> 4;
@@ -73,7 +78,6 @@ __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double
   } else if (e < 14) {
     cx = e - 10;
   }
-  double t = 1.0;
   int iters = 0, result = 0;
   for (int outer = 0; outer < BP_LP_OUTER_MAX; ++outer) {
     for (int inner = 0; inner < BP_LP_INNER_MAX; ++inner) {

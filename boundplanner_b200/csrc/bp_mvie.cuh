@@ -30,6 +30,9 @@
 #ifndef BP_MVIE_PRED_FROM
 #define BP_MVIE_PRED_FROM 300.0
 #endif
+#ifndef BP_MVIE_WS_BETA
+#define BP_MVIE_WS_BETA 0.9
+#endif
 #define BP_MVIE_OUTER_MAX 48
 #define BP_MVIE_INNER_MAX 40
 #define BP_MVIE_GAP_TOL 1e-11
@@ -83,7 +86,8 @@ BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx) {
 // ROWS: a(i,k), b(i) accessors.  c0: fixed centre (NV==6) or interior hint (NV==9).
 // Out: L[6] (tril packed), d[3] centre.  Returns a BP_* status.
 template <int NV, class ROWS>
-BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout, double* dout, int* iters_out) {
+BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout, double* dout, int* iters_out,
+                        const double* L0 = nullptr, double t0 = 1.0) {
   constexpr int NH = NV * (NV + 1) / 2;
   double x[NV];
   // strictly feasible start: ball of half the inradius around c0
@@ -104,10 +108,30 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
   x[0] = r; x[1] = 0.0; x[2] = r; x[3] = 0.0; x[4] = 0.0; x[5] = r;
   if (NV == 9) { x[6] = c0[0]; x[7] = c0[1]; x[8] = c0[2]; }
   double cen[3] = {c0[0], c0[1], c0[2]};
+  double t = 1.0;
+  if (L0) {
+    // warm start: a previous shape L0 around the same centre, scaled to BP_MVIE_WS_BETA of the
+    // largest factor that keeps it inside, entered at barrier parameter t0
+    double beta = BP_INF;
+    for (int i = 0; i < m; ++i) {
+      double a0 = rows.a(i, 0), a1 = rows.a(i, 1), a2 = rows.a(i, 2);
+      double s = rows.b(i) - (a0 * c0[0] + a1 * c0[1] + a2 * c0[2]);
+      double u0 = L0[0] * a0 + L0[1] * a1 + L0[3] * a2;
+      double u1 = L0[2] * a1 + L0[4] * a2;
+      double u2 = L0[5] * a2;
+      double un = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+      if (un > 0.0) { double q = s / un; beta = q < beta ? q : beta; }
+    }
+    if (beta < BP_INF && beta > 0.0 && L0[0] > 0.0 && L0[2] > 0.0 && L0[5] > 0.0) {
+      beta *= BP_MVIE_WS_BETA;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) x[k] = beta * L0[k];
+      t = t0;
+    }
+  }
 
   const double nu = 2.0 * m + 4.0;
   const double t_final = nu / BP_MVIE_GAP_TOL;
-  double t = 1.0;
   int iters = 0;
   int status = BP_OK;
   double xc_prev[NV];           // previous centre x(t_prev), for the secant predictor

@@ -586,6 +586,7 @@ struct GlobalRows {
 };
 
 #define BP_AABB_EPS 1e-9
+#define BP_LP_T0_SCALE 8.0
 
 __global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, const double* __restrict__ b,
                                                   const int* __restrict__ m, int S, int m_max,
@@ -597,39 +598,39 @@ __global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, 
   const double* bs = b + (size_t)s * m_max;
   const int ms = m[s];
   double lo[3] = {BP_INF, BP_INF, BP_INF}, hi[3] = {-BP_INF, -BP_INF, -BP_INF};
-  const int npairs = ms * (ms - 1) / 2;
-  for (int pidx = lane; pidx < npairs; pidx += 32) {
-    // unrank pidx -> (i < j)
-    int i = 0, rem = pidx;
-    while (rem >= ms - 1 - i) { rem -= ms - 1 - i; ++i; }
-    const int j = i + 1 + rem;
+  // all row triples (i < j < k), flattened over the lanes so that every lane walks
+  // the same number of candidates (the nested-loop version ran at 8.7 active threads/warp)
+  const int ntrip = ms * (ms - 1) * (ms - 2) / 6;
+  for (int t = lane; t < ntrip; t += 32) {
+    int i = 0, rem = t;
+    for (;;) { const int c = (ms - 1 - i) * (ms - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
+    int j = i + 1;
+    for (;;) { const int c = ms - 1 - j; if (rem < c) break; rem -= c; ++j; }
+    const int k = j + 1 + rem;
     const double a0 = __ldg(As + 3 * i), a1 = __ldg(As + 3 * i + 1), a2 = __ldg(As + 3 * i + 2), ab = __ldg(bs + i);
     const double c0 = __ldg(As + 3 * j), c1 = __ldg(As + 3 * j + 1), c2 = __ldg(As + 3 * j + 2), cb = __ldg(bs + j);
-    // n = a x c
-    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;
-    for (int k = j + 1; k < ms; ++k) {
-      const double d0 = __ldg(As + 3 * k), d1 = __ldg(As + 3 * k + 1), d2 = __ldg(As + 3 * k + 2), db = __ldg(bs + k);
-      const double det = n0 * d0 + n1 * d1 + n2 * d2;
-      const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
-      if (!(fabs(det) > 1e-12 * scale)) continue;
-      // v = (ab (c x d) + cb (d x a) + db (a x c)) / det
-      const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
-      const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
-      const double id = 1.0 / det;
-      const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
-      const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
-      const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
-      bool inside = true;
-      for (int r = 0; r < ms && inside; ++r) {
-        const double q0 = __ldg(As + 3 * r), q1 = __ldg(As + 3 * r + 1), q2 = __ldg(As + 3 * r + 2);
-        const double viol = q0 * v0 + q1 * v1 + q2 * v2 - __ldg(bs + r);
-        if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
-      }
-      if (inside) {
-        lo[0] = fmin(lo[0], v0); hi[0] = fmax(hi[0], v0);
-        lo[1] = fmin(lo[1], v1); hi[1] = fmax(hi[1], v1);
-        lo[2] = fmin(lo[2], v2); hi[2] = fmax(hi[2], v2);
-      }
+    const double d0 = __ldg(As + 3 * k), d1 = __ldg(As + 3 * k + 1), d2 = __ldg(As + 3 * k + 2), db = __ldg(bs + k);
+    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;      // a x c
+    const double det = n0 * d0 + n1 * d1 + n2 * d2;
+    const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
+    if (!(fabs(det) > 1e-12 * scale)) continue;
+    // v = (ab (c x d) + cb (d x a) + db (a x c)) / det
+    const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
+    const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
+    const double id = 1.0 / det;
+    const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
+    const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
+    const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
+    bool inside = true;
+    for (int r = 0; r < ms; ++r) {
+      const double q0 = __ldg(As + 3 * r), q1 = __ldg(As + 3 * r + 1), q2 = __ldg(As + 3 * r + 2);
+      const double viol = q0 * v0 + q1 * v1 + q2 * v2 - __ldg(bs + r);
+      if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
+    }
+    if (inside) {
+      lo[0] = fmin(lo[0], v0); hi[0] = fmax(hi[0], v0);
+      lo[1] = fmin(lo[1], v1); hi[1] = fmax(hi[1], v1);
+      lo[2] = fmin(lo[2], v2); hi[2] = fmax(hi[2], v2);
     }
   }
 #pragma unroll
@@ -678,7 +679,8 @@ __global__ void __launch_bounds__(256) k_pair_filter(const double* __restrict__ 
 
 __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
                                                  const int* __restrict__ m, int S, int m_max, double tol,
-                                                 int row_begin, const int2* __restrict__ list,
+                                                 int row_begin, const double* __restrict__ aabb,
+                                                 const int2* __restrict__ list,
                                                  const unsigned int* __restrict__ count,
                                                  unsigned int* __restrict__ adj, double* __restrict__ x_feas) {
   __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
@@ -689,10 +691,17 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
   const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int p = warp; p < n; p += nwarps) {       // one warp per surviving pair
     const int2 pr = list[p];
-    double xi[3];
+    double xi[3], x0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                       // start at the middle of the overlap of the two boxes
+      const double lo = fmax(__ldg(aabb + (size_t)pr.x * 6 + k), __ldg(aabb + (size_t)pr.y * 6 + k));
+      const double hi = fmin(__ldg(aabb + (size_t)pr.x * 6 + 3 + k), __ldg(aabb + (size_t)pr.y * 6 + 3 + k));
+      x0[k] = 0.5 * (lo + hi);
+      if (!(fabs(x0[k]) < 1e6)) x0[k] = 0.0;            // unbounded description: no box
+    }
     const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                           A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
-                                          scratch[wib], nullptr, xi);
+                                          scratch[wib], nullptr, xi, x0, BP_LP_T0_SCALE);
     if (lane == 0 && res) {
       atomicOr(adj + (size_t)(pr.x - row_begin) * words + (pr.y >> 5), 1u << (pr.y & 31));
       if (x_feas) {
@@ -980,7 +989,7 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   long long ctas = (max_pairs + 7) / 8;              // 8 warps per CTA, one pair per warp per trip
   if (ctas > (long long)nsm * 8) ctas = (long long)nsm * 8;
   if (ctas < 1) ctas = 1;
-  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, list, count, adj_bits_dev,
+  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count, adj_bits_dev,
                                                        x_feas_dev);
   BP_CUDA(cudaGetLastError());
   return 0;

@@ -28,6 +28,19 @@ int hh_mvie(const double* A, const double* b, int m, int free_centre, const doub
   return st;
 }
 
+int hh_mvie_ws(const double* A, const double* b, int m, int free_centre, const double* c0, const double* L0, double t0,
+               double* E, double* Lout, double* centre, int* iters) {
+  HostRows rows{A, b};
+  double L[6], d[3];
+  int st = free_centre ? bp_mvie_solve<9>(rows, m, c0, L, d, iters, L0, t0)
+                       : bp_mvie_solve<6>(rows, m, c0, L, d, iters, L0, t0);
+  double Q[9], det;
+  bp_shape_from_L(L, E, Q, &det);
+  for (int k = 0; k < 6; ++k) Lout[k] = L[k];
+  centre[0] = d[0]; centre[1] = d[1]; centre[2] = d[2];
+  return st;
+}
+
 // closest points of n boxes to p in the metric of E (q_inv): y[n,3], dist[n]
 void hh_box_qp(const double* E, const double* p, const double* lb, const double* ub, int n, double* y,
                double* dist) {
@@ -61,6 +74,12 @@ int hh_pair_lp(const double* A1, const double* b1, int m1, const double* A2, con
                double* xout, int* iters) {
   HostRows r1{A1, b1}, r2{A2, b2};
   return bp_pair_feasible(r1, m1, r2, m2, tol, xout, iters);
+}
+
+int hh_pair_lp_t0(const double* A1, const double* b1, int m1, const double* A2, const double* b2, int m2, double tol,
+                  double* xout, int* iters, double t0_scale) {
+  HostRows r1{A1, b1}, r2{A2, b2};
+  return bp_pair_feasible(r1, m1, r2, m2, tol, xout, iters, true, t0_scale);
 }
 
 void hh_fk(const double* q, int n, double* p_ee, double* p_col, double* T_ee, double* jac) {
