@@ -39,28 +39,42 @@
 
 // LDL^T solve of an NV x NV SPD system, H stored as packed lower triangle
 // (index r*(r+1)/2 + c).  Returns false when a pivot is not positive.
+// 1/x.  On the device: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16,
+// not correctly rounded) -- it only steers Newton directions, and it takes the
+// IEEE-division slow path off the critical path of every pivot.
+BP_HD double bp_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 template <int NV>
 BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx) {
-  double dd[NV], dinv[NV];
+  // right-looking (outer-product) LDL^T: after column j is scaled the trailing
+  // updates are mutually independent, so the dependent chain per column is
+  // reciprocal -> scale -> one update of the next pivot.
+  double dinv[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    // ld[k] = L_jk * d_k
-    double ld[NV];
-    double dj = H[j * (j + 1) / 2 + j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) {
-      ld[k] = H[j * (j + 1) / 2 + k] * dd[k];
-      dj -= H[j * (j + 1) / 2 + k] * ld[k];
-    }
+    const double dj = H[j * (j + 1) / 2 + j];
     if (!(dj > 0.0)) return false;
-    dd[j] = dj;
-    dinv[j] = 1.0 / dj;
+    dinv[j] = bp_rcp(dj);
+    double col[NV];                       // unscaled column j below the diagonal: L_ij d_j
 #pragma unroll
     for (int i = j + 1; i < NV; ++i) {
-      double v = H[i * (i + 1) / 2 + j];
+      col[i] = H[i * (i + 1) / 2 + j];
+      H[i * (i + 1) / 2 + j] = col[i] * dinv[j];
+    }
 #pragma unroll
-      for (int k = 0; k < j; ++k) v -= H[i * (i + 1) / 2 + k] * ld[k];
-      H[i * (i + 1) / 2 + j] = v * dinv[j];
+    for (int i = j + 1; i < NV; ++i) {
+#pragma unroll
+      for (int k = j + 1; k <= i; ++k) H[i * (i + 1) / 2 + k] -= H[i * (i + 1) / 2 + j] * col[k];
     }
   }
   // forward: L y = -g

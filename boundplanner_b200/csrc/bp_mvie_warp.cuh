@@ -140,7 +140,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         rs[q] = s; ru[q][0] = u0; ru[q][1] = u1; ru[q][2] = u2; rpsi[q] = psi;
         rtw[q] = 0.0;
         if (rv[q]) {
-          const double tw = 2.0 * (1.0 / psi);
+          const double tw = 2.0 * bp_rcp(psi);
           rtw[q] = tw;
           double* f = F + (lane + 32 * q) * W;
           f[0] = -u0 * a0 * tw; f[1] = -u0 * a1 * tw; f[2] = -u1 * a1 * tw;
@@ -158,17 +158,33 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         const int ax0 = cx[0], ay0 = cy[0];
         if (NOUT > 40) {
           const int ax1 = cx[1] >= 0 ? cx[1] : 0, ay1 = cx[1] >= 0 ? cy[1] : 0;
-          for (int i = 0; i < m; ++i) {
+          double acc0b = 0.0, acc1b = 0.0;
+          int i = 0;
+          for (; i + 1 < m; i += 2) {
+            const double* f = F + i * W;
+            acc0 += f[ax0] * f[ay0];
+            acc1 += f[ax1] * f[ay1];
+            acc0b += f[W + ax0] * f[W + ay0];
+            acc1b += f[W + ax1] * f[W + ay1];
+          }
+          if (i < m) {
             const double* f = F + i * W;
             acc0 += f[ax0] * f[ay0];
             acc1 += f[ax1] * f[ay1];
           }
+          acc0 += acc0b;
+          acc1 += acc1b;
           if (cx[1] >= 0) OUT[lane + 32] = acc1;
         } else {
-          for (int i = 0; i < m; ++i) {
+          double acc0b = 0.0;
+          int i = 0;
+          for (; i + 1 < m; i += 2) {
             const double* f = F + i * W;
             acc0 += f[ax0] * f[ay0];
+            acc0b += f[W + ax0] * f[W + ay0];
           }
+          if (i < m) acc0 += F[i * W + ax0] * F[i * W + ay0];
+          acc0 += acc0b;
           // NV == 6: 33 outputs; the last one (W22) comes from a butterfly sum
           const double w22 = bp_warp_sum(rtw[0] * ra[0][2] * ra[0][2] + rtw[1] * ra[1][2] * ra[1][2]);
           if (lane == 0) OUT[32] = w22;
@@ -177,6 +193,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
       }
       __syncwarp();
       double g[NV], H[NH];
+      double i0, i2, i5;                 // 1 / (L00, L11, L22)
 #pragma unroll
       for (int k = 0; k < NH; ++k) H[k] = OUT[k];
 #pragma unroll
@@ -187,7 +204,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         H[0] += w00; H[1] += w01; H[2] += w11; H[6] += w02; H[7] += w12; H[9] += w22;
         H[5] += w11; H[12] += w12; H[14] += w22; H[20] += w22;
         if (NV == 9) { H[27] -= w00; H[34] -= w01; H[35] -= w11; H[42] -= w02; H[43] -= w12; H[44] -= w22; }
-        const double i0 = 1.0 / x[0], i2 = 1.0 / x[2], i5 = 1.0 / x[5];
+        i0 = bp_rcp(x[0]); i2 = bp_rcp(x[2]); i5 = bp_rcp(x[5]);
         g[0] -= t * i0; g[2] -= 2.0 * t * i2; g[5] -= t * i5;
         H[0] += t * i0 * i0; H[5] += 2.0 * t * i2 * i2; H[20] += t * i5 * i5;
       }
@@ -224,7 +241,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (rv[q]) {
-            const double rel = alpha * (rB1[q] + alpha * rA2[q]) / rpsi[q];
+            const double rel = alpha * (rB1[q] + alpha * rA2[q]) * (0.5 * rtw[q]);     // / psi
             if (!(rs[q] + alpha * rds[q] > 0.0) || !(rel > -1.0)) ok = false;
             prod *= 1.0 + rel;
           }
@@ -234,8 +251,8 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
           if (lam2 < 0.01) accepted = true;
           else {
             const double logsum = log(bp_warp_prod(prod));
-            const double dF = -t * (log1p(alpha * dx[0] / x[0]) + 2.0 * log1p(alpha * dx[2] / x[2]) +
-                                    log1p(alpha * dx[5] / x[5])) - logsum;
+            const double dF = -t * (log1p(alpha * dx[0] * i0) + 2.0 * log1p(alpha * dx[2] * i2) +
+                                    log1p(alpha * dx[5] * i5)) - logsum;
             if (dF <= -0.25 * alpha * lam2) accepted = true;
           }
           if (accepted) {
