@@ -714,54 +714,124 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
 }
 
 // ---------------------------------------------------------------------------
-// K7: FK, one thread per configuration.  q and the outputs are staged through
-// shared memory so that global traffic is fully coalesced 16-byte accesses.
+// K7: FK, one thread per configuration, 128 configurations per CTA.
+// HBM-bound streaming kernel: the q tile comes in and the result tiles go out
+// through shared memory with TMA bulk copies (cp.async.bulk, one elected
+// thread, mbarrier completion) so that every global transaction is a full
+// line and no LSU instructions are spent on staging; a plain coalesced loop
+// handles a ragged last tile or unaligned pointers.
 // ---------------------------------------------------------------------------
 #define FK_T 128
-__device__ __forceinline__ void block_copy_out(double* __restrict__ dst, const double* src_smem, int count) {
-  // dst is 16-byte aligned when the tile start is (tile * FK_T * width doubles, width*FK_T even)
-  for (int e = threadIdx.x; e < count; e += FK_T) dst[e] = src_smem[e];
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+template <bool POSE, bool JAC>
 __global__ void __launch_bounds__(FK_T) k_fk(const double* __restrict__ q, int B, double* __restrict__ p_ee,
                                              double* __restrict__ p_col, double* __restrict__ T_ee,
-                                             double* __restrict__ jac) {
-  __shared__ double s_q[FK_T * 7];
-  __shared__ double s_pe[FK_T * 3];
-  __shared__ double s_pc[FK_T * 21];
-  extern __shared__ double s_T[];          // FK_T*16 when T_ee requested
+                                             double* __restrict__ jac, int use_tma) {
+  extern __shared__ __align__(128) double s_fk[];
+  __shared__ __align__(8) uint64_t bar;
+  double* s_q = s_fk;                       // [FK_T*7]
+  double* s_pe = s_q + FK_T * 7;            // [FK_T*3]
+  double* s_pc = s_pe + FK_T * 3;           // [FK_T*21]
+  double* s_T = s_pc + FK_T * 21;           // [FK_T*16]  (POSE)
+  double* s_J = s_T + (POSE ? FK_T * 16 : 0);   // [FK_T*42]  (JAC)
   const int base = blockIdx.x * FK_T;
   const int nb = min(FK_T, B - base);
-  for (int e = threadIdx.x; e < nb * 7; e += FK_T) s_q[e] = q[(size_t)base * 7 + e];
-  __syncthreads();
+  const bool bulk = use_tma && nb == FK_T;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tma_load_1d(s_q, q + (size_t)base * 7, FK_T * 7 * 8, &bar);
+    mbar_wait(&bar, 0);
+  } else {
+    for (int e = threadIdx.x; e < nb * 7; e += FK_T) s_q[e] = q[(size_t)base * 7 + e];
+    __syncthreads();
+  }
   if (threadIdx.x < nb) {
     double qq[7], pe[3], pc[21], T[16], J[42];
 #pragma unroll
     for (int k = 0; k < 7; ++k) qq[k] = s_q[threadIdx.x * 7 + k];
-    bp_fk_iiwa14(qq, pe, pc, T_ee ? T : nullptr, jac ? J : nullptr);
+    bp_fk_iiwa14(qq, pe, pc, POSE ? T : nullptr, JAC ? J : nullptr);
 #pragma unroll
     for (int k = 0; k < 3; ++k) s_pe[threadIdx.x * 3 + k] = pe[k];
 #pragma unroll
     for (int k = 0; k < 21; ++k) s_pc[threadIdx.x * 21 + k] = pc[k];
-    if (T_ee) {
+    if (POSE) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) s_T[threadIdx.x * 16 + k] = T[k];
     }
-    if (jac) {
-      double* jo = jac + (size_t)(base + threadIdx.x) * 42;
+    if (JAC) {
 #pragma unroll
-      for (int k = 0; k < 42; ++k) jo[k] = J[k];
+      for (int k = 0; k < 42; ++k) s_J[threadIdx.x * 42 + k] = J[k];
     }
   }
-  __syncthreads();
-  block_copy_out(p_ee + (size_t)base * 3, s_pe, nb * 3);
-  block_copy_out(p_col + (size_t)base * 21, s_pc, nb * 21);
-  if (T_ee) block_copy_out(T_ee + (size_t)base * 16, s_T, nb * 16);
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tma_store_1d(p_ee + (size_t)base * 3, s_pe, FK_T * 3 * 8);
+      tma_store_1d(p_col + (size_t)base * 21, s_pc, FK_T * 21 * 8);
+      if (POSE) tma_store_1d(T_ee + (size_t)base * 16, s_T, FK_T * 16 * 8);
+      if (JAC) tma_store_1d(jac + (size_t)base * 42, s_J, FK_T * 42 * 8);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until read
+    }
+  } else {
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * 3; e += FK_T) p_ee[(size_t)base * 3 + e] = s_pe[e];
+    for (int e = threadIdx.x; e < nb * 21; e += FK_T) p_col[(size_t)base * 21 + e] = s_pc[e];
+    if (POSE) for (int e = threadIdx.x; e < nb * 16; e += FK_T) T_ee[(size_t)base * 16 + e] = s_T[e];
+    if (JAC) for (int e = threadIdx.x; e < nb * 42; e += FK_T) jac[(size_t)base * 42 + e] = s_J[e];
+  }
 }
 
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
+template <bool POSE, bool JAC>
+static int launch_fk(const double* q, int B, double* p_ee, double* p_col, double* T_ee, double* jac, int use_tma,
+                     cudaStream_t stream) {
+  const size_t smem = sizeof(double) * FK_T * (7 + 3 + 21 + (POSE ? 16 : 0) + (JAC ? 42 : 0));
+  if (smem > 48 * 1024)
+    BP_CUDA(cudaFuncSetAttribute((const void*)k_fk<POSE, JAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_fk<POSE, JAC><<<(B + FK_T - 1) / FK_T, FK_T, smem, stream>>>(q, B, p_ee, p_col, T_ee, jac, use_tma);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int poly_threads(int n) { return n <= 256 ? 128 : (n <= 4096 ? 256 : 512); }
 
 static int set_dyn_smem(const void* fn, size_t bytes) {
@@ -999,10 +1069,15 @@ int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev
                  void* stream) {
   if (B < 0 || !p_ee_dev || !p_col_dev) return bp_fail("bp_fk_iiwa14: bad arguments");
   if (B == 0) return 0;
-  size_t smem = T_ee_dev ? sizeof(double) * FK_T * 16 : 0;
-  k_fk<<<(B + FK_T - 1) / FK_T, FK_T, smem, (cudaStream_t)stream>>>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev);
-  BP_CUDA(cudaGetLastError());
-  return 0;
+  // bulk (TMA) copies need 16-byte aligned global addresses; every tile offset is a multiple of 16 bytes
+  const uintptr_t al = (uintptr_t)q_dev | (uintptr_t)p_ee_dev | (uintptr_t)p_col_dev | (uintptr_t)T_ee_dev |
+                       (uintptr_t)jac_dev;
+  const int use_tma = (al & 15) == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T_ee_dev && jac_dev) return launch_fk<true, true>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
+  if (T_ee_dev) return launch_fk<true, false>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
+  if (jac_dev) return launch_fk<false, true>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
+  return launch_fk<false, false>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
 }
 
 }  // extern "C"
