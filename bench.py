@@ -288,6 +288,7 @@ def run_gpu(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": prof["roofline"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),
+            "roofline_fk": prof["roofline_fk"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),
             "kernels": prof["kernels"],
         }
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
@@ -304,20 +305,25 @@ def run_gpu(args):
 
 
 def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
-    """Time the kernels of one step in isolation (CUDA events on the launch
-    stream, L2-cold) and build the roofline entry of the dominant one."""
+    """Time the kernels of one step in isolation (CUDA events on the launch stream,
+    several back-to-back launches per measurement) and build the roofline entries."""
+    import ctypes
     import statistics
 
-    def timeit(fn, reps=5):
+    from boundplanner_b200 import _lib
+    from boundplanner_b200.robot_model import Q_LIM_UPPER
+
+    def timeit(fn, reps=5, inner=4):
         ts = []
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record()
-            fn()
+            for _ in range(inner):
+                fn()
             b.record()
             torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
+            ts.append(a.elapsed_time(b) / inner)
         return statistics.median(ts)
 
     S = seeds_dev.shape[0]
@@ -330,44 +336,69 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
         init_rows[:, 2 * i, 3] = float(ws_max[i])
         init_rows[:, 2 * i + 1, i] = -1.0
         init_rows[:, 2 * i + 1, 3] = -float(ws_min[i])
-    t_poly = timeit(lambda: geo.polyhedron(scene, seeds_dev, q0 * 1e-4, q0 * 1e4, init_rows))
+    qi, qe = q0 * 1e-4, q0 * 1e4
+    t_poly = timeit(lambda: geo.polyhedron(scene, seeds_dev, qi, qe, init_rows))
     t_mvie_fm = timeit(lambda: geo.mvie(out.A, out.b, out.m, seeds_dev, False))
-    res = geo.mvie(out.A, out.b, out.m, seeds_dev, True)
     t_mvie_free = timeit(lambda: geo.mvie(out.A, out.b, out.m, seeds_dev, True))
-    newton_free = float(res[4].double().mean().item())
+    newton_free = float(geo.mvie(out.A, out.b, out.m, seeds_dev, True)[4].double().mean().item())
     newton_fm = float(geo.mvie(out.A, out.b, out.m, seeds_dev, False)[4].double().mean().item())
     t_pair = timeit(lambda: geo.pair_feasible(out.A, out.b, out.m, TOL))
     m_mean = float(out.m.double().mean().item())
+
+    # FP64 pipe peak of this part (dependent-free DFMA chains, full chip)
+    lib = _lib.load()
+    probe_out = torch.empty(296 * 256, dtype=torch.float64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    iters = 20000
+    t_probe = timeit(lambda: lib.bp_probe_fp64(8, 296, 256, iters, ctypes.c_void_p(probe_out.data_ptr()), st),
+                     reps=3, inner=1)
+    fp64_peak_tflops = 296 * 256 * 8 * iters * 2 / (t_probe * 1e-3) / 1e12
+
+    # K7 FK micro-benchmark (C5): B = 2^20 configurations, inputs larger than L2 are flushed between runs
+    B = 1 << 20
+    lim = torch.as_tensor(Q_LIM_UPPER, device="cuda")
+    qq = (torch.rand((B, 7), dtype=torch.float64, device="cuda") * 2 - 1) * lim
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    ts = []
+    for k in range(8):
+        flush.fill_(float(k))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        geo.fk_iiwa14(qq)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    t_fk = statistics.median(ts[2:])
+    fk_bytes = B * (56 + 24 + 168)
+
     kernels = {
         "k_poly_point_ms": t_poly, "k_mvie_fixed_mid_ms": t_mvie_fm, "k_mvie_free_ms": t_mvie_free,
-        "k_pair_feasible_ms": t_pair, "newton_iters_fixed_mid": newton_fm, "newton_iters_free": newton_free,
-        "mean_rows": m_mean,
+        "pair_pipeline_ms": t_pair, "k_fk_1M_ms": t_fk, "newton_iters_fixed_mid": newton_fm,
+        "newton_iters_free": newton_free, "mean_rows": m_mean, "fp64_peak_tflops_measured": fp64_peak_tflops,
     }
 
     def roofline(hbm_peak, which):
-        # dominant kernel of the step: k_mvie (5 fixed-mid + 1 free per seed) vs 5 x k_poly_point
-        t_m = 5 * t_mvie_fm + t_mvie_free
-        t_p = 5 * t_poly
-        if t_m >= t_p:
-            # algorithmic bytes per launch: rows in (m*32 B) + shape/centre out (9+9+3)*8 B per set
-            bytes_alg = S * (m_mean * 32 + 21 * 8)
-            dur = t_mvie_free
-            name = "k_mvie(free centre)"
-            flops = S * newton_free * (m_mean * 200.0 + 250.0)
-        else:
-            # scene read once per CTA (N*48 B) + rows out per set
-            bytes_alg = S * (N * 48 + m_mean * 32)
-            dur = t_poly
-            name = "k_poly_point"
-            flops = S * N * (1100.0 + 64.0 * (m_mean - 6))
+        # dominant kernel of the step: k_mvie (5 fixed-mid + 1 free launch per step)
+        bytes_alg = S * (m_mean * 32 + 21 * 8)          # rows in + shape/centre out, per launch
+        flops = S * newton_fm * (m_mean * 200.0 + 250.0)  # per-Newton-iteration flop model
+        dur = t_mvie_fm
         ach = bytes_alg / (dur * 1e-3) / 1e9
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": which,
-                "note": "fp64-latency-bound kernel: operands are L2/shared-memory resident, HBM traffic is "
-                        "compulsory input/output only; see fp64_gflops",
-                "fp64_gflops": flops / (dur * 1e-3) / 1e9}
+        return {"kernel": "k_mvie (fixed centre, one launch = one IRIS pass over 256 sets)", "bound": "hbm",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": which,
+                "note": "latency-bound fp64 kernel (one warp per set, ~35 dependent Newton iterations): it moves "
+                        "only its compulsory bytes, so the HBM fraction is tiny by construction; see fp64 below "
+                        "and roofline_fk for the HBM-bound kernel of the path",
+                "fp64": {"achieved_gflops": flops / (dur * 1e-3) / 1e9, "peak_gflops": fp64_peak_tflops * 1e3,
+                         "frac": flops / (dur * 1e-3) / 1e12 / fp64_peak_tflops}}
 
-    return {"kernels": kernels, "roofline": roofline}
+    def roofline_fk(hbm_peak, which):
+        ach = fk_bytes / (t_fk * 1e-3) / 1e9
+        return {"kernel": "k_fk<false,false> (B = 2^20 configurations, 248 B each)", "bound": "hbm", "achieved": ach,
+                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": which,
+                "poses_per_sec": B / (t_fk * 1e-3)}
+
+    return {"kernels": kernels, "roofline": roofline, "roofline_fk": roofline_fk}
 
 
 def main():

@@ -214,6 +214,7 @@ struct PolyParams {
   int m_max;
   int mode;
   int max_iter;
+  int cache_y;               // closest points kept in shared memory (y[3][N] after dist[N])
 };
 
 __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr) {
@@ -268,13 +269,16 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr)
   // phase 1: closest points and distances
   double lmin = BP_INF;
   int lidx = 0x7fffffff;
+  double* s_y = s_dist + sc.n;               // [3][N] when pr.cache_y
   for (int j = tid; j < sc.n; j += T) {
     double lb[3], ub[3], y[3];
     load_box(sc, j, lb, ub);
     double d = closest_on_box(pm, p, lb, ub, y);
     s_dist[j] = d;
+    if (pr.cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
     if (d < lmin) { lmin = d; lidx = j; }
   }
+  // (the barrier inside block_argmin orders these writes before the winner's point is read)
 
   // phase 2: greedy halfspaces
   int m_cur = 6;
@@ -286,9 +290,14 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr)
     block_argmin(val, idx, red_val, red_idx, buf);
     if (!(val < BP_INF)) break;                      // no obstacle left
     if (val < 0.99) { status = BP_ELLIPSE_VIOLATION; break; }   // :433-438
-    double lb[3], ub[3], y[3];
-    load_box(sc, idx, lb, ub);
-    closest_on_box(pm, p, lb, ub, y);
+    double y[3];
+    if (pr.cache_y) {
+      y[0] = s_y[idx]; y[1] = s_y[sc.n + idx]; y[2] = s_y[2 * sc.n + idx];
+    } else {                                   // large scenes: re-solve the winner's QP (same inputs, same bits)
+      double lb[3], ub[3];
+      load_box(sc, idx, lb, ub);
+      closest_on_box(pm, p, lb, ub, y);
+    }
     double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
     double a[3];
     bp_mat3_vec(pm.G, zz, a);
@@ -566,7 +575,7 @@ __global__ void k_state_init_line(SeedState* st, const double* __restrict__ p0, 
 // ---------------------------------------------------------------------------
 // K6: pairwise feasibility (BoundPlanner.set_intersection, BoundPlanner.py:774-798).
 // Three kernels per call:
-//   k_set_aabb      one warp per set: exact axis-aligned bounding box of the
+//   k_set_aabb      one CTA per set: exact axis-aligned bounding box of the
 //                   polytope by vertex enumeration (all row triples);
 //   k_pair_filter   every pair (i, j>i) of the row block: pairs whose boxes are
 //                   disjoint cannot intersect (the tol-shrunk sets lie inside
@@ -591,9 +600,9 @@ struct GlobalRows {
 __global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, const double* __restrict__ b,
                                                   const int* __restrict__ m, int S, int m_max,
                                                   double* __restrict__ aabb) {
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= S) return;
+  __shared__ double red[4][6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x;                     // one 128-thread CTA per set
   const double* As = A + (size_t)s * m_max * 3;
   const double* bs = b + (size_t)s * m_max;
   const int ms = m[s];
@@ -601,7 +610,7 @@ __global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, 
   // all row triples (i < j < k), flattened over the lanes so that every lane walks
   // the same number of candidates (the nested-loop version ran at 8.7 active threads/warp)
   const int ntrip = ms * (ms - 1) * (ms - 2) / 6;
-  for (int t = lane; t < ntrip; t += 32) {
+  for (int t = threadIdx.x; t < ntrip; t += 128) {
     int i = 0, rem = t;
     for (;;) { const int c = (ms - 1 - i) * (ms - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
     int j = i + 1;
@@ -642,6 +651,16 @@ __global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, 
     }
   }
   if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], red[w][k]); hi[k] = fmax(hi[k], red[w][3 + k]); }
+    }
     // no vertex found (unbounded or empty description): never reject on this set
     const bool none = !(lo[0] <= hi[0]);
 #pragma unroll
@@ -832,6 +851,12 @@ static int launch_fk(const double* q, int B, double* p_ee, double* p_col, double
   return 0;
 }
 
+// closest points are cached in shared memory while dist[N] + y[3][N] stays within 96 KB per CTA
+static int poly_cache_y(int n) { return (size_t)n * 32 <= 96 * 1024; }
+static size_t poly_smem_bytes(int n) {
+  if (n < 1) n = 1;
+  return sizeof(double) * (size_t)n * (poly_cache_y(n) ? 4 : 1);
+}
 static int poly_threads(int n) { return n <= 256 ? 128 : (n <= 4096 ? 256 : 512); }
 
 static int set_dyn_smem(const void* fn, size_t bytes) {
@@ -927,7 +952,8 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
   memset(&pr, 0, sizeof(pr));
   pr.seeds = seeds_dev; pr.q_ellipse = q_ellipse_dev; pr.init_rows = init_rows_dev;
   pr.A = A_dev; pr.b = b_dev; pr.m = m_dev; pr.status = status_dev; pr.m_max = m_max; pr.mode = 0;
-  size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
+  pr.cache_y = poly_cache_y(scene->n);
+  size_t smem = poly_smem_bytes(scene->n);
   if (set_dyn_smem((const void*)k_poly_point, smem)) return 1;
   k_poly_point<<<S, poly_threads(scene->n), smem, (cudaStream_t)stream>>>(view_of(scene), pr);
   BP_CUDA(cudaGetLastError());
@@ -974,7 +1000,8 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
   MvieParams mp;
   memset(&mp, 0, sizeof(mp));
   mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st;
-  size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
+  pp.cache_y = poly_cache_y(scene->n);
+  size_t smem = poly_smem_bytes(scene->n);
   if (set_dyn_smem((const void*)k_poly_point, smem)) return 1;
   const int T = poly_threads(scene->n);
   const int passes = optimize ? max_iter : 1;
@@ -1047,7 +1074,7 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   const int words = (S + 31) / 32;
   BP_CUDA(cudaMemsetAsync(adj_bits_dev, 0, sizeof(unsigned int) * (size_t)rows * words, stream));
   BP_CUDA(cudaMemsetAsync(count, 0, 16, stream));
-  k_set_aabb<<<(S + 3) / 4, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
+  k_set_aabb<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
   dim3 grid((S + 31) / 32, (rows + 7) / 8);
   k_pair_filter<<<grid, 256, 0, stream>>>(aabb, S, row_begin, row_end, list, count);
   int nsm = 148;
