@@ -326,6 +326,12 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr)
     }
   }
   if (status == BP_OK && m_cur > pr.m_max) status = BP_ROW_OVERFLOW;
+  // rows past the last one keep the padding of normalize_set_size (A = 0, b = 10): an earlier,
+  // longer pass may have left its rows there
+  for (int r = m_cur + tid; r < pr.m_max; r += T) {
+    Arow[3 * r] = 0.0; Arow[3 * r + 1] = 0.0; Arow[3 * r + 2] = 0.0;
+    brow[r] = 10.0;
+  }
   if (tid == 0) {
     pr.m[s] = m_cur < pr.m_max ? m_cur : pr.m_max;
     if (pr.mode == 1) {
@@ -438,6 +444,10 @@ __global__ void __launch_bounds__(512) k_poly_line(SceneView sc, LineParams pr) 
         lmin = dd; lidx = j;
       }
     }
+  }
+  for (int r = m_cur + tid; r < pr.m_max; r += T) {
+    Arow[3 * r] = 0.0; Arow[3 * r + 1] = 0.0; Arow[3 * r + 2] = 0.0;
+    brow[r] = 10.0;
   }
   if (tid == 0) {
     pr.m[s] = m_cur < pr.m_max ? m_cur : pr.m_max;
