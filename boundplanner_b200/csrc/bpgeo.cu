@@ -743,6 +743,137 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
 }
 
 // ---------------------------------------------------------------------------
+// K8 ("next" row 1): redundancy removal of a set's rows.
+// Replaces reduce_ineqs (bound_planner/utils/util_functions.py:82-88; cddlib
+// dd_MatrixRedundancyRemove): a row is kept iff it supports a facet, i.e. the
+// polytope has three non-collinear vertices on it.  One 128-thread CTA per set:
+// phase 1 enumerates the vertices (all row triples, as k_set_aabb) into shared
+// memory; phase 2, one thread per row, measures the spread of the vertices on
+// its plane; of two identical planes the later row goes (cddlib walks the rows
+// from the last to the first and removes on the spot).  Kept rows keep their
+// order and coefficients.
+// ---------------------------------------------------------------------------
+#define BP_RED_VMAX 768
+#define BP_RED_ON_FACE 1e-8
+#define BP_RED_SPREAD 1e-7
+
+__global__ void __launch_bounds__(128) k_reduce_rows(const double* __restrict__ A, const double* __restrict__ b,
+                                                     const int* __restrict__ m, int m_max, double* __restrict__ A_out,
+                                                     double* __restrict__ b_out, int* __restrict__ m_out,
+                                                     unsigned char* __restrict__ keep_out, int* __restrict__ status) {
+  __shared__ double sA[BP_MAX_ROWS * 3], sb[BP_MAX_ROWS];
+  __shared__ double sv[BP_RED_VMAX * 3];
+  __shared__ int nverts;
+  __shared__ unsigned char skeep[BP_MAX_ROWS];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int ms = m[s];
+  for (int e = tid; e < ms * 3; e += 128) sA[e] = A[(size_t)s * m_max * 3 + e];
+  for (int e = tid; e < ms; e += 128) sb[e] = b[(size_t)s * m_max + e];
+  if (tid == 0) nverts = 0;
+  __syncthreads();
+  const int ntrip = ms * (ms - 1) * (ms - 2) / 6;
+  for (int t = tid; t < ntrip; t += 128) {
+    int i = 0, rem = t;
+    for (;;) { const int c = (ms - 1 - i) * (ms - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
+    int j = i + 1;
+    for (;;) { const int c = ms - 1 - j; if (rem < c) break; rem -= c; ++j; }
+    const int k = j + 1 + rem;
+    const double a0 = sA[3 * i], a1 = sA[3 * i + 1], a2 = sA[3 * i + 2], ab = sb[i];
+    const double c0 = sA[3 * j], c1 = sA[3 * j + 1], c2 = sA[3 * j + 2], cb = sb[j];
+    const double d0 = sA[3 * k], d1 = sA[3 * k + 1], d2 = sA[3 * k + 2], db = sb[k];
+    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;
+    const double det = n0 * d0 + n1 * d1 + n2 * d2;
+    const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
+    if (!(fabs(det) > 1e-12 * scale)) continue;
+    const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
+    const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
+    const double id = 1.0 / det;
+    const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
+    const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
+    const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
+    bool inside = true;
+    for (int r = 0; r < ms; ++r) {
+      const double q0 = sA[3 * r], q1 = sA[3 * r + 1], q2 = sA[3 * r + 2];
+      const double viol = q0 * v0 + q1 * v1 + q2 * v2 - sb[r];
+      if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
+    }
+    if (inside) {
+      const int slot = atomicAdd(&nverts, 1);
+      if (slot < BP_RED_VMAX) { sv[3 * slot] = v0; sv[3 * slot + 1] = v1; sv[3 * slot + 2] = v2; }
+    }
+  }
+  __syncthreads();
+  const int nv = nverts < BP_RED_VMAX ? nverts : BP_RED_VMAX;
+  const bool overflow = nverts > BP_RED_VMAX;
+  if (tid < ms) {
+    const int r = tid;
+    const double q0 = sA[3 * r], q1 = sA[3 * r + 1], q2 = sA[3 * r + 2], qb = sb[r];
+    const double qn = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+    bool keep = true;
+    if (!(qn > 0.0)) keep = qb < 0.0;                 // 0 <= b is always implied
+    else if (!overflow) {
+      // the later of two identical planes is redundant
+      for (int e = 0; e < r && keep; ++e) {
+        const double en = sqrt(sA[3 * e] * sA[3 * e] + sA[3 * e + 1] * sA[3 * e + 1] + sA[3 * e + 2] * sA[3 * e + 2]);
+        if (en > 0.0 && fabs(sA[3 * e] / en - q0 / qn) <= 1e-12 && fabs(sA[3 * e + 1] / en - q1 / qn) <= 1e-12 &&
+            fabs(sA[3 * e + 2] / en - q2 / qn) <= 1e-12 && fabs(sb[e] / en - qb / qn) <= 1e-12)
+          keep = false;
+      }
+      if (keep) {
+        // spread of the vertices lying on the plane of row r: point, segment or polygon?
+        const double tolf = BP_RED_ON_FACE * (qn + fabs(qb));
+        int first = -1;
+        for (int v = 0; v < nv && first < 0; ++v)
+          if (fabs(q0 * sv[3 * v] + q1 * sv[3 * v + 1] + q2 * sv[3 * v + 2] - qb) <= tolf) first = v;
+        if (first < 0) keep = false;
+        else {
+          const double p0 = sv[3 * first], p1 = sv[3 * first + 1], p2 = sv[3 * first + 2];
+          double dmax = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+          for (int v = 0; v < nv; ++v) {
+            const double x0 = sv[3 * v], x1 = sv[3 * v + 1], x2 = sv[3 * v + 2];
+            if (fabs(q0 * x0 + q1 * x1 + q2 * x2 - qb) > tolf) continue;
+            const double dd = (x0 - p0) * (x0 - p0) + (x1 - p1) * (x1 - p1) + (x2 - p2) * (x2 - p2);
+            if (dd > dmax) { dmax = dd; w0 = x0 - p0; w1 = x1 - p1; w2 = x2 - p2; }
+          }
+          if (!(dmax > BP_RED_SPREAD * BP_RED_SPREAD)) keep = false;      // the plane touches in a point
+          else {
+            double amax = 0.0;
+            for (int v = 0; v < nv; ++v) {
+              const double x0 = sv[3 * v], x1 = sv[3 * v + 1], x2 = sv[3 * v + 2];
+              if (fabs(q0 * x0 + q1 * x1 + q2 * x2 - qb) > tolf) continue;
+              const double u0 = x0 - p0, u1 = x1 - p1, u2 = x2 - p2;
+              const double cx = w1 * u2 - w2 * u1, cy = w2 * u0 - w0 * u2, cz = w0 * u1 - w1 * u0;
+              const double ar = cx * cx + cy * cy + cz * cz;
+              amax = ar > amax ? ar : amax;
+            }
+            if (!(amax > BP_RED_SPREAD * BP_RED_SPREAD * dmax)) keep = false;   // ... or along an edge
+          }
+        }
+      }
+    }
+    skeep[r] = keep ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int k = 0;
+    double* Ao = A_out + (size_t)s * m_max * 3;
+    double* bo = b_out + (size_t)s * m_max;
+    for (int r = 0; r < ms; ++r) {
+      if (keep_out) keep_out[(size_t)s * m_max + r] = skeep[r];
+      if (skeep[r]) {
+        Ao[3 * k] = sA[3 * r]; Ao[3 * k + 1] = sA[3 * r + 1]; Ao[3 * k + 2] = sA[3 * r + 2];
+        bo[k] = sb[r];
+        ++k;
+      }
+    }
+    for (int r = k; r < m_max; ++r) { Ao[3 * r] = 0.0; Ao[3 * r + 1] = 0.0; Ao[3 * r + 2] = 0.0; bo[r] = 10.0; }
+    if (keep_out) for (int r = ms; r < m_max; ++r) keep_out[(size_t)s * m_max + r] = 0;
+    m_out[s] = k;
+    if (status) status[s] = overflow ? BP_ROW_OVERFLOW : BP_OK;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K7: FK, one thread per configuration, 128 configurations per CTA.
 // HBM-bound streaming kernel: the q tile comes in and the result tiles go out
 // through shared memory with TMA bulk copies (cp.async.bulk, one elected
@@ -1098,6 +1229,17 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   if (ctas < 1) ctas = 1;
   k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count, adj_bits_dev,
                                                        x_feas_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double* A_out_dev,
+                    double* b_out_dev, int* m_out_dev, unsigned char* keep_out_dev, int* status_dev, void* stream) {
+  if (S < 0 || m_max < 1 || m_max > BP_MAX_ROWS || !A_out_dev || !b_out_dev || !m_out_dev)
+    return bp_fail("bp_reduce_ineqs: bad arguments");
+  if (S == 0) return 0;
+  k_reduce_rows<<<S, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, A_out_dev, b_out_dev, m_out_dev,
+                                                      keep_out_dev, status_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -232,6 +232,23 @@ def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=Fals
     return bits
 
 
+def reduce_ineqs(A, b, m):
+    """reduce_ineqs (util_functions.py:82-88) for S sets: returns (A_red, b_red, m_red, keep [S,m_max] bool)."""
+    lib = _lib.load()
+    A = _dev(A)
+    S, m_max = A.shape[0], A.shape[1]
+    b = _dev(b).reshape(S, m_max)
+    m = _dev(m, torch.int32).reshape(S)
+    Ao = torch.empty_like(A)
+    bo = torch.empty_like(b)
+    mo = torch.zeros_like(m)
+    keep = torch.zeros((S, m_max), dtype=torch.uint8, device="cuda")
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    check(lib.bp_reduce_ineqs(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(Ao), _ptr(bo), _ptr(mo), _ptr(keep),
+                              _ptr(status), _stream()))
+    return Ao, bo, mo, keep.bool(), status
+
+
 def unpack_adjacency(bits, S, row_begin=0):
     """int32 words [rows, words] -> bool [rows, S]."""
     shifts = torch.arange(32, device=bits.device, dtype=torch.int32)

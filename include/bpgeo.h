@@ -115,6 +115,14 @@ int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*
                                            (the reference's sol_lin.x, BoundPlanner.py:785) */,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- K8 (next row 1): redundancy removal ---------------------------------------------
+ * Replaces reduce_ineqs (bound_planner/utils/util_functions.py:82-88, cddlib
+ * matrix_redundancy_remove) for S sets.  Kept rows keep their order and coefficients;
+ * A_out/b_out are padded with A = 0, b = 10; keep_out[S,m_max] (or NULL) flags kept rows;
+ * status[S] (or NULL) is BP_ROW_OVERFLOW when the vertex table overflowed (rows all kept). */
+int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double* A_out_dev,
+                    double* b_out_dev, int* m_out_dev, unsigned char* keep_out_dev, int* status_dev, void* stream);
+
 /* ---- K7: iiwa14 forward kinematics -----------------------------------------------
  * Replaces the numeric branch of RobotModel.fk_pos (RobotModel.py:146-160),
  * fk_pos_col (:162-181), hom_transform_endeffector (:197-211), jacobian_fk

@@ -94,3 +94,20 @@ def test_fk_constants_equal_the_reference_urdf():
         assert [float(v) for v in o.get("xyz").split()] == list(spec[1])
         assert [float(v) for v in o.get("rpy").split()] == list(spec[2])
         assert joints[name].find("parent").get("link") == {4: "link_4", 7: "link_7"}[spec[0]]
+
+
+def test_reduce_ineqs_oracle_known_answers():
+    """oracle/reduce_ineqs.py (restating cddlib's redundancy removal, util_functions.py:82-88)."""
+    from oracle.reduce_ineqs import reduce_ineqs, redundant_row_mask
+
+    A = np.vstack((BOX, [[1, 1, 1], [1, 1, 1], [1, 0, 0], [1, 0, 0]]))
+    b = np.concatenate((np.ones(6), [2.5, 3.0, 5.0, 1.0]))
+    red = redundant_row_mask(A, b)
+    # cut (2.5) kept; vertex-touching plane (3.0), far plane (5.0) and the LATER duplicate of the x face removed
+    assert red.tolist() == [False] * 6 + [False, True, True, True]
+    Ar, br = reduce_ineqs(A, b)
+    assert np.array_equal(Ar, A[:7]) and np.array_equal(br, b[:7])
+    # zero (padding) rows are redundant
+    Ap = np.vstack((BOX, np.zeros((3, 3))))
+    bp_ = np.concatenate((np.ones(6), 10 * np.ones(3)))
+    assert redundant_row_mask(Ap, bp_).tolist() == [False] * 6 + [True] * 3
