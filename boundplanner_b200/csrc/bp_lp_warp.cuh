@@ -15,13 +15,12 @@
 #define BP_LP_SLOTS 3                                   // rows per lane: m1 + m2 <= 96
 #define BP_LP_SCRATCH_DOUBLES (96 * 5 + 16)
 
-__device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double* __restrict__ b1, int m1,
-                                     const double* __restrict__ A2, const double* __restrict__ b2, int m2,
-                                     double tol, double* scratch, int* iters_out, double* xout = nullptr,
-                                     const double* x0 = nullptr, double t0_scale = 0.0) {
+// ROWFN(i, a[3], c): row i of the system a.x <= c, i in [0, m), m <= 96.
+template <class ROWFN>
+__device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, int* iters_out, double* xout = nullptr,
+                                   const double* x0 = nullptr, double t0_scale = 0.0) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int m = m1 + m2;
   double* F = scratch;              // [m][5]: v0 v1 v2 v3 (stride 5: conflict-free row writes)
   double* OUT = scratch + 96 * 5;   // [16]
   double ra[BP_LP_SLOTS][3], rc[BP_LP_SLOTS];
@@ -35,10 +34,7 @@ __device__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double
     rc[q] = 1.0;
     rv[q] = false;
     if (i < m) {
-      const double* A = i < m1 ? A1 + 3 * i : A2 + 3 * (i - m1);
-      const double bb = i < m1 ? b1[i] : b2[i - m1];
-      ra[q][0] = A[0]; ra[q][1] = A[1]; ra[q][2] = A[2];
-      rc[q] = bb - tol;
+      rowfn(i, ra[q], rc[q]);
       rv[q] = (ra[q][0] != 0.0 || ra[q][1] != 0.0 || ra[q][2] != 0.0);
       if (!rv[q] && rc[q] < 0.0) empty = true;        // 0 <= c violated
     }
@@ -174,4 +170,25 @@ done:
   if (iters_out) *iters_out = iters;
   if (xout) { xout[0] = x[0]; xout[1] = x[1]; xout[2] = x[2]; }   // last iterate: strictly inside when result == 1
   return result;
+}
+
+// rows of set 1 then set 2, every offset shrunk by tol (BoundPlanner.set_intersection, :774-787)
+struct BpPairRows {
+  const double *A1, *b1, *A2, *b2;
+  int m1;
+  double tol;
+  __device__ __forceinline__ void operator()(int i, double* a, double& c) const {
+    const double* A = i < m1 ? A1 + 3 * i : A2 + 3 * (i - m1);
+    a[0] = A[0]; a[1] = A[1]; a[2] = A[2];
+    c = (i < m1 ? b1[i] : b2[i - m1]) - tol;
+  }
+};
+
+__device__ __forceinline__ int bp_pair_feasible_warp(const double* __restrict__ A1, const double* __restrict__ b1,
+                                                     int m1, const double* __restrict__ A2,
+                                                     const double* __restrict__ b2, int m2, double tol, double* scratch,
+                                                     int* iters_out, double* xout = nullptr,
+                                                     const double* x0 = nullptr, double t0_scale = 0.0) {
+  BpPairRows rows{A1, b1, A2, b2, m1, tol};
+  return bp_lp_feasible_warp(rows, m1 + m2, scratch, iters_out, xout, x0, t0_scale);
 }

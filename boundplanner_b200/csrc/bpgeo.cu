@@ -874,6 +874,163 @@ __global__ void __launch_bounds__(128) k_reduce_rows(const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// K9 ("next" row 2, part 1): does the end effector fit into an intersection set?
+// Replaces BoundPlanner.check_intersection (BoundPlanner.py:745-772): for omega_k =
+// k/19, k = 0..19, l_k = Rodrigues(omega_hat, |omega| omega_k) l_ee (rotated on the
+// host, optimization_functions.py:83-104); the qpOASES feasibility QP (J = 0,
+// optimization_functions.py:140-183) of  A p <= b - 0.001,  A (p + l_k) <= b - 0.001
+// is the same phase-I LP as K6 on the doubled row set.  First feasible k wins.
+// One warp per (set i, set j) pair of the work list; rows = rows of i then rows of j.
+// ---------------------------------------------------------------------------
+#define BP_FIT_SAMPLES 20
+struct FitParams {
+  double l[BP_FIT_SAMPLES][3];    // rotated end-effector offsets
+  double margin;                  // 0.001 (:746)
+  int n_samples;
+};
+
+struct BpFitRows {
+  const double *A1, *b1, *A2, *b2;
+  int m1, mtot;                   // mtot = m1 + m2; rows [mtot, 2 mtot) are the shifted copies
+  double l0, l1, l2, margin;
+  __device__ __forceinline__ void operator()(int i, double* a, double& c) const {
+    const int r = i < mtot ? i : i - mtot;
+    const double* A = r < m1 ? A1 + 3 * r : A2 + 3 * (r - m1);
+    a[0] = A[0]; a[1] = A[1]; a[2] = A[2];
+    c = (r < m1 ? b1[r] : b2[r - m1]) - margin;
+    if (i >= mtot) c -= a[0] * l0 + a[1] * l1 + a[2] * l2;      // A (p + l) <= b - margin
+  }
+};
+
+__global__ void __launch_bounds__(256) k_fit_check(const double* __restrict__ A, const double* __restrict__ b,
+                                                   const int* __restrict__ m, int m_max, const int2* __restrict__ pairs,
+                                                   int P, const double* __restrict__ x0s, FitParams fp,
+                                                   int* __restrict__ fits, int* __restrict__ first_sample) {
+  __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int p = blockIdx.x * 8 + wib;
+  if (p >= P) return;
+  const int2 pr = pairs[p];
+  const int m1 = m[pr.x], m2 = (pr.y == pr.x) ? 0 : m[pr.y];     // i == j: a single set
+  const int mtot = m1 + m2;
+  int found = -1;
+  if (2 * mtot <= 32 * BP_LP_SLOTS) {
+    double x0[3] = {0.0, 0.0, 0.0};
+    if (x0s) { x0[0] = x0s[3 * p]; x0[1] = x0s[3 * p + 1]; x0[2] = x0s[3 * p + 2]; }
+    for (int k = 0; k < fp.n_samples && found < 0; ++k) {
+      BpFitRows rows{A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, A + (size_t)pr.y * m_max * 3,
+                     b + (size_t)pr.y * m_max, m1, mtot, fp.l[k][0], fp.l[k][1], fp.l[k][2], fp.margin};
+      if (bp_lp_feasible_warp(rows, 2 * mtot, scratch[wib], nullptr, nullptr, x0, BP_LP_T0_SCALE)) found = k;
+      __syncwarp();
+    }
+  } else {
+    found = -2;                                                   // too many rows for one warp
+  }
+  if (lane == 0) { fits[p] = found >= 0 ? 1 : (found == -2 ? -1 : 0); first_sample[p] = found; }
+}
+
+// ---------------------------------------------------------------------------
+// K10 ("next" row 2, part 2): projection of a point onto an intersection set.
+// Replaces the qpOASES projection QP of add_edges (BoundPlanner.py:842-864; problem
+// optimization_functions.py:107-137):  min |x - x_d|^2  s.t.  [A_i; A_j] x <= [b_i; b_j].
+// Exact: the projection is the projection onto the affine hull of its <= 3 active rows;
+// one warp per pair enumerates all active sets of size 0..3 (lanes stride the
+// candidates), keeps the feasible ones and takes the closest.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_project(const double* __restrict__ A, const double* __restrict__ b,
+                                                 const int* __restrict__ m, int m_max, const int2* __restrict__ pairs,
+                                                 int P, const double* __restrict__ xd, double* __restrict__ xout,
+                                                 int* __restrict__ status) {
+  __shared__ double sA[8][2 * BP_MAX_ROWS * 3], sb[8][2 * BP_MAX_ROWS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int p = blockIdx.x * 8 + wib;
+  if (p >= P) return;
+  const int2 pr = pairs[p];
+  const int m1 = m[pr.x], m2 = (pr.y == pr.x) ? 0 : m[pr.y];
+  const int mt = m1 + m2;
+  double* rA = sA[wib];
+  double* rb = sb[wib];
+  const double d0 = xd[3 * p], d1 = xd[3 * p + 1], d2 = xd[3 * p + 2];
+  for (int r = lane; r < mt; r += 32) {
+    const double* Ar = r < m1 ? A + ((size_t)pr.x * m_max + r) * 3 : A + ((size_t)pr.y * m_max + (r - m1)) * 3;
+    const double br = r < m1 ? b[(size_t)pr.x * m_max + r] : b[(size_t)pr.y * m_max + (r - m1)];
+    rA[3 * r] = Ar[0]; rA[3 * r + 1] = Ar[1]; rA[3 * r + 2] = Ar[2];
+    rb[r] = br - (Ar[0] * d0 + Ar[1] * d1 + Ar[2] * d2);         // shift: z = x - x_d, rows A z <= b - A x_d
+  }
+  __syncwarp();
+  double best = BP_INF, z0 = 0.0, z1 = 0.0, z2 = 0.0;
+  auto feasible = [&](double a, double c, double e) {
+    bool ok = true;
+    for (int r = 0; r < mt; ++r) {
+      const double q0 = rA[3 * r], q1 = rA[3 * r + 1], q2 = rA[3 * r + 2];
+      const double v = q0 * a + q1 * c + q2 * e - rb[r];
+      if (v > 1e-10 * (1.0 + fabs(rb[r]) + fabs(q0 * a) + fabs(q1 * c) + fabs(q2 * e))) ok = false;
+    }
+    return ok;
+  };
+  auto consider = [&](double a, double c, double e) {
+    const double n2 = a * a + c * c + e * e;
+    if (n2 < best && feasible(a, c, e)) { best = n2; z0 = a; z1 = c; z2 = e; }
+  };
+  if (lane == 0) consider(0.0, 0.0, 0.0);                        // x_d already inside
+  // one active row: z = a h / |a|^2
+  for (int i = lane; i < mt; i += 32) {
+    const double a0 = rA[3 * i], a1 = rA[3 * i + 1], a2 = rA[3 * i + 2];
+    const double nn = a0 * a0 + a1 * a1 + a2 * a2;
+    if (nn > 0.0) { const double t = rb[i] / nn; consider(a0 * t, a1 * t, a2 * t); }
+  }
+  // two active rows: z = lam_i a_i + lam_j a_j with the 2x2 Gram system
+  const int np2 = mt * (mt - 1) / 2;
+  for (int t = lane; t < np2; t += 32) {
+    int i = 0, rem = t;
+    while (rem >= mt - 1 - i) { rem -= mt - 1 - i; ++i; }
+    const int j = i + 1 + rem;
+    const double a0 = rA[3 * i], a1 = rA[3 * i + 1], a2 = rA[3 * i + 2];
+    const double c0 = rA[3 * j], c1 = rA[3 * j + 1], c2 = rA[3 * j + 2];
+    const double gaa = a0 * a0 + a1 * a1 + a2 * a2, gcc = c0 * c0 + c1 * c1 + c2 * c2;
+    const double gac = a0 * c0 + a1 * c1 + a2 * c2;
+    const double det = gaa * gcc - gac * gac;
+    if (!(det > 1e-12 * gaa * gcc)) continue;
+    const double li = (rb[i] * gcc - rb[j] * gac) / det, lj = (rb[j] * gaa - rb[i] * gac) / det;
+    consider(li * a0 + lj * c0, li * a1 + lj * c1, li * a2 + lj * c2);
+  }
+  // three active rows: the vertex of the three planes
+  const int np3 = mt * (mt - 1) * (mt - 2) / 6;
+  for (int t = lane; t < np3; t += 32) {
+    int i = 0, rem = t;
+    for (;;) { const int c = (mt - 1 - i) * (mt - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
+    int j = i + 1;
+    for (;;) { const int c = mt - 1 - j; if (rem < c) break; rem -= c; ++j; }
+    const int k = j + 1 + rem;
+    const double a0 = rA[3 * i], a1 = rA[3 * i + 1], a2 = rA[3 * i + 2], ab = rb[i];
+    const double c0 = rA[3 * j], c1 = rA[3 * j + 1], c2 = rA[3 * j + 2], cb = rb[j];
+    const double e0 = rA[3 * k], e1 = rA[3 * k + 1], e2 = rA[3 * k + 2], eb = rb[k];
+    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;
+    const double det = n0 * e0 + n1 * e1 + n2 * e2;
+    const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(e0) + fabs(e1) + fabs(e2));
+    if (!(fabs(det) > 1e-12 * scale)) continue;
+    const double f0 = c1 * e2 - c2 * e1, f1 = c2 * e0 - c0 * e2, f2 = c0 * e1 - c1 * e0;
+    const double g0 = e1 * a2 - e2 * a1, g1 = e2 * a0 - e0 * a2, g2 = e0 * a1 - e1 * a0;
+    const double id = 1.0 / det;
+    consider((ab * f0 + cb * g0 + eb * n0) * id, (ab * f1 + cb * g1 + eb * n1) * id, (ab * f2 + cb * g2 + eb * n2) * id);
+  }
+  // warp argmin (ties -> lowest lane: the point is unique)
+  double bv = best;
+  int bl = lane;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    const int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+    if (ov < bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+  }
+  z0 = __shfl_sync(0xffffffffu, z0, bl); z1 = __shfl_sync(0xffffffffu, z1, bl); z2 = __shfl_sync(0xffffffffu, z2, bl);
+  if (lane == 0) {
+    xout[3 * p] = d0 + z0; xout[3 * p + 1] = d1 + z1; xout[3 * p + 2] = d2 + z2;
+    if (status) status[p] = bv < BP_INF ? BP_OK : BP_MVIE_NO_INTERIOR;      // empty intersection
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K7: FK, one thread per configuration, 128 configurations per CTA.
 // HBM-bound streaming kernel: the q tile comes in and the result tiles go out
 // through shared memory with TMA bulk copies (cp.async.bulk, one elected
@@ -1240,6 +1397,37 @@ int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, 
   if (S == 0) return 0;
   k_reduce_rows<<<S, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, A_out_dev, b_out_dev, m_out_dev,
                                                       keep_out_dev, status_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_check_fit(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, const int* pairs_dev,
+                 int P, const double* x0_dev, const double* l_ee_samples_host, int n_samples, double margin,
+                 int* fits_dev, int* first_sample_dev, void* stream) {
+  if (S < 0 || P < 0 || m_max < 1 || m_max > BP_MAX_ROWS || n_samples < 1 || n_samples > BP_FIT_SAMPLES ||
+      !l_ee_samples_host || !fits_dev || !first_sample_dev)
+    return bp_fail("bp_check_fit: bad arguments");
+  if (P == 0) return 0;
+  FitParams fp;
+  memset(&fp, 0, sizeof(fp));
+  for (int k = 0; k < n_samples; ++k)
+    for (int c = 0; c < 3; ++c) fp.l[k][c] = l_ee_samples_host[3 * k + c];
+  fp.margin = margin;
+  fp.n_samples = n_samples;
+  k_fit_check<<<(P + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, (const int2*)pairs_dev, P,
+                                                             x0_dev, fp, fits_dev, first_sample_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_project_points(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max,
+                      const int* pairs_dev, int P, const double* xd_dev, double* x_out_dev, int* status_dev,
+                      void* stream) {
+  if (S < 0 || P < 0 || m_max < 1 || m_max > BP_MAX_ROWS || !xd_dev || !x_out_dev)
+    return bp_fail("bp_project_points: bad arguments");
+  if (P == 0) return 0;
+  k_project<<<(P + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, (const int2*)pairs_dev, P,
+                                                           xd_dev, x_out_dev, status_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -249,6 +249,46 @@ def reduce_ineqs(A, b, m):
     return Ao, bo, mo, keep.bool(), status
 
 
+def rodrigues_matrix(omega, phi):
+    """R = I + sin(phi) K + (1 - cos(phi)) K^2 (optimization_functions.py:83-104)."""
+    k = np.array([[0.0, -omega[2], omega[1]], [omega[2], 0.0, -omega[0]], [-omega[1], omega[0], 0.0]])
+    return np.eye(3) + np.sin(phi) * k + (1.0 - np.cos(phi)) * (k @ k)
+
+
+def check_fit(A, b, m, pairs, l_ee, omega_normed, omega_norm, x0=None, n_samples=20, margin=0.001):
+    """BoundPlanner.check_intersection (BoundPlanner.py:745-772) for P intersection sets.
+    pairs [P,2] int32: set indices (i, j); returns (fits [P] bool, omega_sample [P] float, -1 where none)."""
+    lib = _lib.load()
+    S, m_max = A.shape[0], A.shape[1]
+    pairs = _dev(pairs, torch.int32).reshape(-1, 2)
+    P = pairs.shape[0]
+    ls = np.ascontiguousarray([rodrigues_matrix(omega_normed, omega_norm * k / (n_samples - 1)) @ np.asarray(l_ee, float)
+                               for k in range(n_samples)])
+    fits = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    first = torch.full((P,), -1, dtype=torch.int32, device="cuda")
+    x0 = _dev(x0).reshape(P, 3) if x0 is not None else None
+    check(lib.bp_check_fit(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(pairs), P, _ptr(x0), ls.ctypes.data_as(_dp),
+                           int(n_samples), float(margin), _ptr(fits), _ptr(first), _stream()))
+    if bool((fits < 0).any().item()):
+        raise _lib.BpGeoError("check_fit: an intersection set has more than 48 rows")
+    omega = torch.where(first >= 0, first.double() / (n_samples - 1), torch.full_like(first, -1).double())
+    return fits.bool(), omega
+
+
+def project_points(A, b, m, pairs, xd):
+    """Projection QP of add_edges (BoundPlanner.py:842-864) for P (intersection set, point) pairs -> x [P,3]."""
+    lib = _lib.load()
+    S, m_max = A.shape[0], A.shape[1]
+    pairs = _dev(pairs, torch.int32).reshape(-1, 2)
+    P = pairs.shape[0]
+    xd = _dev(xd).reshape(P, 3)
+    x = torch.empty((P, 3), dtype=torch.float64, device="cuda")
+    status = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    check(lib.bp_project_points(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(pairs), P, _ptr(xd), _ptr(x), _ptr(status),
+                                _stream()))
+    return x, status
+
+
 def unpack_adjacency(bits, S, row_begin=0):
     """int32 words [rows, words] -> bool [rows, S]."""
     shifts = torch.arange(32, device=bits.device, dtype=torch.int32)

@@ -123,6 +123,22 @@ int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*
 int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double* A_out_dev,
                     double* b_out_dev, int* m_out_dev, unsigned char* keep_out_dev, int* status_dev, void* stream);
 
+/* ---- K9 / K10 (next row 2): end-effector fit and projection on intersection sets ------
+ * pairs_dev: [P,2] int32 (i, j) set indices; the intersection set is the stacked rows of
+ * set i and set j (i == j: the set itself).
+ * bp_check_fit replaces BoundPlanner.check_intersection (BoundPlanner.py:745-772):
+ * l_ee_samples_host [n_samples,3] are the rotated offsets Rodrigues(omega_hat, |omega| k/19) l_ee
+ * (n_samples = 20), margin = 0.001; fits[P] = 1/0 (-1: too many rows), first_sample[P] = the
+ * first k that fits or -1; x0_dev (or NULL) [P,3] start points.
+ * bp_project_points replaces the projection QP of add_edges (BoundPlanner.py:842-864):
+ * x_out[P,3] = argmin |x - xd|^2 over the intersection set. */
+int bp_check_fit(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, const int* pairs_dev,
+                 int P, const double* x0_dev, const double* l_ee_samples_host, int n_samples, double margin,
+                 int* fits_dev, int* first_sample_dev, void* stream);
+int bp_project_points(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max,
+                      const int* pairs_dev, int P, const double* xd_dev, double* x_out_dev, int* status_dev,
+                      void* stream);
+
 /* ---- K7: iiwa14 forward kinematics -----------------------------------------------
  * Replaces the numeric branch of RobotModel.fk_pos (RobotModel.py:146-160),
  * fk_pos_col (:162-181), hom_transform_endeffector (:197-211), jacobian_fk
