@@ -1,0 +1,63 @@
+"""Planned set sequence: the planner loop (boundplanner_b200/planner.py, restating
+BoundPlanner.plan_convex_set_path up to the shortest path) run with the oracle
+backend on CPU and, on the GPU box, with the kernel backend -- same sequences."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation as R
+
+from boundplanner_b200 import scenes
+from boundplanner_b200.planner import SetSequencePlanner
+from tests.util import OracleBackend
+
+P0 = np.array([0.3, 0.0, 0.7])                  # boundplanner_example.py:89-92
+P1 = np.array([0.45, -0.5, 0.2])
+R0 = R.from_euler("XYZ", [0, 90, 0], degrees=True).as_matrix()
+
+
+def _plan(backend_cls, seed=0, **kw):
+    boxes, ws_min, ws_max, inflate = scenes.example_scene()
+    backend = backend_cls(boxes, inflate, list(ws_max), list(ws_min)) if backend_cls else None
+    planner = SetSequencePlanner(boxes, inflate, list(ws_max), list(ws_min), backend=backend,
+                                 rng=np.random.default_rng(seed))
+    return planner.plan_set_sequence(P0.copy(), P1.copy(), R0, R0, **kw), planner
+
+
+def test_example_plan_with_oracle_backend():
+    res, planner = _plan(OracleBackend)
+    path, ids, p_via = res["path"], res["set_ids"], res["p_via"]
+    assert path[0] == 0 and path[-1] == 1 and ids[-1] == 1 and len(ids) == len(p_via) - 1
+    assert np.allclose(p_via[0], P0) and np.allclose(p_via[-1], P1)
+    g, ig = res["graph"], res["inter_graph"]
+    # every via point lies in the two consecutive sets it connects (they are projections onto intersections)
+    for k in range(1, len(p_via) - 1):
+        for sid in (ids[k - 1], ids[k]):
+            A, b = g.nodes[sid]["cset"]
+            assert np.max(A @ p_via[k] - b) < 1e-7
+    # consecutive sets of the sequence intersect
+    from oracle.set_graph import set_intersection
+
+    for a, b_ in zip(ids[:-1], ids[1:]):
+        assert set_intersection(g.nodes[a]["cset"], g.nodes[b_]["cset"], 0.01)[2]
+    # determinism with a seeded generator (quirk Q4)
+    res2, _ = _plan(OracleBackend)
+    assert res2["path"] == path and res2["set_ids"] == ids and np.allclose(res2["p_via"], p_via)
+
+
+@pytest.mark.gpu
+def test_example_plan_gpu_matches_oracle_sequence():
+    import torch
+
+    assert torch.cuda.is_available()
+    from boundplanner_b200.planner import GpuBackend
+
+    for seed, kw in ((0, {}), (3, {}), (1, {"first_sample": np.array([0.5, -0.2, 0.6])})):
+        want, _ = _plan(OracleBackend, seed, **kw)
+        got, _ = _plan(GpuBackend, seed, **kw)
+        assert got["path"] == want["path"], f"seed {seed}"                       # index work: exact
+        assert got["set_ids"] == want["set_ids"]
+        assert got["graph"].number_of_nodes() == want["graph"].number_of_nodes()
+        assert sorted((d["id0"], d["id1"]) for _, d in got["inter_graph"].nodes.items()) == \
+            sorted((d["id0"], d["id1"]) for _, d in want["inter_graph"].nodes.items())     # graph adjacency
+        assert np.abs(got["p_via"] - want["p_via"]).max() < 1e-6
+        for (ga, gb), (wa, wb) in zip(got["sets_via"], want["sets_via"]):
+            assert ga.shape == wa.shape and np.abs(ga - wa).max() < 1e-6 and np.abs(gb - wb).max() < 1e-6

@@ -18,3 +18,39 @@ def assert_rows_close(A, b, Ao, bo, tag=""):
     scale = max(1.0, np.abs(bo).max())
     assert np.abs(A - Ao).max() <= RTOL, f"{tag}: normals differ {np.abs(A - Ao).max()}"
     assert np.abs(b - bo).max() <= RTOL * scale, f"{tag}: offsets differ {np.abs(b - bo).max()}"
+
+
+class OracleBackend:
+    """Planner-loop primitives served by the oracle (same interface as planner.GpuBackend)."""
+
+    def __init__(self, obstacles, obs_size_increase, workspace_max, workspace_min):
+        from oracle.obstacles import obstacle_reps
+
+        self.obs_sets, pts, _ = obstacle_reps(obstacles, obs_size_increase)
+        self.set_finder = OracleFinder(self.obs_sets, pts, list(workspace_max), list(workspace_min))
+
+    def find_set_around_point(self, p, fixed_mid, optimize):
+        return self.set_finder.find_set_around_point(p, fixed_mid=fixed_mid, optimize=optimize)
+
+    def find_set_collision_avoidance(self, p0, p1, compute_ellipsoid):
+        return self.set_finder.find_set_collision_avoidance(p0, p1, compute_ellipsoid)
+
+    def reduce_ineqs(self, a_set, b_set):
+        from oracle.reduce_ineqs import reduce_ineqs
+
+        return reduce_ineqs(a_set, b_set)
+
+    def set_intersection(self, set1, set2, tol):
+        from oracle.set_graph import set_intersection
+
+        return set_intersection(set1, set2, tol)
+
+    def check_intersection(self, a_set, b_set, l_ee, sample, omega_normed, omega_norm):
+        from oracle.planner_graph import check_intersection
+
+        return check_intersection(a_set, b_set, l_ee, sample, omega_normed, omega_norm)
+
+    def project(self, a_set, b_set, x_d, x0=None):
+        from oracle.planner_graph import project_point
+
+        return project_point(a_set, b_set, x_d)
