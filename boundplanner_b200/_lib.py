@@ -20,6 +20,7 @@ STATUS_ELLIPSE_VIOLATION = 1
 STATUS_ROW_OVERFLOW = 2
 STATUS_MVIE_NO_INTERIOR = 3
 STATUS_MVIE_NOT_CONVERGED = 4
+STATUS_ROW_CAP = 5
 
 _c = ctypes
 _vp, _i, _d, _sz = _c.c_void_p, _c.c_int, _c.c_double, _c.c_size_t
@@ -38,8 +39,8 @@ SIGNATURES = {
     "bp_polyhedron": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "bp_mvie": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_build_sets_workspace_bytes": (_sz, [_i]),
-    "bp_build_sets_point": (_i, [_vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _sz, _vp]),
+    "bp_build_sets_point": (_i, [_vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _i, _vp, _sz, _vp]),
     "bp_build_sets_line": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _vp]),
     "bp_pair_workspace_bytes": (_sz, [_i, _i]),

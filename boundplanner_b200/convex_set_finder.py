@@ -24,7 +24,7 @@ import torch
 
 from . import geometry as geo
 from ._lib import (BP_MAX_ROWS, STATUS_ELLIPSE_VIOLATION, STATUS_MVIE_NO_INTERIOR, STATUS_MVIE_NOT_CONVERGED,
-                   STATUS_OK, STATUS_ROW_OVERFLOW)
+                   STATUS_OK, STATUS_ROW_CAP, STATUS_ROW_OVERFLOW)
 
 _BOX = np.concatenate((np.eye(3), -np.eye(3)))
 
@@ -95,6 +95,10 @@ class ConvexSetFinder:
             raise RuntimeError("Ellipse violates constraints")           # :438
         if status == STATUS_ROW_OVERFLOW:
             raise ValueError(f"convex set needs more than {BP_MAX_ROWS} rows")
+        if status == STATUS_ROW_CAP:
+            # d2[: a_set.shape[0]] = b_set with more than 20 rows (:516)
+            raise ValueError(
+                f"could not broadcast input array from shape ({m},) into shape ({self.REFERENCE_MAX_ROWS},)")
         if status in (STATUS_MVIE_NO_INTERIOR, STATUS_MVIE_NOT_CONVERGED):
             raise RuntimeError(f"MVIE failed (status {status})")
         if self.strict_rows and m is not None and m > self.REFERENCE_MAX_ROWS:
@@ -193,7 +197,7 @@ class ConvexSetFinder:
         out = self.find_sets_around_points(np.asarray(p_seed, float)[None], fixed_mid=fixed_mid, optimize=optimize)
         status = int(out.status.item())
         m = int(out.m.item())
-        self._raise_for_status(status, m if optimize else None)
+        self._raise_for_status(status, int(out.rows_peak.item()) if optimize else None)
         return (out.A[0, :m].cpu().numpy(), out.b[0, :m].cpu().numpy(), out.q_ellipse[0].cpu().numpy(),
                 out.p_mid[0].cpu().numpy())
 
@@ -201,8 +205,10 @@ class ConvexSetFinder:
         """Batched form: S seeds -> geometry.SetBatch (device tensors)."""
         start = time.perf_counter()
         ws_min, ws_max = self._ws()
+        # the reference overflows its 20-row MVIE buffers in whichever pass first exceeds them (quirk Q5)
         out = geo.build_sets_point(self._scene, seeds, ws_min, ws_max, fixed_mid=bool(fixed_mid),
-                                   optimize=bool(optimize), max_iter=self.max_iter, m_max=m_max)
+                                   optimize=bool(optimize), max_iter=self.max_iter, m_max=m_max,
+                                   row_cap=self.REFERENCE_MAX_ROWS if self.strict_rows else 0)
         torch.cuda.current_stream().synchronize()
         self.ell_time += time.perf_counter() - start      # projections and MVIE are fused on the device
         return out

@@ -23,6 +23,7 @@ enum {
   BP_ROW_OVERFLOW = 2,        // more rows than BP_MAX_ROWS
   BP_MVIE_NO_INTERIOR = 3,    // centre / hint not strictly inside the polytope
   BP_MVIE_NOT_CONVERGED = 4,
+  BP_ROW_CAP = 5,             // more rows than the caller's row_cap (reference MVIE buffers: 20 rows, quirk Q5)
 };
 
 // ---------------------------------------------------------------------------

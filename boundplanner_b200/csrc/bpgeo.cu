@@ -76,7 +76,7 @@ struct SeedState {
   int k;            // loop counter
   int active;       // still inside the while loop
   int status;
-  int pad;
+  int rows_peak;    // largest row count any pass handed to the MVIE (the reference raises above 20, quirk Q5)
 };
 
 struct Vec3 { double v[3]; };
@@ -215,6 +215,7 @@ struct PolyParams {
   int mode;
   int max_iter;
   int cache_y;               // closest points kept in shared memory (y[3][N] after dist[N])
+  int row_cap;               // > 0: stop a seed whose pass produced more rows (reference: 20, quirk Q5)
 };
 
 __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr) {
@@ -335,7 +336,9 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr)
   if (tid == 0) {
     pr.m[s] = m_cur < pr.m_max ? m_cur : pr.m_max;
     if (pr.mode == 1) {
+      if (status == BP_OK && pr.row_cap > 0 && m_cur > pr.row_cap) status = BP_ROW_CAP;
       if (status != BP_OK) { pr.state[s].status = status; pr.state[s].active = 0; }
+      if (m_cur > pr.state[s].rows_peak) pr.state[s].rows_peak = m_cur;
     } else {
       pr.status[s] = status;
     }
@@ -545,12 +548,13 @@ __global__ void k_state_init(SeedState* st, const double* __restrict__ seeds, in
   v.Q[0] = v.Q[4] = v.Q[8] = 1.0 / 1e-4;                 // q_ellipse = diag(1/a) (:192-194)
   v.p[0] = seeds[3 * s]; v.p[1] = seeds[3 * s + 1]; v.p[2] = seeds[3 * s + 2];
   v.det = 100.0; v.det_old = 1.0;                        // :200-201
-  v.k = 0; v.active = 1; v.status = BP_OK; v.pad = 0;
+  v.k = 0; v.active = 1; v.status = BP_OK; v.rows_peak = 0;
   st[s] = v;
 }
 
 __global__ void k_state_export(const SeedState* st, int S, int max_iter, double* __restrict__ q_ellipse,
-                               double* __restrict__ p_mid, int* __restrict__ status, int* __restrict__ iters) {
+                               double* __restrict__ p_mid, int* __restrict__ status, int* __restrict__ iters,
+                               int* __restrict__ rows_peak) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   if (q_ellipse) {
@@ -559,6 +563,7 @@ __global__ void k_state_export(const SeedState* st, int S, int max_iter, double*
   }
   if (p_mid) { p_mid[3 * s] = st[s].p[0]; p_mid[3 * s + 1] = st[s].p[1]; p_mid[3 * s + 2] = st[s].p[2]; }
   if (status) status[s] = st[s].status;
+  if (rows_peak) rows_peak[s] = st[s].rows_peak;
   if (iters) {
     // the reference's while test runs once more after the last pass and bumps k
     // before breaking on k > max_iter (:203-207)
@@ -578,7 +583,7 @@ __global__ void k_state_init_line(SeedState* st, const double* __restrict__ p0, 
   for (int k = 0; k < 9; ++k) v.Q[k] = 0.0;
   v.p[0] = p0[3 * s]; v.p[1] = p0[3 * s + 1]; v.p[2] = p0[3 * s + 2];
   v.det = 100.0; v.det_old = 1.0;
-  v.k = 0; v.active = 0; v.status = status[s]; v.pad = 0;
+  v.k = 0; v.active = 0; v.status = status[s]; v.rows_peak = 0;
   st[s] = v;
 }
 
@@ -1282,7 +1287,8 @@ size_t bp_build_sets_workspace_bytes(int S) { return sizeof(SeedState) * (size_t
 int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, const double* ws_min_host,
                         const double* ws_max_host, int fixed_mid, int optimize, int max_iter, int m_max,
                         double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev, double* p_mid_dev,
-                        int* status_dev, int* iters_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+                        int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap, void* workspace_dev,
+                        size_t workspace_bytes, void* stream_) {
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || max_iter < 1 || !ws_min_host || !ws_max_host)
     return bp_fail("bp_build_sets_point: bad arguments");
   if (S == 0) return 0;
@@ -1294,6 +1300,7 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
   memset(&pp, 0, sizeof(pp));
   pp.state = st; pp.A = A_dev; pp.b = b_dev; pp.m = m_dev; pp.status = status_dev; pp.m_max = m_max;
   pp.mode = 1; pp.max_iter = max_iter;
+  pp.row_cap = optimize ? row_cap : 0;
   for (int i = 0; i < 3; ++i) { pp.ws_rows[2 * i] = ws_max_host[i]; pp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
   MvieParams mp;
   memset(&mp, 0, sizeof(mp));
@@ -1313,7 +1320,8 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
     mp.mode = 2;
     if (launch_mvie(mp, stream)) return 1;
   }
-  k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, optimize ? max_iter : 1 << 30, q_ellipse_dev, p_mid_dev, status_dev, iters_dev);
+  k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, optimize ? max_iter : 1 << 30, q_ellipse_dev, p_mid_dev, status_dev, iters_dev,
+                                                      rows_peak_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1344,7 +1352,7 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
     memset(&mp, 0, sizeof(mp));
     mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st; mp.mode = 2;
     if (launch_mvie(mp, stream)) return 1;
-    k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, 0, q_ellipse_dev, p_mid_dev, status_dev, nullptr);
+    k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, 0, q_ellipse_dev, p_mid_dev, status_dev, nullptr, nullptr);
   }
   BP_CUDA(cudaGetLastError());
   return 0;

@@ -91,6 +91,7 @@ class SetBatch:
     p_mid: torch.Tensor        # [S,3]
     status: torch.Tensor       # [S] int32
     iters: torch.Tensor | None = None      # [S] int32 (k of the IRIS loop)
+    rows_peak: torch.Tensor | None = None  # [S] int32 largest row count of any pass (reference cap: 20)
     collision: torch.Tensor | None = None  # [S] int32 (line sets)
 
     def to_sets(self):
@@ -108,8 +109,10 @@ def _alloc_sets(S, m_max):
     return A, b, m
 
 
-def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS):
-    """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds."""
+def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS,
+                     row_cap=0):
+    """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds.
+    row_cap=20 reproduces the reference's failure on passes with more than 20 rows (status 5)."""
     lib = _lib.load()
     seeds = _dev(seeds).reshape(-1, 3)
     S = seeds.shape[0]
@@ -118,15 +121,17 @@ def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=Tru
     p = torch.zeros((S, 3), dtype=torch.float64, device="cuda")
     status = torch.zeros((S,), dtype=torch.int32, device="cuda")
     iters = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    peak = torch.zeros((S,), dtype=torch.int32, device="cuda")
     wbytes = lib.bp_build_sets_workspace_bytes(S)
     work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
     amin, pmin = _host3(ws_min)      # host arrays must outlive the call
     amax, pmax = _host3(ws_max)
     check(lib.bp_build_sets_point(scene._h, _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)), int(bool(optimize)),
                                   int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m), _ptr(q), _ptr(p),
-                                  _ptr(status), _ptr(iters), _ptr(work), wbytes, _stream()))
+                                  _ptr(status), _ptr(iters), _ptr(peak), int(row_cap), _ptr(work), wbytes,
+                                  _stream()))
     del amin, amax
-    return SetBatch(A, b, m, q, p, status, iters=iters)
+    return SetBatch(A, b, m, q, p, status, iters=iters, rows_peak=peak)
 
 
 def build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False, limit_space=False, e_max=0.3,

@@ -108,3 +108,15 @@ def config_c4(n_obs=10000, n_seeds=2048, seed=2):
     obstacles = shelf_scene(n_obs, rng)
     seeds = free_points(n_seeds, obstacles, inflate, rng)
     return obstacles, inflate, seeds, WORKSPACE_MIN.copy(), WORKSPACE_MAX.copy()
+
+
+def config_c3_query(i, n_obs=200):
+    """Query i of C3: 200 boxes (edge U[0.05,0.2], inflate 0.01), free start/end at least 0.3 m apart."""
+    rng = np.random.default_rng(1000 + i)
+    inflate = 0.01
+    obstacles = random_box_scene(n_obs, rng, 0.05, 0.2)
+    while True:
+        pts = free_points(2, obstacles, inflate + 0.06, rng, WORKSPACE_MIN + 0.1, WORKSPACE_MAX - 0.1)
+        if np.linalg.norm(pts[0] - pts[1]) >= 0.3:
+            break
+    return obstacles, inflate, pts[0], pts[1], WORKSPACE_MIN.copy(), WORKSPACE_MAX.copy()

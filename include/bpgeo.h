@@ -23,7 +23,7 @@
  *   - Per-item status codes (int32, one per seed / segment):
  *       BP_OK 0, BP_ELLIPSE_VIOLATION 1 (ConvexSetFinder.py:433-438 RuntimeError),
  *       BP_ROW_OVERFLOW 2 (more than m_max rows), BP_MVIE_NO_INTERIOR 3,
- *       BP_MVIE_NOT_CONVERGED 4.
+ *       BP_MVIE_NOT_CONVERGED 4, BP_ROW_CAP 5 (more rows than row_cap in an IRIS pass).
  *   - There is NO CPU fallback: every compute entry point needs a CUDA device.
  */
 #ifndef BPGEO_H
@@ -90,7 +90,11 @@ size_t bp_build_sets_workspace_bytes(int S);
 int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, const double* ws_min_host,
                         const double* ws_max_host, int fixed_mid, int optimize, int max_iter, int m_max,
                         double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev, double* p_mid_dev,
-                        int* status_dev, int* iters_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+                        int* status_dev, int* iters_dev,
+                        int* rows_peak_dev /* NULL or [S]: largest row count of any pass */,
+                        int row_cap /* 0, or: a pass with more rows ends the seed with BP_ROW_CAP, like the
+                                       reference's 20-row MVIE buffers do (ValueError, quirk Q5) */,
+                        void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Replaces ConvexSetFinder.find_set_collision_avoidance (:309-375) for S segments.
  * limit_space selects init_halfspaces_point(p0, e_max) (:400-421).  collision[S]
