@@ -9,6 +9,10 @@ reference (Thieso/BoundPlanner, pure Python) runs on its hot path:
 * ``set_graph``         -- bound_planner/BoundPlanner/BoundPlanner.py:774-798
 * ``fk_iiwa14``         -- bound_planner/RobotModel/RobotModel.py:146-211 +
                            bound_planner/RobotModel/iiwa.urdf
+* ``casadi_blob``       -- decoder / VM for the reference's *.ca FK functions
+* ``reduce_ineqs``      -- bound_planner/utils/util_functions.py:82-88 (cddlib)
+* ``planner_graph``     -- BoundPlanner.check_intersection / projection QP
+                           (BoundPlanner.py:745-772, :842-864)
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 / ``--impl reference`` legs may import it, and only as the *checker* or the
@@ -24,10 +28,12 @@ golden vectors.  What IS pinned:
 * ``set_graph.set_intersection`` executes the reference's own call verbatim
   (scipy.optimize.linprog / HiGHS, BoundPlanner.py:779-784) -- this row is
   pinned against the real third-party solver, run here.
-* ``fk_iiwa14`` is pinned against the reference's serialized CasADi functions
-  (fk_pos.ca, fk_pos_col_{0..5}.ca, hom_trans.ca), decoded and evaluated by
+* ``fk_iiwa14`` is pinned against the reference's own serialized CasADi
+  functions (fk_pos.ca, fk_pos_col_{0..5}.ca, hom_trans.ca, jacobian.ca -- the
+  files RobotModel.py:158,179,209,229 load), decoded and evaluated by
   ``oracle/casadi_blob.py`` without CasADi; golden vectors generated from those
-  blobs are committed under tests/golden/ (script: tests/golden/make_golden.py).
+  blobs are committed as tests/golden/fk_reference_blobs.npz (script:
+  tests/golden/make_golden.py).  Agreement: <= 7e-16.
 * closest-point QPs (OSQP / qpOASES in the reference) and the MVIE SOCP
   (Clarabel) are restated with exact solvers (active-set enumeration, barrier
   Newton + KKT check).  For these rows **parity is unpinned** against the true

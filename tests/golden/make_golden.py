@@ -7,6 +7,11 @@ fk_golden.npz       iiwa14 FK at fixed configurations.  Source: the ORACLE
                     iiwa.urdf).  The reference's own numeric FK needs pinocchio,
                     which is not installable here; the anchors of SURVEY.md 8c
                     are asserted separately in tests/test_oracle_graph_fk.py.
+fk_reference_blobs.npz  The reference's OWN serialized CasADi functions (bound_planner/RobotModel/
+                    fk_pos.ca, fk_pos_col_{0..5}.ca, hom_trans.ca, jacobian.ca -- what RobotModel.py:158,179,
+                    209,229 load) evaluated at 64 configurations by oracle/casadi_blob.py (a CasADi-free
+                    decoder + SX virtual machine).  Reference-generated golden vectors: they pin the FK oracle
+                    and the FK kernel.  Needs /root/reference (this container only).
 c1_sets_golden.npz  The first two convex sets the reference's example plan builds
                     (boundplanner_example.py:89-92 -> BoundPlanner.py:278-294,
                     :381-389) as computed by the ORACLE; lets the GPU box check
@@ -38,6 +43,24 @@ def main():
              p_col=np.array([ofk.fk_pos_col_all(x) for x in q]),
              T_ee=np.array([ofk.hom_transform_endeffector(x) for x in q]),
              jac=np.array([ofk.jacobian_fk(x) for x in q]))
+
+    ref_dir = "/root/reference/bound_planner/RobotModel/"
+    if os.path.isdir(ref_dir):
+        from oracle.casadi_blob import SXFunctionBlob
+
+        qg = rng.uniform(ofk.Q_LOWER, ofk.Q_UPPER, (64, 7))
+        qg[0] = 0.0
+        qg[1] = [0, 0, 0, -np.pi / 2, 0, np.pi / 2, 0]
+        f_pos = SXFunctionBlob(ref_dir + "fk_pos.ca")
+        f_col = [SXFunctionBlob(ref_dir + f"fk_pos_col_{i}.ca") for i in range(6)]
+        f_hom = SXFunctionBlob(ref_dir + "hom_trans.ca")
+        f_jac = SXFunctionBlob(ref_dir + "jacobian.ca")
+        np.savez(os.path.join(HERE, "fk_reference_blobs.npz"), q=qg,
+                 fk_pos=np.array([f_pos(x).ravel() for x in qg]),
+                 fk_pos_col=np.array([[f(x).ravel() for f in f_col] for x in qg]),
+                 hom_trans=np.array([f_hom(x) for x in qg]),
+                 jacobian=np.array([f_jac(x) for x in qg]))
+        print("wrote fk_reference_blobs.npz from the reference's .ca files")
 
     boxes, ws_min, ws_max, inflate = scenes.example_scene()
     obs_sets, pts, _ = obstacle_reps(boxes, inflate)

@@ -181,6 +181,13 @@ def test_against_committed_golden_fixtures(c1):
     A, b, Q, p, coll = gpu.find_set_collision_avoidance(g["p1"], g["p1"] + g["l_ee"], True)
     assert_rows_close(A, b, g["A1"], g["b1"], "golden end set")
     assert np.abs(Q - g["Q1"]).max() <= 1e-5 * np.abs(g["Q1"]).max() and bool(coll) == bool(g["collision1"])
+    # FK kernel vs the reference's own serialized CasADi functions (fk_reference_blobs.npz)
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_reference_blobs.npz"))
+    p_ee, p_col, T, J = bp.RobotModel.fk_batch(ref["q"], want_pose=True, want_jacobian=True)
+    assert np.abs(p_ee.cpu().numpy() - ref["fk_pos"]).max() < 1e-12
+    assert np.abs(p_col.cpu().numpy()[:, :6] - ref["fk_pos_col"]).max() < 1e-12
+    assert np.abs(T.cpu().numpy() - ref["hom_trans"]).max() < 1e-12
+    assert np.abs(J.cpu().numpy() - ref["jacobian"]).max() < 1e-12
     fk = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_golden.npz"))
     p_ee, p_col, T, J = bp.RobotModel.fk_batch(fk["q"], want_pose=True, want_jacobian=True)
     assert np.abs(p_ee.cpu().numpy() - fk["p_ee"]).max() < 1e-12

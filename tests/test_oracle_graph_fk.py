@@ -111,3 +111,30 @@ def test_reduce_ineqs_oracle_known_answers():
     Ap = np.vstack((BOX, np.zeros((3, 3))))
     bp_ = np.concatenate((np.ones(6), 10 * np.ones(3)))
     assert redundant_row_mask(Ap, bp_).tolist() == [False] * 6 + [True] * 3
+
+
+def test_fk_oracle_pinned_to_reference_casadi_blobs():
+    """tests/golden/fk_reference_blobs.npz = the reference's serialized CasADi FK functions evaluated
+    by oracle/casadi_blob.py (see tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_reference_blobs.npz"))
+    for i, q in enumerate(g["q"]):
+        assert np.abs(ofk.fk_pos(q) - g["fk_pos"][i]).max() < 1e-12
+        assert np.abs(ofk.fk_pos_col_all(q)[:6] - g["fk_pos_col"][i]).max() < 1e-12     # no fk_pos_col_6.ca exists
+        assert np.abs(ofk.hom_transform_endeffector(q) - g["hom_trans"][i]).max() < 1e-12
+        assert np.abs(ofk.jacobian_fk(q) - g["jacobian"][i]).max() < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/bound_planner/RobotModel/fk_pos.ca"),
+                    reason="reference tree not present (GPU box)")
+def test_casadi_blob_decoder_reproduces_committed_golden():
+    from oracle.casadi_blob import SXFunctionBlob
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_reference_blobs.npz"))
+    d = "/root/reference/bound_planner/RobotModel/"
+    f_pos, f_c5, f_jac = SXFunctionBlob(d + "fk_pos.ca"), SXFunctionBlob(d + "fk_pos_col_5.ca"), SXFunctionBlob(d + "jacobian.ca")
+    assert f_pos.name_in == ["i0"] and f_pos.sp_in[0][:2] == (7, 1) and f_jac.sp_out[0][:2] == (6, 7)
+    for i in (0, 1, 17, 63):
+        q = g["q"][i]
+        assert np.array_equal(f_pos(q).ravel(), g["fk_pos"][i])
+        assert np.array_equal(f_c5(q).ravel(), g["fk_pos_col"][i][5])
+        assert np.array_equal(f_jac(q), g["jacobian"][i])
