@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -291,6 +291,8 @@ def run_gpu(args):
             "roofline_fk": prof["roofline_fk"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),
             "kernels": prof["kernels"],
         }
+        if world == 1 and not args.no_plan_latency:
+            line["plan_latency"] = plan_latency(not args.no_cpu_baseline)
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = 24
@@ -302,6 +304,56 @@ def run_gpu(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def plan_latency(with_cpu):
+    """p50 plan latency (BASELINE.json metric, third part): SetSequencePlanner.plan_set_sequence -- the
+    reference's plan_convex_set_path up to the planned set sequence -- on the C1 example and on the
+    C3-style queries that plan successfully, every primitive a batch-of-one kernel call."""
+    import statistics
+
+    from scipy.spatial.transform import Rotation as R
+
+    from boundplanner_b200 import scenes
+    from boundplanner_b200.planner import SetSequencePlanner
+
+    r0 = R.from_euler("XYZ", [0, 90, 0], degrees=True).as_matrix()
+
+    def cases():
+        boxes, ws_min, ws_max, inflate = scenes.example_scene()
+        yield "C1", boxes, inflate, np.array([0.3, 0.0, 0.7]), np.array([0.45, -0.5, 0.2]), ws_min, ws_max, 0
+        for i in (0, 7, 8, 11):
+            ob, infl, st, en, wmin, wmax = scenes.config_c3_query(i)
+            yield f"C3[{i}]", ob, infl, st, en, wmin, wmax, i
+
+    def run(backend_factory, names=None):
+        lat = {}
+        for name, ob, infl, st, en, wmin, wmax, seed in cases():
+            if names is not None and name not in names:
+                continue
+            backend = backend_factory(ob, infl, list(wmax), list(wmin))
+            for rep in range(3 if names is None else 1):
+                planner = SetSequencePlanner(ob, infl, list(wmax), list(wmin), backend=backend,
+                                             rng=np.random.default_rng(seed))
+                t0 = time.perf_counter()
+                res = planner.plan_set_sequence(st.copy(), en.copy(), r0, r0)
+                lat[name] = (time.perf_counter() - t0) * 1e3, len(res["set_ids"]), res["graph"].number_of_nodes()
+        return lat
+
+    from boundplanner_b200.planner import GpuBackend
+
+    gpu = run(GpuBackend)
+    vals = sorted(v[0] for v in gpu.values())
+    out = {"unit": "ms", "p50": statistics.median(vals), "max": vals[-1],
+           "queries": {k: {"ms": v[0], "sets_in_sequence": v[1], "sets_built": v[2]} for k, v in gpu.items()},
+           "what": "plan_convex_set_path up to the planned set sequence (no final Ipopt NLP), host loop + "
+                   "batch-of-one kernel calls"}
+    if with_cpu:
+        from tests.util import OracleBackend
+
+        cpu = run(OracleBackend, names=("C1", "C3[7]"))
+        out["cpu_port_ms"] = {k: v[0] for k, v in cpu.items()}
+    return out
 
 
 def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
@@ -404,10 +456,11 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plan-latency", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
