@@ -92,6 +92,7 @@ class SetBatch:
     status: torch.Tensor       # [S] int32
     iters: torch.Tensor | None = None      # [S] int32 (k of the IRIS loop)
     rows_peak: torch.Tensor | None = None  # [S] int32 largest row count of any pass (reference cap: 20)
+    work: torch.Tensor | None = None       # loop workspace (kept with the batch so that it can be reused)
     collision: torch.Tensor | None = None  # [S] int32 (line sets)
 
     def to_sets(self):
@@ -109,21 +110,33 @@ def _alloc_sets(S, m_max):
     return A, b, m
 
 
+def alloc_set_batch(S, m_max=BP_MAX_ROWS):
+    """Device buffers of one SetBatch plus the loop workspace (reusable across calls via ``out=``)."""
+    lib = _lib.load()
+    A, b, m = _alloc_sets(S, m_max)
+    batch = SetBatch(A, b, m, torch.zeros((S, 3, 3), dtype=torch.float64, device="cuda"),
+                     torch.zeros((S, 3), dtype=torch.float64, device="cuda"),
+                     torch.zeros((S,), dtype=torch.int32, device="cuda"),
+                     iters=torch.zeros((S,), dtype=torch.int32, device="cuda"),
+                     rows_peak=torch.zeros((S,), dtype=torch.int32, device="cuda"))
+    batch.work = torch.empty((lib.bp_build_sets_workspace_bytes(S),), dtype=torch.uint8, device="cuda")
+    return batch
+
+
 def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS,
-                     row_cap=0):
+                     row_cap=0, out=None):
     """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds.
-    row_cap=20 reproduces the reference's failure on passes with more than 20 rows (status 5)."""
+    row_cap=20 reproduces the reference's failure on passes with more than 20 rows (status 5).
+    out: a batch from alloc_set_batch to write into (no allocation, CUDA-graph capturable)."""
     lib = _lib.load()
     seeds = _dev(seeds).reshape(-1, 3)
     S = seeds.shape[0]
-    A, b, m = _alloc_sets(S, m_max)
-    q = torch.zeros((S, 3, 3), dtype=torch.float64, device="cuda")
-    p = torch.zeros((S, 3), dtype=torch.float64, device="cuda")
-    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
-    iters = torch.zeros((S,), dtype=torch.int32, device="cuda")
-    peak = torch.zeros((S,), dtype=torch.int32, device="cuda")
-    wbytes = lib.bp_build_sets_workspace_bytes(S)
-    work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
+    if out is None:
+        out = alloc_set_batch(S, m_max)
+    A, b, m, q, p, status, iters, peak, work = (out.A, out.b, out.m, out.q_ellipse, out.p_mid, out.status, out.iters,
+                                                out.rows_peak, out.work)
+    m_max = A.shape[1]
+    wbytes = work.numel()
     amin, pmin = _host3(ws_min)      # host arrays must outlive the call
     amax, pmax = _host3(ws_max)
     check(lib.bp_build_sets_point(scene._h, _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)), int(bool(optimize)),
@@ -131,7 +144,7 @@ def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=Tru
                                   _ptr(status), _ptr(iters), _ptr(peak), int(row_cap), _ptr(work), wbytes,
                                   _stream()))
     del amin, amax
-    return SetBatch(A, b, m, q, p, status, iters=iters, rows_peak=peak)
+    return out
 
 
 def build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False, limit_space=False, e_max=0.3,
@@ -216,7 +229,15 @@ def mvie(A, b, m, centre, free_centre):
     return q_inv, q_ell, c_out, status, its
 
 
-def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=False):
+def alloc_pair_buffers(S, rows=None):
+    lib = _lib.load()
+    rows = S if rows is None else rows
+    bits = torch.empty((rows, (S + 31) // 32), dtype=torch.int32, device="cuda")
+    work = torch.empty((lib.bp_pair_workspace_bytes(S, rows),), dtype=torch.uint8, device="cuda")
+    return bits, work
+
+
+def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=False, out=None):
     """BoundPlanner.set_intersection (BoundPlanner.py:774-787, tol from :797) for all
     pairs (i, j>i), i in [row_begin,row_end).  Returns uint32-packed bits as an
     int32 tensor [rows, ceil(S/32)]; with want_points also x [rows,S,3], a point of
@@ -226,9 +247,11 @@ def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=Fals
     if row_end is None:
         row_end = S
     words = (S + 31) // 32
-    bits = torch.empty((row_end - row_begin, words), dtype=torch.int32, device="cuda")
-    wbytes = lib.bp_pair_workspace_bytes(S, row_end - row_begin)
-    work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
+    if out is None:
+        out = alloc_pair_buffers(S, row_end - row_begin)
+    bits, work = out
+    wbytes = work.numel()
+    assert bits.shape == (row_end - row_begin, words)
     x = torch.zeros((row_end - row_begin, S, 3), dtype=torch.float64, device="cuda") if want_points else None
     check(lib.bp_pair_feasible(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), int(row_begin), int(row_end),
                                _ptr(bits), _ptr(x), _ptr(work), wbytes, _stream()))

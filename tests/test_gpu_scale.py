@@ -127,3 +127,24 @@ def test_row_overflow_and_reference_cap(geo):
     small = geo.build_sets_point(sc, seeds, scenes.WORKSPACE_MIN, scenes.WORKSPACE_MAX, fixed_mid=True, m_max=12)
     st = small.status.cpu().numpy()
     assert (st == 2).any() and small.m.cpu().numpy().max() <= 12
+
+
+def test_cuda_graph_pipeline_equals_eager(geo):
+    """Static-buffer CUDA-graph replay of a step gives bit-identical results to the eager calls,
+    also when the seeds change between replays."""
+    import torch
+    from boundplanner_b200 import scenes
+    from boundplanner_b200.pipeline import SetGraphPipeline
+
+    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(1000, 128)
+    sc = geo.Scene(boxes, inflate)
+    pipe = SetGraphPipeline(sc, 64, ws_min, ws_max, fixed_mid=True, optimize=True, tol=0.01)
+    for part in (seeds[:64], seeds[64:]):
+        host = torch.as_tensor(part).pin_memory()
+        A, b, m, q, p, status, bits = [t.clone() for t in pipe.run(host)]
+        out = geo.build_sets_point(sc, part, ws_min, ws_max, fixed_mid=True, optimize=True)
+        ebits = geo.pair_feasible(out.A, out.b, out.m, 0.01)
+        assert np.array_equal(A.numpy(), out.A.cpu().numpy()) and np.array_equal(b.numpy(), out.b.cpu().numpy())
+        assert np.array_equal(m.numpy(), out.m.cpu().numpy()) and np.array_equal(q.numpy(), out.q_ellipse.cpu().numpy())
+        assert np.array_equal(status.numpy(), out.status.cpu().numpy())
+        assert np.array_equal(bits.numpy(), ebits.cpu().numpy())
