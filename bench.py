@@ -214,9 +214,21 @@ def run_gpu(args):
         pipe = SetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
         pipe.seeds_dev.copy_(seeds_dev)
 
+    spipe = None
+    if world > 1 and not args.no_cuda_graph:
+        from boundplanner_b200.pipeline import ShardedSetGraphPipeline
+
+        spipe = ShardedSetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
+        spipe.seeds_dev.copy_(seeds_dev)
+
     def step_device(seeds_d):
         if pipe is not None:
             return pipe.run_device()
+        if spipe is not None:
+            if seeds_d is not spipe.seeds_dev and seeds_d is not seeds_dev:
+                spipe.seeds_dev.copy_(seeds_d)
+            out, _ = spipe.run_device()
+            return out, spipe.bits_gathered
         out = geo.build_sets_point(scene, seeds_d, ws_min, ws_max, fixed_mid=True, optimize=True)
         bits, _ = bpd.sharded_adjacency(out.A, out.b, out.m, pair_fn, TOL)
         return out, bits
@@ -292,10 +304,14 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_obstacles": N_OBS, "seeds_per_gpu": N_SEEDS, "pairs": n_pairs,
                        "l2": "flushed between timed steps (256 MiB fill)",
-                       "launch": "one CUDA graph per step" if pipe is not None else "eager launches",
+                       "launch": ("one CUDA graph per step" if pipe is not None else
+                                  "two CUDA graphs + two NCCL all-gathers per step" if spipe is not None else
+                                  "eager launches"),
                        "frac_sets_over_20_rows": float((mrows > 20).mean()),
                        "frac_status_ok": float((status == 0).mean()),
-                       "adjacency_density": float(geo.unpack_adjacency(bits, S_total).sum().item()) / max(n_pairs, 1)},
+                       "adjacency_density": float(geo.unpack_adjacency(
+                           spipe.adjacency_bits() if spipe is not None else bits, S_total).sum().item())
+                       / max(n_pairs, 1)},
             "pair_checks_per_sec": n_pairs * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},

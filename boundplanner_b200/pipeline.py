@@ -69,3 +69,83 @@ class SetGraphPipeline:
             h.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._host
+
+
+class ShardedSetGraphPipeline:
+    """Multi-GPU step (one process per GPU, NCCL): every rank builds its S_loc seeds (CUDA graph 1),
+    the packed halfspace tensors are all-gathered, every rank tests a balanced row block of the global
+    pair matrix (CUDA graph 2 on the gathered static buffers) and the bit rows are all-gathered.
+    Two collectives per step, nothing else crosses NVLink."""
+
+    def __init__(self, scene, n_seeds_local, ws_min, ws_max, fixed_mid=True, optimize=True, max_iter=5, tol=0.01,
+                 m_max=geo.BP_MAX_ROWS, group=None):
+        import torch.distributed as dist
+
+        from . import distributed as bpd
+
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.scene, self.S_loc, self.S = scene, int(n_seeds_local), int(n_seeds_local) * self.world
+        self.ws_min, self.ws_max, self.tol = ws_min, ws_max, tol
+        self.kw = dict(fixed_mid=fixed_mid, optimize=optimize, max_iter=max_iter)
+        dev = "cuda"
+        self.seeds_dev = torch.zeros((self.S_loc, 3), dtype=torch.float64, device=dev)
+        self.batch = geo.alloc_set_batch(self.S_loc, m_max)
+        self.m_max = m_max
+        # packed rows (a0,a1,a2,b) + one extra row carrying the row count: one all-gather message per step
+        self.packed = torch.empty((self.S_loc, m_max + 1, 4), dtype=torch.float64, device=dev)
+        self.gathered = torch.empty((self.S, m_max + 1, 4), dtype=torch.float64, device=dev)
+        self.Ag = torch.empty((self.S, m_max, 3), dtype=torch.float64, device=dev)
+        self.bg = torch.empty((self.S, m_max), dtype=torch.float64, device=dev)
+        self.mg = torch.empty((self.S,), dtype=torch.int32, device=dev)
+        self.blocks = bpd.balanced_row_blocks(self.S, self.world)
+        self.r0, self.r1 = self.blocks[self.rank]
+        self.max_rows = max(hi - lo for lo, hi in self.blocks)
+        self.words = (self.S + 31) // 32
+        self.pair_buf = geo.alloc_pair_buffers(self.S, self.r1 - self.r0)
+        self.bits_padded = torch.zeros((self.max_rows, self.words), dtype=torch.int32, device=dev)
+        self.bits_gathered = torch.empty((self.world * self.max_rows, self.words), dtype=torch.int32, device=dev)
+        self._stream = torch.cuda.Stream()
+        self._g1 = self._capture(self._build)
+        self._g2 = None                      # captured after the first all-gather filled the static buffers
+
+    def _build(self):
+        geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
+        self.packed[:, : self.m_max, :3] = self.batch.A
+        self.packed[:, : self.m_max, 3] = self.batch.b
+        self.packed[:, self.m_max, :] = self.batch.m.to(torch.float64).unsqueeze(1)
+
+    def _pairs(self):
+        self.Ag.copy_(self.gathered[:, : self.m_max, :3])
+        self.bg.copy_(self.gathered[:, : self.m_max, 3])
+        self.mg.copy_(self.gathered[:, self.m_max, 0].to(torch.int32))
+        if self.r1 > self.r0:
+            geo.pair_feasible(self.Ag, self.bg, self.mg, self.tol, self.r0, self.r1, out=self.pair_buf)
+            self.bits_padded[: self.r1 - self.r0].copy_(self.pair_buf[0])
+
+    def _capture(self, fn):
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            for _ in range(2):
+                fn()
+        self._stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._stream):
+            fn()
+        return g
+
+    def run_device(self):
+        self._g1.replay()
+        self.dist.all_gather_into_tensor(self.gathered, self.packed, group=self.group)
+        if self._g2 is None:
+            torch.cuda.current_stream().synchronize()
+            self._g2 = self._capture(self._pairs)
+        self._g2.replay()
+        self.dist.all_gather_into_tensor(self.bits_gathered, self.bits_padded, group=self.group)
+        return self.batch, self.bits_gathered
+
+    def adjacency_bits(self):
+        """Global bit matrix [S, words] assembled from the gathered, padded row blocks."""
+        return torch.cat([self.bits_gathered[r * self.max_rows: r * self.max_rows + (hi - lo)]
+                          for r, (lo, hi) in enumerate(self.blocks)])
