@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/bpgeo.h"
@@ -218,6 +219,76 @@ struct PolyParams {
   int row_cap;               // > 0: stop a seed whose pass produced more rows (reference: 20, quirk Q5)
 };
 
+// One compute_polyhedron pass for the seed of this CTA (all threads call it): rows 6.. are written
+// to Arow/brow (global or shared memory), *m_out = 6 + picks, *status_out = BP_OK / BP_ELLIPSE_VIOLATION.
+__device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassMetric& pm, const double* p,
+                                                double* s_dist, int cache_y, double (*red_val)[32],
+                                                int (*red_idx)[32], double* Arow, double* brow, int m_max,
+                                                int* m_out, int* status_out) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  // phase 1: closest points and distances
+  double lmin = BP_INF;
+  int lidx = 0x7fffffff;
+  double* s_y = s_dist + sc.n;               // [3][N] when cache_y
+  for (int j = tid; j < sc.n; j += T) {
+    double lb[3], ub[3], y[3];
+    load_box(sc, j, lb, ub);
+    double d = closest_on_box(pm, p, lb, ub, y);
+    s_dist[j] = d;
+    if (cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
+    if (d < lmin) { lmin = d; lidx = j; }
+  }
+  // (the barrier inside block_argmin orders these writes before the winner's point is read)
+
+  // phase 2: greedy halfspaces
+  int m_cur = 6;
+  int status = BP_OK;
+  int buf = 0;
+  while (true) {
+    double val = lmin;
+    int idx = lidx;
+    block_argmin(val, idx, red_val, red_idx, buf);
+    if (!(val < BP_INF)) break;                      // no obstacle left
+    if (val < 0.99) { status = BP_ELLIPSE_VIOLATION; break; }   // :433-438
+    double y[3];
+    if (cache_y) {
+      y[0] = s_y[idx]; y[1] = s_y[sc.n + idx]; y[2] = s_y[2 * sc.n + idx];
+    } else {                                   // large scenes: re-solve the winner's QP (same inputs, same bits)
+      double lb[3], ub[3];
+      load_box(sc, idx, lb, ub);
+      closest_on_box(pm, p, lb, ub, y);
+    }
+    double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
+    double a[3];
+    bp_mat3_vec(pm.G, zz, a);
+    a[0] *= 2.0; a[1] *= 2.0; a[2] *= 2.0;           // 2 (Q Q^T)(cp - p)   (:440)
+    double bh = a[0] * y[0] + a[1] * y[1] + a[2] * y[2];
+    double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    a[0] /= nrm; a[1] /= nrm; a[2] /= nrm; bh /= nrm;
+    if (tid == 0 && m_cur < m_max) {
+      Arow[3 * m_cur + 0] = a[0]; Arow[3 * m_cur + 1] = a[1]; Arow[3 * m_cur + 2] = a[2];
+      brow[m_cur] = bh;
+    }
+    ++m_cur;
+    // delete the winner and every obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458)
+    lmin = BP_INF;
+    lidx = 0x7fffffff;
+    for (int j = tid; j < sc.n; j += T) {
+      double d = s_dist[j];
+      if (!(d < BP_INF)) continue;
+      double l2[3], u2[3];
+      load_box(sc, j, l2, u2);
+      if (j == idx || bp_box_min_halfspace(a, bh, l2, u2) >= -1e-4) {
+        s_dist[j] = BP_INF;
+      } else if (d < lmin) {
+        lmin = d; lidx = j;
+      }
+    }
+  }
+  *m_out = m_cur;
+  *status_out = status;
+}
+
 __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr) {
   extern __shared__ double s_dist[];
   __shared__ double red_val[2][32];
@@ -267,65 +338,8 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr)
     }
   }
 
-  // phase 1: closest points and distances
-  double lmin = BP_INF;
-  int lidx = 0x7fffffff;
-  double* s_y = s_dist + sc.n;               // [3][N] when pr.cache_y
-  for (int j = tid; j < sc.n; j += T) {
-    double lb[3], ub[3], y[3];
-    load_box(sc, j, lb, ub);
-    double d = closest_on_box(pm, p, lb, ub, y);
-    s_dist[j] = d;
-    if (pr.cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
-    if (d < lmin) { lmin = d; lidx = j; }
-  }
-  // (the barrier inside block_argmin orders these writes before the winner's point is read)
-
-  // phase 2: greedy halfspaces
-  int m_cur = 6;
-  int status = BP_OK;
-  int buf = 0;
-  while (true) {
-    double val = lmin;
-    int idx = lidx;
-    block_argmin(val, idx, red_val, red_idx, buf);
-    if (!(val < BP_INF)) break;                      // no obstacle left
-    if (val < 0.99) { status = BP_ELLIPSE_VIOLATION; break; }   // :433-438
-    double y[3];
-    if (pr.cache_y) {
-      y[0] = s_y[idx]; y[1] = s_y[sc.n + idx]; y[2] = s_y[2 * sc.n + idx];
-    } else {                                   // large scenes: re-solve the winner's QP (same inputs, same bits)
-      double lb[3], ub[3];
-      load_box(sc, idx, lb, ub);
-      closest_on_box(pm, p, lb, ub, y);
-    }
-    double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
-    double a[3];
-    bp_mat3_vec(pm.G, zz, a);
-    a[0] *= 2.0; a[1] *= 2.0; a[2] *= 2.0;           // 2 (Q Q^T)(cp - p)   (:440)
-    double bh = a[0] * y[0] + a[1] * y[1] + a[2] * y[2];
-    double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    a[0] /= nrm; a[1] /= nrm; a[2] /= nrm; bh /= nrm;
-    if (tid == 0 && m_cur < pr.m_max) {
-      Arow[3 * m_cur + 0] = a[0]; Arow[3 * m_cur + 1] = a[1]; Arow[3 * m_cur + 2] = a[2];
-      brow[m_cur] = bh;
-    }
-    ++m_cur;
-    // delete the winner and every obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458)
-    lmin = BP_INF;
-    lidx = 0x7fffffff;
-    for (int j = tid; j < sc.n; j += T) {
-      double d = s_dist[j];
-      if (!(d < BP_INF)) continue;
-      double l2[3], u2[3];
-      load_box(sc, j, l2, u2);
-      if (j == idx || bp_box_min_halfspace(a, bh, l2, u2) >= -1e-4) {
-        s_dist[j] = BP_INF;
-      } else if (d < lmin) {
-        lmin = d; lidx = j;
-      }
-    }
-  }
+  int m_cur, status;
+  poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
   if (status == BP_OK && m_cur > pr.m_max) status = BP_ROW_OVERFLOW;
   // rows past the last one keep the padding of normalize_set_size (A = 0, b = 10): an earlier,
   // longer pass may have left its rows there
@@ -342,6 +356,132 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr)
     } else {
       pr.status[s] = status;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5 fused: the whole find_set_around_point loop (ConvexSetFinder.py:190-240) for one seed in one
+// persistent CTA of 128 threads: polyhedron pass (all threads) -> MVIE (warp 0, rows in shared
+// memory) -> loop tests, up to max_iter times, + the trailing free-centre MVIE.  Compared with the
+// (k_poly_point, k_mvie) launch sequence every seed advances at its own pace: a pass no longer waits
+// for the slowest MVIE of the whole batch, and the rows never leave shared memory between the phases.
+// Used for scenes whose distance table leaves room for two CTAs per SM (N <= 4096).
+// ---------------------------------------------------------------------------
+struct FusedParams {
+  const double* seeds;
+  double ws_rows[6];
+  double* A;
+  double* b;
+  int* m;
+  double* q_ellipse;
+  double* p_mid;
+  int* status;
+  int* iters;
+  int* rows_peak;
+  int m_max, max_iter, fixed_mid, optimize, row_cap, cache_y;
+};
+
+__global__ void __launch_bounds__(128) k_iris_fused(SceneView sc, FusedParams pr) {
+  extern __shared__ double s_dist[];
+  __shared__ double red_val[2][32];
+  __shared__ int red_idx[2][32];
+  __shared__ double sA[BP_MAX_ROWS * 3], sb[BP_MAX_ROWS];
+  __shared__ double scratch[BP_MVIE_SCRATCH_DOUBLES];
+  __shared__ double c_Q[9], c_p[3], c_det;
+  __shared__ int c_status, c_small;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  double Q[9] = {1e4, 0, 0, 0, 1e4, 0, 0, 0, 1e4};          // q_ellipse = diag(1/1e-4) (:192-194)
+  double p[3] = {pr.seeds[3 * (size_t)s], pr.seeds[3 * (size_t)s + 1], pr.seeds[3 * (size_t)s + 2]};
+  double det = 100.0, det_old = 1.0;                          // :200-201
+  int k = 0, status = BP_OK, rows_peak = 0, m_cur = 6;
+  if (tid < 6) {                                              // init_halfspaces (:377-398)
+    const int ax = tid >> 1;
+    const double sgn = (tid & 1) ? -1.0 : 1.0;
+    sA[3 * tid + 0] = ax == 0 ? sgn : 0.0;
+    sA[3 * tid + 1] = ax == 1 ? sgn : 0.0;
+    sA[3 * tid + 2] = ax == 2 ? sgn : 0.0;
+    sb[tid] = pr.ws_rows[tid];
+  }
+  while (fabs(det - det_old) / det_old > 0.01) {              // :203
+    ++k;
+    if (k > pr.max_iter) break;                               // :204-207
+    PassMetric pm;
+    pass_metric_init(Q, &pm);
+    __syncthreads();                                          // previous rows / control words consumed
+    int st;
+    poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
+    rows_peak = m_cur > rows_peak ? m_cur : rows_peak;
+    if (st == BP_OK && m_cur > pr.m_max) st = BP_ROW_OVERFLOW;
+    if (st == BP_OK && pr.optimize && pr.row_cap > 0 && m_cur > pr.row_cap) st = BP_ROW_CAP;
+    if (st != BP_OK) { status = st; break; }
+    if (!pr.optimize) break;                                  // :214-215
+    det_old = det;                                            // :217
+    __syncthreads();                                          // thread 0 has written the picked rows
+    if (tid < 32) {
+      double L[6], d[3];
+      const int ms = pr.fixed_mid ? bp_mvie_warp<6>(sA, sb, m_cur, p, scratch, L, d, nullptr)
+                                  : bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
+      if (tid == 0) {
+        double E[9], Qn[9], dq;
+        bp_shape_from_L(L, E, Qn, &dq);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c_Q[q] = Qn[q];
+        c_p[0] = d[0]; c_p[1] = d[1]; c_p[2] = d[2];
+        c_det = dq;                                           // :229
+        c_status = ms;
+        c_small = (ms == BP_OK && bp_sym3_min_eig(E) < 1e-3) ? 1 : 0;   // :232-233
+      }
+    }
+    __syncthreads();
+    if (c_status != BP_OK) { status = c_status; break; }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Q[q] = c_Q[q];
+    p[0] = c_p[0]; p[1] = c_p[1]; p[2] = c_p[2];
+    det = c_det;
+    if (c_small) break;
+  }
+  if (pr.optimize && pr.fixed_mid && status == BP_OK) {       // :235-238
+    __syncthreads();
+    if (tid < 32) {
+      double L[6], d[3];
+      const int ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
+      if (tid == 0) {
+        double E[9], Qn[9], dq;
+        bp_shape_from_L(L, E, Qn, &dq);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c_Q[q] = Qn[q];
+        c_p[0] = d[0]; c_p[1] = d[1]; c_p[2] = d[2];
+        c_status = ms;
+      }
+    }
+    __syncthreads();
+    if (c_status != BP_OK) status = c_status;
+    else {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Q[q] = c_Q[q];
+      p[0] = c_p[0]; p[1] = c_p[1]; p[2] = c_p[2];
+    }
+  }
+  __syncthreads();
+  // outputs: rows padded like normalize_set_size (A = 0, b = 10)
+  const int mw = m_cur < pr.m_max ? m_cur : pr.m_max;
+  double* Arow = pr.A + (size_t)s * pr.m_max * 3;
+  double* brow = pr.b + (size_t)s * pr.m_max;
+  for (int r = tid; r < pr.m_max; r += blockDim.x) {
+    const bool live = r < mw;
+    Arow[3 * r] = live ? sA[3 * r] : 0.0;
+    Arow[3 * r + 1] = live ? sA[3 * r + 1] : 0.0;
+    Arow[3 * r + 2] = live ? sA[3 * r + 2] : 0.0;
+    brow[r] = live ? sb[r] : 10.0;
+  }
+  if (tid == 0) {
+    pr.m[s] = mw;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) pr.q_ellipse[(size_t)s * 9 + q] = Q[q];
+    pr.p_mid[3 * (size_t)s] = p[0]; pr.p_mid[3 * (size_t)s + 1] = p[1]; pr.p_mid[3 * (size_t)s + 2] = p[2];
+    pr.status[s] = status;
+    if (pr.iters) pr.iters[s] = k;
+    if (pr.rows_peak) pr.rows_peak[s] = rows_peak;
   }
 }
 
@@ -1160,6 +1300,15 @@ static size_t poly_smem_bytes(int n) {
   if (n < 1) n = 1;
   return sizeof(double) * (size_t)n * (poly_cache_y(n) ? 4 : 1);
 }
+// fused per-seed kernel for small / medium scenes; BPGEO_FUSED=0 forces the launch sequence
+static bool use_fused_iris(int n) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("BPGEO_FUSED");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env == 1 && n <= 4096;
+}
 static int poly_threads(int n) { return n <= 256 ? 128 : (n <= 4096 ? 256 : 512); }
 
 static int set_dyn_smem(const void* fn, size_t bytes) {
@@ -1294,6 +1443,21 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
   if (S == 0) return 0;
   if (workspace_bytes < bp_build_sets_workspace_bytes(S)) return bp_fail("bp_build_sets_point: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (use_fused_iris(scene->n)) {
+    FusedParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.seeds = seeds_dev;
+    for (int i = 0; i < 3; ++i) { fp.ws_rows[2 * i] = ws_max_host[i]; fp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
+    fp.A = A_dev; fp.b = b_dev; fp.m = m_dev; fp.q_ellipse = q_ellipse_dev; fp.p_mid = p_mid_dev;
+    fp.status = status_dev; fp.iters = iters_dev; fp.rows_peak = rows_peak_dev;
+    fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = fixed_mid; fp.optimize = optimize;
+    fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
+    const size_t fsmem = poly_smem_bytes(scene->n);
+    if (set_dyn_smem((const void*)k_iris_fused, fsmem)) return 1;
+    k_iris_fused<<<S, 128, fsmem, stream>>>(view_of(scene), fp);
+    BP_CUDA(cudaGetLastError());
+    return 0;
+  }
   SeedState* st = (SeedState*)workspace_dev;
   k_state_init<<<(S + 127) / 128, 128, 0, stream>>>(st, seeds_dev, S);
   PolyParams pp;
@@ -1365,9 +1529,18 @@ size_t bp_pair_workspace_bytes(int S, int rows) {
   return sizeof(double) * 6 * (size_t)S + 16 + sizeof(int2) * (size_t)rows * (size_t)S;
 }
 
+int bp_set_aabb(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double* aabb_out_dev,
+                void* stream) {
+  if (S < 0 || m_max < 1 || m_max > BP_MAX_ROWS || !aabb_out_dev) return bp_fail("bp_set_aabb: bad arguments");
+  if (S == 0) return 0;
+  k_set_aabb<<<S, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb_out_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
                      int row_begin, int row_end, unsigned int* adj_bits_dev, double* x_feas_dev,
-                     void* workspace_dev, size_t workspace_bytes, void* stream_) {
+                     const double* aabb_in_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
   if (S < 0 || row_begin < 0 || row_end > S || row_begin > row_end || m_max < 1 || m_max > BP_MAX_ROWS)
     return bp_fail("bp_pair_feasible: bad arguments");
   if (row_end == row_begin) return 0;
@@ -1380,7 +1553,8 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   const int words = (S + 31) / 32;
   BP_CUDA(cudaMemsetAsync(adj_bits_dev, 0, sizeof(unsigned int) * (size_t)rows * words, stream));
   BP_CUDA(cudaMemsetAsync(count, 0, 16, stream));
-  k_set_aabb<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
+  if (aabb_in_dev) aabb = const_cast<double*>(aabb_in_dev);      // boxes computed elsewhere (e.g. all-gathered)
+  else k_set_aabb<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
   dim3 grid((S + 31) / 32, (rows + 7) / 8);
   k_pair_filter<<<grid, 256, 0, stream>>>(aabb, S, row_begin, row_end, list, count);
   int nsm = 148;

@@ -237,7 +237,17 @@ def alloc_pair_buffers(S, rows=None):
     return bits, work
 
 
-def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=False, out=None):
+def set_aabb(A, b, m, out=None):
+    """Exact axis-aligned bounding boxes [S,6] (lo | hi) of S sets (pre-filter of pair_feasible)."""
+    lib = _lib.load()
+    S, m_max = A.shape[0], A.shape[1]
+    if out is None:
+        out = torch.empty((S, 6), dtype=torch.float64, device="cuda")
+    check(lib.bp_set_aabb(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(out), _stream()))
+    return out
+
+
+def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=False, out=None, aabb=None):
     """BoundPlanner.set_intersection (BoundPlanner.py:774-787, tol from :797) for all
     pairs (i, j>i), i in [row_begin,row_end).  Returns uint32-packed bits as an
     int32 tensor [rows, ceil(S/32)]; with want_points also x [rows,S,3], a point of
@@ -254,7 +264,7 @@ def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=Fals
     assert bits.shape == (row_end - row_begin, words)
     x = torch.zeros((row_end - row_begin, S, 3), dtype=torch.float64, device="cuda") if want_points else None
     check(lib.bp_pair_feasible(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), int(row_begin), int(row_end),
-                               _ptr(bits), _ptr(x), _ptr(work), wbytes, _stream()))
+                               _ptr(bits), _ptr(x), _ptr(aabb), _ptr(work), wbytes, _stream()))
     if want_points:
         return bits, x
     return bits

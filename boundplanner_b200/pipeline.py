@@ -93,9 +93,12 @@ class ShardedSetGraphPipeline:
         self.seeds_dev = torch.zeros((self.S_loc, 3), dtype=torch.float64, device=dev)
         self.batch = geo.alloc_set_batch(self.S_loc, m_max)
         self.m_max = m_max
-        # packed rows (a0,a1,a2,b) + one extra row carrying the row count: one all-gather message per step
-        self.packed = torch.empty((self.S_loc, m_max + 1, 4), dtype=torch.float64, device=dev)
-        self.gathered = torch.empty((self.S, m_max + 1, 4), dtype=torch.float64, device=dev)
+        # packed rows (a0,a1,a2,b) + three extra rows carrying the row count and the set's bounding box
+        # (computed by its owner, so no rank recomputes all S boxes): one all-gather message per step
+        self.packed = torch.zeros((self.S_loc, m_max + 3, 4), dtype=torch.float64, device=dev)
+        self.gathered = torch.empty((self.S, m_max + 3, 4), dtype=torch.float64, device=dev)
+        self.aabb_loc = torch.empty((self.S_loc, 6), dtype=torch.float64, device=dev)
+        self.aabb_g = torch.empty((self.S, 6), dtype=torch.float64, device=dev)
         self.Ag = torch.empty((self.S, m_max, 3), dtype=torch.float64, device=dev)
         self.bg = torch.empty((self.S, m_max), dtype=torch.float64, device=dev)
         self.mg = torch.empty((self.S,), dtype=torch.int32, device=dev)
@@ -115,13 +118,19 @@ class ShardedSetGraphPipeline:
         self.packed[:, : self.m_max, :3] = self.batch.A
         self.packed[:, : self.m_max, 3] = self.batch.b
         self.packed[:, self.m_max, :] = self.batch.m.to(torch.float64).unsqueeze(1)
+        geo.set_aabb(self.batch.A, self.batch.b, self.batch.m, out=self.aabb_loc)
+        self.packed[:, self.m_max + 1, :3] = self.aabb_loc[:, :3]
+        self.packed[:, self.m_max + 2, :3] = self.aabb_loc[:, 3:]
 
     def _pairs(self):
         self.Ag.copy_(self.gathered[:, : self.m_max, :3])
         self.bg.copy_(self.gathered[:, : self.m_max, 3])
         self.mg.copy_(self.gathered[:, self.m_max, 0].to(torch.int32))
+        self.aabb_g[:, :3] = self.gathered[:, self.m_max + 1, :3]
+        self.aabb_g[:, 3:] = self.gathered[:, self.m_max + 2, :3]
         if self.r1 > self.r0:
-            geo.pair_feasible(self.Ag, self.bg, self.mg, self.tol, self.r0, self.r1, out=self.pair_buf)
+            geo.pair_feasible(self.Ag, self.bg, self.mg, self.tol, self.r0, self.r1, out=self.pair_buf,
+                              aabb=self.aabb_g)
             self.bits_padded[: self.r1 - self.r0].copy_(self.pair_buf[0])
 
     def _capture(self, fn):

@@ -112,11 +112,17 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
  * [row_begin,row_end), j in (i, S).  adj_bits_dev: [(row_end-row_begin), words]
  * uint32 words, words = (S+31)/32; bit j of row i is 1 iff sets i and j intersect.
  * Bits with j <= i are 0. */
+/* bp_set_aabb: exact axis-aligned bounding boxes of S sets, aabb_out[S,6] = (lo xyz | hi xyz); the
+ * rigorous pre-filter of bp_pair_feasible.  Pass them back through aabb_in_dev (or NULL to have
+ * bp_pair_feasible compute them), e.g. after all-gathering them together with the sets. */
+int bp_set_aabb(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double* aabb_out_dev,
+                void* stream);
 size_t bp_pair_workspace_bytes(int S, int rows /* row_end - row_begin */);
 int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*[S,m_max]*/, const int* m_dev /*[S]*/,
                      int S, int m_max, double tol, int row_begin, int row_end, unsigned int* adj_bits_dev,
                      double* x_feas_dev /* NULL or [rows,S,3]: a point of the intersection where the bit is 1
                                            (the reference's sol_lin.x, BoundPlanner.py:785) */,
+                     const double* aabb_in_dev /* NULL or [S,6] from bp_set_aabb */,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- K8 (next row 1): redundancy removal ---------------------------------------------
