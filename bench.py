@@ -290,7 +290,9 @@ def run_gpu(args):
     mrows = out.m.cpu().numpy()
     n_pairs = S_total * (S_total - 1) // 2
     value = S_total * args.steps / (dev_ms * 1e-3)
-    launches_per_step = 1 + 5 * 2 + 1 + 1 + 3      # state_init, 5x(poly,mvie), final mvie, export, aabb+filter+lp
+    fused = os.environ.get("BPGEO_FUSED", "1") != "0" and N_OBS <= 4096
+    # fused: k_iris_fused + aabb + filter + lp;  else state_init, 5x(poly,mvie), final mvie, export, aabb+filter+lp
+    launches_per_step = (1 + 3) if fused else (1 + 5 * 2 + 1 + 1 + 3)
     if rank == 0:
         peaks = {}
         try:
@@ -425,6 +427,10 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
     newton_free = float(geo.mvie(out.A, out.b, out.m, seeds_dev, True)[4].double().mean().item())
     newton_fm = float(geo.mvie(out.A, out.b, out.m, seeds_dev, False)[4].double().mean().item())
     t_pair = timeit(lambda: geo.pair_feasible(out.A, out.b, out.m, TOL))
+    sb = geo.alloc_set_batch(S)
+    t_build = timeit(lambda: geo.build_sets_point(scene, seeds_dev, ws_min, ws_max, fixed_mid=True, optimize=True,
+                                                  out=sb))
+    passes_mean = float(torch.clamp(sb.iters.double(), max=5).mean().item())
     m_mean = float(out.m.double().mean().item())
 
     # FP64 pipe peak of this part (dependent-free DFMA chains, full chip)
@@ -454,31 +460,43 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
     fk_bytes = B * (56 + 24 + 168)
 
     kernels = {
+        "build_sets_point_ms": t_build, "iris_passes_mean": passes_mean,
         "k_poly_point_ms": t_poly, "k_mvie_fixed_mid_ms": t_mvie_fm, "k_mvie_free_ms": t_mvie_free,
         "pair_pipeline_ms": t_pair, "k_fk_1M_ms": t_fk, "newton_iters_fixed_mid": newton_fm,
         "newton_iters_free": newton_free, "mean_rows": m_mean, "fp64_peak_tflops_measured": fp64_peak_tflops,
     }
 
     def roofline(hbm_peak, which):
-        # dominant kernel of the step: k_mvie (5 fixed-mid + 1 free launch per step)
-        bytes_alg = S * (m_mean * 32 + 21 * 8)          # rows in + shape/centre out, per launch
-        flops = S * newton_fm * (m_mean * 200.0 + 250.0)  # per-Newton-iteration flop model
-        dur = t_mvie_fm
+        # dominant kernel of the step: the set build (k_iris_fused: one launch = the whole IRIS loop of S seeds;
+        # with BPGEO_FUSED=0 the same work is the (k_poly_point, k_mvie) launch sequence).
+        # Algorithmic bytes per launch: seeds in, the scene once, one padded set + ellipsoid
+        # out per seed.  Algorithmic flops: passes x [N x (1.1 kflop QP + 64 flop x picked rows)] per seed for
+        # the polyhedron passes + Newton iterations x (m x 200 + 250) flop for the MVIEs (passes + 1 per seed).
+        picks = max(m_mean - 6.0, 0.0)
+        bytes_alg = S * 24 + N * 48 + S * (m_mean * 32 + 12 * 8 + 12)
+        flops = S * (passes_mean * N * (1100.0 + 64.0 * picks)
+                     + (passes_mean * newton_fm + newton_free) * (m_mean * 200.0 + 250.0))
+        dur = t_build
         ach = bytes_alg / (dur * 1e-3) / 1e9
-        return {"kernel": "k_mvie (fixed centre, one launch = one IRIS pass over 256 sets)", "bound": "hbm",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        return {"kernel": "k_iris_fused (set build: whole find_set_around_point loop, one CTA per seed)",
+                "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": 171520, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_final_iris_fused.txt",
                 "peak_source": which,
-                "note": "latency-bound fp64 kernel (one warp per set, ~35 dependent Newton iterations): it moves "
-                        "only its compulsory bytes, so the HBM fraction is tiny by construction; see fp64 below "
-                        "and roofline_fk for the HBM-bound kernel of the path",
+                "note": "latency-bound fp64 kernel: 256 independent chains of ~5 x (polyhedron pass + ~35 dependent "
+                        "Newton iterations); it moves only its compulsory bytes (operands live in L2 / shared "
+                        "memory), so the HBM fraction is tiny by construction -- see fp64 below, and roofline_fk "
+                        "for the HBM-bound kernel of the path",
                 "fp64": {"achieved_gflops": flops / (dur * 1e-3) / 1e9, "peak_gflops": fp64_peak_tflops * 1e3,
                          "frac": flops / (dur * 1e-3) / 1e12 / fp64_peak_tflops}}
 
     def roofline_fk(hbm_peak, which):
         ach = fk_bytes / (t_fk * 1e-3) / 1e9
         return {"kernel": "k_fk<false,false> (B = 2^20 configurations, 248 B each)", "bound": "hbm", "achieved": ach,
-                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": which,
-                "poses_per_sec": B / (t_fk * 1e-3)}
+                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 201795328,
+                "traffic_source": "ncu dram__bytes_read+write per launch (below the 260 MB algorithmic bytes: part "
+                                  "of the output is still dirty in the 126 MB L2 at kernel end), "
+                                  "profiles/r01_ncu_final_pair_fk.txt",
+                "peak_source": which, "poses_per_sec": B / (t_fk * 1e-3)}
 
     return {"kernels": kernels, "roofline": roofline, "roofline_fk": roofline_fk}
 
