@@ -30,6 +30,9 @@
 #ifndef BP_MVIE_PRED_FROM
 #define BP_MVIE_PRED_FROM 300.0
 #endif
+#ifndef BP_MVIE_T0
+#define BP_MVIE_T0 1.0
+#endif
 #ifndef BP_MVIE_WS_BETA
 #define BP_MVIE_WS_BETA 0.9
 #endif
@@ -122,7 +125,7 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
   x[0] = r; x[1] = 0.0; x[2] = r; x[3] = 0.0; x[4] = 0.0; x[5] = r;
   if (NV == 9) { x[6] = c0[0]; x[7] = c0[1]; x[8] = c0[2]; }
   double cen[3] = {c0[0], c0[1], c0[2]};
-  double t = 1.0;
+  double t = BP_MVIE_T0;
   if (L0) {
     // warm start: a previous shape L0 around the same centre, scaled to BP_MVIE_WS_BETA of the
     // largest factor that keeps it inside, entered at barrier parameter t0
