@@ -31,6 +31,7 @@ SIGNATURES = {
     "bpgeo_abi_version": (_i, []),
     "bp_last_error_string": (_c.c_char_p, []),
     "bp_scene_create": (_i, [_dp, _i, _d, _c.POINTER(_vp)]),
+    "bp_scene_create_batch": (_i, [_dp, _c.POINTER(_c.c_int), _i, _d, _c.POINTER(_vp)]),
     "bp_scene_update": (_i, [_vp, _dp, _i, _d, _vp]),
     "bp_scene_destroy": (_i, [_vp]),
     "bp_scene_size": (_i, [_vp]),
@@ -41,6 +42,11 @@ SIGNATURES = {
     "bp_build_sets_workspace_bytes": (_sz, [_i]),
     "bp_build_sets_point": (_i, [_vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _i, _vp, _sz, _vp]),
+    "bp_build_sets_point_ms": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _i, _vp, _sz, _vp]),
+    "bp_build_sets_line_ms": (_i, [_vp, _vp, _vp, _vp, _i, _dp, _dp, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _sz, _vp]),
+    "bp_pairs_feasible_list": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "bp_build_sets_line": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _vp]),
     "bp_pair_workspace_bytes": (_sz, [_i, _i]),

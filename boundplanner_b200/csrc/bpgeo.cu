@@ -48,15 +48,19 @@ static int bp_fail(const char* what, cudaError_t e = cudaSuccess) {
 
 struct bp_scene {
   double* cols;   // device, 6 * cap doubles: lbx | lby | lbz | ubx | uby | ubz (stride cap)
-  int n;
+  int n;          // obstacles of a single scene, or of the largest scene of a batch
   int cap;
   double inflate;
+  int* seg_off;   // device [n_seg + 1] or NULL: a batch of scenes stored back to back (one per planning query)
+  int n_seg;
 };
 
 struct SceneView {
   const double* lb[3];
   const double* ub[3];
   int n;
+  const int* seg_off;     // scene batch: obstacle range of scene k is [seg_off[k], seg_off[k+1])
+  const int* item_seg;    // scene index of every seed / segment (device, [S]) when seg_off != NULL
 };
 
 static SceneView view_of(const bp_scene* s) {
@@ -66,6 +70,28 @@ static SceneView view_of(const bp_scene* s) {
     v.ub[k] = s->cols + (size_t)(3 + k) * s->cap;
   }
   v.n = s->n;
+  v.seg_off = s->seg_off;
+  v.item_seg = nullptr;
+  return v;
+}
+
+static SceneView view_of(const bp_scene* s, const int* item_seg) {
+  SceneView v = view_of(s);
+  v.item_seg = item_seg;
+  return v;
+}
+
+// the scene seen by work item `item`: the whole table, or the item's segment of a scene batch
+__device__ __forceinline__ SceneView scene_of_item(const SceneView& sc, int item) {
+  if (!sc.seg_off || !sc.item_seg) return sc;
+  const int k = sc.item_seg[item];
+  const int o = sc.seg_off[k];
+  SceneView v;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { v.lb[a] = sc.lb[a] + o; v.ub[a] = sc.ub[a] + o; }
+  v.n = sc.seg_off[k + 1] - o;
+  v.seg_off = nullptr;
+  v.item_seg = nullptr;
   return v;
 }
 
@@ -289,7 +315,8 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
   *status_out = status;
 }
 
-__global__ void __launch_bounds__(512) k_poly_point(SceneView sc, PolyParams pr) {
+__global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams pr) {
+  const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
   __shared__ double red_val[2][32];
   __shared__ int red_idx[2][32];
@@ -381,7 +408,8 @@ struct FusedParams {
   int m_max, max_iter, fixed_mid, optimize, row_cap, cache_y;
 };
 
-__global__ void __launch_bounds__(128) k_iris_fused(SceneView sc, FusedParams pr) {
+__global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
+  const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
   __shared__ double red_val[2][32];
   __shared__ int red_idx[2][32];
@@ -514,7 +542,8 @@ __device__ __forceinline__ double seg_closest(const double* p0, const double* d,
   return sqrt(e0 * e0 + e1 * e1 + e2 * e2);                                           // :327
 }
 
-__global__ void __launch_bounds__(512) k_poly_line(SceneView sc, LineParams pr) {
+__global__ void __launch_bounds__(512) k_poly_line(SceneView sc_all, LineParams pr) {
+  const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
   __shared__ double red_val[2][32];
   __shared__ int red_idx[2][32];
@@ -884,6 +913,39 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
       }
     }
     __syncwarp();
+  }
+}
+
+// K6 over an explicit pair list (batched planner rounds: the pairs "new set vs every existing set" of
+// many queries at once).  One warp per listed pair: box test, then the LP from the middle of the overlap.
+__global__ void __launch_bounds__(256) k_pair_list(const double* __restrict__ A, const double* __restrict__ b,
+                                                   const int* __restrict__ m, int m_max, double tol,
+                                                   const double* __restrict__ aabb, const int2* __restrict__ pairs,
+                                                   int P, int* __restrict__ result, double* __restrict__ x_feas) {
+  __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int p = blockIdx.x * 8 + wib;
+  if (p >= P) return;
+  const int2 pr = pairs[p];
+  bool apart = false;
+  double x0[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double loi = __ldg(aabb + (size_t)pr.x * 6 + k), hii = __ldg(aabb + (size_t)pr.x * 6 + 3 + k);
+    const double loj = __ldg(aabb + (size_t)pr.y * 6 + k), hij = __ldg(aabb + (size_t)pr.y * 6 + 3 + k);
+    if (loi > hij + BP_AABB_EPS || loj > hii + BP_AABB_EPS) apart = true;
+    x0[k] = 0.5 * (fmax(loi, loj) + fmin(hii, hij));
+    if (!(fabs(x0[k]) < 1e6)) x0[k] = 0.0;
+  }
+  int res = 0;
+  double xi[3] = {0.0, 0.0, 0.0};
+  if (!apart)
+    res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
+                                A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol, scratch[wib],
+                                nullptr, xi, x0, BP_LP_T0_SCALE);
+  if (lane == 0) {
+    result[p] = res;
+    if (x_feas) { x_feas[3 * (size_t)p] = xi[0]; x_feas[3 * (size_t)p + 1] = xi[1]; x_feas[3 * (size_t)p + 2] = xi[2]; }
   }
 }
 
@@ -1360,13 +1422,38 @@ int bp_scene_create(const double* boxes_host, int n, double inflate, bp_scene** 
   return 0;
 }
 
+int bp_scene_create_batch(const double* boxes_host, const int* offsets_host, int n_scenes, double inflate,
+                          bp_scene** out) {
+  if (!out || n_scenes < 1 || !offsets_host || offsets_host[0] != 0) return bp_fail("bp_scene_create_batch: bad arguments");
+  int n_max = 0;
+  for (int k = 0; k < n_scenes; ++k) {
+    const int nk = offsets_host[k + 1] - offsets_host[k];
+    if (nk < 0) return bp_fail("bp_scene_create_batch: offsets must be non-decreasing");
+    n_max = nk > n_max ? nk : n_max;
+  }
+  const int total = offsets_host[n_scenes];
+  bp_scene* sc = nullptr;
+  int rc = bp_scene_create(boxes_host, total, inflate, &sc);
+  if (rc) return rc;
+  sc->n = n_max;                                  // sizes shared memory / picks the kernel variant
+  sc->n_seg = n_scenes;
+  cudaError_t e = cudaMalloc(&sc->seg_off, sizeof(int) * (size_t)(n_scenes + 1));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(sc->seg_off, offsets_host, sizeof(int) * (size_t)(n_scenes + 1), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { bp_scene_destroy(sc); return bp_fail("bp_scene_create_batch", e); }
+  *out = sc;
+  return 0;
+}
+
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream) {
+  if (scene && scene->seg_off) return bp_fail("bp_scene_update: not supported for scene batches");
   if (!scene || n < 0 || (n > 0 && !boxes_host)) return bp_fail("bp_scene_update: bad arguments");
   return scene_upload(scene, boxes_host, n, inflate, (cudaStream_t)stream);
 }
 
 int bp_scene_destroy(bp_scene* scene) {
   if (!scene) return 0;
+  if (scene->seg_off) cudaFree(scene->seg_off);
   if (scene->cols) cudaFree(scene->cols);
   free(scene);
   return 0;
@@ -1376,7 +1463,7 @@ int bp_scene_size(const bp_scene* scene) { return scene ? scene->n : -1; }
 
 int bp_closest_points(const bp_scene* scene, const double* seeds_dev, const double* q_inv_dev, int S,
                       double* y_out_dev, double* dist_out_dev, void* stream) {
-  if (!scene || S < 0) return bp_fail("bp_closest_points: bad arguments");
+  if (!scene || S < 0 || scene->seg_off) return bp_fail("bp_closest_points: bad arguments");
   if (S == 0 || scene->n == 0) return 0;
   dim3 grid((scene->n + 255) / 256, S);
   k_closest_points<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(scene), seeds_dev, q_inv_dev, y_out_dev, dist_out_dev);
@@ -1386,7 +1473,7 @@ int bp_closest_points(const bp_scene* scene, const double* seeds_dev, const doub
 
 int bp_closest_points_line(const bp_scene* scene, const double* p0_dev, const double* p1_dev, int S,
                            double* x_out_dev, double* phi_out_dev, void* stream) {
-  if (!scene || S < 0) return bp_fail("bp_closest_points_line: bad arguments");
+  if (!scene || S < 0 || scene->seg_off) return bp_fail("bp_closest_points_line: bad arguments");
   if (S == 0 || scene->n == 0) return 0;
   dim3 grid((scene->n + 255) / 256, S);
   k_closest_points_line<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(scene), p0_dev, p1_dev, x_out_dev, phi_out_dev);
@@ -1398,7 +1485,8 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
                   const double* init_rows_dev, int S, int m_max, double* A_dev, double* b_dev, int* m_dev,
                   int* status_dev, void* stream) {
   (void)q_inv_dev;   // the pass metric is derived from q_ellipse (= q_inv^-1, :227-228)
-  if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS) return bp_fail("bp_polyhedron: bad arguments");
+  if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || scene->seg_off)
+    return bp_fail("bp_polyhedron: bad arguments");
   if (S == 0) return 0;
   PolyParams pr;
   memset(&pr, 0, sizeof(pr));
@@ -1438,6 +1526,18 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
                         double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev, double* p_mid_dev,
                         int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap, void* workspace_dev,
                         size_t workspace_bytes, void* stream_) {
+  return bp_build_sets_point_ms(scene, nullptr, seeds_dev, S, ws_min_host, ws_max_host, fixed_mid, optimize, max_iter,
+                                m_max, A_dev, b_dev, m_dev, q_ellipse_dev, p_mid_dev, status_dev, iters_dev,
+                                rows_peak_dev, row_cap, workspace_dev, workspace_bytes, stream_);
+}
+
+int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, const double* seeds_dev, int S,
+                           const double* ws_min_host, const double* ws_max_host, int fixed_mid, int optimize,
+                           int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                           double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                           void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (scene && ((scene->seg_off != nullptr) != (seed_scene_dev != nullptr)))
+    return bp_fail("bp_build_sets_point: a scene batch needs seed_scene, a single scene must not have it");
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || max_iter < 1 || !ws_min_host || !ws_max_host)
     return bp_fail("bp_build_sets_point: bad arguments");
   if (S == 0) return 0;
@@ -1454,7 +1554,7 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
     fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
     const size_t fsmem = poly_smem_bytes(scene->n);
     if (set_dyn_smem((const void*)k_iris_fused, fsmem)) return 1;
-    k_iris_fused<<<S, 128, fsmem, stream>>>(view_of(scene), fp);
+    k_iris_fused<<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     BP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1475,7 +1575,7 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
   const int T = poly_threads(scene->n);
   const int passes = optimize ? max_iter : 1;
   for (int it = 0; it < passes; ++it) {
-    k_poly_point<<<S, T, smem, stream>>>(view_of(scene), pp);
+    k_poly_point<<<S, T, smem, stream>>>(view_of(scene, seed_scene_dev), pp);
     if (!optimize) break;                                 // :214-215
     mp.mode = fixed_mid ? 0 : 1;
     if (launch_mvie(mp, stream)) return 1;
@@ -1495,6 +1595,18 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
                        int compute_ellipsoid, int m_max, double* A_dev, double* b_dev, int* m_dev,
                        double* q_ellipse_dev, double* p_mid_dev, int* collision_dev, int* status_dev,
                        void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  return bp_build_sets_line_ms(scene, nullptr, p0_dev, p1_dev, S, ws_min_host, ws_max_host, limit_space, e_max,
+                               compute_ellipsoid, m_max, A_dev, b_dev, m_dev, q_ellipse_dev, p_mid_dev, collision_dev,
+                               status_dev, workspace_dev, workspace_bytes, stream_);
+}
+
+int bp_build_sets_line_ms(const bp_scene* scene, const int* seg_scene_dev, const double* p0_dev, const double* p1_dev,
+                          int S, const double* ws_min_host, const double* ws_max_host, int limit_space, double e_max,
+                          int compute_ellipsoid, int m_max, double* A_dev, double* b_dev, int* m_dev,
+                          double* q_ellipse_dev, double* p_mid_dev, int* collision_dev, int* status_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (scene && ((scene->seg_off != nullptr) != (seg_scene_dev != nullptr)))
+    return bp_fail("bp_build_sets_line: a scene batch needs seg_scene, a single scene must not have it");
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || !ws_min_host || !ws_max_host)
     return bp_fail("bp_build_sets_line: bad arguments");
   if (S == 0) return 0;
@@ -1508,7 +1620,7 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
   lp.A = A_dev; lp.b = b_dev; lp.m = m_dev; lp.status = status_dev; lp.collision = collision_dev; lp.m_max = m_max;
   size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
   if (set_dyn_smem((const void*)k_poly_line, smem)) return 1;
-  k_poly_line<<<S, poly_threads(scene->n), smem, stream>>>(view_of(scene), lp);
+  k_poly_line<<<S, poly_threads(scene->n), smem, stream>>>(view_of(scene, seg_scene_dev), lp);
   if (compute_ellipsoid) {
     SeedState* st = (SeedState*)workspace_dev;
     k_state_init_line<<<(S + 127) / 128, 128, 0, stream>>>(st, p0_dev, status_dev, S);
@@ -1568,6 +1680,21 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   if (ctas < 1) ctas = 1;
   k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count, adj_bits_dev,
                                                        x_feas_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_pairs_feasible_list(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                           const int* pairs_dev, int P, int* result_dev, double* x_feas_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream_) {
+  if (S < 0 || P < 0 || m_max < 1 || m_max > BP_MAX_ROWS || !result_dev) return bp_fail("bp_pairs_feasible_list: bad arguments");
+  if (P == 0 || S == 0) return 0;
+  if (workspace_bytes < sizeof(double) * 6 * (size_t)S) return bp_fail("bp_pairs_feasible_list: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  double* aabb = (double*)workspace_dev;
+  k_set_aabb<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
+  k_pair_list<<<(P + 7) / 8, 256, 0, stream>>>(A_dev, b_dev, m_dev, m_max, tol, aabb, (const int2*)pairs_dev, P,
+                                               result_dev, x_feas_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

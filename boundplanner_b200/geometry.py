@@ -80,6 +80,29 @@ class Scene:
             pass
 
 
+class SceneBatch(Scene):
+    """Several scenes stored back to back in HBM (one per planning query, BASELINE config C3).
+    ``boxes_list``: list of [N_k,6] arrays.  Use with build_sets_point / build_sets_line and
+    ``item_scene`` = scene index of every seed / segment."""
+
+    def __init__(self, boxes_list, inflate=0.0):
+        _require_cuda()
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p(0)
+        offs = np.zeros(len(boxes_list) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([np.asarray(bx).reshape(-1, 6).shape[0] for bx in boxes_list])
+        boxes = np.ascontiguousarray(np.vstack([np.asarray(bx, dtype=np.float64).reshape(-1, 6) for bx in boxes_list]))
+        torch.cuda.current_device()
+        check(self._lib.bp_scene_create_batch(boxes.ctypes.data_as(_dp), offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                              len(boxes_list), float(inflate), ctypes.byref(self._h)))
+        self.n = int(np.diff(offs).max()) if len(boxes_list) else 0
+        self.n_scenes = len(boxes_list)
+        self.inflate = float(inflate)
+
+    def update(self, boxes, inflate=None):
+        raise _lib.BpGeoError("SceneBatch is immutable")
+
+
 @dataclass
 class SetBatch:
     """S convex sets {x : A[s,:m[s]] x <= b[s,:m[s]]} plus their ellipsoids."""
@@ -124,7 +147,7 @@ def alloc_set_batch(S, m_max=BP_MAX_ROWS):
 
 
 def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS,
-                     row_cap=0, out=None):
+                     row_cap=0, out=None, item_scene=None):
     """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds.
     row_cap=20 reproduces the reference's failure on passes with more than 20 rows (status 5).
     out: a batch from alloc_set_batch to write into (no allocation, CUDA-graph capturable)."""
@@ -139,16 +162,18 @@ def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=Tru
     wbytes = work.numel()
     amin, pmin = _host3(ws_min)      # host arrays must outlive the call
     amax, pmax = _host3(ws_max)
-    check(lib.bp_build_sets_point(scene._h, _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)), int(bool(optimize)),
-                                  int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m), _ptr(q), _ptr(p),
-                                  _ptr(status), _ptr(iters), _ptr(peak), int(row_cap), _ptr(work), wbytes,
-                                  _stream()))
+    if item_scene is not None:
+        item_scene = _dev(item_scene, torch.int32).reshape(S)
+    check(lib.bp_build_sets_point_ms(scene._h, _ptr(item_scene), _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)),
+                                     int(bool(optimize)), int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m),
+                                     _ptr(q), _ptr(p), _ptr(status), _ptr(iters), _ptr(peak), int(row_cap),
+                                     _ptr(work), wbytes, _stream()))
     del amin, amax
     return out
 
 
 def build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False, limit_space=False, e_max=0.3,
-                    m_max=BP_MAX_ROWS):
+                    m_max=BP_MAX_ROWS, item_scene=None):
     """ConvexSetFinder.find_set_collision_avoidance (ConvexSetFinder.py:309-375) for S segments."""
     lib = _lib.load()
     p0 = _dev(p0).reshape(-1, 3)
@@ -163,9 +188,12 @@ def build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False, limi
     work = torch.empty((wbytes,), dtype=torch.uint8, device="cuda")
     amin, pmin = _host3(ws_min)      # host arrays must outlive the call
     amax, pmax = _host3(ws_max)
-    check(lib.bp_build_sets_line(scene._h, _ptr(p0), _ptr(p1), S, pmin, pmax, int(bool(limit_space)), float(e_max),
-                                 int(bool(compute_ellipsoid)), int(m_max), _ptr(A), _ptr(b), _ptr(m), _ptr(q),
-                                 _ptr(p), _ptr(coll), _ptr(status), _ptr(work), wbytes, _stream()))
+    if item_scene is not None:
+        item_scene = _dev(item_scene, torch.int32).reshape(S)
+    check(lib.bp_build_sets_line_ms(scene._h, _ptr(item_scene), _ptr(p0), _ptr(p1), S, pmin, pmax,
+                                    int(bool(limit_space)), float(e_max), int(bool(compute_ellipsoid)), int(m_max),
+                                    _ptr(A), _ptr(b), _ptr(m), _ptr(q), _ptr(p), _ptr(coll), _ptr(status), _ptr(work),
+                                    wbytes, _stream()))
     del amin, amax
     return SetBatch(A, b, m, q, p, status, collision=coll)
 
@@ -325,6 +353,20 @@ def project_points(A, b, m, pairs, xd):
     check(lib.bp_project_points(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(pairs), P, _ptr(xd), _ptr(x), _ptr(status),
                                 _stream()))
     return x, status
+
+
+def pairs_feasible_list(A, b, m, pairs, tol=0.01):
+    """set_intersection for an explicit list of set pairs [P,2] -> (ok [P] bool, x [P,3])."""
+    lib = _lib.load()
+    S, m_max = A.shape[0], A.shape[1]
+    pairs = _dev(pairs, torch.int32).reshape(-1, 2)
+    P = pairs.shape[0]
+    res = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    x = torch.zeros((P, 3), dtype=torch.float64, device="cuda")
+    work = torch.empty((max(S, 1) * 6,), dtype=torch.float64, device="cuda")
+    check(lib.bp_pairs_feasible_list(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), _ptr(pairs), P, _ptr(res),
+                                     _ptr(x), _ptr(work), work.numel() * 8, _stream()))
+    return res.bool(), x
 
 
 def unpack_adjacency(bits, S, row_begin=0):

@@ -13,9 +13,23 @@ replanning branch (:231-276) -- both stay with the reference.  The output is wha
 precedes them: the shortest path through the intersection graph, the sets it
 visits ("planned set sequence") and the position via points.
 
-The geometric primitives come from a ``backend``; the default ``GpuBackend``
-calls libbpgeo through the drop-in classes.  (The parity tests run the same loop
-with an oracle-backed backend and compare the sequences.)
+The loop is written ONCE, as a generator that yields *requests* for geometric
+primitives and receives their results:
+
+  ("set_point", p, fixed_mid, optimize) -> (A, b, q_ellipse, p_mid, A_red, b_red)   find_set_around_point + reduce_ineqs
+  ("set_line", p0, p1)                  -> (A, b, q_ellipse, p_mid, collision, A_red, b_red)
+  ("intersect_many", sets, set_new, tol)-> [(point | None, ok), ...]                 set_intersection vs every existing set
+  ("fit_many", [(A, b, sample), ...])   -> [(fits, via), ...]                        check_intersection
+  ("project", A, b, x_d)                -> x                                         projection QP of add_edges
+
+Drivers: ``plan_set_sequence`` answers every request at once through a backend
+(batch-of-one kernel calls; the parity tests plug the oracle in here), and
+``plan_batch`` advances many queries in lock step, answering the pending
+requests of ALL queries with one batched kernel call per primitive and round
+(BASELINE config C3: thousands of independent queries, one scene each).
+The intersections / fit checks of one add_edges call are independent of the
+graph state that call mutates, so they are requested up front; the graph
+bookkeeping then runs in the reference's order.
 """
 from __future__ import annotations
 
@@ -23,9 +37,24 @@ import networkx as nx
 import numpy as np
 from scipy.spatial.transform import Rotation as R
 
+REFERENCE_MAX_ROWS = 20
+
+
+def _set_errors(status, rows):
+    """Exception the reference would raise for a per-seed status (ConvexSetFinder.py:438, :516)."""
+    if status == 1:
+        return RuntimeError("Ellipse violates constraints")
+    if status == 2:
+        return ValueError("convex set needs more rows than the kernels hold")
+    if status == 5 or (status == 0 and rows is not None and rows > REFERENCE_MAX_ROWS):
+        return ValueError(f"could not broadcast input array from shape ({rows},) into shape ({REFERENCE_MAX_ROWS},)")
+    if status in (3, 4):
+        return RuntimeError(f"MVIE failed (status {status})")
+    return None
+
 
 class GpuBackend:
-    """Primitives of the planner loop, batch-of-one calls into the kernels."""
+    """Answers planner requests one at a time with batch-of-one kernel calls."""
 
     def __init__(self, obstacles, obs_size_increase, workspace_max, workspace_min):
         from . import geometry as geo
@@ -34,56 +63,67 @@ class GpuBackend:
 
         self._geo = geo
         self._pack = pack_sets
-        boxes = np.asarray(obstacles, float).reshape(-1, 6)
-        box = np.concatenate((np.eye(3), -np.eye(3)))
-        # add_obstacle_reps (:131-152): inflated boxes padded to 15 rows
-        self.obs_sets = []
-        for ob in boxes:
-            a = np.zeros((15, 3))
-            b = 10.0 * np.ones(15)
-            a[:6] = box
-            b[:6] = np.concatenate((ob[3:], -ob[:3])) + obs_size_increase
-            self.obs_sets.append([a, b])
+        self.obs_sets = obstacle_sets(obstacles, obs_size_increase)
         self.set_finder = ConvexSetFinder(self.obs_sets, [None] * len(self.obs_sets), workspace_max, workspace_min)
 
-    def find_set_around_point(self, p, fixed_mid, optimize):
-        return self.set_finder.find_set_around_point(p, fixed_mid=fixed_mid, optimize=optimize)
-
-    def find_set_collision_avoidance(self, p0, p1, compute_ellipsoid):
-        return self.set_finder.find_set_collision_avoidance(p0, p1, compute_ellipsoid)
-
-    def reduce_ineqs(self, a_set, b_set):
-        from .utils import reduce_ineqs
-
-        return reduce_ineqs(a_set, b_set)
-
-    def set_intersection(self, set1, set2, tol):
-        from .set_graph import set_intersection
-
-        return set_intersection(set1, set2, tol)
-
-    def _one_set(self, a_set, b_set):
+    def execute(self, req):
         import torch
 
-        A, b, m = self._pack([[a_set, b_set]])
-        return torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(), torch.as_tensor(m).cuda()
+        from .set_graph import set_intersection
+        from .utils import reduce_ineqs
 
-    def check_intersection(self, a_set, b_set, l_ee, sample, omega_normed, omega_norm):
-        A, b, m = self._one_set(a_set, b_set)
-        fits, omega = self._geo.check_fit(A, b, m, np.array([[0, 0]], np.int32), l_ee, omega_normed, omega_norm,
-                                          x0=np.asarray(sample, float)[None])
-        ok = bool(fits.item())
-        return ok, np.concatenate((sample, [float(omega.item()) if ok else 0.0]))
+        kind = req[0]
+        if kind == "set_point":
+            A, b, Q, p = self.set_finder.find_set_around_point(req[1], fixed_mid=req[2], optimize=req[3])
+            Ar, br = reduce_ineqs(A, b)
+            return A, b, Q, p, Ar, br
+        if kind == "set_line":
+            A, b, Q, p, coll = self.set_finder.find_set_collision_avoidance(req[1], req[2], True)
+            Ar, br = reduce_ineqs(A, b)
+            return A, b, Q, p, coll, Ar, br
+        if kind == "intersect_many":
+            out = []
+            for setc in req[1]:
+                x, _, ok = set_intersection(setc, req[2], req[3])
+                out.append((x, ok))
+            return out
+        if kind == "fit_many":
+            l_ee, omega_normed, omega_norm = req[2]
+            out = []
+            for a_set, b_set, sample in req[1]:
+                A, b, m = self._pack([[a_set, b_set]])
+                fits, omega = self._geo.check_fit(torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(),
+                                                  torch.as_tensor(m).cuda(), np.array([[0, 0]], np.int32), l_ee,
+                                                  omega_normed, omega_norm, x0=np.asarray(sample, float)[None])
+                ok = bool(fits.item())
+                out.append((ok, np.concatenate((sample, [float(omega.item()) if ok else 0.0]))))
+            return out
+        if kind == "project":
+            A, b, m = self._pack([[req[1], req[2]]])
+            x, _ = self._geo.project_points(torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(),
+                                            torch.as_tensor(m).cuda(), np.array([[0, 0]], np.int32),
+                                            np.asarray(req[3], float)[None])
+            return x[0].cpu().numpy()
+        raise ValueError(f"unknown request {kind}")
 
-    def project(self, a_set, b_set, x_d, x0=None):
-        A, b, m = self._one_set(a_set, b_set)
-        x, _ = self._geo.project_points(A, b, m, np.array([[0, 0]], np.int32), np.asarray(x_d, float)[None])
-        return x[0].cpu().numpy()
+
+def obstacle_sets(obstacles, obs_size_increase):
+    """add_obstacle_reps (:131-152): inflated boxes as [A (15x3), b (15)] padded like normalize_set_size."""
+    boxes = np.asarray(obstacles, float).reshape(-1, 6)
+    box = np.concatenate((np.eye(3), -np.eye(3)))
+    out = []
+    for ob in boxes:
+        a = np.zeros((15, 3))
+        b = 10.0 * np.ones(15)
+        a[:6] = box
+        b[:6] = np.concatenate((ob[3:], -ob[:3])) + obs_size_increase
+        out.append([a, b])
+    return out
 
 
 class SetSequencePlanner:
     def __init__(self, obstacles=(), obs_size_increase=0.08, workspace_max=(1.0, 1.0, 1.2),
-                 workspace_min=(-1.0, -1.0, 0.0), backend=None, rng=None):
+                 workspace_min=(-1.0, -1.0, 0.0), backend=None, rng=None, obs_sets=None):
         self.obs_size_increase = obs_size_increase
         self.workspace_max = list(workspace_max)
         self.workspace_min = list(workspace_min)
@@ -98,59 +138,76 @@ class SetSequencePlanner:
         self.nr_free_mid = 5
         self.max_samples = 500
         self.rng = rng if rng is not None else np.random.default_rng()      # unseeded in the reference (quirk Q4)
-        self.backend = backend if backend is not None else GpuBackend(obstacles, obs_size_increase, workspace_max,
-                                                                      workspace_min)
-        self.obs_sets = self.backend.obs_sets
-        self.verbose = False
+        self.backend = backend
+        if obs_sets is not None:
+            self.obs_sets = obs_sets
+        elif backend is not None and hasattr(backend, "obs_sets"):
+            self.obs_sets = backend.obs_sets
+        else:
+            self.obs_sets = obstacle_sets(obstacles, obs_size_increase)
+        self._obstacles = obstacles
+        # inflated box bounds for the vectorised form of the "sample in collision" test (:467-471): for a box
+        # row (+-e_k) the reference's A x - b is exactly x_k - ub_k / lb_k - x_k, padded rows give -10
+        ob_b = np.array([ob[1][:6] for ob in self.obs_sets]).reshape(-1, 6)
+        self._ub, self._lb = ob_b[:, :3], -ob_b[:, 3:]
+
+    def _in_collision(self, sample):
+        if self._ub.shape[0] == 0:
+            return False
+        viol = np.maximum(sample - self._ub, self._lb - sample).max(axis=1)
+        return bool((viol < 1e-3).any())
 
     # ---- :789-896 -----------------------------------------------------------
-    def add_edges(self, id_new, graph, inter_graph, end, start):
+    def _add_edges(self, id_new, graph, inter_graph, end, start):
         connected = False
         set_new = graph.nodes[id_new]["cset"]
-        for vertex in list(graph.nodes.items()):
-            if vertex[0] != id_new:
-                setc = vertex[1]["cset"]
-                idc = vertex[0]
-                p_intersect, set_inter, intersects = self.backend.set_intersection(setc, set_new, 0.01)
-            else:
-                intersects = False
-            if not intersects:
-                continue
-            fits, via = self.backend.check_intersection(set_inter[0], set_inter[1], self.l_ee, p_intersect,
-                                                        self.omega_normed, self.omega_norm)
+        others = [(vid, vdata) for vid, vdata in graph.nodes.items() if vid != id_new]
+        if not others:
+            return connected
+        inter = yield ("intersect_many", [v["cset"] for _, v in others], set_new, 0.01)
+        hits = []
+        for (vid, vdata), (p_intersect, ok) in zip(others, inter):
+            if ok:
+                set_inter = [np.concatenate((vdata["cset"][0], set_new[0])), np.concatenate((vdata["cset"][1], set_new[1]))]
+                hits.append((vid, vdata, p_intersect, set_inter))
+        if not hits:
+            return connected
+        fit_res = yield ("fit_many", [(h[3][0], h[3][1], h[2]) for h in hits],
+                         (self.l_ee, self.omega_normed, self.omega_norm))
+        for (vid, vdata, p_intersect, set_inter), (fits, via) in zip(hits, fit_res):
             self.id_inter += 1
-            inter_graph.add_node(self.id_inter, cset=set_inter, id0=idc, id1=id_new, conn_to_start=False,
+            inter_graph.add_node(self.id_inter, cset=set_inter, id0=vid, id1=id_new, conn_to_start=False,
                                  conn_to_end=False, p_proj=None, p_via=via, fits=fits)
             self.nr_inter_set += 2
-            for edge in list(inter_graph.nodes.items()):
-                v0, v1 = edge[1]["id0"], edge[1]["id1"]
-                cond1 = v0 == vertex[0] or v1 == vertex[0]
+            me = inter_graph.nodes[self.id_inter]
+            for eid, edata in list(inter_graph.nodes.items()):
+                v0, v1 = edata["id0"], edata["id1"]
+                cond1 = v0 == vid or v1 == vid
                 cond2 = v0 == id_new or v1 == id_new
                 if cond1:
-                    size = vertex[1]["size"]
+                    size = vdata["size"]
                 elif cond2:
                     size = graph.nodes[id_new]["size"]
-                if self.id_inter != edge[0] and (cond1 or cond2):
+                if self.id_inter != eid and (cond1 or cond2):
                     self.nr_edges += 2
-                    p_proj = edge[1]["p_proj"]
+                    p_proj = edata["p_proj"]
                     if p_proj is None:
                         p_proj = end
-                    me = inter_graph.nodes[self.id_inter]
                     if me["p_proj"] is None:
-                        me["p_proj"] = self.backend.project(set_inter[0], set_inter[1], p_proj, p_intersect)
+                        me["p_proj"] = yield ("project", set_inter[0], set_inter[1], np.array(p_proj, float))
                     dist = np.linalg.norm(me["p_proj"] - p_proj)
-                    conn_to_start = me["conn_to_start"] or edge[1]["conn_to_start"]
-                    conn_to_end = me["conn_to_end"] or edge[1]["conn_to_end"]
+                    conn_to_start = me["conn_to_start"] or edata["conn_to_start"]
+                    conn_to_end = me["conn_to_end"] or edata["conn_to_end"]
                     me["conn_to_start"] = conn_to_start
                     me["conn_to_end"] = conn_to_end
-                    edge[1]["conn_to_start"] = conn_to_start
-                    edge[1]["conn_to_end"] = conn_to_end
+                    edata["conn_to_start"] = conn_to_start
+                    edata["conn_to_end"] = conn_to_end
                     connected = bool(conn_to_start and conn_to_end)          # last edge wins (quirk Q6)
                     c_size = np.tanh(0.25 - np.cbrt(size))
                     cost = dist * (1 + self.w_size * c_size) + self.w_bias
                     if not fits:
                         cost += self.c_fit
-                    inter_graph.add_edge(self.id_inter, edge[0], weight=cost)
+                    inter_graph.add_edge(self.id_inter, eid, weight=cost)
         return connected
 
     # ---- :586-743 (with_rot=False) ---------------------------------------------
@@ -190,8 +247,8 @@ class SetSequencePlanner:
         return np.array(p_via), p_via, sets_via, seq_via
 
     # ---- :174-534 -------------------------------------------------------------
-    def plan_set_sequence(self, start, end, r0, r1, first_sample=None):
-        """Returns dict(path, set_ids, sets_via, p_via, graph, inter_graph)."""
+    def plan_gen(self, start, end, r0, r1, first_sample=None):
+        """Generator form of the planner loop (see the module docstring for the request protocol)."""
         start = np.array(start, float)
         end = np.array(end, float)
         sampled_first = False
@@ -208,14 +265,13 @@ class SetSequencePlanner:
         graph, inter_graph = nx.Graph(), nx.Graph()
         self.nr_sets = self.nr_edges = self.nr_inter_set = 0
 
-        a_set, b_set, q_start, p_mid_start = self.backend.find_set_around_point(start, True, True)   # :278-283
+        a_set, b_set, q_start, p_mid_start, a_red, b_red = yield ("set_point", start, True, True)     # :278-283
         collision = False
         if np.max(a_set @ (start + self.l_ee) - b_set) > 1e-8:
-            a_set, b_set, q_start, p_mid_start, collision = self.backend.find_set_collision_avoidance(
-                start, start + self.l_ee, True)
+            a_set, b_set, q_start, p_mid_start, collision, a_red, b_red = yield ("set_line", start, start + self.l_ee)
         if collision:
             raise RuntimeError("start point in collision (the replanning fallbacks of :296-324 are not restated)")
-        a_set, b_set = self.backend.reduce_ineqs(a_set, b_set)
+        a_set, b_set = a_red, b_red                               # reduce_ineqs (:327)
         set_start = [a_set, b_set]
         self.id_inter = 0
         self.id_graph = 0
@@ -224,13 +280,11 @@ class SetSequencePlanner:
         inter_graph.add_node(0, cset=set_start, id0=0, id1=0, conn_to_start=True, conn_to_end=False, p_proj=start,
                              p_via=np.concatenate((start, [0.0])), fits=True)
         self.nr_sets += 1
-        connected = self.add_edges(0, graph, inter_graph, end, start)
+        connected = yield from self._add_edges(0, graph, inter_graph, end, start)
         if np.max(a_set @ end - b_set) < 1e-8 and np.max(a_set @ (end + self.l_ee_end) - b_set) < 1e-8:   # :361-375
             return dict(path=[0], set_ids=[0], sets_via=[set_start], p_via=np.array([start, end]), graph=graph,
                         inter_graph=inter_graph)
-        a_set, b_set, q_end, p_mid_end, collision = self.backend.find_set_collision_avoidance(
-            end, end + self.l_ee_end, True)                                                     # :381-389
-        a_set, b_set = self.backend.reduce_ineqs(a_set, b_set)
+        _, _, q_end, p_mid_end, collision, a_set, b_set = yield ("set_line", end, end + self.l_ee_end)  # :381-390
         set_end = [a_set, b_set]
         self.id_graph += 1
         self.id_inter += 1
@@ -239,7 +293,7 @@ class SetSequencePlanner:
         inter_graph.add_node(1, cset=set_end, id0=1, id1=1, conn_to_start=False, conn_to_end=True, p_proj=end,
                              p_via=np.concatenate((end, [1.0])), fits=True)
         self.nr_sets += 1
-        conn = self.add_edges(1, graph, inter_graph, end, start)
+        conn = yield from self._add_edges(1, graph, inter_graph, end, start)
         connected = conn or connected
 
         j = 0
@@ -247,7 +301,6 @@ class SetSequencePlanner:
         p_via_old = None
         path = None
         while True:                                               # :430-534
-            via_sample = False
             if connected:
                 path = nx.shortest_path(inter_graph, 0, 1, weight="weight")
                 p_via, p_via_list, sets_via, seq_via = self.compute_via_points(path, start, end, graph, inter_graph)
@@ -255,7 +308,6 @@ class SetSequencePlanner:
                         np.linalg.norm(p_via_old - p_via) < 1e-4:
                     break                                         # "Found path solution"
                 samples = p_via_list[1:-1]
-                via_sample = True
                 p_via_old = np.copy(p_via)
             elif not sampled_first and first_sample is not None:
                 samples = [first_sample]
@@ -266,10 +318,7 @@ class SetSequencePlanner:
                     in_collision = in_safe = False
                     sample = self.rng.uniform(self.workspace_min, self.workspace_max, 3)
                     nr_sampled += 1
-                    for ob in self.obs_sets:
-                        if np.max(ob[0] @ sample - ob[1]) < 1e-3:
-                            in_collision = True
-                            break
+                    in_collision = self._in_collision(sample)        # any obstacle with max(A x - b) < 1e-3
                     for setc in graph.nodes.items():
                         if np.max(setc[1]["a_set"] @ sample - setc[1]["b_set"]) < 1e-3:
                             in_safe = True
@@ -284,9 +333,7 @@ class SetSequencePlanner:
                 j += 1
                 optimize = not (nr_samples >= self.nr_optimized)
                 # fixed_mid = (via_sample or (not sampled_first),) is a 1-tuple: always truthy (quirk Q3)
-                a_set, b_set, q_ellipse, p_mid = self.backend.find_set_around_point(np.asarray(sample, float), True,
-                                                                                    optimize)
-                a_set, b_set = self.backend.reduce_ineqs(a_set, b_set)
+                _, _, q_ellipse, p_mid, a_set, b_set = yield ("set_point", np.asarray(sample, float), True, optimize)
                 sampled_first = True
                 dvertex = np.inf
                 for vertex in graph.nodes.items():
@@ -297,7 +344,196 @@ class SetSequencePlanner:
                     graph.add_node(self.id_graph, cset=[a_set, b_set], size=1 / np.linalg.det(q_ellipse),
                                    q_ellipse=q_ellipse, p_mid=p_mid, a_set=np.array(a_set), b_set=np.array(b_set))
                     self.nr_sets += 1
-                    conn = self.add_edges(self.id_graph, graph, inter_graph, end, start)
+                    conn = yield from self._add_edges(self.id_graph, graph, inter_graph, end, start)
                     connected = conn or connected
         self.graph, self.inter_graph = graph, inter_graph
         return dict(path=path, set_ids=seq_via, sets_via=sets_via, p_via=p_via, graph=graph, inter_graph=inter_graph)
+
+    def plan_set_sequence(self, start, end, r0, r1, first_sample=None):
+        """Sequential driver: every request is answered at once by ``self.backend.execute``.
+        Returns dict(path, set_ids, sets_via, p_via, graph, inter_graph)."""
+        if self.backend is None:
+            self.backend = GpuBackend(self._obstacles, self.obs_size_increase, self.workspace_max, self.workspace_min)
+        gen = self.plan_gen(start, end, r0, r1, first_sample)
+        try:
+            req = next(gen)
+            while True:
+                try:
+                    res = self.backend.execute(req)
+                except (RuntimeError, ValueError) as e:
+                    req = gen.throw(e)
+                    continue
+                req = gen.send(res)
+        except StopIteration as stop:
+            return stop.value
+
+
+# ---------------------------------------------------------------------------------------------
+# Batched driver (BASELINE config C3): many independent queries, one scene each, in lock step
+# ---------------------------------------------------------------------------------------------
+class BatchedGpuExecutor:
+    """Answers the pending requests of many queries with one batched kernel call per primitive."""
+
+    def __init__(self, obstacles_list, obs_size_increase, workspace_max, workspace_min):
+        from . import geometry as geo
+
+        self.geo = geo
+        self.scene = geo.SceneBatch(obstacles_list, obs_size_increase)
+        self.ws_min = np.asarray(workspace_min, float)
+        self.ws_max = np.asarray(workspace_max, float)
+        self.calls = 0
+
+    # -- helpers ----------------------------------------------------------------
+    def _reduced(self, batch):
+        import torch
+
+        Ar, br, mr, _, _ = self.geo.reduce_ineqs(batch.A, batch.b, batch.m)
+        host = [t.cpu().numpy() for t in (batch.A, batch.b, batch.m, batch.q_ellipse, batch.p_mid, batch.status, Ar, br, mr)]
+        torch.cuda.current_stream().synchronize()
+        return host
+
+    def _pack(self, sets):
+        import torch
+
+        m_max = max(max(s[0].shape[0] for s in sets), 1)
+        A = np.zeros((len(sets), m_max, 3))
+        b = np.full((len(sets), m_max), 10.0)
+        m = np.zeros(len(sets), np.int32)
+        for k, s in enumerate(sets):
+            n = s[0].shape[0]
+            A[k, :n], b[k, :n], m[k] = s[0], s[1], n
+        return torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(), torch.as_tensor(m).cuda()
+
+    # -- one round ----------------------------------------------------------------
+    def execute(self, pending):
+        """pending: {qid: request}.  Returns {qid: result | Exception}."""
+        geo = self.geo
+        out = {}
+        by_kind = {}
+        for qid, req in pending.items():
+            by_kind.setdefault(req[0], []).append(qid)
+
+        for (fixed_mid, optimize) in ((True, True), (True, False), (False, True), (False, False)):
+            qids = [q for q in by_kind.get("set_point", []) if (pending[q][2], pending[q][3]) == (fixed_mid, optimize)]
+            if not qids:
+                continue
+            self.calls += 1
+            seeds = np.array([pending[q][1] for q in qids])
+            batch = geo.build_sets_point(self.scene, seeds, self.ws_min, self.ws_max, fixed_mid=fixed_mid,
+                                         optimize=optimize, row_cap=REFERENCE_MAX_ROWS,
+                                         item_scene=np.asarray(qids, np.int32))
+            peak = batch.rows_peak.cpu().numpy()
+            A, b, m, Q, P, st, Ar, br, mr = self._reduced(batch)
+            for k, q in enumerate(qids):
+                err = _set_errors(int(st[k]), int(peak[k]) if optimize else None)
+                out[q] = err if err is not None else (A[k, : m[k]].copy(), b[k, : m[k]].copy(), Q[k].copy(), P[k].copy(),
+                                                      Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy())
+
+        qids = by_kind.get("set_line", [])
+        if qids:
+            self.calls += 1
+            p0 = np.array([pending[q][1] for q in qids])
+            p1 = np.array([pending[q][2] for q in qids])
+            batch = geo.build_sets_line(self.scene, p0, p1, self.ws_min, self.ws_max, compute_ellipsoid=True,
+                                        item_scene=np.asarray(qids, np.int32))
+            coll = batch.collision.cpu().numpy()
+            A, b, m, Q, P, st, Ar, br, mr = self._reduced(batch)
+            for k, q in enumerate(qids):
+                err = _set_errors(int(st[k]), int(m[k]))
+                out[q] = err if err is not None else (A[k, : m[k]].copy(), b[k, : m[k]].copy(), Q[k].copy(), P[k].copy(),
+                                                      bool(coll[k]), Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy())
+
+        qids = by_kind.get("intersect_many", [])
+        if qids:
+            self.calls += 1
+            sets, pairs, spans = [], [], []
+            tol = pending[qids[0]][3]
+            for q in qids:
+                _, others, set_new, _ = pending[q]
+                base = len(sets)
+                sets.append(set_new)
+                sets.extend(others)
+                pairs.extend((base + 1 + k, base) for k in range(len(others)))      # rows of the old set first
+                spans.append(len(others))
+            A, b, m = self._pack(sets)
+            ok, x = geo.pairs_feasible_list(A, b, m, np.asarray(pairs, np.int32), tol)
+            ok, x = ok.cpu().numpy(), x.cpu().numpy()
+            o = 0
+            for q, n in zip(qids, spans):
+                out[q] = [(x[o + k].copy() if ok[o + k] else None, bool(ok[o + k])) for k in range(n)]
+                o += n
+
+        qids = by_kind.get("fit_many", [])
+        if qids:
+            groups = {}
+            for q in qids:
+                l_ee, om, on = pending[q][2]
+                groups.setdefault((tuple(np.round(l_ee, 15)), tuple(np.round(om, 15)), round(float(on), 15)), []).append(q)
+            for gq in groups.values():
+                self.calls += 1
+                l_ee, om, on = pending[gq[0]][2]
+                sets, x0, spans = [], [], []
+                for q in gq:
+                    items = pending[q][1]
+                    sets.extend([[a, b_] for a, b_, _ in items])
+                    x0.extend(s for _, _, s in items)
+                    spans.append(len(items))
+                A, b, m = self._pack(sets)
+                idx = np.arange(len(sets), dtype=np.int32)
+                fits, omega = geo.check_fit(A, b, m, np.stack((idx, idx), axis=1), l_ee, om, on, x0=np.array(x0))
+                fits, omega = fits.cpu().numpy(), omega.cpu().numpy()
+                o = 0
+                for q, n in zip(gq, spans):
+                    items = pending[q][1]
+                    out[q] = [(bool(fits[o + k]), np.concatenate((items[k][2], [omega[o + k] if fits[o + k] else 0.0])))
+                              for k in range(n)]
+                    o += n
+
+        qids = by_kind.get("project", [])
+        if qids:
+            self.calls += 1
+            A, b, m = self._pack([[pending[q][1], pending[q][2]] for q in qids])
+            idx = np.arange(len(qids), dtype=np.int32)
+            x, _ = geo.project_points(A, b, m, np.stack((idx, idx), axis=1), np.array([pending[q][3] for q in qids]))
+            x = x.cpu().numpy()
+            for k, q in enumerate(qids):
+                out[q] = x[k].copy()
+        return out
+
+
+def plan_batch(queries, obs_size_increase=0.01, workspace_max=(1.0, 1.0, 1.2), workspace_min=(-1.0, -1.0, 0.0),
+               rng_seeds=None, executor=None):
+    """Plan many independent queries in lock step.
+
+    queries: list of dicts(obstacles [N,6], start, end, r0, r1[, first_sample]).
+    Returns (results, stats): results[i] is the planner's dict or the exception the sequential planner
+    would have raised for that query."""
+    if executor is None:
+        executor = BatchedGpuExecutor([q["obstacles"] for q in queries], obs_size_increase, workspace_max,
+                                      workspace_min)
+    planners, gens, pending, results = [], {}, {}, [None] * len(queries)
+    for i, q in enumerate(queries):
+        pl = SetSequencePlanner(q["obstacles"], obs_size_increase, workspace_max, workspace_min,
+                                rng=np.random.default_rng(rng_seeds[i] if rng_seeds is not None else None))
+        planners.append(pl)
+        gens[i] = pl.plan_gen(q["start"], q["end"], q["r0"], q["r1"], q.get("first_sample"))
+        try:
+            pending[i] = next(gens[i])
+        except StopIteration as stop:
+            results[i] = stop.value
+        except (RuntimeError, ValueError) as e:
+            results[i] = e
+    rounds = 0
+    while pending:
+        rounds += 1
+        answers = executor.execute(pending)
+        nxt = {}
+        for i, ans in answers.items():
+            try:
+                nxt[i] = gens[i].throw(ans) if isinstance(ans, Exception) else gens[i].send(ans)
+            except StopIteration as stop:
+                results[i] = stop.value
+            except (RuntimeError, ValueError) as e:
+                results[i] = e
+        pending = nxt
+    return results, {"rounds": rounds, "kernel_batches": executor.calls}

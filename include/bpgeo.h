@@ -46,6 +46,11 @@ const char* bp_last_error_string(void);
  * box k = [lbx,lby,lbz,ubx,uby,ubz]; the library stores lb - inflate, ub + inflate
  * (b += obs_size_increase, :141) as SoA columns in HBM.  boxes_host: [n,6]. */
 int bp_scene_create(const double* boxes_host, int n, double inflate, bp_scene** out);
+/* A batch of scenes stored back to back (one per planning query, BASELINE config C3): scene k owns boxes
+ * [offsets[k], offsets[k+1]) of boxes_host.  Use with the *_ms entry points, which take the scene index of
+ * every seed / segment. */
+int bp_scene_create_batch(const double* boxes_host, const int* offsets_host /*[n_scenes+1]*/, int n_scenes,
+                          double inflate, bp_scene** out);
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream);
 int bp_scene_destroy(bp_scene* scene);
 int bp_scene_size(const bp_scene* scene);
@@ -96,6 +101,13 @@ int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, c
                                        reference's 20-row MVIE buffers do (ValueError, quirk Q5) */,
                         void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Same over a scene batch: seed_scene_dev[S] (int32) = scene index of every seed. */
+int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, const double* seeds_dev, int S,
+                           const double* ws_min_host, const double* ws_max_host, int fixed_mid, int optimize,
+                           int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                           double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Replaces ConvexSetFinder.find_set_collision_avoidance (:309-375) for S segments.
  * limit_space selects init_halfspaces_point(p0, e_max) (:400-421).  collision[S]
  * is the reference's `collision` flag (:336-345).  q_ellipse / p_mid are written
@@ -105,6 +117,12 @@ int bp_build_sets_line(const bp_scene* scene, const double* p0_dev, const double
                        int compute_ellipsoid, int m_max, double* A_dev, double* b_dev, int* m_dev,
                        double* q_ellipse_dev, double* p_mid_dev, int* collision_dev, int* status_dev,
                        void* workspace_dev, size_t workspace_bytes, void* stream);
+
+int bp_build_sets_line_ms(const bp_scene* scene, const int* seg_scene_dev, const double* p0_dev, const double* p1_dev,
+                          int S, const double* ws_min_host, const double* ws_max_host, int limit_space, double e_max,
+                          int compute_ellipsoid, int m_max, double* A_dev, double* b_dev, int* m_dev,
+                          double* q_ellipse_dev, double* p_mid_dev, int* collision_dev, int* status_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- K6: pairwise set-intersection test -----------------------------------------
  * Replaces BoundPlanner.set_intersection (BoundPlanner.py:774-787) as called by
@@ -124,6 +142,12 @@ int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*
                                            (the reference's sol_lin.x, BoundPlanner.py:785) */,
                      const double* aabb_in_dev /* NULL or [S,6] from bp_set_aabb */,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* The same test over an explicit list of pairs (i, j) (pairs_dev [P,2] int32): result[P] = 1/0,
+ * x_feas[P,3] (or NULL).  Workspace: 6*S doubles. */
+int bp_pairs_feasible_list(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                           const int* pairs_dev, int P, int* result_dev, double* x_feas_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream);
 
 /* ---- K8 (next row 1): redundancy removal ---------------------------------------------
  * Replaces reduce_ineqs (bound_planner/utils/util_functions.py:82-88, cddlib

@@ -100,3 +100,30 @@ def test_c3_queries_gpu_matches_oracle_sequence():
         assert got["path"] == want["path"] and got["set_ids"] == want["set_ids"], f"query {i}"
         assert np.abs(got["p_via"] - want["p_via"]).max() < 1e-6
     assert n_ok >= 3
+
+
+@pytest.mark.gpu
+def test_batched_lockstep_planner_matches_sequential():
+    """plan_batch (all queries advance together, one batched kernel call per primitive and round, one
+    scene per query in a SceneBatch) == the sequential planner, query by query, incl. the error exits."""
+    from boundplanner_b200.planner import GpuBackend, plan_batch
+
+    ids = list(range(12))
+    queries = []
+    for i in ids:
+        obstacles, inflate, start, end, ws_min, ws_max = scenes.config_c3_query(i)
+        queries.append(dict(obstacles=obstacles, start=start, end=end, r0=R0, r1=R0))
+    results, stats = plan_batch(queries, 0.01, list(ws_max), list(ws_min), rng_seeds=ids)
+    assert stats["rounds"] > 10 and stats["kernel_batches"] < 40 * stats["rounds"]
+    n_ok = 0
+    for i, res in zip(ids, results):
+        want = _plan_c3(GpuBackend, i)
+        if "error" in want:
+            assert isinstance(res, Exception), f"query {i}"
+            assert type(res).__name__ + ": " + str(res).split("(")[0] == want["error"], f"query {i}"
+            continue
+        n_ok += 1
+        assert not isinstance(res, Exception), f"query {i}: {res}"
+        assert res["path"] == want["path"] and res["set_ids"] == want["set_ids"], f"query {i}"
+        assert np.abs(res["p_via"] - want["p_via"]).max() < 1e-9
+    assert n_ok >= 3

@@ -54,3 +54,27 @@ class OracleBackend:
         from oracle.planner_graph import project_point
 
         return project_point(a_set, b_set, x_d)
+
+    def execute(self, req):
+        """Request protocol of boundplanner_b200/planner.py, answered by the oracle."""
+        kind = req[0]
+        if kind == "set_point":
+            A, b, Q, p = self.find_set_around_point(req[1], req[2], req[3])
+            Ar, br = self.reduce_ineqs(A, b)
+            return A, b, Q, p, Ar, br
+        if kind == "set_line":
+            A, b, Q, p, coll = self.find_set_collision_avoidance(req[1], req[2], True)
+            Ar, br = self.reduce_ineqs(A, b)
+            return A, b, Q, p, coll, Ar, br
+        if kind == "intersect_many":
+            out = []
+            for setc in req[1]:
+                x, _, ok = self.set_intersection(setc, req[2], req[3])
+                out.append((x, ok))
+            return out
+        if kind == "fit_many":
+            l_ee, omega_normed, omega_norm = req[2]
+            return [self.check_intersection(a, b, l_ee, s, omega_normed, omega_norm) for a, b, s in req[1]]
+        if kind == "project":
+            return self.project(req[1], req[2], req[3])
+        raise ValueError(kind)
