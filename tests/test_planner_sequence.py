@@ -127,3 +127,43 @@ def test_batched_lockstep_planner_matches_sequential():
         assert res["path"] == want["path"] and res["set_ids"] == want["set_ids"], f"query {i}"
         assert np.abs(res["p_via"] - want["p_via"]).max() < 1e-9
     assert n_ok >= 3
+
+
+class _OracleLockstepExecutor:
+    """CPU stand-in for planner.BatchedGpuExecutor: answers every pending request with the oracle."""
+
+    def __init__(self, queries, inflate, ws_max, ws_min):
+        self.backends = [OracleBackend(q["obstacles"], inflate, ws_max, ws_min) for q in queries]
+        self.calls = 0
+
+    def execute(self, pending):
+        out = {}
+        self.calls += 1
+        for qid, req in pending.items():
+            try:
+                out[qid] = self.backends[qid].execute(req)
+            except (RuntimeError, ValueError) as e:
+                out[qid] = e
+        return out
+
+
+def test_lockstep_driver_equals_sequential_driver_on_cpu():
+    """The lock-step driver (plan_batch) is pure host logic: with the oracle answering the requests it
+    must reproduce the sequential driver query by query (mixed scenes, early finishers, error exits)."""
+    from boundplanner_b200.planner import plan_batch
+
+    ids = [0, 5, 7]
+    queries = []
+    for i in ids:
+        obstacles, inflate, start, end, ws_min, ws_max = scenes.config_c3_query(i)
+        queries.append(dict(obstacles=obstacles, start=start, end=end, r0=R0, r1=R0))
+    ex = _OracleLockstepExecutor(queries, 0.01, list(ws_max), list(ws_min))
+    results, stats = plan_batch(queries, 0.01, list(ws_max), list(ws_min), rng_seeds=ids, executor=ex)
+    assert stats["rounds"] == ex.calls and stats["rounds"] > 5
+    for i, res in zip(ids, results):
+        want = _plan_c3(OracleBackend, i)
+        if "error" in want:
+            assert isinstance(res, Exception) and type(res).__name__ + ": " + str(res).split("(")[0] == want["error"]
+        else:
+            assert res["path"] == want["path"] and res["set_ids"] == want["set_ids"]
+            assert np.array_equal(res["p_via"], want["p_via"])
