@@ -1374,7 +1374,18 @@ static bool use_fused_iris(int n) {
 static int poly_threads(int n) { return n <= 256 ? 128 : (n <= 4096 ? 256 : 512); }
 
 static int set_dyn_smem(const void* fn, size_t bytes) {
-  if (bytes > 227 * 1024) return bp_fail("scene too large for the shared-memory distance table (N > 29056)");
+  // the opt-in limit (227 KB on sm_100a) covers the kernel's static shared memory as well
+  cudaFuncAttributes fa;
+  BP_CUDA(cudaFuncGetAttributes(&fa, fn));
+  int dev = 0, optin = 0;
+  BP_CUDA(cudaGetDevice(&dev));
+  BP_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (bytes + fa.sharedSizeBytes > (size_t)optin) {
+    snprintf(g_err, sizeof(g_err),
+             "scene too large for the shared-memory distance table (%zu B dynamic + %zu B static > %d B per CTA; "
+             "N <= %zu)", bytes, (size_t)fa.sharedSizeBytes, optin, ((size_t)optin - fa.sharedSizeBytes) / sizeof(double));
+    return 1;
+  }
   if (bytes > 48 * 1024) BP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }

@@ -148,3 +148,18 @@ def test_cuda_graph_pipeline_equals_eager(geo):
         assert np.array_equal(m.numpy(), out.m.cpu().numpy()) and np.array_equal(q.numpy(), out.q_ellipse.cpu().numpy())
         assert np.array_equal(status.numpy(), out.status.cpu().numpy())
         assert np.array_equal(bits.numpy(), ebits.cpu().numpy())
+
+
+def test_maximum_scene_size_and_loud_failure(geo):
+    """The distance table lives in shared memory: N up to 28960 works (227 KB opt-in minus 768 B static), larger scenes fail loudly."""
+    from boundplanner_b200 import _lib, scenes
+
+    rng = np.random.default_rng(4)
+    boxes = scenes.random_box_scene(28900, rng, 0.004, 0.012)
+    seeds = scenes.free_points(4, boxes, 0.0, rng)
+    sc = geo.Scene(boxes, 0.0)
+    out = geo.build_sets_point(sc, seeds, scenes.WORKSPACE_MIN, scenes.WORKSPACE_MAX, fixed_mid=True, optimize=False)
+    assert (out.status.cpu().numpy() == 0).all() and (out.m.cpu().numpy() > 6).all()
+    too_big = geo.Scene(scenes.random_box_scene(30000, rng, 0.004, 0.012), 0.0)
+    with pytest.raises(_lib.BpGeoError, match="too large"):
+        geo.build_sets_point(too_big, seeds, scenes.WORKSPACE_MIN, scenes.WORKSPACE_MAX)
