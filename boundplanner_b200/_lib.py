@@ -39,6 +39,9 @@ SIGNATURES = {
     "bp_closest_points_line": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "bp_polyhedron": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "bp_mvie": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bp_mvie_fixed_r": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bp_build_sets_around_line": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _i, _vp]),
     "bp_build_sets_workspace_bytes": (_sz, [_i]),
     "bp_build_sets_point": (_i, [_vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _i, _vp, _sz, _vp]),

@@ -188,9 +188,21 @@ class ConvexSetFinder:
         q_new, _ = self._mvie(a_set, b_set, p_mid, False)
         return q_new, p_mid
 
+    # ---- :564-588 ---------------------------------------------------------
     def mvie_socp_fixed_r(self, a_set, b_set, p_mid, r_ellipse, a_lb):
-        raise NotImplementedError("mvie_socp_fixed_r is only reached from find_set_around_line, which the "
-                                  "reference never calls (BoundPlanner.py:378-380 is commented out)")
+        a_set = np.asarray(a_set, float)
+        b_set = np.asarray(b_set, float)
+        m = a_set.shape[0]
+        self._raise_for_status(STATUS_OK, m)
+        if m > BP_MAX_ROWS:
+            raise ValueError(f"convex set needs more than {BP_MAX_ROWS} rows")
+        A = np.zeros((1, BP_MAX_ROWS, 3))
+        b = np.full((1, BP_MAX_ROWS), 10.0)
+        A[0, :m], b[0, :m] = a_set, b_set
+        q_new, q_ell, eigs, status, _ = geo.mvie_fixed_r(A, b, np.array([m], np.int32), np.asarray(p_mid, float)[None],
+                                                         np.asarray(r_ellipse, float)[None], np.array([float(a_lb)]))
+        self._raise_for_status(int(status.item()))
+        return q_new[0].cpu().numpy(), q_ell[0].cpu().numpy(), eigs[0].cpu().numpy()
 
     # ---- :190-240 ---------------------------------------------------------
     def find_set_around_point(self, p_seed, fixed_mid=False, optimize=True):
@@ -213,9 +225,27 @@ class ConvexSetFinder:
         self.ell_time += time.perf_counter() - start      # projections and MVIE are fused on the device
         return out
 
+    # ---- :242-307 (the reference planner's call is commented out, BoundPlanner.py:378-380) ----
     def find_set_around_line(self, p0, dp1, optimize=True):
-        raise NotImplementedError("find_set_around_line is not called by the reference planner "
-                                  "(BoundPlanner.py:378-380 is commented out)")
+        out = self.find_sets_around_lines(np.asarray(p0, float)[None], np.asarray(dp1, float)[None], optimize=optimize)
+        status = int(out.status.item())
+        m = int(out.m.item())
+        self._raise_for_status(status, int(out.rows_peak.item()))
+        A, b = out.A[0, :m].cpu().numpy(), out.b[0, :m].cpu().numpy()
+        # the reference returns the Python lists of compute_polyhedron here (:307)
+        return ([A[i].copy() for i in range(m)], [float(b[i]) for i in range(m)], out.q_ellipse[0].cpu().numpy(),
+                out.p_mid[0].cpu().numpy())
+
+    def find_sets_around_lines(self, p0, dp1, optimize=True, m_max=BP_MAX_ROWS):
+        """Batched form: S segments -> geometry.SetBatch (device tensors)."""
+        start = time.perf_counter()
+        ws_min, ws_max = self._ws()
+        out = geo.build_sets_around_line(self._scene, p0, dp1, ws_min, ws_max, optimize=bool(optimize),
+                                         max_iter=self.max_iter, m_max=m_max,
+                                         row_cap=self.REFERENCE_MAX_ROWS if self.strict_rows else 0)
+        torch.cuda.current_stream().synchronize()
+        self.ell_time += time.perf_counter() - start
+        return out
 
     # ---- :309-375 ---------------------------------------------------------
     def find_set_collision_avoidance(self, p0, p1, compute_ellipsoid=False, limit_space=False, e_max=0.3):

@@ -24,6 +24,7 @@
 #include "bp_math.cuh"
 #include "bp_mvie.cuh"
 #include "bp_mvie_warp.cuh"
+#include "bp_mvie_fixed_r.cuh"
 #include "bp_lp.cuh"
 #include "bp_lp_warp.cuh"
 #include "bp_fk.cuh"
@@ -395,7 +396,8 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams
 // Used for scenes whose distance table leaves room for two CTAs per SM (N <= 4096).
 // ---------------------------------------------------------------------------
 struct FusedParams {
-  const double* seeds;
+  const double* seeds;       // [S,3] seeds (MODE 0) / segment starts p0 (MODE 1)
+  const double* dp1;         // [S,3] segment vectors (MODE 1)
   double ws_rows[6];
   double* A;
   double* b;
@@ -408,6 +410,24 @@ struct FusedParams {
   int m_max, max_iter, fixed_mid, optimize, row_cap, cache_y;
 };
 
+struct GlobalRows {
+  const double* A;
+  const double* B;
+  __device__ __forceinline__ double a(int i, int k) const { return __ldg(A + 3 * i + k); }
+  __device__ __forceinline__ double b(int i) const { return __ldg(B + i); }
+};
+
+struct SharedRows {
+  const double* A;
+  const double* B;
+  __device__ __forceinline__ double a(int i, int k) const { return A[3 * i + k]; }
+  __device__ __forceinline__ double b(int i) const { return B[i]; }
+};
+
+// MODE 0: find_set_around_point (:190-240).  MODE 1: find_set_around_line (:242-307) -- the same loop around
+// the midpoint of the segment p0 .. p0 + dp1 with the fixed-rotation MVIE (mvie_socp_fixed_r); no trailing MVIE,
+// and with optimize == 0 one free-centre MVIE after the first pass (:278-282).
+template <int MODE>
 __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
@@ -420,6 +440,19 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
   const int s = blockIdx.x, tid = threadIdx.x;
   double Q[9] = {1e4, 0, 0, 0, 1e4, 0, 0, 0, 1e4};          // q_ellipse = diag(1/1e-4) (:192-194)
   double p[3] = {pr.seeds[3 * (size_t)s], pr.seeds[3 * (size_t)s + 1], pr.seeds[3 * (size_t)s + 2]};
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double a_lb = 0.0;
+  if (MODE == 1) {                                            // :243-261
+    const double dp1[3] = {pr.dp1[3 * (size_t)s], pr.dp1[3 * (size_t)s + 1], pr.dp1[3 * (size_t)s + 2]};
+    const double p1[3] = {p[0] + dp1[0], p[1] + dp1[1], p[2] + dp1[2]};
+    double l_seg;
+    bp_line_frame(dp1, R, &l_seg);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) p[q] = (p[q] + p1[q]) / 2;
+    a_lb = l_seg * l_seg / 4;
+    const double y0[3] = {a_lb, 1e-4, 1e-4};
+    bp_shape_from_axes_sq(R, y0, nullptr, Q, nullptr);
+  }
   double det = 100.0, det_old = 1.0;                          // :200-201
   int k = 0, status = BP_OK, rows_peak = 0, m_cur = 6;
   if (tid < 6) {                                              // init_halfspaces (:377-398)
@@ -440,9 +473,52 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
     rows_peak = m_cur > rows_peak ? m_cur : rows_peak;
     if (st == BP_OK && m_cur > pr.m_max) st = BP_ROW_OVERFLOW;
-    if (st == BP_OK && pr.optimize && pr.row_cap > 0 && m_cur > pr.row_cap) st = BP_ROW_CAP;
+    if (st == BP_OK && (MODE == 1 || pr.optimize) && pr.row_cap > 0 && m_cur > pr.row_cap) st = BP_ROW_CAP;
     if (st != BP_OK) { status = st; break; }
-    if (!pr.optimize) break;                                  // :214-215
+    if (MODE == 0 && !pr.optimize) break;                     // :214-215
+    if (MODE == 1) {
+      __syncthreads();                                        // thread 0 has written the picked rows
+      if (!pr.optimize) {                                     // :278-282: one free-centre MVIE, then out
+        if (tid < 32) {
+          double L[6], d[3];
+          const int ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
+          if (tid == 0) {
+            double E[9], Qn[9], dq;
+            bp_shape_from_L(L, E, Qn, &dq);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) c_Q[q] = Qn[q];
+            c_p[0] = d[0]; c_p[1] = d[1]; c_p[2] = d[2];
+            c_status = ms;
+          }
+        }
+      } else {
+        det_old = det;                                        // :284
+        if (tid < 32) {
+          SharedRows rows{sA, sb};
+          BpWarpRed red;
+          double x[3];
+          const int ms = bp_mvie_fixed_r(rows, m_cur, p, R, a_lb, red, x, nullptr);
+          if (tid == 0) {
+            double Qn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, dq = 0.0;
+            if (ms == BP_OK) bp_shape_from_axes(R, x, nullptr, Qn, &dq);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) c_Q[q] = Qn[q];
+            c_p[0] = p[0]; c_p[1] = p[1]; c_p[2] = p[2];
+            c_det = dq;                                       // :299
+            c_status = ms;
+            c_small = (ms == BP_OK && fmin(x[0], fmin(x[1], x[2])) < 1e-3) ? 1 : 0;   // :293-294
+          }
+        }
+      }
+      __syncthreads();
+      if (c_status != BP_OK) { status = c_status; break; }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Q[q] = c_Q[q];
+      p[0] = c_p[0]; p[1] = c_p[1]; p[2] = c_p[2];
+      if (!pr.optimize || c_small) break;                     // the small-axis exit leaves det alone (:293-299)
+      det = c_det;
+      continue;
+    }
     det_old = det;                                            // :217
     __syncthreads();                                          // thread 0 has written the picked rows
     if (tid < 32) {
@@ -468,7 +544,7 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     det = c_det;
     if (c_small) break;
   }
-  if (pr.optimize && pr.fixed_mid && status == BP_OK) {       // :235-238
+  if (MODE == 0 && pr.optimize && pr.fixed_mid && status == BP_OK) {       // :235-238
     __syncthreads();
     if (tid < 32) {
       double L[6], d[3];
@@ -708,6 +784,34 @@ __global__ void __launch_bounds__(32) k_mvie(MvieParams pr) {
   }
 }
 
+// K4b: one warp per set (mvie_socp_fixed_r, :564-588)
+__global__ void __launch_bounds__(32) k_mvie_fixed_r(const double* __restrict__ A, const double* __restrict__ b,
+                                                     const int* __restrict__ m, int m_max,
+                                                     const double* __restrict__ centre, const double* __restrict__ Rs,
+                                                     const double* __restrict__ a_lb, double* __restrict__ q_inv_out,
+                                                     double* __restrict__ q_ellipse_out, double* __restrict__ eigs_out,
+                                                     int* __restrict__ status_out, int* __restrict__ iters_out) {
+  const int s = blockIdx.x;
+  GlobalRows rows{A + (size_t)s * m_max * 3, b + (size_t)s * m_max};
+  BpWarpRed red;
+  double p[3], R[9], x[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = centre[3 * (size_t)s + k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = Rs[9 * (size_t)s + k];
+  int iters = 0;
+  const int st = bp_mvie_fixed_r(rows, m[s], p, R, a_lb[s], red, x, &iters);
+  if (threadIdx.x != 0) return;
+  double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (st == BP_OK) bp_shape_from_axes(R, x, E, Q, nullptr);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { q_inv_out[9 * (size_t)s + k] = E[k]; q_ellipse_out[9 * (size_t)s + k] = Q[k]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) eigs_out[3 * (size_t)s + k] = x[k];
+  status_out[s] = st;
+  if (iters_out) iters_out[s] = iters;
+}
+
 __global__ void k_state_init(SeedState* st, const double* __restrict__ seeds, int S) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
@@ -771,12 +875,6 @@ __global__ void k_state_init_line(SeedState* st, const double* __restrict__ p0, 
 // The filter only decides WHO runs the LP; every answer that is 1 comes from
 // the LP, every 0 from the LP or from a rigorous box separation.
 // ---------------------------------------------------------------------------
-struct GlobalRows {
-  const double* A;
-  const double* B;
-  __device__ __forceinline__ double a(int i, int k) const { return __ldg(A + 3 * i + k); }
-  __device__ __forceinline__ double b(int i) const { return __ldg(B + i); }
-};
 
 #define BP_AABB_EPS 1e-9
 #define BP_LP_T0_SCALE 8.0
@@ -1530,6 +1628,43 @@ int bp_mvie(const double* A_dev, const double* b_dev, const int* m_dev, int S, i
   return launch_mvie(pr, (cudaStream_t)stream);
 }
 
+int bp_mvie_fixed_r(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max,
+                    const double* centre_dev, const double* r_ellipse_dev, const double* a_lb_dev,
+                    double* q_inv_out_dev, double* q_ellipse_out_dev, double* eigs_out_dev, int* status_dev,
+                    int* newton_iters_dev, void* stream) {
+  if (S < 0 || m_max < 1 || m_max > BP_MAX_ROWS) return bp_fail("bp_mvie_fixed_r: bad arguments");
+  if (S == 0) return 0;
+  k_mvie_fixed_r<<<S, 32, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, centre_dev, r_ellipse_dev, a_lb_dev,
+                                                     q_inv_out_dev, q_ellipse_out_dev, eigs_out_dev, status_dev,
+                                                     newton_iters_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_build_sets_around_line(const bp_scene* scene, const double* p0_dev, const double* dp1_dev, int S,
+                              const double* ws_min_host, const double* ws_max_host, int optimize, int max_iter,
+                              int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                              double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                              void* stream) {
+  if (!scene || scene->seg_off || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || max_iter < 1 || !ws_min_host ||
+      !ws_max_host)
+    return bp_fail("bp_build_sets_around_line: bad arguments");
+  if (S == 0) return 0;
+  FusedParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.seeds = p0_dev; fp.dp1 = dp1_dev;
+  for (int i = 0; i < 3; ++i) { fp.ws_rows[2 * i] = ws_max_host[i]; fp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
+  fp.A = A_dev; fp.b = b_dev; fp.m = m_dev; fp.q_ellipse = q_ellipse_dev; fp.p_mid = p_mid_dev;
+  fp.status = status_dev; fp.iters = iters_dev; fp.rows_peak = rows_peak_dev;
+  fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = 0; fp.optimize = optimize;
+  fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
+  const size_t fsmem = poly_smem_bytes(scene->n);
+  if (set_dyn_smem((const void*)k_iris_fused<1>, fsmem)) return 1;
+  k_iris_fused<1><<<S, 128, fsmem, (cudaStream_t)stream>>>(view_of(scene), fp);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 size_t bp_build_sets_workspace_bytes(int S) { return sizeof(SeedState) * (size_t)(S > 0 ? S : 1); }
 
 int bp_build_sets_point(const bp_scene* scene, const double* seeds_dev, int S, const double* ws_min_host,
@@ -1564,8 +1699,8 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
     fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = fixed_mid; fp.optimize = optimize;
     fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
     const size_t fsmem = poly_smem_bytes(scene->n);
-    if (set_dyn_smem((const void*)k_iris_fused, fsmem)) return 1;
-    k_iris_fused<<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    if (set_dyn_smem((const void*)k_iris_fused<0>, fsmem)) return 1;
+    k_iris_fused<0><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     BP_CUDA(cudaGetLastError());
     return 0;
   }

@@ -172,6 +172,25 @@ def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=Tru
     return out
 
 
+def build_sets_around_line(scene, p0, dp1, ws_min, ws_max, optimize=True, max_iter=5, m_max=BP_MAX_ROWS, row_cap=0):
+    """ConvexSetFinder.find_set_around_line (ConvexSetFinder.py:242-307) for S segments p0 .. p0 + dp1."""
+    lib = _lib.load()
+    if getattr(scene, "n_scenes", 1) > 1:
+        raise ValueError("build_sets_around_line works on a single scene")
+    p0 = _dev(p0).reshape(-1, 3)
+    dp1 = _dev(dp1).reshape(-1, 3)
+    S = p0.shape[0]
+    out = alloc_set_batch(S, m_max)
+    amin, pmin = _host3(ws_min)      # host arrays must outlive the call
+    amax, pmax = _host3(ws_max)
+    check(lib.bp_build_sets_around_line(scene._h, _ptr(p0), _ptr(dp1), S, pmin, pmax, int(bool(optimize)),
+                                        int(max_iter), int(m_max), _ptr(out.A), _ptr(out.b), _ptr(out.m),
+                                        _ptr(out.q_ellipse), _ptr(out.p_mid), _ptr(out.status), _ptr(out.iters),
+                                        _ptr(out.rows_peak), int(row_cap), _stream()))
+    del amin, amax
+    return out
+
+
 def build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False, limit_space=False, e_max=0.3,
                     m_max=BP_MAX_ROWS, item_scene=None):
     """ConvexSetFinder.find_set_collision_avoidance (ConvexSetFinder.py:309-375) for S segments."""
@@ -255,6 +274,27 @@ def mvie(A, b, m, centre, free_centre):
     check(lib.bp_mvie(_ptr(A), _ptr(b), _ptr(m), S, m_max, int(bool(free_centre)), _ptr(centre), _ptr(q_inv),
                       _ptr(q_ell), _ptr(c_out), _ptr(status), _ptr(its), _stream()))
     return q_inv, q_ell, c_out, status, its
+
+
+def mvie_fixed_r(A, b, m, centre, r_ellipse, a_lb):
+    """mvie_socp_fixed_r (:564-588) for S sets.  Returns q_inv (= R diag(x^2) R^T), q_ellipse, eigs (= x), status,
+    newton_iters."""
+    lib = _lib.load()
+    A = _dev(A)
+    S, m_max = A.shape[0], A.shape[1]
+    b = _dev(b).reshape(S, m_max)
+    m = _dev(m, torch.int32).reshape(S)
+    centre = _dev(centre).reshape(S, 3)
+    r_ellipse = _dev(r_ellipse).reshape(S, 3, 3)
+    a_lb = _dev(a_lb).reshape(S)
+    q_inv = torch.empty((S, 3, 3), dtype=torch.float64, device="cuda")
+    q_ell = torch.empty((S, 3, 3), dtype=torch.float64, device="cuda")
+    eigs = torch.empty((S, 3), dtype=torch.float64, device="cuda")
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    its = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    check(lib.bp_mvie_fixed_r(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(centre), _ptr(r_ellipse), _ptr(a_lb),
+                              _ptr(q_inv), _ptr(q_ell), _ptr(eigs), _ptr(status), _ptr(its), _stream()))
+    return q_inv, q_ell, eigs, status, its
 
 
 def alloc_pair_buffers(S, rows=None):

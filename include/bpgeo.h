@@ -86,6 +86,15 @@ int bp_mvie(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*[S,m_max]
             double* q_ellipse_out_dev, double* centre_out_dev, int* status_dev, int* newton_iters_dev /*or NULL*/,
             void* stream);
 
+/* Replaces ConvexSetFinder.mvie_socp_fixed_r (:564-588): rotation r_ellipse_dev [S,3,3] (columns = axes) and
+ * centre fixed, first semi-axis >= a_lb_dev[S].  q_inv_out = R diag(x^2) R^T, q_ellipse_out = R diag(1/x^2) R^T,
+ * eigs_out [S,3] = x.  status BP_MVIE_NO_INTERIOR when the centre is not strictly inside or a_lb cannot be met
+ * (the reference's SOCP is infeasible there). */
+int bp_mvie_fixed_r(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max,
+                    const double* centre_dev /*[S,3]*/, const double* r_ellipse_dev /*[S,3,3]*/,
+                    const double* a_lb_dev /*[S]*/, double* q_inv_out_dev, double* q_ellipse_out_dev,
+                    double* eigs_out_dev, int* status_dev, int* newton_iters_dev /*or NULL*/, void* stream);
+
 /* ---- K5: the whole IRIS loop ---------------------------------------------------
  * Replaces ConvexSetFinder.find_set_around_point (:190-240) for S seeds.
  * ws_min/ws_max (host, 3 each) are the workspace box of init_halfspaces (:377-398).
@@ -107,6 +116,16 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
                            int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
                            double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
                            void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces ConvexSetFinder.find_set_around_line (:242-307) for S segments p0 .. p0 + dp1: the IRIS loop around
+ * the segment midpoint with the fixed-rotation MVIE (not called by the reference planner on main,
+ * BoundPlanner.py:378-380, but part of ConvexSetFinder's surface).  optimize == 0: one pass + one free-centre
+ * MVIE (:278-282).  p_mid = the midpoint (optimize) or the free MVIE's centre. */
+int bp_build_sets_around_line(const bp_scene* scene, const double* p0_dev, const double* dp1_dev, int S,
+                              const double* ws_min_host, const double* ws_max_host, int optimize, int max_iter,
+                              int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                              double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                              void* stream);
 
 /* Replaces ConvexSetFinder.find_set_collision_avoidance (:309-375) for S segments.
  * limit_space selects init_halfspaces_point(p0, e_max) (:400-421).  collision[S]

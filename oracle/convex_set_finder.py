@@ -55,15 +55,25 @@ def min_norm_point_polytopes(G, h):
     for S in _active_sets(r):
         Gs = G[:, S, :]                      # (N,k,3)
         hs = h[:, S]                         # (N,k)
-        gram = Gs @ Gs.transpose(0, 2, 1)    # (N,k,k)
-        det = np.linalg.det(gram)
         nrm = np.prod(np.einsum("nkj,nkj->nk", Gs, Gs), axis=1)
-        ok = det > 1e-12 * nrm
-        if not np.any(ok):
-            continue
-        lam = np.zeros_like(hs)
-        lam[ok] = np.linalg.solve(gram[ok], hs[ok][..., None])[..., 0]
-        x = np.einsum("nkj,nk->nj", Gs, lam)
+        if len(S) == 3:
+            # a vertex: solve G_S x = h_S directly -- the Gram matrix squares the condition number, which for a
+            # strongly anisotropic metric (fixed-R ellipsoids, sigma ratios 1e3) drops below any safe threshold
+            det = np.linalg.det(Gs)
+            ok = det * det > 1e-24 * nrm
+            if not np.any(ok):
+                continue
+            x = np.zeros((N, 3))
+            x[ok] = np.linalg.solve(Gs[ok], hs[ok][..., None])[..., 0]
+        else:
+            gram = Gs @ Gs.transpose(0, 2, 1)    # (N,k,k)
+            det = np.linalg.det(gram)
+            ok = det > 1e-14 * nrm               # parallel rows (opposite box faces) give exactly 0
+            if not np.any(ok):
+                continue
+            lam = np.zeros_like(hs)
+            lam[ok] = np.linalg.solve(gram[ok], hs[ok][..., None])[..., 0]
+            x = np.einsum("nkj,nk->nj", Gs, lam)
         viol = np.einsum("nrj,nj->nr", G, x) - h
         mag = np.einsum("nrj,nj->nr", np.abs(G), np.abs(x)) + scale
         feas = ok & np.all(viol <= 1e-10 * mag, axis=1)
@@ -295,6 +305,42 @@ class ConvexSetFinder:
             q_ellipse = svd.Vh.T @ np.diag(1 / svd.S) @ svd.U.T
         return a_set_np, b_set_np, q_ellipse, p_seed
 
+    # ---- :242-307 (not called by the reference planner on main, BoundPlanner.py:378-380) ----
+    def find_set_around_line(self, p0, dp1, optimize=True):
+        p0 = np.asarray(p0, float)
+        dp1 = np.asarray(dp1, float)
+        p1 = p0 + dp1
+        r_ellipse, l_seg = line_frame(dp1)
+        p_seed = (p0 + p1) / 2
+        a_lb = l_seg**2 / 4
+        b = c = 1e-4
+        q_inv = r_ellipse @ np.diag((a_lb, b, c)) @ r_ellipse.T
+        q_ellipse = r_ellipse @ np.diag((1 / a_lb, 1 / b, 1 / c)) @ r_ellipse.T
+        a_set_init, b_set_init = self.init_halfspaces()
+        det_ellipse_old = 1
+        det_ellipse = 100
+        k = 0
+        a_set = b_set = None
+        while np.abs(det_ellipse - det_ellipse_old) / det_ellipse_old > 0.01:
+            k += 1
+            if k > self.max_iter:
+                break
+            a_set, b_set = self.compute_polyhedron(q_inv, q_ellipse, p_seed, a_set_init, b_set_init)
+            a_set_np = np.array(a_set)
+            b_set_np = np.array(b_set)
+            if not optimize:
+                q_inv, p_seed = self.mvie_socp(a_set_np, b_set_np, p_hint=p_seed)
+                svd = np.linalg.svd(q_inv)
+                q_ellipse = svd.Vh.T @ np.diag(1 / svd.S) @ svd.U.T
+                break
+            det_ellipse_old = np.copy(det_ellipse)
+            q_inv, q_ellipse, eigs = self.mvie_socp_fixed_r(a_set_np, b_set_np, p_seed, r_ellipse, a_lb)
+            if np.min(eigs) < 1e-3:
+                break
+            det_ellipse = np.linalg.det(q_ellipse)
+        self.last_iters = k
+        return a_set, b_set, q_ellipse, p_seed
+
     # ---- :309-375 ---------------------------------------------------------
     def find_set_collision_avoidance(self, p0, p1, compute_ellipsoid=False, limit_space=False, e_max=0.3):
         collision = False
@@ -338,3 +384,20 @@ class ConvexSetFinder:
             q_ellipse = svd.Vh.T @ np.diag(1 / svd.S) @ svd.U.T
             return a_set_np, b_set_np, q_ellipse, p_seed, collision
         return a_set_np, b_set_np, collision
+
+
+def line_frame(dp1):
+    """Rotation used by find_set_around_line (ConvexSetFinder.py:245-258): columns dp_ref, b1, b2.
+    gram_schmidt is util_functions.py:108-116."""
+    dp1 = np.asarray(dp1, float)
+    l_seg = np.linalg.norm(dp1)
+    dp_ref = dp1 / l_seg
+    if np.abs(dp_ref[2]) < 0.99:
+        b1d = np.array([0, 0, 1.0])
+    else:
+        b1d = np.array([0, 1.0, 0])
+    b1 = b1d - (dp_ref.T @ b1d) * dp_ref
+    b1 /= np.linalg.norm(b1)
+    b2 = np.cross(dp_ref, b1)
+    b2 /= np.linalg.norm(b2)
+    return np.vstack((dp_ref, b1, b2)).T, l_seg

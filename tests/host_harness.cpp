@@ -5,6 +5,7 @@
 // loads it and libbpgeo.so has no CPU path.
 #include "../boundplanner_b200/csrc/bp_math.cuh"
 #include "../boundplanner_b200/csrc/bp_mvie.cuh"
+#include "../boundplanner_b200/csrc/bp_mvie_fixed_r.cuh"
 #include "../boundplanner_b200/csrc/bp_lp.cuh"
 #include "../boundplanner_b200/csrc/bp_fk.cuh"
 
@@ -40,6 +41,18 @@ int hh_mvie_ws(const double* A, const double* b, int m, int free_centre, const d
   centre[0] = d[0]; centre[1] = d[1]; centre[2] = d[2];
   return st;
 }
+
+// fixed-rotation MVIE (mvie_socp_fixed_r): E = q_new, Q = q_ellipse, eigs = semi-axes
+int hh_mvie_fixed_r(const double* A, const double* b, int m, const double* p_mid, const double* R, double a_lb,
+                    double* E, double* Q, double* eigs, int* iters) {
+  HostRows rows{A, b};
+  BpSerialRed red;
+  int st = bp_mvie_fixed_r(rows, m, p_mid, R, a_lb, red, eigs, iters);
+  if (st == BP_OK) bp_shape_from_axes(R, eigs, E, Q, nullptr);
+  return st;
+}
+
+void hh_line_frame(const double* dp1, double* R, double* l_seg) { bp_line_frame(dp1, R, l_seg); }
 
 // closest points of n boxes to p in the metric of E (q_inv): y[n,3], dist[n]
 void hh_box_qp(const double* E, const double* p, const double* lb, const double* ub, int n, double* y,

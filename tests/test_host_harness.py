@@ -132,3 +132,68 @@ def test_min_eig_primitive(host_harness):
         L[np.diag_indices(3)] = rng.uniform(1e-3, 1, 3)
         E = np.ascontiguousarray(L @ L.T)
         assert abs(host_harness.hh_min_eig(dp(E)) - np.linalg.svd(E)[1].min()) < 1e-13 * max(1.0, np.abs(E).max())
+
+
+def _random_frame(rng):
+    dp1 = rng.normal(size=3) * rng.uniform(0.05, 0.6)
+    R, l = np.zeros((3, 3)), ctypes.c_double()
+    return dp1, R, l
+
+
+def test_line_frame_primitive(host_harness):
+    """bp_line_frame against find_set_around_line's frame (ConvexSetFinder.py:245-258)."""
+    from oracle.convex_set_finder import line_frame
+
+    rng = np.random.default_rng(11)
+    cases = [rng.normal(size=3) for _ in range(10)] + [np.array([0, 0, 0.3]), np.array([1e-3, 0, -0.5])]
+    for dp1 in cases:
+        R, l = np.zeros((3, 3)), ctypes.c_double()
+        host_harness.hh_line_frame(dp(np.ascontiguousarray(dp1)), dp(R), ctypes.byref(l))
+        Ro, lo = line_frame(dp1)
+        assert abs(l.value - lo) < 1e-15 and np.abs(R - Ro).max() < 1e-14
+        assert np.abs(R.T @ R - np.eye(3)).max() < 1e-12
+
+
+def test_mvie_fixed_r_primitive(host_harness):
+    """mvie_socp_fixed_r (ConvexSetFinder.py:564-588): device primitive vs the oracle and analytic boxes."""
+    from oracle.convex_set_finder import line_frame
+
+    rng = np.random.default_rng(12)
+    host_harness.hh_mvie_fixed_r.restype = ctypes.c_int
+    worst = 0.0
+    n_done = 0
+    for trial in range(30):
+        k = rng.integers(2, 14)
+        c = rng.uniform(-0.4, 0.4, 3)
+        c[2] += 0.6
+        An = rng.normal(size=(k, 3))
+        An /= np.linalg.norm(An, axis=1)[:, None]
+        A = np.ascontiguousarray(np.vstack((BOX, An)))
+        b = np.concatenate((np.array([1, 1, 1.2, 1, 1, 0.0]), An @ c + rng.uniform(0.02, 0.4, k)))
+        R, _ = line_frame(rng.normal(size=3))
+        R = np.ascontiguousarray(R)
+        a_lb = 0.0 if trial % 3 == 0 else rng.uniform(0.0, 0.02)
+        E, Q, eigs, it = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), ctypes.c_int()
+        st = host_harness.hh_mvie_fixed_r(dp(A), dp(b), A.shape[0], dp(c), dp(R), ctypes.c_double(a_lb), dp(E), dp(Q),
+                                          dp(eigs), ctypes.byref(it))
+        try:
+            Eo, Qo, so = omvie.mvie_fixed_r(A, b, c, R, a_lb)
+        except omvie.MVIEError:
+            assert st == 3
+            continue
+        assert st == 0
+        assert eigs[0] >= a_lb - 1e-12
+        worst = max(worst, np.abs(eigs - so).max() / so.max())
+        assert np.abs(E - R @ np.diag(eigs**2) @ R.T).max() < 1e-14
+        assert np.abs(Q @ E - np.eye(3)).max() < 1e-9
+        n_done += 1
+    assert n_done >= 20 and worst < 1e-7
+    # analytic: axis-aligned box, R = I  ->  semi-axes = half widths; with a_lb above the optimum of x0 the bound is active
+    b = np.array([0.3, 0.2, 0.5, 0.3, 0.2, 0.5])
+    E, Q, eigs, it = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), ctypes.c_int()
+    st = host_harness.hh_mvie_fixed_r(dp(BOX.copy()), dp(b), 6, dp(np.zeros(3)), dp(np.eye(3)), ctypes.c_double(0.0),
+                                      dp(E), dp(Q), dp(eigs), ctypes.byref(it))
+    assert st == 0 and np.abs(eigs - b[:3]).max() < 1e-9
+    st = host_harness.hh_mvie_fixed_r(dp(BOX.copy()), dp(b), 6, dp(np.zeros(3)), dp(np.eye(3)), ctypes.c_double(0.31),
+                                      dp(E), dp(Q), dp(eigs), ctypes.byref(it))
+    assert st == 3                      # a_lb larger than the box allows: the reference's SOCP is infeasible
