@@ -79,7 +79,8 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  boundplanner_b200 has no CPU fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    # BPGEO_LIB: an alternative build of the same library (tools/prof_phases.py loads the -DBPGEO_PROFILE one)
+    lib = ctypes.CDLL(os.environ.get("BPGEO_LIB", LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res

@@ -36,6 +36,12 @@
 #ifndef BP_MVIE_WS_BETA
 #define BP_MVIE_WS_BETA 0.9
 #endif
+// Newton decrement^2 below which the full step is taken without the Armijo test: for a self-concordant
+// function the full step at lambda < 0.5 is feasible and decreases F_t by at least
+// lambda^2 - (-lambda - log(1 - lambda)) > 0, so the (log-heavy) test cannot fail there.
+#ifndef BP_MVIE_FULLSTEP_LAM2
+#define BP_MVIE_FULLSTEP_LAM2 0.25
+#endif
 #define BP_MVIE_OUTER_MAX 48
 #define BP_MVIE_INNER_MAX 40
 #define BP_MVIE_GAP_TOL 1e-11
@@ -57,6 +63,9 @@ BP_HD double bp_rcp(double x) {
 #endif
 }
 
+#ifdef BP_MVIE_COUNT
+static int bp_mvie_count_armijo = 0;
+#endif
 template <int NV>
 BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx) {
   // right-looking (outer-product) LDL^T: after column j is scaled the trailing
@@ -231,6 +240,9 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
       double dcn[3] = {0.0, 0.0, 0.0};
       if (NV == 9) { dcn[0] = dx[6]; dcn[1] = dx[7]; dcn[2] = dx[8]; }
       double alpha = 1.0;
+#ifdef BP_MVIE_DAMPED
+      if (lam2 >= BP_MVIE_FULLSTEP_LAM2) alpha = 1.0 / (1.0 + sqrt(lam2));
+#endif
       bool accepted = false;
       for (int bt = 0; bt < 60; ++bt) {
         bool ok = (x[0] + alpha * dx[0] > 0.0) && (x[2] + alpha * dx[2] > 0.0) && (x[5] + alpha * dx[5] > 0.0);
@@ -254,8 +266,11 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
           if ((i & 7) == 7) { logsum += log(prod); prod = 1.0; }
         }
         if (ok) {
-          if (lam2 < 0.01) { accepted = true; }
+          if (lam2 < BP_MVIE_FULLSTEP_LAM2) { accepted = true; }
           else {
+#ifdef BP_MVIE_COUNT
+            ++bp_mvie_count_armijo;
+#endif
             logsum += log(prod);
             double dF = -t * (log1p(alpha * dx[0] / x[0]) + 2.0 * log1p(alpha * dx[2] / x[2]) +
                               log1p(alpha * dx[5] / x[5])) - logsum;

@@ -19,6 +19,17 @@
 
 // feature columns: rr[NV], tw*a[3], a[3], one; the row stride is kept odd so that
 // the per-lane row writes spread over the shared-memory banks
+#ifdef BPGEO_PROFILE
+__device__ long long g_prof_mvie[8 * 65536];   // [cta][rows, dots, ldl, linesearch, predictor, newton iters, armijo evals, backtracks]
+#define BP_MPROF_MARK() long long mprof_t_ = clock64()
+#define BP_MPROF_LAP(slot) { const long long now_ = clock64(); if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof_mvie[8 * blockIdx.x + (slot)] += now_ - mprof_t_; mprof_t_ = now_; }
+#define BP_MPROF_COUNT(slot) { if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof_mvie[8 * blockIdx.x + (slot)] += 1; }
+#else
+#define BP_MPROF_MARK()
+#define BP_MPROF_LAP(slot)
+#define BP_MPROF_COUNT(slot)
+#endif
+
 #define BP_MVIE_W(NV) ((((NV) + 7) & 1) ? ((NV) + 7) : ((NV) + 8))
 #define BP_MVIE_SCRATCH_DOUBLES (BP_MAX_ROWS * 17 + 64)
 
@@ -89,6 +100,9 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
       F[i * W + NV + 6] = 1.0;
     }
   }
+  // rows m .. ceil4(m)-1 stay all-zero so that the column-dot loops can run in unrolled groups of four
+  const int m4 = (m + 3) & ~3;
+  for (int e = m * W + lane; e < m4 * W; e += 32) F[e] = 0.0;
   int cx[2], cy[2];
   bp_mvie_decode_output<NV>(lane, &cx[0], &cy[0]);
   bp_mvie_decode_output<NV>(lane + 32, &cx[1], &cy[1]);
@@ -126,6 +140,8 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
     bool centred = false;
     for (int inner = 0; inner < BP_MVIE_INNER_MAX; ++inner) {
       ++iters;
+      BP_MPROF_COUNT(5);
+      BP_MPROF_MARK();
       if (NV == 9) { cen[0] = x[6]; cen[1] = x[7]; cen[2] = x[8]; }
       // ---- per-row barrier pieces -> feature rows
       double rs[2], ru[2][3], rpsi[2], rtw[2];
@@ -150,46 +166,35 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         }
       }
       __syncwarp();
+      BP_MPROF_LAP(0);
       // ---- column dots over the rows (ascending row order, like the serial code).
       // Control flow is kept warp-uniform: with more than 32 outputs every lane
       // walks two column pairs (lanes without a second output walk a dummy).
       {
-        double acc0 = 0.0, acc1 = 0.0;
         const int ax0 = cx[0], ay0 = cy[0];
+        double acc0 = 0.0, acc0b = 0.0;
         if (NOUT > 40) {
           const int ax1 = cx[1] >= 0 ? cx[1] : 0, ay1 = cx[1] >= 0 ? cy[1] : 0;
-          double acc0b = 0.0, acc1b = 0.0;
-          int i = 0;
-          for (; i + 1 < m; i += 2) {
+          double acc1 = 0.0, acc1b = 0.0;
+          for (int i = 0; i < m4; i += 4) {
             const double* f = F + i * W;
-            acc0 += f[ax0] * f[ay0];
-            acc1 += f[ax1] * f[ay1];
-            acc0b += f[W + ax0] * f[W + ay0];
-            acc1b += f[W + ax1] * f[W + ay1];
+            const double p0 = f[ax0], q0 = f[ay0], p1 = f[W + ax0], q1 = f[W + ay0];
+            const double p2 = f[2 * W + ax0], q2 = f[2 * W + ay0], p3 = f[3 * W + ax0], q3 = f[3 * W + ay0];
+            const double r0 = f[ax1], s0 = f[ay1], r1 = f[W + ax1], s1 = f[W + ay1];
+            const double r2 = f[2 * W + ax1], s2 = f[2 * W + ay1], r3 = f[3 * W + ax1], s3 = f[3 * W + ay1];
+            acc0 += p0 * q0; acc0b += p1 * q1; acc0 += p2 * q2; acc0b += p3 * q3;
+            acc1 += r0 * s0; acc1b += r1 * s1; acc1 += r2 * s2; acc1b += r3 * s3;
           }
-          if (i < m) {
-            const double* f = F + i * W;
-            acc0 += f[ax0] * f[ay0];
-            acc1 += f[ax1] * f[ay1];
-          }
-          acc0 += acc0b;
-          acc1 += acc1b;
-          if (cx[1] >= 0) OUT[lane + 32] = acc1;
+          if (cx[1] >= 0) OUT[lane + 32] = acc1 + acc1b;
         } else {
-          double acc0b = 0.0;
-          int i = 0;
-          for (; i + 1 < m; i += 2) {
+          for (int i = 0; i < m4; i += 4) {
             const double* f = F + i * W;
-            acc0 += f[ax0] * f[ay0];
-            acc0b += f[W + ax0] * f[W + ay0];
+            const double p0 = f[ax0], q0 = f[ay0], p1 = f[W + ax0], q1 = f[W + ay0];
+            const double p2 = f[2 * W + ax0], q2 = f[2 * W + ay0], p3 = f[3 * W + ax0], q3 = f[3 * W + ay0];
+            acc0 += p0 * q0; acc0b += p1 * q1; acc0 += p2 * q2; acc0b += p3 * q3;
           }
-          if (i < m) acc0 += F[i * W + ax0] * F[i * W + ay0];
-          acc0 += acc0b;
-          // NV == 6: 33 outputs; the last one (W22) comes from a butterfly sum
-          const double w22 = bp_warp_sum(rtw[0] * ra[0][2] * ra[0][2] + rtw[1] * ra[1][2] * ra[1][2]);
-          if (lane == 0) OUT[32] = w22;
         }
-        OUT[lane] = acc0;
+        OUT[lane] = acc0 + acc0b;
       }
       __syncwarp();
       double g[NV], H[NH];
@@ -199,16 +204,20 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
 #pragma unroll
       for (int k = 0; k < NV; ++k) g[k] = -OUT[NH + k];
       {
+        i0 = bp_rcp(x[0]); i2 = bp_rcp(x[2]); i5 = bp_rcp(x[5]);
         const double w00 = OUT[NH + NV], w01 = OUT[NH + NV + 1], w02 = OUT[NH + NV + 2];
-        const double w11 = OUT[NH + NV + 3], w12 = OUT[NH + NV + 4], w22 = OUT[NH + NV + 5];
+        const double w11 = OUT[NH + NV + 3], w12 = OUT[NH + NV + 4];
+        // NV == 6 has 33 outputs for 32 lanes: the last one, W22 = sum tw a2^2, follows from the gradient sum of
+        // rr5 = -x5 tw a2^2 (g[5] = -sum rr5 at this point)
+        const double w22 = (NV == 6) ? g[5] * i5 : OUT[NH + NV + 5];
         H[0] += w00; H[1] += w01; H[2] += w11; H[6] += w02; H[7] += w12; H[9] += w22;
         H[5] += w11; H[12] += w12; H[14] += w22; H[20] += w22;
         if (NV == 9) { H[27] -= w00; H[34] -= w01; H[35] -= w11; H[42] -= w02; H[43] -= w12; H[44] -= w22; }
-        i0 = bp_rcp(x[0]); i2 = bp_rcp(x[2]); i5 = bp_rcp(x[5]);
         g[0] -= t * i0; g[2] -= 2.0 * t * i2; g[5] -= t * i5;
         H[0] += t * i0 * i0; H[5] += 2.0 * t * i2 * i2; H[20] += t * i5 * i5;
       }
       __syncwarp();                      // OUT is rewritten next iteration
+      BP_MPROF_LAP(1);
       double dx[NV];
       if (!bp_ldl_solve<NV>(H, g, dx)) {
         status = (t > 1e8) ? BP_OK : BP_MVIE_NOT_CONVERGED;
@@ -218,6 +227,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
 #pragma unroll
       for (int k = 0; k < NV; ++k) lam2 -= g[k] * dx[k];
       if (!(lam2 > 0.0)) { centred = true; break; }
+      BP_MPROF_LAP(2);
       // ---- line search: psi(x + alpha dx) = psi + alpha B1 + alpha^2 A2 per row
       double dcn[3] = {0.0, 0.0, 0.0};
       if (NV == 9) { dcn[0] = dx[6]; dcn[1] = dx[7]; dcn[2] = dx[8]; }
@@ -236,6 +246,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
       double alpha = 1.0;
       bool accepted = false;
       for (int bt = 0; bt < 60; ++bt) {
+        BP_MPROF_COUNT(7);
         bool ok = (x[0] + alpha * dx[0] > 0.0) && (x[2] + alpha * dx[2] > 0.0) && (x[5] + alpha * dx[5] > 0.0);
         double prod = 1.0;
 #pragma unroll
@@ -248,11 +259,20 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         }
         ok = __all_sync(full, ok);
         if (ok) {
-          if (lam2 < 0.01) accepted = true;
+          if (lam2 < BP_MVIE_FULLSTEP_LAM2) accepted = true;
           else {
-            const double logsum = log(bp_warp_prod(prod));
-            const double dF = -t * (log1p(alpha * dx[0] * i0) + 2.0 * log1p(alpha * dx[2] * i2) +
-                                    log1p(alpha * dx[5] * i5)) - logsum;
+            BP_MPROF_COUNT(6);
+            // the four logarithms of dF are evaluated side by side: lane 0..2 the objective terms, lane 3 the
+            // barrier term (log of the product over the rows)
+            const double ptot = bp_warp_prod(prod);
+            const double arg = lane == 0 ? alpha * dx[0] * i0
+                             : lane == 1 ? alpha * dx[2] * i2
+                             : lane == 2 ? alpha * dx[5] * i5
+                             : ptot - 1.0;
+            const double lg = log1p(arg);
+            const double l0 = __shfl_sync(full, lg, 0), l1 = __shfl_sync(full, lg, 1);
+            const double l2 = __shfl_sync(full, lg, 2), l3 = __shfl_sync(full, lg, 3);
+            const double dF = -t * (l0 + 2.0 * l1 + l2) - l3;
             if (dF <= -0.25 * alpha * lam2) accepted = true;
           }
           if (accepted) {
@@ -263,6 +283,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         }
         alpha *= 0.5;
       }
+      BP_MPROF_LAP(3);
       if (!accepted) { centred = lam2 < 1e-2; break; }
       if (lam2 < inner_tol) { centred = true; break; }
       if (lam2 < 1e-3 && lam2 > 0.1 * lam2_prev) { centred = true; break; }

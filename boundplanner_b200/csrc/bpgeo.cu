@@ -417,6 +417,16 @@ struct GlobalRows {
   __device__ __forceinline__ double b(int i) const { return __ldg(B + i); }
 };
 
+#ifdef BPGEO_PROFILE
+// profile build only (tools/prof_phases.py): per-seed cycle counters of the fused loop
+__device__ long long g_prof[4 * 65536];   // [seed][poly cycles, mvie cycles, passes, total]
+#define BP_PROF_T0() const long long prof_t0_ = clock64()
+#define BP_PROF_ADD(slot) if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof[4 * blockIdx.x + (slot)] += clock64() - prof_t0_
+#else
+#define BP_PROF_T0()
+#define BP_PROF_ADD(slot)
+#endif
+
 struct SharedRows {
   const double* A;
   const double* B;
@@ -470,7 +480,11 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     pass_metric_init(Q, &pm);
     __syncthreads();                                          // previous rows / control words consumed
     int st;
-    poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
+    {
+      BP_PROF_T0();
+      poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
+      BP_PROF_ADD(0);
+    }
     rows_peak = m_cur > rows_peak ? m_cur : rows_peak;
     if (st == BP_OK && m_cur > pr.m_max) st = BP_ROW_OVERFLOW;
     if (st == BP_OK && (MODE == 1 || pr.optimize) && pr.row_cap > 0 && m_cur > pr.row_cap) st = BP_ROW_CAP;
@@ -523,8 +537,10 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     __syncthreads();                                          // thread 0 has written the picked rows
     if (tid < 32) {
       double L[6], d[3];
+      BP_PROF_T0();
       const int ms = pr.fixed_mid ? bp_mvie_warp<6>(sA, sb, m_cur, p, scratch, L, d, nullptr)
                                   : bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
+      BP_PROF_ADD(1);
       if (tid == 0) {
         double E[9], Qn[9], dq;
         bp_shape_from_L(L, E, Qn, &dq);
@@ -545,10 +561,14 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     if (c_small) break;
   }
   if (MODE == 0 && pr.optimize && pr.fixed_mid && status == BP_OK) {       // :235-238
+    // (running this solve speculatively on an idle warp next to every pass's fixed-centre solve was measured
+    // slower: the two solves slow each other down by ~20 % and the pass then waits for the longer one)
     __syncthreads();
     if (tid < 32) {
       double L[6], d[3];
+      BP_PROF_T0();
       const int ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
+      BP_PROF_ADD(2);
       if (tid == 0) {
         double E[9], Qn[9], dq;
         bp_shape_from_L(L, E, Qn, &dq);
@@ -1491,6 +1511,28 @@ static int set_dyn_smem(const void* fn, size_t bytes) {
 extern "C" {
 
 int bpgeo_abi_version(void) { return BPGEO_ABI_VERSION; }
+#ifdef BPGEO_PROFILE
+int bp_prof_read_mvie(long long* host_out, int n_seeds, int reset) {
+  BP_CUDA(cudaDeviceSynchronize());
+  BP_CUDA(cudaMemcpyFromSymbol(host_out, g_prof_mvie, sizeof(long long) * 8 * (size_t)n_seeds));
+  if (reset) {
+    void* ptr = nullptr;
+    BP_CUDA(cudaGetSymbolAddress(&ptr, g_prof_mvie));
+    BP_CUDA(cudaMemset(ptr, 0, sizeof(g_prof_mvie)));
+  }
+  return 0;
+}
+int bp_prof_read(long long* host_out, int n_seeds, int reset) {
+  BP_CUDA(cudaDeviceSynchronize());
+  BP_CUDA(cudaMemcpyFromSymbol(host_out, g_prof, sizeof(long long) * 4 * (size_t)n_seeds));
+  if (reset) {
+    void* ptr = nullptr;
+    BP_CUDA(cudaGetSymbolAddress(&ptr, g_prof));
+    BP_CUDA(cudaMemset(ptr, 0, sizeof(g_prof)));
+  }
+  return 0;
+}
+#endif
 const char* bp_last_error_string(void) { return g_err; }
 
 static int scene_upload(bp_scene* sc, const double* boxes_host, int n, double inflate, cudaStream_t stream) {
