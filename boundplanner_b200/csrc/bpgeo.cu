@@ -109,6 +109,24 @@ struct SeedState {
 
 struct Vec3 { double v[3]; };
 
+#ifdef BPGEO_PROFILE
+// profile build only (tools/prof_phases.py): per-seed cycle counters of the fused loop
+__device__ long long g_prof[4 * 65536];   // [seed][poly cycles, mvie cycles, passes, total]
+__device__ long long g_prof_poly[8 * 65536];   // [cta][phase1, argmin, refine, halfspace, delete scan, picks, refine rounds, qps of thread 0]
+#define BP_PPROF_MARK() long long pprof_t_ = clock64()
+#define BP_PPROF_LAP(slot) { const long long now_ = clock64(); if (threadIdx.x == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + (slot)] += now_ - pprof_t_; pprof_t_ = now_; }
+#define BP_PPROF_COUNT(slot) { if (threadIdx.x == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + (slot)] += 1; }
+#define BP_PROF_T0() const long long prof_t0_ = clock64()
+#define BP_PROF_ADD(slot) if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof[4 * blockIdx.x + (slot)] += clock64() - prof_t0_
+#else
+#define BP_PROF_T0()
+#define BP_PROF_ADD(slot)
+#define BP_PPROF_MARK()
+#define BP_PPROF_LAP(slot)
+#define BP_PPROF_COUNT(slot)
+#endif
+
+
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
@@ -246,36 +264,178 @@ struct PolyParams {
   int row_cap;               // > 0: stop a seed whose pass produced more rows (reference: 20, quirk Q5)
 };
 
+// (value, index) argmin of the lazy distance table: key = |entry| >= 0 (an exact distance or a lower bound of
+// one), ties -> bounds before exact values (a bound that ties with the best exact distance must still be
+// refined), then the smallest index (np.argmin, quirk Q11).  Non-negative doubles order like their bit patterns,
+// so the warp stage is three integer redux.sync minima (high word, low word, code) instead of a 5-round shuffle
+// butterfly.  With WITH_EX the smallest EXACT distance of the block is reduced the same way into `ex`.
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+  const unsigned full = 0xffffffffu;
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mh = __reduce_min_sync(full, hi);
+  const unsigned lo = hi == mh ? (unsigned)__double2loint(v) : 0xffffffffu;
+  const unsigned ml = __reduce_min_sync(full, lo);
+  return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ void block_argmin_lazy(double& key, int& idx, int& exact, double (*red_val)[32],
+                                                  int (*red_idx)[32], int& buf) {
+  const unsigned full = 0xffffffffu;
+  const unsigned tcode = ((unsigned)exact << 31) | (unsigned)idx; // equal keys: bounds first, then the index
+  const unsigned hi = (unsigned)__double2hiint(key);
+  const unsigned mh = __reduce_min_sync(full, hi);
+  const unsigned lo = hi == mh ? (unsigned)__double2loint(key) : 0xffffffffu;
+  const unsigned ml = __reduce_min_sync(full, lo);
+  const unsigned mc = __reduce_min_sync(full, (hi == mh && lo == ml) ? tcode : 0xffffffffu);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red_val[buf][warp] = __hiloint2double((int)mh, (int)ml); red_idx[buf][warp] = (int)mc; }
+  __syncthreads();
+  double bk = red_val[buf][0];
+  unsigned bc = (unsigned)red_idx[buf][0];
+  for (int w = 1; w < nw; ++w) {
+    const double ok = red_val[buf][w];
+    const unsigned oc = (unsigned)red_idx[buf][w];
+    if (ok < bk || (ok == bk && oc < bc)) { bk = ok; bc = oc; }
+  }
+  key = bk; idx = (int)(bc & 0x7fffffffu); exact = (int)(bc >> 31);
+  buf ^= 1;
+}
+// smallest value of `v` (>= 0, +inf allowed) over the block
+__device__ __forceinline__ double block_min_nonneg(double v, double (*red_val)[32], int& buf) {
+  v = warp_min_nonneg(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) red_val[buf][warp] = v;
+  __syncthreads();
+  double bv = red_val[buf][0];
+  for (int w = 1; w < nw; ++w) bv = fmin(bv, red_val[buf][w]);
+  buf ^= 1;
+  return bv;
+}
+
+// Lower bound of the pass-metric distance from p to a box, from the per-axis gaps d_k (0 inside the slab):
+//   z^T M z >= z_k^2 / (M^-1)_kk >= d_k^2 / (M^-1)_kk   and   z^T M z >= lambda_min(M) |d|^2.
+#ifndef BP_LAZY_GROW
+#define BP_LAZY_GROW 3.0
+#endif
+struct PassBound {
+  double c[3];      // (1 - eta) / (M^-1)_kk
+  double lmin;      // (1 - eta) lambda_min(M)
+};
+__device__ __forceinline__ void pass_bound_init(const PassMetric& pm, PassBound* pb) {
+  double M[9], Mi[9];
+  bp_mat3_ata(pm.Q, M);
+  const double det = bp_inv3(M, Mi);
+  const double lm = bp_sym3_min_eig(M);
+  // eta = 1e-3 covers the rounding of the inverse / eigenvalue up to cond(M) ~ 1e12; the bound only decides
+  // WHICH closest-point QPs are solved, never a result
+  const double keep = 1.0 - 1e-3;
+  const bool ok = det > 0.0 && Mi[0] > 0.0 && Mi[4] > 0.0 && Mi[8] > 0.0;
+  pb->c[0] = ok ? keep / Mi[0] : 0.0;
+  pb->c[1] = ok ? keep / Mi[4] : 0.0;
+  pb->c[2] = ok ? keep / Mi[8] : 0.0;
+  pb->lmin = (lm > 0.0 && lm < BP_INF) ? keep * lm : 0.0;
+}
+__device__ __forceinline__ double box_dist_bound(const PassBound& pb, const double* p, const double* lb,
+                                                 const double* ub) {
+  const double d0 = fmax(fmax(lb[0] - p[0], p[0] - ub[0]), 0.0);
+  const double d1 = fmax(fmax(lb[1] - p[1], p[1] - ub[1]), 0.0);
+  const double d2 = fmax(fmax(lb[2] - p[2], p[2] - ub[2]), 0.0);
+  const double q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2;
+  const double b2 = fmax(fmax(pb.c[0] * q0, pb.c[1] * q1), fmax(pb.c[2] * q2, pb.lmin * ((q0 + q1) + q2)));
+  return sqrt(b2);
+}
+
 // One compute_polyhedron pass for the seed of this CTA (all threads call it): rows 6.. are written
 // to Arow/brow (global or shared memory), *m_out = 6 + picks, *status_out = BP_OK / BP_ELLIPSE_VIOLATION.
+//
+// LAZY closest points: the greedy loop only ever needs the exact distance of the obstacle that is currently
+// nearest; everything a picked halfspace cuts off dies by the vertex test, which needs no distance.  The table
+// s_dist[j] therefore starts as a cheap LOWER BOUND of every distance (stored negated), and a box QP is solved
+// only for entries whose bound does not exceed the best exact distance known.  The pick is the argmin over exact
+// values once no bound is smaller or equal -- the same obstacle, the same bits as solving all N QPs (the QP of
+// an entry is the same code on the same inputs whenever it runs).
 __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassMetric& pm, const double* p,
                                                 double* s_dist, int cache_y, double (*red_val)[32],
-                                                int (*red_idx)[32], double* Arow, double* brow, int m_max,
-                                                int* m_out, int* status_out) {
+                                                int (*red_idx)[32], double* Arow,
+                                                double* brow, int m_max, int* m_out, int* status_out) {
   const int tid = threadIdx.x, T = blockDim.x;
-  // phase 1: closest points and distances
-  double lmin = BP_INF;
-  int lidx = 0x7fffffff;
   double* s_y = s_dist + sc.n;               // [3][N] when cache_y
-  for (int j = tid; j < sc.n; j += T) {
-    double lb[3], ub[3], y[3];
-    load_box(sc, j, lb, ub);
-    double d = closest_on_box(pm, p, lb, ub, y);
-    s_dist[j] = d;
-    if (cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
-    if (d < lmin) { lmin = d; lidx = j; }
+  BP_PPROF_MARK();
+  PassBound pb;
+  pass_bound_init(pm, &pb);
+  // Entry k of this thread is obstacle j = tid + k T (k < 64: N <= 64 T, see poly_threads); `alive` has a bit
+  // per entry that no picked halfspace has cut off yet, so the scans below touch live entries only.
+  unsigned long long alive = 0ull;
+  // phase 1: lower bounds (stored negated); a zero bound (p inside the box's slabs) is refined on the spot
+  double lkey = BP_INF;
+  int lidx = 0x3fffffff, lexact = 0;
+  {
+    int k = 0;
+    for (int j = tid; j < sc.n; j += T, ++k) {
+      double lb[3], ub[3];
+      load_box(sc, j, lb, ub);
+      double bd = box_dist_bound(pb, p, lb, ub);
+      int ex = 0;
+      if (!(bd > 0.0)) {
+        double y[3];
+        bd = closest_on_box(pm, p, lb, ub, y);
+        if (cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
+        s_dist[j] = bd;
+        ex = 1;
+      } else {
+        s_dist[j] = -bd;
+      }
+      alive |= 1ull << k;
+      if (bd < lkey || (bd == lkey && ex < lexact)) { lkey = bd; lidx = j; lexact = ex; }
+    }
   }
-  // (the barrier inside block_argmin orders these writes before the winner's point is read)
+  // (the barrier inside block_argmin_lazy orders these writes before the winner's point is read)
 
   // phase 2: greedy halfspaces
   int m_cur = 6;
   int status = BP_OK;
   int buf = 0;
   while (true) {
-    double val = lmin;
-    int idx = lidx;
-    block_argmin(val, idx, red_val, red_idx, buf);
+    double val = lkey;
+    int idx = lidx, exact = lexact;
+    BP_PPROF_LAP(buf == 0 && m_cur == 6 ? 0 : 4);
+    block_argmin_lazy(val, idx, exact, red_val, red_idx, buf);
+    BP_PPROF_LAP(1);
     if (!(val < BP_INF)) break;                      // no obstacle left
+    if (!exact) {
+      BP_PPROF_COUNT(6);
+      // refine: every bound that could still beat (or tie with) the best exact distance -- and, to keep the
+      // number of refinement rounds (one QP latency + one barrier each) small, everything within
+      // BP_LAZY_GROW x the smallest bound: the next picks come from that shell
+      double lex = BP_INF;
+      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+        const double d = s_dist[tid + (__ffsll((long long)mk) - 1) * T];
+        if (d >= 0.0) lex = fmin(lex, d);
+      }
+      const double ex = block_min_nonneg(lex, red_val, buf);
+      const double thr = fmax(ex < BP_INF ? ex : 0.0, BP_LAZY_GROW * val);
+      lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
+      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+        const int j = tid + (__ffsll((long long)mk) - 1) * T;
+        double d = s_dist[j];
+        int e = 1;
+        if (d < 0.0) {
+          if (-d <= thr) {
+            double lb[3], ub[3], y[3];
+            load_box(sc, j, lb, ub);
+            d = closest_on_box(pm, p, lb, ub, y);
+            if (cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
+            s_dist[j] = d;
+          } else {
+            d = -d;
+            e = 0;
+          }
+        }
+        if (d < lkey || (d == lkey && e < lexact)) { lkey = d; lidx = j; lexact = e; }
+      }
+      BP_PPROF_LAP(2);
+      continue;
+    }
+    BP_PPROF_COUNT(5);
     if (val < 0.99) { status = BP_ELLIPSE_VIOLATION; break; }   // :433-438
     double y[3];
     if (cache_y) {
@@ -297,18 +457,35 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       brow[m_cur] = bh;
     }
     ++m_cur;
-    // delete the winner and every obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458)
-    lmin = BP_INF;
-    lidx = 0x7fffffff;
-    for (int j = tid; j < sc.n; j += T) {
-      double d = s_dist[j];
-      if (!(d < BP_INF)) continue;
-      double l2[3], u2[3];
-      load_box(sc, j, l2, u2);
-      if (j == idx || bp_box_min_halfspace(a, bh, l2, u2) >= -1e-4) {
-        s_dist[j] = BP_INF;
-      } else if (d < lmin) {
-        lmin = d; lidx = j;
+    BP_PPROF_LAP(3);
+    // delete the winner and every obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458); live entries
+    // are taken two at a time so that their box loads are in flight together
+    lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
+    for (unsigned long long mk = alive; mk;) {
+      const int k0 = __ffsll((long long)mk) - 1;
+      mk &= mk - 1;
+      const int k1 = mk ? __ffsll((long long)mk) - 1 : k0;
+      mk &= mk - 1;                               // (0 & anything stays 0)
+      const int j0 = tid + k0 * T, j1 = tid + k1 * T;
+      double l0[3], u0[3], l1[3], u1[3];
+      load_box(sc, j0, l0, u0);
+      load_box(sc, j1, l1, u1);
+      const double d0 = s_dist[j0], d1 = s_dist[j1];
+      const bool dead0 = j0 == idx || bp_box_min_halfspace(a, bh, l0, u0) >= -1e-4;
+      const bool dead1 = j1 == idx || bp_box_min_halfspace(a, bh, l1, u1) >= -1e-4;
+      if (dead0) alive &= ~(1ull << k0);
+      else {
+        const int e = d0 >= 0.0;
+        const double d = fabs(d0);
+        if (d < lkey || (d == lkey && e < lexact)) { lkey = d; lidx = j0; lexact = e; }
+      }
+      if (k1 != k0) {
+        if (dead1) alive &= ~(1ull << k1);
+        else {
+          const int e = d1 >= 0.0;
+          const double d = fabs(d1);
+          if (d < lkey || (d == lkey && e < lexact)) { lkey = d; lidx = j1; lexact = e; }
+        }
       }
     }
   }
@@ -417,15 +594,6 @@ struct GlobalRows {
   __device__ __forceinline__ double b(int i) const { return __ldg(B + i); }
 };
 
-#ifdef BPGEO_PROFILE
-// profile build only (tools/prof_phases.py): per-seed cycle counters of the fused loop
-__device__ long long g_prof[4 * 65536];   // [seed][poly cycles, mvie cycles, passes, total]
-#define BP_PROF_T0() const long long prof_t0_ = clock64()
-#define BP_PROF_ADD(slot) if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof[4 * blockIdx.x + (slot)] += clock64() - prof_t0_
-#else
-#define BP_PROF_T0()
-#define BP_PROF_ADD(slot)
-#endif
 
 struct SharedRows {
   const double* A;
@@ -1522,6 +1690,16 @@ int bp_prof_read_mvie(long long* host_out, int n_seeds, int reset) {
   }
   return 0;
 }
+int bp_prof_read_poly(long long* host_out, int n_seeds, int reset) {
+  BP_CUDA(cudaDeviceSynchronize());
+  BP_CUDA(cudaMemcpyFromSymbol(host_out, g_prof_poly, sizeof(long long) * 8 * (size_t)n_seeds));
+  if (reset) {
+    void* ptr = nullptr;
+    BP_CUDA(cudaGetSymbolAddress(&ptr, g_prof_poly));
+    BP_CUDA(cudaMemset(ptr, 0, sizeof(g_prof_poly)));
+  }
+  return 0;
+}
 int bp_prof_read(long long* host_out, int n_seeds, int reset) {
   BP_CUDA(cudaDeviceSynchronize());
   BP_CUDA(cudaMemcpyFromSymbol(host_out, g_prof, sizeof(long long) * 4 * (size_t)n_seeds));
@@ -1692,6 +1870,7 @@ int bp_build_sets_around_line(const bp_scene* scene, const double* p0_dev, const
       !ws_max_host)
     return bp_fail("bp_build_sets_around_line: bad arguments");
   if (S == 0) return 0;
+  if (scene->n > 64 * 128) return bp_fail("bp_build_sets_around_line: scene too large (N > 8192)");
   FusedParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.seeds = p0_dev; fp.dp1 = dp1_dev;

@@ -155,7 +155,7 @@ def test_maximum_scene_size_and_loud_failure(geo):
     from boundplanner_b200 import _lib, scenes
 
     rng = np.random.default_rng(4)
-    boxes = scenes.random_box_scene(28900, rng, 0.004, 0.012)
+    boxes = scenes.random_box_scene(28800, rng, 0.004, 0.012)
     seeds = scenes.free_points(4, boxes, 0.0, rng)
     sc = geo.Scene(boxes, 0.0)
     out = geo.build_sets_point(sc, seeds, scenes.WORKSPACE_MIN, scenes.WORKSPACE_MAX, fixed_mid=True, optimize=False)

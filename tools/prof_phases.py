@@ -4,10 +4,11 @@ Usage (GPU box): BPGEO_LIB is set by this script; run `python tools/prof_phases.
 import ctypes, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-PROF = os.path.join(ROOT, "boundplanner_b200", "libbpgeo_prof.so")
+EXTRA = [a for a in sys.argv[1:] if a.startswith("-D")]
+PROF = os.path.join(ROOT, "boundplanner_b200", os.environ.get("BPGEO_PROF_NAME", "libbpgeo_prof.so"))
 if "--build" in sys.argv or not os.path.exists(PROF):
     import __graft_entry__ as g
-    subprocess.check_call(["/usr/local/cuda/bin/nvcc"] + g.NVCC_FLAGS + ["-DBPGEO_PROFILE", "-o", PROF,
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc"] + g.NVCC_FLAGS + ["-DBPGEO_PROFILE"] + EXTRA + ["-o", PROF,
                                                                         os.path.join(g.CSRC, "bpgeo.cu")], cwd=ROOT)
     if "--build" in sys.argv:
         sys.exit(0)
@@ -21,9 +22,11 @@ lib = _lib.load()
 S = seeds.shape[0]
 buf = np.zeros((S, 4), dtype=np.int64)
 mbuf = np.zeros((S, 8), dtype=np.int64)
+pbuf = np.zeros((S, 8), dtype=np.int64)
 out = geo.build_sets_point(sc, sd, ws_min, ws_max, fixed_mid=True, optimize=True)
 lib.bp_prof_read(buf.ctypes.data_as(ctypes.c_void_p), S, 1)
 lib.bp_prof_read_mvie(mbuf.ctypes.data_as(ctypes.c_void_p), S, 1)
+lib.bp_prof_read_poly(pbuf.ctypes.data_as(ctypes.c_void_p), S, 1)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record()
 out = geo.build_sets_point(sc, sd, ws_min, ws_max, fixed_mid=True, optimize=True)
@@ -48,3 +51,11 @@ for k in range(4):
     print(f"  {names[k]:10s} {mbuf[:, k].sum() / n:8.0f}")
 print(f"  newton iterations per seed {mbuf[:, 5].mean():.1f}, armijo evals per iteration {mbuf[:, 6].sum() / n:.2f}, "
       f"line-search trials per iteration {mbuf[:, 7].sum() / n:.2f}")
+
+lib.bp_prof_read_poly(pbuf.ctypes.data_as(ctypes.c_void_p), S, 1)
+npass = np.minimum(it, 5).sum()
+pn = ["phase 1 (bounds)", "block argmin", "refine rounds", "halfspace", "delete scan"]
+print("polyhedron pass, cycles per pass (thread 0's view):")
+for k in range(5):
+    print(f"  {pn[k]:18s} {pbuf[:, k].sum() / npass:8.0f}")
+print(f"  picks per pass {pbuf[:, 5].sum() / npass:.1f}, refine rounds per pass {pbuf[:, 6].sum() / npass:.1f}")
