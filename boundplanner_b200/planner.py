@@ -110,15 +110,13 @@ class GpuBackend:
 def obstacle_sets(obstacles, obs_size_increase):
     """add_obstacle_reps (:131-152): inflated boxes as [A (15x3), b (15)] padded like normalize_set_size."""
     boxes = np.asarray(obstacles, float).reshape(-1, 6)
-    box = np.concatenate((np.eye(3), -np.eye(3)))
-    out = []
-    for ob in boxes:
-        a = np.zeros((15, 3))
-        b = 10.0 * np.ones(15)
-        a[:6] = box
-        b[:6] = np.concatenate((ob[3:], -ob[:3])) + obs_size_increase
-        out.append([a, b])
-    return out
+    n = boxes.shape[0]
+    a_all = np.zeros((n, 15, 3))
+    a_all[:, :6] = np.concatenate((np.eye(3), -np.eye(3)))
+    b_all = np.full((n, 15), 10.0)
+    b_all[:, :3] = boxes[:, 3:] + obs_size_increase
+    b_all[:, 3:6] = -boxes[:, :3] + obs_size_increase
+    return [[a_all[i], b_all[i]] for i in range(n)]
 
 
 class SetSequencePlanner:
@@ -150,6 +148,36 @@ class SetSequencePlanner:
         # row (+-e_k) the reference's A x - b is exactly x_k - ub_k / lb_k - x_k, padded rows give -10
         ob_b = np.array([ob[1][:6] for ob in self.obs_sets]).reshape(-1, 6)
         self._ub, self._lb = ob_b[:, :3], -ob_b[:, 3:]
+
+    # ---- known sets, stacked (vectorised forms of the per-node loops of :472-476 and :505-512) ----
+    def _nodes_reset(self):
+        self._rows_a = np.empty((0, 3))
+        self._rows_b = np.empty(0)
+        self._row_start = []                 # first stacked row of every node
+        self._node_q = np.empty((0, 9))
+        self._node_p = np.empty((0, 3))
+
+    def _nodes_add(self, a_set, b_set, q_ellipse, p_mid):
+        self._row_start.append(self._rows_a.shape[0])
+        self._rows_a = np.concatenate((self._rows_a, np.asarray(a_set, float).reshape(-1, 3)))
+        self._rows_b = np.concatenate((self._rows_b, np.asarray(b_set, float).reshape(-1)))
+        self._node_q = np.concatenate((self._node_q, np.asarray(q_ellipse, float).reshape(1, 9)))
+        self._node_p = np.concatenate((self._node_p, np.asarray(p_mid, float).reshape(1, 3)))
+
+    def _in_safe(self, sample):
+        """any node with max(a_set @ sample - b_set) < 1e-3  (:472-476)."""
+        if not self._row_start:
+            return False
+        viol = self._rows_a @ sample - self._rows_b
+        return bool((np.maximum.reduceat(viol, self._row_start) < 1e-3).any())
+
+    def _min_node_distance(self, q_ellipse, p_mid):
+        """min over nodes of ||q_ellipse - Q_v||_F + ||p_mid - p_v||  (:505-510)."""
+        if self._node_q.shape[0] == 0:
+            return np.inf
+        dq = self._node_q - np.asarray(q_ellipse, float).reshape(1, 9)
+        dp = self._node_p - np.asarray(p_mid, float).reshape(1, 3)
+        return float((np.sqrt((dq * dq).sum(axis=1)) + np.sqrt((dp * dp).sum(axis=1))).min())
 
     def _in_collision(self, sample):
         if self._ub.shape[0] == 0:
@@ -252,11 +280,19 @@ class SetSequencePlanner:
         start = np.array(start, float)
         end = np.array(end, float)
         sampled_first = False
-        for ob in self.obs_sets:                                  # :199-204
+        # :199-204, obstacle by obstacle in order; the scan for the next obstacle that contains `end` is vectorised
+        # (box rows: A x - b is x_k - ub_k / lb_k - x_k; the padded rows give -10 and never decide)
+        cursor = 0
+        while cursor < len(self.obs_sets):
+            inside = np.flatnonzero((np.maximum(end - self._ub[cursor:], self._lb[cursor:] - end) <= 0).all(axis=1))
+            if inside.size == 0:
+                break
+            ob = self.obs_sets[cursor + int(inside[0])]
             viol = ob[0] @ end - ob[1]
             if not np.any(viol > 0):
                 idx = np.argmax(viol)
                 end -= (viol[idx] - self.obs_size_increase) * ob[0][idx, :]
+            cursor += int(inside[0]) + 1
         self.omega = R.from_matrix(r1 @ r0.T).as_rotvec()        # :207-219
         self.omega_norm = np.linalg.norm(self.omega)
         self.omega_normed = self.omega / self.omega_norm if self.omega_norm > 1e-6 else np.array([0, 0, 1.0])
@@ -264,6 +300,7 @@ class SetSequencePlanner:
         self.l_ee_end = r1 @ np.array([-self.length_ee, 0, 0])
         graph, inter_graph = nx.Graph(), nx.Graph()
         self.nr_sets = self.nr_edges = self.nr_inter_set = 0
+        self._nodes_reset()
 
         a_set, b_set, q_start, p_mid_start, a_red, b_red = yield ("set_point", start, True, True)     # :278-283
         collision = False
@@ -277,6 +314,7 @@ class SetSequencePlanner:
         self.id_graph = 0
         graph.add_node(0, cset=set_start, size=1 / np.linalg.det(q_start), q_ellipse=q_start, p_mid=p_mid_start,
                        a_set=np.array(a_set), b_set=np.array(b_set))
+        self._nodes_add(a_set, b_set, q_start, p_mid_start)
         inter_graph.add_node(0, cset=set_start, id0=0, id1=0, conn_to_start=True, conn_to_end=False, p_proj=start,
                              p_via=np.concatenate((start, [0.0])), fits=True)
         self.nr_sets += 1
@@ -290,6 +328,7 @@ class SetSequencePlanner:
         self.id_inter += 1
         graph.add_node(1, cset=set_end, size=1 / np.linalg.det(q_end), q_ellipse=q_end, p_mid=p_mid_end,
                        a_set=np.array(a_set), b_set=np.array(b_set))
+        self._nodes_add(a_set, b_set, q_end, p_mid_end)
         inter_graph.add_node(1, cset=set_end, id0=1, id1=1, conn_to_start=False, conn_to_end=True, p_proj=end,
                              p_via=np.concatenate((end, [1.0])), fits=True)
         self.nr_sets += 1
@@ -319,10 +358,7 @@ class SetSequencePlanner:
                     sample = self.rng.uniform(self.workspace_min, self.workspace_max, 3)
                     nr_sampled += 1
                     in_collision = self._in_collision(sample)        # any obstacle with max(A x - b) < 1e-3
-                    for setc in graph.nodes.items():
-                        if np.max(setc[1]["a_set"] @ sample - setc[1]["b_set"]) < 1e-3:
-                            in_safe = True
-                            break
+                    in_safe = self._in_safe(sample)                  # any known set with max(A x - b) < 1e-3
                 if nr_sampled >= self.max_samples:
                     raise RuntimeError("(PosPath) Could not find collision-free sample")
                 samples = [sample]
@@ -335,14 +371,12 @@ class SetSequencePlanner:
                 # fixed_mid = (via_sample or (not sampled_first),) is a 1-tuple: always truthy (quirk Q3)
                 _, _, q_ellipse, p_mid, a_set, b_set = yield ("set_point", np.asarray(sample, float), True, optimize)
                 sampled_first = True
-                dvertex = np.inf
-                for vertex in graph.nodes.items():
-                    d = np.linalg.norm(q_ellipse - vertex[1]["q_ellipse"]) + np.linalg.norm(p_mid - vertex[1]["p_mid"])
-                    dvertex = min(dvertex, d)
+                dvertex = self._min_node_distance(q_ellipse, p_mid)
                 if dvertex > 0.01:
                     self.id_graph += 1
                     graph.add_node(self.id_graph, cset=[a_set, b_set], size=1 / np.linalg.det(q_ellipse),
                                    q_ellipse=q_ellipse, p_mid=p_mid, a_set=np.array(a_set), b_set=np.array(b_set))
+                    self._nodes_add(a_set, b_set, q_ellipse, p_mid)
                     self.nr_sets += 1
                     conn = yield from self._add_edges(self.id_graph, graph, inter_graph, end, start)
                     connected = conn or connected
