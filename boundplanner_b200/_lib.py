@@ -58,6 +58,9 @@ SIGNATURES = {
     "bp_reduce_ineqs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_check_fit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _dp, _i, _d, _vp, _vp, _vp]),
     "bp_project_points": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "bp_sample_filter": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "bp_dedupe_distance": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bp_shortest_paths": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "bp_fk_iiwa14": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "bp_probe_fp64": (_i, [_i, _i, _i, _i, _vp, _vp]),
 }

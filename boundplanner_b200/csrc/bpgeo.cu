@@ -1629,6 +1629,147 @@ __global__ void __launch_bounds__(FK_T) k_fk(const double* __restrict__ q, int B
 }
 
 // ---------------------------------------------------------------------------
+// K11-K13: the planner loop's own tests, batched over queries.
+//   k_sample_filter   the rejection loop of plan_convex_set_path (BoundPlanner.py:459-478): candidate points of a
+//                     query in draw order; a candidate is rejected when it lies in an inflated obstacle
+//                     (max(A x - b) < 1e-3, :467-471) or in a known set (max(a_set x - b_set) < 1e-3, :472-476);
+//                     out: the first accepted candidate.  One CTA per query, one warp per candidate in flight.
+//   k_dedupe_dist     the duplicate-set test (:505-512): min over the query's graph nodes of
+//                     ||Q - Q_v||_F + ||p - p_v||.  One warp per new set.
+//   k_shortest_path   nx.shortest_path(inter_graph, 0, 1, weight) (:434): Dijkstra on a small weighted graph in
+//                     CSR form, one warp per graph (lanes over nodes for the argmin, over edges for the relaxation).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const double* __restrict__ cand, int C,
+                                                       const double* __restrict__ A, const double* __restrict__ b,
+                                                       const int* __restrict__ m, int m_max,
+                                                       const int* __restrict__ set_off, int* __restrict__ first_ok,
+                                                       unsigned char* __restrict__ flags) {
+  const SceneView sc = scene_of_item(sc_all, blockIdx.x);
+  __shared__ int s_first;
+  const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  if (threadIdx.x == 0) s_first = 0x7fffffff;
+  __syncthreads();
+  const int s0 = set_off ? set_off[q] : 0, s1 = set_off ? set_off[q + 1] : 0;
+  for (int base = 0; base < C; base += 4) {
+    const int c = base + warp;
+    if (c < C) {
+      const double x0 = cand[((size_t)q * C + c) * 3], x1 = cand[((size_t)q * C + c) * 3 + 1],
+                   x2 = cand[((size_t)q * C + c) * 3 + 2];
+      bool coll = false, safe = false;
+      for (int j = lane; j < sc.n; j += 32) {
+        double lb[3], ub[3];
+        load_box(sc, j, lb, ub);
+        // rows +-e_k of the inflated box: A x - b = x_k - ub_k, lb_k - x_k (padded rows give -10)
+        const double v = fmax(fmax(fmax(x0 - ub[0], lb[0] - x0), fmax(x1 - ub[1], lb[1] - x1)), fmax(x2 - ub[2], lb[2] - x2));
+        coll |= v < 1e-3;
+      }
+      for (int t = s0 + lane; t < s1; t += 32) {
+        const double* At = A + (size_t)t * m_max * 3;
+        const double* bt = b + (size_t)t * m_max;
+        double v = -BP_INF;
+        for (int r = 0; r < m[t]; ++r) v = fmax(v, (At[3 * r] * x0 + At[3 * r + 1] * x1 + At[3 * r + 2] * x2) - bt[r]);
+        safe |= (m[t] > 0) && (v < 1e-3);
+      }
+      coll = __any_sync(full, coll);
+      safe = __any_sync(full, safe);
+      if (lane == 0) {
+        if (flags) flags[(size_t)q * C + c] = (unsigned char)((coll ? 1 : 0) | (safe ? 2 : 0));
+        if (!coll && !safe) atomicMin(&s_first, c);
+      }
+    }
+    __syncthreads();
+    if (!flags && s_first < 0x7fffffff) break;       // (with flags every candidate is classified)
+  }
+  if (threadIdx.x == 0) first_ok[q] = s_first < 0x7fffffff ? s_first : -1;
+}
+
+__global__ void __launch_bounds__(32) k_dedupe_dist(const double* __restrict__ q_new, const double* __restrict__ p_new,
+                                                    const double* __restrict__ q_nodes,
+                                                    const double* __restrict__ p_nodes,
+                                                    const int* __restrict__ node_off, double* __restrict__ dmin,
+                                                    int* __restrict__ argmin) {
+  const int i = blockIdx.x, lane = threadIdx.x;
+  double best = BP_INF;
+  int bidx = 0x7fffffff;
+  for (int v = node_off[i] + lane; v < node_off[i + 1]; v += 32) {
+    double sq = 0.0, sp = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double d = q_new[(size_t)i * 9 + k] - q_nodes[(size_t)v * 9 + k]; sq += d * d; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double d = p_new[(size_t)i * 3 + k] - p_nodes[(size_t)v * 3 + k]; sp += d * d; }
+    const double d = sqrt(sq) + sqrt(sp);
+    if (d < best) { best = d; bidx = v - node_off[i]; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+    if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  if (lane == 0) { dmin[i] = best; if (argmin) argmin[i] = bidx < 0x7fffffff ? bidx : -1; }
+}
+
+#define BP_SP_MAX_NODES 1024
+__global__ void __launch_bounds__(32) k_shortest_path(const int* __restrict__ node_off, const int* __restrict__ edge_off,
+                                                      const int* __restrict__ edge_dst,
+                                                      const double* __restrict__ edge_w, const int* __restrict__ src,
+                                                      const int* __restrict__ dst, int max_len,
+                                                      int* __restrict__ path, int* __restrict__ path_len,
+                                                      double* __restrict__ cost) {
+  __shared__ double s_d[BP_SP_MAX_NODES];
+  __shared__ int s_pred[BP_SP_MAX_NODES];
+  __shared__ unsigned char s_done[BP_SP_MAX_NODES];
+  const int g = blockIdx.x, lane = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int n0 = node_off[g], n = node_off[g + 1] - n0;        // nodes of this graph are n0 .. n0 + n - 1
+  const int* eoff = edge_off + n0;                              // CSR rows of the graph's nodes (global edge ids)
+  for (int v = lane; v < n; v += 32) { s_d[v] = BP_INF; s_pred[v] = -1; s_done[v] = 0; }
+  __syncwarp();
+  const int a = src[g], z = dst[g];
+  int len = -1;
+  if (n > 0 && n <= BP_SP_MAX_NODES && a >= 0 && a < n && z >= 0 && z < n) {
+    if (lane == 0) s_d[a] = 0.0;
+    __syncwarp();
+    for (int it = 0; it < n; ++it) {
+      double best = BP_INF;
+      int u = 0x7fffffff;
+      for (int v = lane; v < n; v += 32)
+        if (!s_done[v] && s_d[v] < best) { best = s_d[v]; u = v; }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(full, best, off);
+        const int ou = __shfl_xor_sync(full, u, off);
+        if (ov < best || (ov == best && ou < u)) { best = ov; u = ou; }
+      }
+      if (!(best < BP_INF)) break;                              // the rest is unreachable
+      if (lane == 0) s_done[u] = 1;
+      if (u == z) break;
+      __syncwarp();
+      for (int e = eoff[u] + lane; e < eoff[u + 1]; e += 32) {
+        const int v = edge_dst[e];
+        const double nd = best + edge_w[e];
+        if (!s_done[v] && nd < s_d[v]) { s_d[v] = nd; s_pred[v] = u; }   // distinct v per edge of u (simple graph)
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+    if (s_d[z] < BP_INF) {
+      len = 1;
+      for (int v = z; v != a; v = s_pred[v]) ++len;
+      if (len <= max_len && lane == 0) {
+        int v = z;
+        for (int k = len - 1; k >= 0; --k) { path[(size_t)g * max_len + k] = v; v = s_pred[v]; }
+      }
+    }
+  }
+  if (lane == 0) {
+    path_len[g] = len;
+    cost[g] = len > 0 ? s_d[z] : BP_INF;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
 template <bool POSE, bool JAC>
@@ -2068,9 +2209,9 @@ int bp_pairs_feasible_list(const double* A_dev, const double* b_dev, const int* 
 
 int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double* A_out_dev,
                     double* b_out_dev, int* m_out_dev, unsigned char* keep_out_dev, int* status_dev, void* stream) {
+  if (S == 0) return 0;                       // an empty batch has no buffers
   if (S < 0 || m_max < 1 || m_max > BP_MAX_ROWS || !A_out_dev || !b_out_dev || !m_out_dev)
     return bp_fail("bp_reduce_ineqs: bad arguments");
-  if (S == 0) return 0;
   k_reduce_rows<<<S, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, A_out_dev, b_out_dev, m_out_dev,
                                                       keep_out_dev, status_dev);
   BP_CUDA(cudaGetLastError());
@@ -2104,6 +2245,44 @@ int bp_project_points(const double* A_dev, const double* b_dev, const int* m_dev
   if (P == 0) return 0;
   k_project<<<(P + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, (const int2*)pairs_dev, P,
                                                            xd_dev, x_out_dev, status_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_sample_filter(const bp_scene* scene, const int* item_scene_dev, const double* cand_dev, int Q, int C,
+                     const double* A_dev, const double* b_dev, const int* m_dev, int m_max, const int* set_off_dev,
+                     int* first_ok_dev, unsigned char* flags_dev, void* stream) {
+  if (!scene || Q < 0 || C < 1 || !cand_dev || !first_ok_dev || (set_off_dev && (m_max < 1 || !A_dev || !b_dev || !m_dev)))
+    return bp_fail("bp_sample_filter: bad arguments");
+  if ((scene->seg_off != nullptr) != (item_scene_dev != nullptr))
+    return bp_fail("bp_sample_filter: a scene batch needs item_scene, a single scene must not have it");
+  if (Q == 0) return 0;
+  k_sample_filter<<<Q, 128, 0, (cudaStream_t)stream>>>(view_of(scene, item_scene_dev), cand_dev, C, A_dev, b_dev, m_dev,
+                                                       m_max, set_off_dev, first_ok_dev, flags_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_dedupe_distance(const double* q_new_dev, const double* p_new_dev, int P, const double* q_nodes_dev,
+                       const double* p_nodes_dev, const int* node_off_dev, double* dmin_dev, int* argmin_dev,
+                       void* stream) {
+  if (P < 0 || !q_new_dev || !p_new_dev || !node_off_dev || !dmin_dev) return bp_fail("bp_dedupe_distance: bad arguments");
+  if (P == 0) return 0;
+  k_dedupe_dist<<<P, 32, 0, (cudaStream_t)stream>>>(q_new_dev, p_new_dev, q_nodes_dev, p_nodes_dev, node_off_dev,
+                                                    dmin_dev, argmin_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_shortest_paths(const int* node_off_dev, const int* edge_off_dev, const int* edge_dst_dev,
+                      const double* edge_w_dev, const int* src_dev, const int* dst_dev, int G, int max_len,
+                      int* path_dev, int* path_len_dev, double* cost_dev, void* stream) {
+  if (G < 0 || max_len < 1 || !node_off_dev || !edge_off_dev || !src_dev || !dst_dev || !path_dev || !path_len_dev ||
+      !cost_dev)
+    return bp_fail("bp_shortest_paths: bad arguments");
+  if (G == 0) return 0;
+  k_shortest_path<<<G, 32, 0, (cudaStream_t)stream>>>(node_off_dev, edge_off_dev, edge_dst_dev, edge_w_dev, src_dev,
+                                                      dst_dev, max_len, path_dev, path_len_dev, cost_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -409,6 +409,67 @@ def pairs_feasible_list(A, b, m, pairs, tol=0.01):
     return res.bool(), x
 
 
+def sample_filter(scene, cand, A=None, b=None, m=None, set_off=None, item_scene=None, want_flags=False):
+    """Rejection loop of plan_convex_set_path (BoundPlanner.py:459-478) for Q queries: cand [Q,C,3] candidate
+    points in draw order; known sets of query q are rows set_off[q]:set_off[q+1] of (A, b, m).
+    Returns first_ok [Q] int32 (index of the first accepted candidate, -1: none) and, with want_flags, flags [Q,C]
+    uint8 (bit 0: in an inflated obstacle, bit 1: in a known set)."""
+    lib = _lib.load()
+    cand = _dev(cand)
+    Q, C = cand.shape[0], cand.shape[1]
+    first = torch.empty((Q,), dtype=torch.int32, device="cuda")
+    flags = torch.zeros((Q, C), dtype=torch.uint8, device="cuda") if want_flags else None
+    if set_off is not None:
+        A, b = _dev(A), _dev(b)
+        m = _dev(m, torch.int32)
+        set_off = _dev(set_off, torch.int32).reshape(Q + 1)
+        m_max = A.shape[1]
+    else:
+        A = b = m = None
+        m_max = 0
+    if item_scene is not None:
+        item_scene = _dev(item_scene, torch.int32).reshape(Q)
+    check(lib.bp_sample_filter(scene._h, _ptr(item_scene), _ptr(cand), Q, C, _ptr(A), _ptr(b), _ptr(m), m_max,
+                               _ptr(set_off), _ptr(first), _ptr(flags), _stream()))
+    return (first, flags) if want_flags else first
+
+
+def dedupe_distance(q_new, p_new, q_nodes, p_nodes, node_off):
+    """Duplicate-set test of plan_convex_set_path (BoundPlanner.py:505-512): for P new sets, the smallest
+    ||Q_new - Q_v||_F + ||p_new - p_v|| over nodes node_off[i]:node_off[i+1].  Returns (dmin [P], argmin [P])."""
+    lib = _lib.load()
+    q_new = _dev(q_new).reshape(-1, 9)
+    P = q_new.shape[0]
+    p_new = _dev(p_new).reshape(P, 3)
+    q_nodes = _dev(q_nodes).reshape(-1, 9)
+    p_nodes = _dev(p_nodes).reshape(-1, 3)
+    node_off = _dev(node_off, torch.int32).reshape(P + 1)
+    dmin = torch.empty((P,), dtype=torch.float64, device="cuda")
+    arg = torch.empty((P,), dtype=torch.int32, device="cuda")
+    check(lib.bp_dedupe_distance(_ptr(q_new), _ptr(p_new), P, _ptr(q_nodes), _ptr(p_nodes), _ptr(node_off), _ptr(dmin),
+                                 _ptr(arg), _stream()))
+    return dmin, arg
+
+
+def shortest_paths(node_off, edge_off, edge_dst, edge_w, src, dst, max_len=64):
+    """nx.shortest_path(inter_graph, src, dst, weight="weight") (BoundPlanner.py:434) for G graphs in CSR form
+    (see include/bpgeo.h).  Returns (path [G,max_len] local ids, path_len [G], cost [G])."""
+    lib = _lib.load()
+    node_off = _dev(node_off, torch.int32)
+    G = node_off.numel() - 1
+    edge_off = _dev(edge_off, torch.int32)
+    edge_dst = _dev(edge_dst, torch.int32)
+    edge_w = _dev(edge_w)
+    src = _dev(src, torch.int32).reshape(G)
+    dst = _dev(dst, torch.int32).reshape(G)
+    path = torch.full((G, max_len), -1, dtype=torch.int32, device="cuda")
+    plen = torch.empty((G,), dtype=torch.int32, device="cuda")
+    cost = torch.empty((G,), dtype=torch.float64, device="cuda")
+    check(lib.bp_shortest_paths(_ptr(node_off), _ptr(edge_off), _ptr(edge_dst), _ptr(edge_w), _ptr(src), _ptr(dst), G,
+                                int(max_len), _ptr(path), _ptr(plen), _ptr(cost), _stream()))
+    return path, plen, cost
+
+
 def unpack_adjacency(bits, S, row_begin=0):
     """int32 words [rows, words] -> bool [rows, S]."""
     shifts = torch.arange(32, device=bits.device, dtype=torch.int32)

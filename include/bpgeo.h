@@ -192,6 +192,29 @@ int bp_project_points(const double* A_dev, const double* b_dev, const int* m_dev
                       const int* pairs_dev, int P, const double* xd_dev, double* x_out_dev, int* status_dev,
                       void* stream);
 
+/* ---- K11 - K13 (next rows 3-4): the planner loop's own tests, batched over queries -------------
+ * bp_sample_filter replaces the rejection loop of plan_convex_set_path (BoundPlanner.py:459-478) for Q queries:
+ * cand_dev [Q,C,3] are each query's candidate points in draw order (the caller draws them from the query's own
+ * generator so the stream is the reference's); a candidate is rejected when max(A x - b) < 1e-3 for an inflated
+ * obstacle of the query's scene (:467-471) or for one of its known sets (:472-476): sets set_off[q] .. set_off[q+1]-1
+ * of A[.,m_max,3], b, m (set_off_dev NULL: no sets).  first_ok[Q] = index of the first accepted candidate or -1;
+ * flags_dev (or NULL) [Q,C]: bit 0 in collision, bit 1 in a known set (every candidate is classified when given).
+ * bp_dedupe_distance replaces the duplicate test (:505-512): dmin[P] = min over nodes node_off[i] .. node_off[i+1]-1
+ * of |Q_new - Q_v|_F + |p_new - p_v| (+inf without nodes), argmin (or NULL) the node's local index.
+ * bp_shortest_paths replaces nx.shortest_path(inter_graph, 0, 1, weight="weight") (:434) for G graphs in CSR form:
+ * graph g owns nodes node_off[g] .. node_off[g+1]-1 (at most 1024), node v's edges are edge_off[v] .. edge_off[v+1]-1
+ * with LOCAL destination ids edge_dst and weights edge_w (both directions listed); src/dst [G] local ids.
+ * path[G,max_len] local node ids, path_len[G] (-1: unreachable; > max_len: path not written), cost[G]. */
+int bp_sample_filter(const bp_scene* scene, const int* item_scene_dev, const double* cand_dev, int Q, int C,
+                     const double* A_dev, const double* b_dev, const int* m_dev, int m_max, const int* set_off_dev,
+                     int* first_ok_dev, unsigned char* flags_dev, void* stream);
+int bp_dedupe_distance(const double* q_new_dev, const double* p_new_dev, int P, const double* q_nodes_dev,
+                       const double* p_nodes_dev, const int* node_off_dev, double* dmin_dev, int* argmin_dev,
+                       void* stream);
+int bp_shortest_paths(const int* node_off_dev, const int* edge_off_dev, const int* edge_dst_dev,
+                      const double* edge_w_dev, const int* src_dev, const int* dst_dev, int G, int max_len,
+                      int* path_dev, int* path_len_dev, double* cost_dev, void* stream);
+
 /* ---- K7: iiwa14 forward kinematics -----------------------------------------------
  * Replaces the numeric branch of RobotModel.fk_pos (RobotModel.py:146-160),
  * fk_pos_col (:162-181), hom_transform_endeffector (:197-211), jacobian_fk

@@ -50,3 +50,51 @@ def project_point(a_set, b_set, x_d):
     A, b = a_set[keep], b_set[keep]
     z = min_norm_point_polytopes(A[None], (b - A @ x_d)[None])[0]
     return x_d + z
+
+
+# ---- plan_convex_set_path's own tests (BoundPlanner.py:459-478, :505-512, :434) ------------------------------
+def sample_flags(obs_sets, node_sets, sample):
+    """(in_collision, in_safe) of one candidate, the reference's loops verbatim (:467-476)."""
+    in_collision = in_safe = False
+    for ob in obs_sets:
+        if np.max(ob[0] @ sample - ob[1]) < 1e-3:
+            in_collision = True
+            break
+    for a_set, b_set in node_sets:
+        if np.max(a_set @ sample - b_set) < 1e-3:
+            in_safe = True
+            break
+    return in_collision, in_safe
+
+
+def first_free_sample(obs_sets, node_sets, candidates):
+    """Index of the first candidate the rejection loop would accept, or -1."""
+    for k, c in enumerate(candidates):
+        coll, safe = sample_flags(obs_sets, node_sets, c)
+        if not coll and not safe:
+            return k
+    return -1
+
+
+def dedupe_distance(q_ellipse, p_mid, nodes):
+    """dvertex of :505-510; nodes = [(q_ellipse_v, p_mid_v), ...]."""
+    dvertex = np.inf
+    for qv, pv in nodes:
+        d = np.linalg.norm(q_ellipse - qv) + np.linalg.norm(p_mid - pv)
+        dvertex = min(dvertex, d)
+    return dvertex
+
+
+def shortest_path(n_nodes, edges, src, dst):
+    """The reference's own call (:434): networkx shortest_path with weights.  edges = [(u, v, w), ...]."""
+    import networkx as nx
+
+    g = nx.Graph()
+    g.add_nodes_from(range(n_nodes))
+    for u, v, w in edges:
+        g.add_edge(u, v, weight=w)
+    try:
+        path = nx.shortest_path(g, src, dst, weight="weight")
+    except nx.NetworkXNoPath:
+        return None, np.inf
+    return path, nx.path_weight(g, path, weight="weight")

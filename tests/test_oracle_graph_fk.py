@@ -138,3 +138,26 @@ def test_casadi_blob_decoder_reproduces_committed_golden():
         assert np.array_equal(f_pos(q).ravel(), g["fk_pos"][i])
         assert np.array_equal(f_c5(q).ravel(), g["fk_pos_col"][i][5])
         assert np.array_equal(f_jac(q), g["jacobian"][i])
+
+
+def test_planner_loop_tests_oracle_known_answers():
+    """oracle.planner_graph restatements of the planner's rejection / duplicate / shortest-path steps
+    (BoundPlanner.py:459-478, :505-512, :434)."""
+    from oracle.planner_graph import dedupe_distance, first_free_sample, sample_flags, shortest_path
+
+    box = np.vstack((np.eye(3), -np.eye(3)))
+    obs = [[np.vstack((box, np.zeros((9, 3)))), np.concatenate(([0.2, 0.2, 0.2, 0.2, 0.2, 0.2], 10 * np.ones(9)))]]
+    node = [[box, np.array([1.0, 1.0, 1.0, -0.6, 1.0, 1.0])]]                    # 0.6 <= x <= 1
+    assert sample_flags(obs, node, np.zeros(3)) == (True, False)
+    assert sample_flags(obs, node, np.array([0.8, 0, 0])) == (False, True)
+    assert sample_flags(obs, node, np.array([0.2005, 0, 0])) == (True, False)    # max(Ax - b) = 5e-4 < 1e-3: still "in"
+    assert sample_flags(obs, node, np.array([0.202, 0, 0])) == (False, False)
+    cands = np.array([[0, 0, 0], [0.8, 0, 0], [0.4, 0, 0], [0.5, 0, 0]])
+    assert first_free_sample(obs, node, cands) == 2
+    assert first_free_sample(obs, node, cands[:2]) == -1
+    q, p = np.eye(3), np.zeros(3)
+    assert dedupe_distance(q, p, []) == np.inf
+    assert abs(dedupe_distance(q, p, [(2 * np.eye(3), np.ones(3)), (np.eye(3), np.array([0.003, 0.004, 0]))]) - 0.005) < 1e-15
+    path, cost = shortest_path(3, [(0, 2, 0.4), (2, 1, 0.3), (0, 1, 0.9)], 0, 1)
+    assert path == [0, 2, 1] and abs(cost - 0.7) < 1e-15
+    assert shortest_path(2, [], 0, 1) == (None, np.inf)
