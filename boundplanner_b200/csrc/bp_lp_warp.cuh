@@ -49,6 +49,11 @@ __device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, i
   if (iters_out) *iters_out = 0;
   if (empty) return 0;
   if (mm == 0) return 1;
+  const int m8 = (m + 7) & ~7;                        // F rows m .. m8-1 stay zero; F[.][4] = 1 on the real rows
+  for (int i = lane; i < m8; i += 32) {
+    F[i * 5 + 4] = i < m ? 1.0 : 0.0;
+    if (i >= m) { F[i * 5] = 0.0; F[i * 5 + 1] = 0.0; F[i * 5 + 2] = 0.0; F[i * 5 + 3] = 0.0; }
+  }
   double x[4] = {0.0, 0.0, 0.0, 0.0};
   if (x0) { x[0] = x0[0]; x[1] = x0[1]; x[2] = x0[2]; }
   double t = 1.0;
@@ -78,16 +83,18 @@ __device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, i
   for (int outer = 0; outer < BP_LP_OUTER_MAX; ++outer) {
     for (int inner = 0; inner < BP_LP_INNER_MAX; ++inner) {
       ++iters;
-      double rslack[BP_LP_SLOTS];
+      double rslack[BP_LP_SLOTS], rinv[BP_LP_SLOTS];
       double minq = BP_INF;
 #pragma unroll
       for (int q = 0; q < BP_LP_SLOTS; ++q) {
         const double slack = rc[q] - (ra[q][0] * x[0] + ra[q][1] * x[1] + ra[q][2] * x[2]) + x[3];
         rslack[q] = slack;
+        rinv[q] = 0.0;
         if (lane + 32 * q < m) {
           double* f = F + (lane + 32 * q) * 5;
           if (rv[q]) {
-            const double r = 1.0 / slack;
+            const double r = bp_rcp(slack);             // steers the Newton direction only
+            rinv[q] = r;
             minq = fmin(minq, slack);
             f[0] = ra[q][0] * r; f[1] = ra[q][1] * r; f[2] = ra[q][2] * r; f[3] = -r;
           } else {
@@ -98,11 +105,17 @@ __device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, i
       minq = bp_warp_min(minq);
       __syncwarp();
       {
-        double acc = 0.0;
-        if (e < 14) {
-          if (cy >= 0) { for (int i = half; i < m; i += 2) acc += F[i * 5 + cx] * F[i * 5 + cy]; }
-          else { for (int i = half; i < m; i += 2) acc += F[i * 5 + cx]; }
+        // lanes 0-15 sum the even rows, lanes 16-31 the odd rows, four rows of a parity per trip (rows m .. m8-1 of
+        // F are zero); the 14 outputs are H (10) and g (4), g as the dot with the all-ones "column" F[.][4]
+        double acc = 0.0, accb = 0.0;
+        const int cyy = cy >= 0 ? cy : 4;
+        for (int i = half; i < m8; i += 8) {
+          const double* f = F + i * 5;
+          const double p0 = f[cx], q0 = f[cyy], p1 = f[10 + cx], q1 = f[10 + cyy];
+          const double p2 = f[20 + cx], q2 = f[20 + cyy], p3 = f[30 + cx], q3 = f[30 + cyy];
+          acc += p0 * q0; accb += p1 * q1; acc += p2 * q2; accb += p3 * q3;
         }
+        acc += accb;
         acc += __shfl_xor_sync(full, acc, 16);
         if (lane < 14) OUT[lane] = acc;
       }
@@ -118,7 +131,7 @@ __device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, i
       // exits
       if (x[3] - minq <= 0.0) { result = 1; goto done; }
       {
-        const double irn = 1.0 / rn;
+        const double irn = 1.0 / rn;                    // (exact: this bound decides "disjoint")
         const double rho0 = g[0] * irn, rho1 = g[1] * irn, rho2 = g[2] * irn;
         const double lb = x[3] - mm * irn - sqrt(rho0 * rho0 + rho1 * rho1 + rho2 * rho2) * BP_LP_DIAMETER;
         if (lb > 0.0) { result = 0; goto done; }
@@ -141,7 +154,7 @@ __device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, i
         for (int q = 0; q < BP_LP_SLOTS; ++q) {
           if (rv[q]) {
             if (!(rslack[q] + alpha * rdsl[q] > 0.0)) ok = false;
-            if (want_armijo) prod *= 1.0 + alpha * rdsl[q] / rslack[q];
+            if (want_armijo) prod *= 1.0 + alpha * rdsl[q] * rinv[q];
           }
         }
         ok = __all_sync(full, ok);

@@ -112,6 +112,7 @@ struct Vec3 { double v[3]; };
 #ifdef BPGEO_PROFILE
 // profile build only (tools/prof_phases.py): per-seed cycle counters of the fused loop
 __device__ long long g_prof[4 * 65536];   // [seed][poly cycles, mvie cycles, passes, total]
+__device__ long long g_prof_pair[128];        // [0..63] histogram of Newton iterations per LP (bucket = iters / 2), [64] LPs, [65] sum of iterations, [66] max warp cycles, [67] answers 1
 __device__ long long g_prof_poly[8 * 65536];   // [cta][phase1, argmin, refine, halfspace, delete scan, picks, refine rounds, qps of thread 0]
 #define BP_PPROF_MARK() long long pprof_t_ = clock64()
 #define BP_PPROF_LAP(slot) { const long long now_ = clock64(); if (threadIdx.x == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + (slot)] += now_ - pprof_t_; pprof_t_ = now_; }
@@ -1166,6 +1167,67 @@ __global__ void __launch_bounds__(256) k_pair_filter(const double* __restrict__ 
   if (keep) list[base + __popc(mask & ((1u << lane) - 1u))] = make_int2(i, j);
 }
 
+// Rigorous pre-test of one pair by one warp, using the sets' bounding boxes AND the tolerance: a point x of the
+// tol-shrunk set j (a_s.x <= b_s - tol for every row) has the ball B(x, rho_j), rho_j = tol / max_s |a_s|, inside
+// the unshrunk set j, hence inside its bounding box: x lies in the box eroded by rho_j.  The pair is disjoint when
+//   * the two eroded boxes do not overlap, or
+//   * for some row r of set i the smallest a_r.x over the eroded box of j already exceeds b_r - tol
+//     (the oriented test the box-box test misses), or the same with i and j exchanged.
+// Only "disjoint" is ever concluded here; every "intersects" still comes from the LP.
+__device__ __forceinline__ bool bp_pair_margin_reject(const double* __restrict__ Ai, const double* __restrict__ bi,
+                                                      int mi, const double* __restrict__ boxi,
+                                                      const double* __restrict__ Aj, const double* __restrict__ bj,
+                                                      int mj, const double* __restrict__ boxj, double tol) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double lo_i[3], hi_i[3], lo_j[3], hi_j[3];
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    lo_i[k] = __ldg(boxi + k); hi_i[k] = __ldg(boxi + 3 + k);
+    lo_j[k] = __ldg(boxj + k); hi_j[k] = __ldg(boxj + 3 + k);
+    finite = finite && fabs(lo_i[k]) < 1e6 && fabs(hi_i[k]) < 1e6 && fabs(lo_j[k]) < 1e6 && fabs(hi_j[k]) < 1e6;
+  }
+  if (!finite) return false;                       // no bounding box (unbounded / degenerate description)
+  // largest row norm of each set
+  double ni = 0.0, nj = 0.0;
+  for (int r = lane; r < mi; r += 32) {
+    const double a0 = __ldg(Ai + 3 * r), a1 = __ldg(Ai + 3 * r + 1), a2 = __ldg(Ai + 3 * r + 2);
+    ni = fmax(ni, a0 * a0 + a1 * a1 + a2 * a2);
+  }
+  for (int r = lane; r < mj; r += 32) {
+    const double a0 = __ldg(Aj + 3 * r), a1 = __ldg(Aj + 3 * r + 1), a2 = __ldg(Aj + 3 * r + 2);
+    nj = fmax(nj, a0 * a0 + a1 * a1 + a2 * a2);
+  }
+  ni = sqrt(-bp_warp_min(-ni));
+  nj = sqrt(-bp_warp_min(-nj));
+  if (!(ni > 0.0) || !(nj > 0.0) || !(tol >= 0.0)) return false;
+  // erosion, kept a hair smaller than rho so that rounding can only weaken the test
+  const double ri = (tol / ni) * (1.0 - 1e-9) - BP_AABB_EPS, rj = (tol / nj) * (1.0 - 1e-9) - BP_AABB_EPS;
+  bool apart = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    lo_i[k] += ri; hi_i[k] -= ri; lo_j[k] += rj; hi_j[k] -= rj;
+    if (lo_i[k] > hi_i[k] || lo_j[k] > hi_j[k]) apart = true;            // a shrunk set is empty
+    if (lo_i[k] > hi_j[k] || lo_j[k] > hi_i[k]) apart = true;            // eroded boxes apart
+  }
+  if (!apart) {
+    for (int r = lane; r < mi; r += 32) {           // rows of i against the eroded box of j
+      const double a0 = __ldg(Ai + 3 * r), a1 = __ldg(Ai + 3 * r + 1), a2 = __ldg(Ai + 3 * r + 2);
+      const double mu = (fmin(a0 * lo_j[0], a0 * hi_j[0]) + fmin(a1 * lo_j[1], a1 * hi_j[1])) + fmin(a2 * lo_j[2], a2 * hi_j[2]);
+      const double rhs = __ldg(bi + r) - tol;
+      if (mu - rhs > 1e-9 * (1.0 + fabs(rhs))) apart = true;
+    }
+    for (int r = lane; r < mj; r += 32) {           // rows of j against the eroded box of i
+      const double a0 = __ldg(Aj + 3 * r), a1 = __ldg(Aj + 3 * r + 1), a2 = __ldg(Aj + 3 * r + 2);
+      const double mu = (fmin(a0 * lo_i[0], a0 * hi_i[0]) + fmin(a1 * lo_i[1], a1 * hi_i[1])) + fmin(a2 * lo_i[2], a2 * hi_i[2]);
+      const double rhs = __ldg(bj + r) - tol;
+      if (mu - rhs > 1e-9 * (1.0 + fabs(rhs))) apart = true;
+    }
+  }
+  return __any_sync(full, apart);
+}
+
 __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
                                                  const int* __restrict__ m, int S, int m_max, double tol,
                                                  int row_begin, const double* __restrict__ aabb,
@@ -1180,6 +1242,14 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
   const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int p = warp; p < n; p += nwarps) {       // one warp per surviving pair
     const int2 pr = list[p];
+    if (bp_pair_margin_reject(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x], aabb + (size_t)pr.x * 6,
+                              A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], aabb + (size_t)pr.y * 6,
+                              tol)) {
+#ifdef BPGEO_PROFILE
+      if (lane == 0) atomicAdd((unsigned long long*)&g_prof_pair[68], 1ull);
+#endif
+      continue;
+    }
     double xi[3], x0[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {                       // start at the middle of the overlap of the two boxes
@@ -1188,9 +1258,25 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
       x0[k] = 0.5 * (lo + hi);
       if (!(fabs(x0[k]) < 1e6)) x0[k] = 0.0;            // unbounded description: no box
     }
+#ifdef BPGEO_PROFILE
+    int lp_iters = 0;
+    const long long lp_t0 = clock64();
+    const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
+                                          A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
+                                          scratch[wib], &lp_iters, xi, x0, BP_LP_T0_SCALE);
+    if (lane == 0) {
+      int bk = lp_iters / 2; if (bk > 63) bk = 63;
+      atomicAdd((unsigned long long*)&g_prof_pair[bk], 1ull);
+      atomicAdd((unsigned long long*)&g_prof_pair[64], 1ull);
+      atomicAdd((unsigned long long*)&g_prof_pair[65], (unsigned long long)lp_iters);
+      atomicMax((unsigned long long*)&g_prof_pair[66], (unsigned long long)(clock64() - lp_t0));
+      if (res) atomicAdd((unsigned long long*)&g_prof_pair[67], 1ull);
+    }
+#else
     const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                           A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
                                           scratch[wib], nullptr, xi, x0, BP_LP_T0_SCALE);
+#endif
     if (lane == 0 && res) {
       atomicOr(adj + (size_t)(pr.x - row_begin) * words + (pr.y >> 5), 1u << (pr.y & 31));
       if (x_feas) {
@@ -1225,6 +1311,10 @@ __global__ void __launch_bounds__(256) k_pair_list(const double* __restrict__ A,
   }
   int res = 0;
   double xi[3] = {0.0, 0.0, 0.0};
+  if (!apart)
+    apart = bp_pair_margin_reject(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
+                                  aabb + (size_t)pr.x * 6, A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max,
+                                  m[pr.y], aabb + (size_t)pr.y * 6, tol);
   if (!apart)
     res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                 A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol, scratch[wib],
@@ -1828,6 +1918,16 @@ int bp_prof_read_mvie(long long* host_out, int n_seeds, int reset) {
     void* ptr = nullptr;
     BP_CUDA(cudaGetSymbolAddress(&ptr, g_prof_mvie));
     BP_CUDA(cudaMemset(ptr, 0, sizeof(g_prof_mvie)));
+  }
+  return 0;
+}
+int bp_prof_read_pair(long long* host_out, int reset) {
+  BP_CUDA(cudaDeviceSynchronize());
+  BP_CUDA(cudaMemcpyFromSymbol(host_out, g_prof_pair, sizeof(g_prof_pair)));
+  if (reset) {
+    void* ptr = nullptr;
+    BP_CUDA(cudaGetSymbolAddress(&ptr, g_prof_pair));
+    BP_CUDA(cudaMemset(ptr, 0, sizeof(g_prof_pair)));
   }
   return 0;
 }

@@ -59,3 +59,18 @@ print("polyhedron pass, cycles per pass (thread 0's view):")
 for k in range(5):
     print(f"  {pn[k]:18s} {pbuf[:, k].sum() / npass:8.0f}")
 print(f"  picks per pass {pbuf[:, 5].sum() / npass:.1f}, refine rounds per pass {pbuf[:, 6].sum() / npass:.1f}")
+
+# pair LP statistics on the same sets
+qbuf = np.zeros(128, dtype=np.int64)
+geo.pair_feasible(out.A, out.b, out.m, 0.01)
+lib.bp_prof_read_pair(qbuf.ctypes.data_as(ctypes.c_void_p), 1)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+geo.pair_feasible(out.A, out.b, out.m, 0.01)
+e1.record()
+torch.cuda.synchronize()
+lib.bp_prof_read_pair(qbuf.ctypes.data_as(ctypes.c_void_p), 1)
+print(f"pair pipeline {e0.elapsed_time(e1) * 1e3:.0f} us: {qbuf[64]} LPs of {S * (S - 1) // 2} pairs, {qbuf[67]} intersect, "
+      f"mean Newton iterations {qbuf[65] / max(qbuf[64], 1):.1f}, slowest LP {qbuf[66]} cycles, "
+      f"{qbuf[68]} more pairs rejected by the margin test before the LP")
+print("  iterations histogram (bucket of 2):", [int(v) for v in qbuf[:40]])
