@@ -18,8 +18,9 @@ primitives and receives their results:
 
   ("set_point", p, fixed_mid, optimize) -> (A, b, q_ellipse, p_mid, A_red, b_red)   find_set_around_point + reduce_ineqs
   ("set_line", p0, p1)                  -> (A, b, q_ellipse, p_mid, collision, A_red, b_red)
-  ("intersect_many", sets, set_new, tol)-> [(point | None, ok), ...]                 set_intersection vs every existing set
-  ("fit_many", [(A, b, sample), ...])   -> [(fits, via), ...]                        check_intersection
+  ("edges", sets, set_new, tol, ee)     -> [(point | None, ok, fits, via), ...]      set_intersection of the new set with
+                                           every existing set + check_intersection of every hit (one device round:
+                                           the fit check starts from the LP's point and never leaves the GPU)
   ("project", A, b, x_d)                -> x                                         projection QP of add_edges
 
 Drivers: ``plan_set_sequence`` answers every request at once through a backend
@@ -81,6 +82,16 @@ class GpuBackend:
             A, b, Q, p, coll = self.set_finder.find_set_collision_avoidance(req[1], req[2], True)
             Ar, br = reduce_ineqs(A, b)
             return A, b, Q, p, coll, Ar, br
+        if kind == "edges":
+            others, set_new, tol, (l_ee, omega_normed, omega_norm) = req[1], req[2], req[3], req[4]
+            A, b, m = self._pack([set_new] + list(others))
+            A, b, m = torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(), torch.as_tensor(m).cuda()
+            pairs = np.array([(1 + k, 0) for k in range(len(others))], np.int32)      # rows of the old set first
+            ok, x = self._geo.pairs_feasible_list(A, b, m, pairs, tol)
+            fits, omega = self._geo.check_fit(A, b, m, pairs, l_ee, omega_normed, omega_norm, x0=x)
+            ok, x, fits, omega = ok.cpu().numpy(), x.cpu().numpy(), fits.cpu().numpy(), omega.cpu().numpy()
+            return [(x[k].copy() if ok[k] else None, bool(ok[k]), bool(fits[k]),
+                     np.concatenate((x[k], [float(omega[k]) if fits[k] else 0.0]))) for k in range(len(others))]
         if kind == "intersect_many":
             out = []
             for setc in req[1]:
@@ -192,17 +203,16 @@ class SetSequencePlanner:
         others = [(vid, vdata) for vid, vdata in graph.nodes.items() if vid != id_new]
         if not others:
             return connected
-        inter = yield ("intersect_many", [v["cset"] for _, v in others], set_new, 0.01)
+        res = yield ("edges", [v["cset"] for _, v in others], set_new, 0.01,
+                     (self.l_ee, self.omega_normed, self.omega_norm))
         hits = []
-        for (vid, vdata), (p_intersect, ok) in zip(others, inter):
+        for (vid, vdata), (p_intersect, ok, fits, via) in zip(others, res):
             if ok:
                 set_inter = [np.concatenate((vdata["cset"][0], set_new[0])), np.concatenate((vdata["cset"][1], set_new[1]))]
-                hits.append((vid, vdata, p_intersect, set_inter))
+                hits.append((vid, vdata, p_intersect, set_inter, fits, via))
         if not hits:
             return connected
-        fit_res = yield ("fit_many", [(h[3][0], h[3][1], h[2]) for h in hits],
-                         (self.l_ee, self.omega_normed, self.omega_norm))
-        for (vid, vdata, p_intersect, set_inter), (fits, via) in zip(hits, fit_res):
+        for vid, vdata, p_intersect, set_inter, fits, via in hits:
             self.id_inter += 1
             inter_graph.add_node(self.id_inter, cset=set_inter, id0=vid, id1=id_new, conn_to_start=False,
                                  conn_to_end=False, p_proj=None, p_via=via, fits=fits)
@@ -476,6 +486,36 @@ class BatchedGpuExecutor:
                 err = _set_errors(int(st[k]), int(m[k]))
                 out[q] = err if err is not None else (A[k, : m[k]].copy(), b[k, : m[k]].copy(), Q[k].copy(), P[k].copy(),
                                                       bool(coll[k]), Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy())
+
+        qids = by_kind.get("edges", [])
+        if qids:
+            groups = {}
+            for q in qids:
+                l_ee, om, on = pending[q][4]
+                groups.setdefault((tuple(np.round(l_ee, 15)), tuple(np.round(om, 15)), round(float(on), 15),
+                                   float(pending[q][3])), []).append(q)
+            for gq in groups.values():
+                self.calls += 1
+                l_ee, om, on = pending[gq[0]][4]
+                tol = pending[gq[0]][3]
+                sets, pairs, spans = [], [], []
+                for q in gq:
+                    _, others, set_new, _, _ = pending[q]
+                    base = len(sets)
+                    sets.append(set_new)
+                    sets.extend(others)
+                    pairs.extend((base + 1 + k, base) for k in range(len(others)))  # rows of the old set first
+                    spans.append(len(others))
+                A, b, m = self._pack(sets)
+                pairs = np.asarray(pairs, np.int32)
+                ok, x = geo.pairs_feasible_list(A, b, m, pairs, tol)
+                fits, omega = geo.check_fit(A, b, m, pairs, l_ee, om, on, x0=x)       # x stays on the device
+                ok, x, fits, omega = ok.cpu().numpy(), x.cpu().numpy(), fits.cpu().numpy(), omega.cpu().numpy()
+                o = 0
+                for q, n in zip(gq, spans):
+                    out[q] = [(x[o + k].copy() if ok[o + k] else None, bool(ok[o + k]), bool(fits[o + k]),
+                               np.concatenate((x[o + k], [omega[o + k] if fits[o + k] else 0.0]))) for k in range(n)]
+                    o += n
 
         qids = by_kind.get("intersect_many", [])
         if qids:

@@ -66,6 +66,18 @@ class OracleBackend:
             A, b, Q, p, coll = self.find_set_collision_avoidance(req[1], req[2], True)
             Ar, br = self.reduce_ineqs(A, b)
             return A, b, Q, p, coll, Ar, br
+        if kind == "edges":
+            l_ee, omega_normed, omega_norm = req[4]
+            out = []
+            for setc in req[1]:
+                x, _, ok = self.set_intersection(setc, req[2], req[3])
+                fits, via = False, None
+                if ok:
+                    a_set = np.concatenate((setc[0], req[2][0]))
+                    b_set = np.concatenate((setc[1], req[2][1]))
+                    fits, via = self.check_intersection(a_set, b_set, l_ee, x, omega_normed, omega_norm)
+                out.append((x, ok, fits, via))
+            return out
         if kind == "intersect_many":
             out = []
             for setc in req[1]:
