@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbpgeo.so")
 
 BP_MAX_ROWS = 48
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 STATUS_OK = 0
 STATUS_ELLIPSE_VIOLATION = 1
@@ -56,7 +56,7 @@ SIGNATURES = {
     "bp_set_aabb": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "bp_pair_feasible": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bp_reduce_ineqs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "bp_check_fit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _dp, _i, _d, _vp, _vp, _vp]),
+    "bp_check_fit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _dp, _i, _d, _vp, _vp, _vp]),
     "bp_project_points": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_sample_filter": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_dedupe_distance": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1487,12 +1487,17 @@ struct BpFitRows {
 
 __global__ void __launch_bounds__(256) k_fit_check(const double* __restrict__ A, const double* __restrict__ b,
                                                    const int* __restrict__ m, int m_max, const int2* __restrict__ pairs,
-                                                   int P, const double* __restrict__ x0s, FitParams fp,
+                                                   int P, const double* __restrict__ x0s,
+                                                   const int* __restrict__ active, FitParams fp,
                                                    int* __restrict__ fits, int* __restrict__ first_sample) {
   __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int p = blockIdx.x * 8 + wib;
   if (p >= P) return;
+  if (active && !active[p]) {                 // e.g. the pair does not intersect: no fit check (fits = 0)
+    if (lane == 0) { fits[p] = 0; first_sample[p] = -1; }
+    return;
+  }
   const int2 pr = pairs[p];
   const int m1 = m[pr.x], m2 = (pr.y == pr.x) ? 0 : m[pr.y];     // i == j: a single set
   const int mtot = m1 + m2;
@@ -2319,8 +2324,8 @@ int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, 
 }
 
 int bp_check_fit(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, const int* pairs_dev,
-                 int P, const double* x0_dev, const double* l_ee_samples_host, int n_samples, double margin,
-                 int* fits_dev, int* first_sample_dev, void* stream) {
+                 int P, const double* x0_dev, const int* active_dev, const double* l_ee_samples_host, int n_samples,
+                 double margin, int* fits_dev, int* first_sample_dev, void* stream) {
   if (S < 0 || P < 0 || m_max < 1 || m_max > BP_MAX_ROWS || n_samples < 1 || n_samples > BP_FIT_SAMPLES ||
       !l_ee_samples_host || !fits_dev || !first_sample_dev)
     return bp_fail("bp_check_fit: bad arguments");
@@ -2332,7 +2337,7 @@ int bp_check_fit(const double* A_dev, const double* b_dev, const int* m_dev, int
   fp.margin = margin;
   fp.n_samples = n_samples;
   k_fit_check<<<(P + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, (const int2*)pairs_dev, P,
-                                                             x0_dev, fp, fits_dev, first_sample_dev);
+                                                             x0_dev, active_dev, fp, fits_dev, first_sample_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -361,9 +361,11 @@ def rodrigues_matrix(omega, phi):
     return np.eye(3) + np.sin(phi) * k + (1.0 - np.cos(phi)) * (k @ k)
 
 
-def check_fit(A, b, m, pairs, l_ee, omega_normed, omega_norm, x0=None, n_samples=20, margin=0.001):
+def check_fit(A, b, m, pairs, l_ee, omega_normed, omega_norm, x0=None, n_samples=20, margin=0.001, active=None):
     """BoundPlanner.check_intersection (BoundPlanner.py:745-772) for P intersection sets.
-    pairs [P,2] int32: set indices (i, j); returns (fits [P] bool, omega_sample [P] float, -1 where none)."""
+    pairs [P,2] int32: set indices (i, j); returns (fits [P] bool, omega_sample [P] float, -1 where none).
+    active [P] (device bool/int, optional): pairs with 0 are skipped (fits False) -- add_edges only checks the
+    pairs that intersect, and that answer is already on the device."""
     lib = _lib.load()
     S, m_max = A.shape[0], A.shape[1]
     pairs = _dev(pairs, torch.int32).reshape(-1, 2)
@@ -373,7 +375,10 @@ def check_fit(A, b, m, pairs, l_ee, omega_normed, omega_norm, x0=None, n_samples
     fits = torch.zeros((P,), dtype=torch.int32, device="cuda")
     first = torch.full((P,), -1, dtype=torch.int32, device="cuda")
     x0 = _dev(x0).reshape(P, 3) if x0 is not None else None
-    check(lib.bp_check_fit(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(pairs), P, _ptr(x0), ls.ctypes.data_as(_dp),
+    if active is not None:
+        active = _dev(active, torch.int32).reshape(P)
+    check(lib.bp_check_fit(_ptr(A), _ptr(b), _ptr(m), S, m_max, _ptr(pairs), P, _ptr(x0), _ptr(active),
+                           ls.ctypes.data_as(_dp),
                            int(n_samples), float(margin), _ptr(fits), _ptr(first), _stream()))
     if bool((fits < 0).any().item()):
         raise _lib.BpGeoError("check_fit: an intersection set has more than 48 rows")

@@ -55,67 +55,19 @@ def _set_errors(status, rows):
 
 
 class GpuBackend:
-    """Answers planner requests one at a time with batch-of-one kernel calls."""
+    """Answers planner requests one at a time: a batch of one through the same executor the lock-step driver
+    uses, so every request is one chain of kernels on the device and one read-back."""
 
     def __init__(self, obstacles, obs_size_increase, workspace_max, workspace_min):
-        from . import geometry as geo
-        from .convex_set_finder import ConvexSetFinder
-        from .set_graph import pack_sets
-
-        self._geo = geo
-        self._pack = pack_sets
         self.obs_sets = obstacle_sets(obstacles, obs_size_increase)
-        self.set_finder = ConvexSetFinder(self.obs_sets, [None] * len(self.obs_sets), workspace_max, workspace_min)
+        self._bx = BatchedGpuExecutor([np.asarray(obstacles, float).reshape(-1, 6)], obs_size_increase, workspace_max,
+                                      workspace_min)
 
     def execute(self, req):
-        import torch
-
-        from .set_graph import set_intersection
-        from .utils import reduce_ineqs
-
-        kind = req[0]
-        if kind == "set_point":
-            A, b, Q, p = self.set_finder.find_set_around_point(req[1], fixed_mid=req[2], optimize=req[3])
-            Ar, br = reduce_ineqs(A, b)
-            return A, b, Q, p, Ar, br
-        if kind == "set_line":
-            A, b, Q, p, coll = self.set_finder.find_set_collision_avoidance(req[1], req[2], True)
-            Ar, br = reduce_ineqs(A, b)
-            return A, b, Q, p, coll, Ar, br
-        if kind == "edges":
-            others, set_new, tol, (l_ee, omega_normed, omega_norm) = req[1], req[2], req[3], req[4]
-            A, b, m = self._pack([set_new] + list(others))
-            A, b, m = torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(), torch.as_tensor(m).cuda()
-            pairs = np.array([(1 + k, 0) for k in range(len(others))], np.int32)      # rows of the old set first
-            ok, x = self._geo.pairs_feasible_list(A, b, m, pairs, tol)
-            fits, omega = self._geo.check_fit(A, b, m, pairs, l_ee, omega_normed, omega_norm, x0=x)
-            ok, x, fits, omega = ok.cpu().numpy(), x.cpu().numpy(), fits.cpu().numpy(), omega.cpu().numpy()
-            return [(x[k].copy() if ok[k] else None, bool(ok[k]), bool(fits[k]),
-                     np.concatenate((x[k], [float(omega[k]) if fits[k] else 0.0]))) for k in range(len(others))]
-        if kind == "intersect_many":
-            out = []
-            for setc in req[1]:
-                x, _, ok = set_intersection(setc, req[2], req[3])
-                out.append((x, ok))
-            return out
-        if kind == "fit_many":
-            l_ee, omega_normed, omega_norm = req[2]
-            out = []
-            for a_set, b_set, sample in req[1]:
-                A, b, m = self._pack([[a_set, b_set]])
-                fits, omega = self._geo.check_fit(torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(),
-                                                  torch.as_tensor(m).cuda(), np.array([[0, 0]], np.int32), l_ee,
-                                                  omega_normed, omega_norm, x0=np.asarray(sample, float)[None])
-                ok = bool(fits.item())
-                out.append((ok, np.concatenate((sample, [float(omega.item()) if ok else 0.0]))))
-            return out
-        if kind == "project":
-            A, b, m = self._pack([[req[1], req[2]]])
-            x, _ = self._geo.project_points(torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(),
-                                            torch.as_tensor(m).cuda(), np.array([[0, 0]], np.int32),
-                                            np.asarray(req[3], float)[None])
-            return x[0].cpu().numpy()
-        raise ValueError(f"unknown request {kind}")
+        ans = self._bx.execute({0: req})[0]
+        if isinstance(ans, Exception):
+            raise ans
+        return ans
 
 
 def obstacle_sets(obstacles, obs_size_increase):
@@ -509,7 +461,7 @@ class BatchedGpuExecutor:
                 A, b, m = self._pack(sets)
                 pairs = np.asarray(pairs, np.int32)
                 ok, x = geo.pairs_feasible_list(A, b, m, pairs, tol)
-                fits, omega = geo.check_fit(A, b, m, pairs, l_ee, om, on, x0=x)       # x stays on the device
+                fits, omega = geo.check_fit(A, b, m, pairs, l_ee, om, on, x0=x, active=ok)   # x, ok stay on the device
                 ok, x, fits, omega = ok.cpu().numpy(), x.cpu().numpy(), fits.cpu().numpy(), omega.cpu().numpy()
                 o = 0
                 for q, n in zip(gq, spans):

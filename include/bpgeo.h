@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BPGEO_ABI_VERSION 1
+#define BPGEO_ABI_VERSION 2
 #define BP_MAX_ROWS 48 /* hard cap on rows per convex set (reference MVIE cap: 20, quirk Q5) */
 
 typedef struct bp_scene bp_scene;
@@ -182,12 +182,14 @@ int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, 
  * bp_check_fit replaces BoundPlanner.check_intersection (BoundPlanner.py:745-772):
  * l_ee_samples_host [n_samples,3] are the rotated offsets Rodrigues(omega_hat, |omega| k/19) l_ee
  * (n_samples = 20), margin = 0.001; fits[P] = 1/0 (-1: too many rows), first_sample[P] = the
- * first k that fits or -1; x0_dev (or NULL) [P,3] start points.
+ * first k that fits or -1; x0_dev (or NULL) [P,3] start points; active_dev lets the result of
+ * bp_pairs_feasible_list gate the check on the device (add_edges only checks pairs that intersect).
  * bp_project_points replaces the projection QP of add_edges (BoundPlanner.py:842-864):
  * x_out[P,3] = argmin |x - xd|^2 over the intersection set. */
 int bp_check_fit(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, const int* pairs_dev,
-                 int P, const double* x0_dev, const double* l_ee_samples_host, int n_samples, double margin,
-                 int* fits_dev, int* first_sample_dev, void* stream);
+                 int P, const double* x0_dev, const int* active_dev /* NULL or [P]: 0 = skip the pair (fits = 0) */,
+                 const double* l_ee_samples_host, int n_samples, double margin, int* fits_dev, int* first_sample_dev,
+                 void* stream);
 int bp_project_points(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max,
                       const int* pairs_dev, int P, const double* xd_dev, double* x_out_dev, int* status_dev,
                       void* stream);

@@ -21,3 +21,22 @@ pr.enable()
 planner.plan_set_sequence(st.copy(), en.copy(), r0, r0)
 pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+
+# per-request-kind wall time of the batch-of-one backend
+import collections
+acc = collections.defaultdict(lambda: [0, 0.0])
+orig = backend.execute
+def timed(req):
+    t0 = time.perf_counter()
+    try:
+        return orig(req)
+    finally:
+        a = acc[req[0]]
+        a[0] += 1
+        a[1] += time.perf_counter() - t0
+backend.execute = timed
+planner = SetSequencePlanner(ob, infl, list(wmax), list(wmin), backend=backend, rng=np.random.default_rng(qid))
+t0 = time.perf_counter()
+planner.plan_set_sequence(st.copy(), en.copy(), r0, r0)
+tot = time.perf_counter() - t0
+print("total ms", tot * 1e3, {k: (v[0], round(v[1] * 1e3, 2)) for k, v in acc.items()})
