@@ -472,6 +472,8 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
         # Algorithmic bytes per launch: seeds in, the scene once, one padded set + ellipsoid
         # out per seed.  Algorithmic flops: passes x [N x (1.1 kflop QP + 64 flop x picked rows)] per seed for
         # the polyhedron passes + Newton iterations x (m x 200 + 250) flop for the MVIEs (passes + 1 per seed).
+        # (SURVEY 8d's per-unit figures; the kernel itself solves far fewer QPs than N per pass -- lazy lower
+        # bounds -- so this is the reference algorithm's work per second, not executed instructions.)
         picks = max(m_mean - 6.0, 0.0)
         bytes_alg = S * 24 + N * 48 + S * (m_mean * 32 + 12 * 8 + 12)
         flops = S * (passes_mean * N * (1100.0 + 64.0 * picks)
@@ -480,7 +482,7 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
         ach = bytes_alg / (dur * 1e-3) / 1e9
         return {"kernel": "k_iris_fused (set build: whole find_set_around_point loop, one CTA per seed)",
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": 171520, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_final_iris_fused.txt",
+                "traffic": 191744, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_final2_iris_fused.txt",
                 "peak_source": which,
                 "note": "latency-bound fp64 kernel: 256 independent chains of ~5 x (polyhedron pass + ~35 dependent "
                         "Newton iterations); it moves only its compulsory bytes (operands live in L2 / shared "
@@ -495,7 +497,7 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
                 "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 201795328,
                 "traffic_source": "ncu dram__bytes_read+write per launch (below the 260 MB algorithmic bytes: part "
                                   "of the output is still dirty in the 126 MB L2 at kernel end), "
-                                  "profiles/r01_ncu_final_pair_fk.txt",
+                                  "profiles/r01_ncu_final2_pair_fk.txt",
                 "peak_source": which, "poses_per_sec": B / (t_fk * 1e-3)}
 
     return {"kernels": kernels, "roofline": roofline, "roofline_fk": roofline_fk}
