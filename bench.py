@@ -216,9 +216,19 @@ def run_gpu(args):
 
     spipe = None
     if world > 1 and not args.no_cuda_graph:
-        from boundplanner_b200.pipeline import ShardedSetGraphPipeline
+        from boundplanner_b200.pipeline import PeerSetGraphPipeline, ShardedSetGraphPipeline
 
-        spipe = ShardedSetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
+        # exchange by peer stores over NVLink (symmetric memory) in one CUDA graph per step; BPGEO_PEER=0 or a
+        # box without peer mappings -> the NCCL all-gather pipeline
+        peer_note = None
+        if os.environ.get("BPGEO_PEER", "1") != "0":
+            try:
+                spipe = PeerSetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
+            except Exception as e:  # noqa: BLE001
+                peer_note = f"symmetric memory unavailable ({type(e).__name__}): NCCL pipeline"
+                spipe = None
+        if spipe is None:
+            spipe = ShardedSetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
         spipe.seeds_dev.copy_(seeds_dev)
 
     def step_device(seeds_d):
@@ -227,8 +237,7 @@ def run_gpu(args):
         if spipe is not None:
             if seeds_d is not spipe.seeds_dev and seeds_d is not seeds_dev:
                 spipe.seeds_dev.copy_(seeds_d)
-            out, _ = spipe.run_device()
-            return out, spipe.bits_gathered
+            return spipe.run_device()
         out = geo.build_sets_point(scene, seeds_d, ws_min, ws_max, fixed_mid=True, optimize=True)
         bits, _ = bpd.sharded_adjacency(out.A, out.b, out.m, pair_fn, TOL)
         return out, bits
@@ -293,6 +302,8 @@ def run_gpu(args):
     fused = os.environ.get("BPGEO_FUSED", "1") != "0" and N_OBS <= 4096
     # fused: k_iris_fused + aabb + filter + lp;  else state_init, 5x(poly,mvie), final mvie, export, aabb+filter+lp
     launches_per_step = (1 + 3) if fused else (1 + 5 * 2 + 1 + 1 + 3)
+    if type(spipe).__name__ == "PeerSetGraphPipeline":
+        launches_per_step += 2                      # the two peer-scatter kernels (barriers are torch's)
     if rank == 0:
         peaks = {}
         try:
@@ -307,6 +318,10 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "n_obstacles": N_OBS, "seeds_per_gpu": N_SEEDS, "pairs": n_pairs,
                        "l2": "flushed between timed steps (256 MiB fill)",
                        "launch": ("one CUDA graph per step" if pipe is not None else
+                                  ("one CUDA graph per step; sets and adjacency rows exchanged by peer stores over "
+                                   "NVLink + two signal-pad barriers (no NCCL on the data path)"
+                                   + ("" if getattr(spipe, "_graph", None) is not None else " [eager: capture refused]"))
+                                  if type(spipe).__name__ == "PeerSetGraphPipeline" else
                                   "two CUDA graphs + two NCCL all-gathers per step" if spipe is not None else
                                   "eager launches"),
                        "frac_sets_over_20_rows": float((mrows > 20).mean()),

@@ -61,6 +61,8 @@ SIGNATURES = {
     "bp_sample_filter": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_dedupe_distance": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_shortest_paths": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "bp_scatter_sets_peers": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _sz, _sz, _sz, _sz, _vp]),
+    "bp_scatter_rows_peers": (_i, [_vp, _i, _i, _i, _vp, _i, _sz, _vp]),
     "bp_fk_iiwa14": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "bp_probe_fp64": (_i, [_i, _i, _i, _i, _vp, _vp]),
 }

@@ -1865,6 +1865,45 @@ __global__ void __launch_bounds__(32) k_shortest_path(const int* __restrict__ no
 }
 
 // ---------------------------------------------------------------------------
+// Multi-GPU exchange by peer stores over NVLink: instead of packing the sets, calling an NCCL
+// all-gather and unpacking, the owner writes every set straight into the global tables of EVERY rank (its own
+// included) through the peers' mapped addresses -- A[S,m_max,3], b[S,m_max], m[S] and the bounding boxes
+// [S,6] at row slot0 + s.  The adjacency row block goes out the same way.  peer_base[r] is the base address
+// of rank r's symmetric allocation (same layout on every rank), off_* the byte offsets of the tables in it.
+// One cross-rank barrier (the symmetric-memory signal pads) follows each scatter; nothing is staged or copied.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_scatter_sets_peers(const double* __restrict__ A, const double* __restrict__ b,
+                                                            const int* __restrict__ m,
+                                                            const double* __restrict__ aabb, int m_max, int slot0,
+                                                            const unsigned long long* __restrict__ peer_base,
+                                                            int world, size_t off_A, size_t off_b, size_t off_m,
+                                                            size_t off_aabb) {
+  const int s = blockIdx.x, g = slot0 + s, tid = threadIdx.x;
+  const double* As = A + (size_t)s * m_max * 3;
+  const double* bs = b + (size_t)s * m_max;
+  for (int r = 0; r < world; ++r) {
+    char* base = (char*)peer_base[r];
+    double* Ad = (double*)(base + off_A) + (size_t)g * m_max * 3;
+    double* bd = (double*)(base + off_b) + (size_t)g * m_max;
+    for (int e = tid; e < 3 * m_max; e += blockDim.x) Ad[e] = As[e];
+    for (int e = tid; e < m_max; e += blockDim.x) bd[e] = bs[e];
+    if (tid < 6) ((double*)(base + off_aabb))[(size_t)g * 6 + tid] = aabb[(size_t)s * 6 + tid];
+    if (tid == 6) ((int*)(base + off_m))[g] = m[s];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_rows_peers(const unsigned int* __restrict__ rows_local, int rows,
+                                                            int words, int row0,
+                                                            const unsigned long long* __restrict__ peer_base,
+                                                            int world, size_t off_bits) {
+  const size_t n = (size_t)rows * words;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const unsigned int v = rows_local[e];
+    for (int r = 0; r < world; ++r) ((unsigned int*)((char*)peer_base[r] + off_bits))[(size_t)row0 * words + e] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
 template <bool POSE, bool JAC>
@@ -2388,6 +2427,31 @@ int bp_shortest_paths(const int* node_off_dev, const int* edge_off_dev, const in
   if (G == 0) return 0;
   k_shortest_path<<<G, 32, 0, (cudaStream_t)stream>>>(node_off_dev, edge_off_dev, edge_dst_dev, edge_w_dev, src_dev,
                                                       dst_dev, max_len, path_dev, path_len_dev, cost_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_scatter_sets_peers(const double* A_dev, const double* b_dev, const int* m_dev, const double* aabb_dev, int S_loc,
+                          int m_max, int slot0, const unsigned long long* peer_base_dev, int world, size_t off_A,
+                          size_t off_b, size_t off_m, size_t off_aabb, void* stream) {
+  if (S_loc < 0 || m_max < 1 || m_max > BP_MAX_ROWS || slot0 < 0 || world < 1 || !peer_base_dev || !A_dev || !b_dev ||
+      !m_dev || !aabb_dev)
+    return bp_fail("bp_scatter_sets_peers: bad arguments");
+  if (S_loc == 0) return 0;
+  k_scatter_sets_peers<<<S_loc, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, aabb_dev, m_max, slot0, peer_base_dev,
+                                                                world, off_A, off_b, off_m, off_aabb);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_scatter_rows_peers(const unsigned int* rows_dev, int rows, int words, int row0,
+                          const unsigned long long* peer_base_dev, int world, size_t off_bits, void* stream) {
+  if (rows < 0 || words < 1 || row0 < 0 || world < 1 || !peer_base_dev) return bp_fail("bp_scatter_rows_peers: bad arguments");
+  if (rows == 0) return 0;
+  const size_t n = (size_t)rows * words;
+  int ctas = (int)((n + 255) / 256);
+  if (ctas > 1184) ctas = 1184;
+  k_scatter_rows_peers<<<ctas, 256, 0, (cudaStream_t)stream>>>(rows_dev, rows, words, row0, peer_base_dev, world, off_bits);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

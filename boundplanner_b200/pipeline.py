@@ -158,3 +158,114 @@ class ShardedSetGraphPipeline:
         """Global bit matrix [S, words] assembled from the gathered, padded row blocks."""
         return torch.cat([self.bits_gathered[r * self.max_rows: r * self.max_rows + (hi - lo)]
                           for r, (lo, hi) in enumerate(self.blocks)])
+
+
+class PeerSetGraphPipeline:
+    """Multi-GPU step with the exchange done by PEER STORES over NVLink instead of NCCL collectives.
+
+    Every rank owns one symmetric allocation (torch symmetric memory: the same layout mapped into every
+    process) holding the global tables  A[S,m_max,3] | b[S,m_max] | aabb[S,6] | m[S] | adjacency[S,words].
+    A step is ONE CUDA graph per rank:
+
+      k_iris_fused (own S_loc seeds) -> k_set_aabb -> k_scatter_sets_peers: the owner writes its sets into
+      the tables of every rank through the peers' mapped addresses (no pack / all-gather / unpack)
+      -> signal-pad barrier -> pair kernels on the own row block of the global pair matrix, reading the
+      local tables -> k_scatter_rows_peers: the adjacency rows go to every rank -> signal-pad barrier.
+
+    The second barrier also protects the tables: no rank starts the next step's scatter before every rank
+    has finished reading.  Same results as ShardedSetGraphPipeline (tools/check_sharded.py --peer)."""
+
+    def __init__(self, scene, n_seeds_local, ws_min, ws_max, fixed_mid=True, optimize=True, max_iter=5, tol=0.01,
+                 m_max=geo.BP_MAX_ROWS, group=None):
+        import numpy as np
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        from . import distributed as bpd
+
+        self._lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.scene, self.S_loc, self.S = scene, int(n_seeds_local), int(n_seeds_local) * self.world
+        self.ws_min, self.ws_max, self.tol, self.m_max = ws_min, ws_max, tol, m_max
+        self.kw = dict(fixed_mid=fixed_mid, optimize=optimize, max_iter=max_iter)
+        S, words = self.S, (self.S + 31) // 32
+        self.words = words
+        # layout of the symmetric allocation (bytes, 256-aligned regions)
+        sizes = [S * m_max * 3 * 8, S * m_max * 8, S * 6 * 8, S * 4, S * words * 4]
+        offs, o = [], 0
+        for sz in sizes:
+            offs.append(o)
+            o += (sz + 255) // 256 * 256
+        self.off_A, self.off_b, self.off_aabb, self.off_m, self.off_bits = offs
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.symm = symm_mem.empty((o,), dtype=torch.uint8, device=dev)
+        self.symm.zero_()
+        self.hdl = symm_mem.rendezvous(self.symm, group.group_name)
+        self.peer_base = torch.as_tensor(np.asarray(self.hdl.buffer_ptrs, dtype=np.uint64).view(np.int64), device=dev)
+
+        def view(off, nbytes, dtype, shape):
+            return self.symm[off: off + nbytes].view(dtype).view(shape)
+
+        self.Ag = view(self.off_A, sizes[0], torch.float64, (S, m_max, 3))
+        self.bg = view(self.off_b, sizes[1], torch.float64, (S, m_max))
+        self.aabb_g = view(self.off_aabb, sizes[2], torch.float64, (S, 6))
+        self.mg = view(self.off_m, sizes[3], torch.int32, (S,))
+        self.bits_g = view(self.off_bits, sizes[4], torch.int32, (S, words))
+        self.seeds_dev = torch.zeros((self.S_loc, 3), dtype=torch.float64, device=dev)
+        self.batch = geo.alloc_set_batch(self.S_loc, m_max)
+        self.aabb_loc = torch.empty((self.S_loc, 6), dtype=torch.float64, device=dev)
+        self.blocks = bpd.balanced_row_blocks(S, self.world)
+        self.r0, self.r1 = self.blocks[self.rank]
+        self.pair_buf = geo.alloc_pair_buffers(S, max(self.r1 - self.r0, 1))
+        self._stream = torch.cuda.Stream()
+        self._graph = None
+        self._capture()
+
+    def _enqueue(self):
+        lib, st = self._lib, geo._stream()
+        geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
+        geo.set_aabb(self.batch.A, self.batch.b, self.batch.m, out=self.aabb_loc)
+        geo.check(lib.bp_scatter_sets_peers(geo._ptr(self.batch.A), geo._ptr(self.batch.b), geo._ptr(self.batch.m),
+                                            geo._ptr(self.aabb_loc), self.S_loc, self.m_max, self.rank * self.S_loc,
+                                            geo._ptr(self.peer_base), self.world, self.off_A, self.off_b, self.off_m,
+                                            self.off_aabb, st))
+        self.hdl.barrier(channel=0)
+        rows = self.r1 - self.r0
+        if rows > 0:
+            bits = self.pair_buf[0][:rows]
+            geo.pair_feasible(self.Ag, self.bg, self.mg, self.tol, self.r0, self.r1, out=(bits, self.pair_buf[1]),
+                              aabb=self.aabb_g)
+            geo.check(lib.bp_scatter_rows_peers(geo._ptr(bits), rows, self.words, self.r0, geo._ptr(self.peer_base),
+                                                self.world, self.off_bits, st))
+        self.hdl.barrier(channel=1)
+
+    def _capture(self):
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            for _ in range(2):
+                self._enqueue()
+        self._stream.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                self._enqueue()
+            self._graph = g
+        except Exception as e:                       # the barrier op may refuse capture on some builds: run eagerly
+            self._graph = None
+            self.capture_error = repr(e)
+            torch.cuda.synchronize()
+
+    def run_device(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._enqueue()
+        return self.batch, self.bits_g
+
+    def adjacency_bits(self):
+        """Global bit matrix [S, words]: already complete on every rank."""
+        return self.bits_g

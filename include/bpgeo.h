@@ -217,6 +217,19 @@ int bp_shortest_paths(const int* node_off_dev, const int* edge_off_dev, const in
                       const double* edge_w_dev, const int* src_dev, const int* dst_dev, int G, int max_len,
                       int* path_dev, int* path_len_dev, double* cost_dev, void* stream);
 
+/* ---- multi-GPU exchange by peer stores -------------------------------------------------------
+ * The owner of S_loc sets writes them into the global tables A[S,m_max,3] | b[S,m_max] | m[S] | aabb[S,6] of EVERY
+ * rank at rows slot0 .. slot0+S_loc-1, through the peers' mapped addresses: peer_base_dev[world] holds the base
+ * address of each rank's symmetric allocation (identical layout everywhere, e.g. torch symmetric memory or
+ * cudaIpc / VMM mappings), off_* are the byte offsets of the tables inside it.  bp_scatter_rows_peers does the same
+ * for a block of adjacency rows (rows x words uint32 at global row row0).  The caller synchronises the ranks after
+ * each call (signal-pad barrier); replaces pack + ncclAllGather + unpack. */
+int bp_scatter_sets_peers(const double* A_dev, const double* b_dev, const int* m_dev, const double* aabb_dev, int S_loc,
+                          int m_max, int slot0, const unsigned long long* peer_base_dev, int world, size_t off_A,
+                          size_t off_b, size_t off_m, size_t off_aabb, void* stream);
+int bp_scatter_rows_peers(const unsigned int* rows_dev, int rows, int words, int row0,
+                          const unsigned long long* peer_base_dev, int world, size_t off_bits, void* stream);
+
 /* ---- K7: iiwa14 forward kinematics -----------------------------------------------
  * Replaces the numeric branch of RobotModel.fk_pos (RobotModel.py:146-160),
  * fk_pos_col (:162-181), hom_transform_endeffector (:197-211), jacobian_fk
