@@ -11,9 +11,11 @@ float64 NumPy arrays) and error behaviour -- so that the unchanged planner
 
 Every method is a batch-of-one call into the batched device API in
 ``geometry.py``; use ``find_sets_around_points`` / ``find_sets_collision_avoidance``
-for real batches.  Obstacles must be the axis-aligned boxes the planner builds
-(A = [I; -I], BoundPlanner.py:126-129); anything else raises NotImplementedError
-(general polytopes are a "next" row in DESIGN.md).  There is no CPU fallback.
+for real batches.  Obstacles are normally the axis-aligned boxes the planner builds
+(A = [I; -I], BoundPlanner.py:126-129); general convex polytopes (<= 15 rows, with
+their vertices in ``obs_points_sets``) are supported by the point-set methods, while
+the segment methods (find_set_collision_avoidance, compute_set_projs_line) raise
+NotImplementedError for them.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -60,6 +62,7 @@ class ConvexSetFinder:
         self.strict_rows = strict_rows
         self.verbose = False
         self._scene = None
+        self._polytopes = False
         self._obs_sets = []
         self._obs_points_sets = []
         self.obs_points_sets = obs_points_sets
@@ -73,8 +76,18 @@ class ConvexSetFinder:
     @obs_sets.setter
     def obs_sets(self, value):
         self._obs_sets = list(value).copy()
-        boxes = boxes_from_obs_sets(self._obs_sets)
-        if self._scene is None:
+        try:
+            boxes = boxes_from_obs_sets(self._obs_sets)
+        except NotImplementedError:
+            # general polytopes: rows + the vertices of obs_points_sets (assigned first by add_obstacle_reps, :150-151)
+            if len(self._obs_points_sets) != len(self._obs_sets):
+                raise ValueError("polytope obstacles need obs_points_sets (one vertex array per obstacle) "
+                                 "to be assigned before obs_sets") from None
+            self._scene = geo.PolytopeScene(self._obs_sets, self._obs_points_sets)
+            self._polytopes = True
+            return
+        self._polytopes = False
+        if self._scene is None or isinstance(self._scene, geo.PolytopeScene):
             self._scene = geo.Scene(boxes, 0.0)       # obs_sets are already inflated (:141)
         else:
             self._scene.update(boxes, 0.0)
@@ -137,7 +150,13 @@ class ConvexSetFinder:
         self.proj_time += time.perf_counter() - start
         return out
 
+    def _no_polytope_segments(self):
+        if self._polytopes:
+            raise NotImplementedError("segment closest points / find_set_collision_avoidance handle box obstacles "
+                                      "only; polytope obstacles are supported by the point-set methods")
+
     def compute_set_projs_line(self, obs_sets, p0, p1):
+        self._no_polytope_segments()
         start = time.perf_counter()
         scene = self._scene_for(obs_sets)
         x, phi = geo.closest_points_line(scene, np.asarray(p0, float)[None], np.asarray(p1, float)[None])
@@ -264,6 +283,7 @@ class ConvexSetFinder:
 
     def find_sets_collision_avoidance(self, p0, p1, compute_ellipsoid=False, limit_space=False, e_max=0.3,
                                       m_max=BP_MAX_ROWS):
+        self._no_polytope_segments()
         start = time.perf_counter()
         ws_min, ws_max = self._ws()
         out = geo.build_sets_line(self._scene, p0, p1, ws_min, ws_max, compute_ellipsoid=bool(compute_ellipsoid),

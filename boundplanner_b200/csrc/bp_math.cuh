@@ -296,3 +296,121 @@ BP_HD double bp_seg_box(const double* p0, const double* d, const double* lb, con
   *dist2_out = best;
   return bphi;
 }
+
+// ---------------------------------------------------------------------------
+// K1p: closest point of a GENERAL convex polytope {y : a_r . y <= b_r, r < R} (R <= BP_OBS_ROWS, the 15-row
+// obstacle sets of BoundPlanner.add_obstacle_reps / normalize_set_size, util_functions.py:119-133) to p in
+// the metric M.  Replaces the same OSQP solve as K1 (ConvexSetFinder.py:465-489) for obstacles that are not
+// boxes.  Exact: the minimiser is the M-projection of p onto the affine hull of its active rows (at most 3 in
+// R^3); every subset of 1..3 rows is a candidate, the feasible candidate of least objective wins (first on
+// ties).  Candidates are numbered 0 (no active row: p itself), then the single rows, the pairs (i < j) and
+// the triples (i < j < k) in lexicographic order; bp_polytope_candidate evaluates ONE of them so that the
+// enumeration can be split over the lanes of a warp (the host harness walks them serially).
+// ---------------------------------------------------------------------------
+#define BP_OBS_ROWS 15
+
+struct BpPolyMetric {
+  double M[6];    // m00 m01 m02 m11 m12 m22
+  double W[6];    // M^-1, same packing
+};
+
+BP_HD void bp_poly_metric_init(const double* M9, BpPolyMetric* pm) {
+  double Wi[9];
+  bp_inv3(M9, Wi);
+  pm->M[0] = M9[0]; pm->M[1] = M9[1]; pm->M[2] = M9[2]; pm->M[3] = M9[4]; pm->M[4] = M9[5]; pm->M[5] = M9[8];
+  pm->W[0] = Wi[0]; pm->W[1] = 0.5 * (Wi[1] + Wi[3]); pm->W[2] = 0.5 * (Wi[2] + Wi[6]);
+  pm->W[3] = Wi[4]; pm->W[4] = 0.5 * (Wi[5] + Wi[7]); pm->W[5] = Wi[8];
+}
+
+BP_HD void bp_sym_mul(const double* S, const double* v, double* o) {
+  o[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
+  o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
+  o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
+}
+
+// ROWS: a(r,k), b(r).  Candidate with active rows (i), (i,j) or (i,j,k) (unused = -1).  Returns true and
+// y / obj (squared M-distance) when the candidate exists (independent rows) and is feasible.
+template <class ROWS>
+BP_HD bool bp_polytope_candidate(const BpPolyMetric& pm, const ROWS& rows, int R, const double* p, int i, int j, int k,
+                                 double* y, double* obj) {
+  if (i < 0) {
+    y[0] = p[0]; y[1] = p[1]; y[2] = p[2];
+  } else if (j < 0) {
+    const double a[3] = {rows.a(i, 0), rows.a(i, 1), rows.a(i, 2)};
+    double w[3];
+    bp_sym_mul(pm.W, a, w);
+    const double den = a[0] * w[0] + a[1] * w[1] + a[2] * w[2];
+    if (!(den > 0.0)) return false;                       // zero (padded) row
+    const double lam = (a[0] * p[0] + a[1] * p[1] + a[2] * p[2] - rows.b(i)) / den;
+    y[0] = p[0] - lam * w[0]; y[1] = p[1] - lam * w[1]; y[2] = p[2] - lam * w[2];
+  } else if (k < 0) {
+    const double a[3] = {rows.a(i, 0), rows.a(i, 1), rows.a(i, 2)};
+    const double c[3] = {rows.a(j, 0), rows.a(j, 1), rows.a(j, 2)};
+    double wa[3], wc[3];
+    bp_sym_mul(pm.W, a, wa);
+    bp_sym_mul(pm.W, c, wc);
+    const double g11 = a[0] * wa[0] + a[1] * wa[1] + a[2] * wa[2];
+    const double g12 = a[0] * wc[0] + a[1] * wc[1] + a[2] * wc[2];
+    const double g22 = c[0] * wc[0] + c[1] * wc[1] + c[2] * wc[2];
+    const double det = g11 * g22 - g12 * g12;
+    if (!(det > 1e-14 * g11 * g22)) return false;         // parallel rows (or a padded one)
+    const double r1 = a[0] * p[0] + a[1] * p[1] + a[2] * p[2] - rows.b(i);
+    const double r2 = c[0] * p[0] + c[1] * p[1] + c[2] * p[2] - rows.b(j);
+    const double l1 = (g22 * r1 - g12 * r2) / det, l2 = (g11 * r2 - g12 * r1) / det;
+    y[0] = p[0] - (l1 * wa[0] + l2 * wc[0]);
+    y[1] = p[1] - (l1 * wa[1] + l2 * wc[1]);
+    y[2] = p[2] - (l1 * wa[2] + l2 * wc[2]);
+  } else {
+    // a vertex: solve the three planes directly (no Gram matrix: it would square the condition number)
+    const double a[3] = {rows.a(i, 0), rows.a(i, 1), rows.a(i, 2)};
+    const double c[3] = {rows.a(j, 0), rows.a(j, 1), rows.a(j, 2)};
+    const double d[3] = {rows.a(k, 0), rows.a(k, 1), rows.a(k, 2)};
+    const double n0 = a[1] * c[2] - a[2] * c[1], n1 = a[2] * c[0] - a[0] * c[2], n2 = a[0] * c[1] - a[1] * c[0];
+    const double det = n0 * d[0] + n1 * d[1] + n2 * d[2];
+    const double na = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], nc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double nd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    if (!(det * det > 1e-24 * na * nc * nd)) return false;
+    const double e0 = c[1] * d[2] - c[2] * d[1], e1 = c[2] * d[0] - c[0] * d[2], e2 = c[0] * d[1] - c[1] * d[0];
+    const double f0 = d[1] * a[2] - d[2] * a[1], f1 = d[2] * a[0] - d[0] * a[2], f2 = d[0] * a[1] - d[1] * a[0];
+    const double ab = rows.b(i), cb = rows.b(j), db = rows.b(k), id = 1.0 / det;
+    y[0] = (ab * e0 + cb * f0 + db * n0) * id;
+    y[1] = (ab * e1 + cb * f1 + db * n1) * id;
+    y[2] = (ab * e2 + cb * f2 + db * n2) * id;
+  }
+  // feasibility on every row
+  for (int r = 0; r < R; ++r) {
+    const double q0 = rows.a(r, 0), q1 = rows.a(r, 1), q2 = rows.a(r, 2), br = rows.b(r);
+    const double viol = q0 * y[0] + q1 * y[1] + q2 * y[2] - br;
+    const double mag = fabs(q0 * y[0]) + fabs(q1 * y[1]) + fabs(q2 * y[2]) + (fabs(br) > 1.0 ? fabs(br) : 1.0);
+    if (viol > 1e-10 * mag) return false;
+  }
+  const double z0 = y[0] - p[0], z1 = y[1] - p[1], z2 = y[2] - p[2];
+  *obj = z0 * (pm.M[0] * z0 + 2.0 * (pm.M[1] * z1 + pm.M[2] * z2)) + z1 * (pm.M[3] * z1 + 2.0 * pm.M[4] * z2) +
+         pm.M[5] * z2 * z2;
+  return true;
+}
+
+// Serial walk over all candidates (host harness / one thread).  Returns false when no candidate is feasible
+// (empty polytope).
+template <class ROWS>
+BP_HD bool bp_polytope_qp(const BpPolyMetric& pm, const ROWS& rows, int R, const double* p, double* y) {
+  double best = BP_INF, yc[3], oc;
+  bool found = false;
+  if (bp_polytope_candidate(pm, rows, R, p, -1, -1, -1, yc, &oc)) { y[0] = yc[0]; y[1] = yc[1]; y[2] = yc[2]; return true; }
+  for (int i = 0; i < R; ++i)
+    if (bp_polytope_candidate(pm, rows, R, p, i, -1, -1, yc, &oc) && oc < best) {
+      best = oc; found = true; y[0] = yc[0]; y[1] = yc[1]; y[2] = yc[2];
+    }
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j)
+      if (bp_polytope_candidate(pm, rows, R, p, i, j, -1, yc, &oc) && oc < best) {
+        best = oc; found = true; y[0] = yc[0]; y[1] = yc[1]; y[2] = yc[2];
+      }
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j)
+      for (int k = j + 1; k < R; ++k)
+        if (bp_polytope_candidate(pm, rows, R, p, i, j, k, yc, &oc) && oc < best) {
+          best = oc; found = true; y[0] = yc[0]; y[1] = yc[1]; y[2] = yc[2];
+        }
+  return found;
+}

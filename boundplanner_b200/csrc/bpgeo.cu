@@ -54,12 +54,23 @@ struct bp_scene {
   double inflate;
   int* seg_off;   // device [n_seg + 1] or NULL: a batch of scenes stored back to back (one per planning query)
   int n_seg;
+  // general polytope obstacles (bp_scene_create_polytopes): cols then hold the obstacles' bounding boxes
+  double* rows;   // device [n, BP_OBS_ROWS, 4] (a0,a1,a2,b), zero rows (b = 10) after the last real one, or NULL
+  int* nrows;     // device [n]
+  double* verts;  // device [n, vmax, 3]
+  int* nverts;    // device [n]
+  int vmax;
 };
 
 struct SceneView {
   const double* lb[3];
   const double* ub[3];
   int n;
+  const double* rows;     // polytope scene (else NULL): see bp_scene
+  const int* nrows;
+  const double* verts;
+  const int* nverts;
+  int vmax;
   const int* seg_off;     // scene batch: obstacle range of scene k is [seg_off[k], seg_off[k+1])
   const int* item_seg;    // scene index of every seed / segment (device, [S]) when seg_off != NULL
 };
@@ -71,6 +82,7 @@ static SceneView view_of(const bp_scene* s) {
     v.ub[k] = s->cols + (size_t)(3 + k) * s->cap;
   }
   v.n = s->n;
+  v.rows = s->rows; v.nrows = s->nrows; v.verts = s->verts; v.nverts = s->nverts; v.vmax = s->vmax;
   v.seg_off = s->seg_off;
   v.item_seg = nullptr;
   return v;
@@ -91,6 +103,7 @@ __device__ __forceinline__ SceneView scene_of_item(const SceneView& sc, int item
 #pragma unroll
   for (int a = 0; a < 3; ++a) { v.lb[a] = sc.lb[a] + o; v.ub[a] = sc.ub[a] + o; }
   v.n = sc.seg_off[k + 1] - o;
+  v.rows = nullptr; v.nrows = nullptr; v.verts = nullptr; v.nverts = nullptr; v.vmax = 0;   // batches hold boxes
   v.seg_off = nullptr;
   v.item_seg = nullptr;
   return v;
@@ -193,6 +206,12 @@ __device__ __forceinline__ double closest_on_box(const PassMetric& pm, const dou
   return sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
 }
 
+struct GlobalRows4 {
+  const double* r;
+  __device__ __forceinline__ double a(int i, int k) const { return __ldg(r + 4 * i + k); }
+  __device__ __forceinline__ double b(int i) const { return __ldg(r + 4 * i + 3); }
+};
+
 // ---------------------------------------------------------------------------
 // K1 test hook / batched compute_set_projs
 // ---------------------------------------------------------------------------
@@ -207,10 +226,30 @@ __global__ void k_closest_points(SceneView sc, const double* __restrict__ seeds,
   bp_inv3(E, Q);
   PassMetric pm;
   pass_metric_init(Q, &pm);
+  BpPolyMetric pmq;
+  if (sc.rows) {
+    double M9[9];
+    bp_mat3_ata(pm.Q, M9);
+    bp_poly_metric_init(M9, &pmq);
+  }
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < sc.n; j += gridDim.x * blockDim.x) {
     double lb[3], ub[3], y[3];
-    load_box(sc, j, lb, ub);
-    double d = closest_on_box(pm, p, lb, ub, y);
+    double d;
+    if (sc.rows) {                                 // general polytope: serial walk over the candidates
+      GlobalRows4 rows{sc.rows + (size_t)j * BP_OBS_ROWS * 4};
+      if (bp_polytope_qp(pmq, rows, sc.nrows[j], p, y)) {
+        const double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
+        double w[3];
+        bp_mat3_vec(pm.Q, zz, w);
+        d = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+      } else {
+        y[0] = y[1] = y[2] = 0.0;
+        d = BP_INF;
+      }
+    } else {
+      load_box(sc, j, lb, ub);
+      d = closest_on_box(pm, p, lb, ub, y);
+    }
     size_t o = (size_t)s * sc.n + j;
     y_out[3 * o] = y[0]; y_out[3 * o + 1] = y[1]; y_out[3 * o + 2] = y[2];
     dist_out[o] = d;
@@ -345,6 +384,62 @@ __device__ __forceinline__ double box_dist_bound(const PassBound& pb, const doub
   return sqrt(b2);
 }
 
+// ---------------------------------------------------------------------------
+// General polytope obstacles: one WARP solves the closest-point QP of one polytope -- the
+// candidates of bp_polytope_candidate (<= 1 + 15 + 105 + 455) are dealt to the lanes, the feasible candidate of
+// least objective wins (first candidate number on ties, like the serial walk).  rows4: the polytope's rows
+// staged in shared memory.  Every lane returns the same y; false: no feasible candidate (empty polytope).
+// ---------------------------------------------------------------------------
+struct SmemRows4 {
+  const double* r;
+  __device__ __forceinline__ double a(int i, int k) const { return r[4 * i + k]; }
+  __device__ __forceinline__ double b(int i) const { return r[4 * i + 3]; }
+};
+
+__device__ __forceinline__ bool polytope_qp_warp(const BpPolyMetric& pmq, const double* rows4, int R, const double* p,
+                                                 double* y) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  SmemRows4 rows{rows4};
+  double best = BP_INF, yb[3] = {0.0, 0.0, 0.0}, yc[3], oc;
+  int bidx = 0x7fffffff, cnt = 0;
+#define BP_POLY_TRY(I, J, K)                                                                            \
+  {                                                                                                     \
+    if ((cnt & 31) == lane && bp_polytope_candidate(pmq, rows, R, p, (I), (J), (K), yc, &oc) && oc < best) { \
+      best = oc; bidx = cnt; yb[0] = yc[0]; yb[1] = yc[1]; yb[2] = yc[2];                               \
+    }                                                                                                   \
+    ++cnt;                                                                                              \
+  }
+  BP_POLY_TRY(-1, -1, -1)
+  for (int i = 0; i < R; ++i) BP_POLY_TRY(i, -1, -1)
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j) BP_POLY_TRY(i, j, -1)
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j)
+      for (int k = j + 1; k < R; ++k) BP_POLY_TRY(i, j, k)
+#undef BP_POLY_TRY
+  const double bmin = warp_min_nonneg(best < 0.0 ? 0.0 : best);
+  if (!(bmin < BP_INF)) return false;
+  const unsigned cand = (best <= bmin) ? (unsigned)bidx : 0xffffffffu;    // (objectives are >= 0 up to rounding)
+  const unsigned widx = __reduce_min_sync(full, cand);
+  const int src = __ffs(__ballot_sync(full, cand == widx)) - 1;
+  y[0] = __shfl_sync(full, yb[0], src);
+  y[1] = __shfl_sync(full, yb[1], src);
+  y[2] = __shfl_sync(full, yb[2], src);
+  return true;
+}
+
+// min over the obstacle's vertices of a.v - b (vertex test of ConvexSetFinder.py:449-451 for a polytope)
+__device__ __forceinline__ double poly_min_halfspace(const SceneView& sc, int j, const double* a, double bh) {
+  const double* v = sc.verts + (size_t)j * sc.vmax * 3;
+  const int nv = sc.nverts[j];
+  double mn = BP_INF;
+  for (int t = 0; t < nv; ++t) mn = fmin(mn, (a[0] * __ldg(v + 3 * t) + a[1] * __ldg(v + 3 * t + 1)) + a[2] * __ldg(v + 3 * t + 2) - bh);
+  return mn;
+}
+
+#define BP_POLY_LIST 128
+
 // One compute_polyhedron pass for the seed of this CTA (all threads call it): rows 6.. are written
 // to Arow/brow (global or shared memory), *m_out = 6 + picks, *status_out = BP_OK / BP_ELLIPSE_VIOLATION.
 //
@@ -354,12 +449,26 @@ __device__ __forceinline__ double box_dist_bound(const PassBound& pb, const doub
 // only for entries whose bound does not exceed the best exact distance known.  The pick is the argmin over exact
 // values once no bound is smaller or equal -- the same obstacle, the same bits as solving all N QPs (the QP of
 // an entry is the same code on the same inputs whenever it runs).
+// POLY: the obstacles are general polytopes (sc.rows != NULL): the bounds come from their bounding boxes, the exact
+// closest points from warp-cooperative QPs over a shared work list, the vertex test walks their vertex lists;
+// needs cache_y.
+template <bool POLY>
 __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassMetric& pm, const double* p,
                                                 double* s_dist, int cache_y, double (*red_val)[32],
                                                 int (*red_idx)[32], double* Arow,
                                                 double* brow, int m_max, int* m_out, int* status_out) {
   const int tid = threadIdx.x, T = blockDim.x;
   double* s_y = s_dist + sc.n;               // [3][N] when cache_y
+  __shared__ int s_list[POLY ? BP_POLY_LIST : 1];
+  __shared__ int s_nlist;
+  __shared__ double s_prow[POLY ? 16 : 1][POLY ? BP_OBS_ROWS * 4 : 1];
+  BpPolyMetric pmq;
+  if (POLY) {
+    double M9[9];
+    bp_mat3_ata(pm.Q, M9);
+    bp_poly_metric_init(M9, &pmq);
+    if (tid == 0) s_nlist = 0;
+  }
   BP_PPROF_MARK();
   PassBound pb;
   pass_bound_init(pm, &pb);
@@ -376,6 +485,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       load_box(sc, j, lb, ub);
       double bd = box_dist_bound(pb, p, lb, ub);
       int ex = 0;
+      if (POLY && !(bd > 0.0)) bd = DBL_MIN;        // inside the bounding box: a (useless) bound, refined on demand
       if (!(bd > 0.0)) {
         double y[3];
         bd = closest_on_box(pm, p, lb, ub, y);
@@ -414,13 +524,49 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       }
       const double ex = block_min_nonneg(lex, red_val, buf);
       const double thr = fmax(ex < BP_INF ? ex : 0.0, BP_LAZY_GROW * val);
+      if (POLY) {
+        // work list of the obstacles to refine (what does not fit waits for the next round)
+        for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+          const int j = tid + (__ffsll((long long)mk) - 1) * T;
+          const double d = s_dist[j];
+          if (d < 0.0 && -d <= thr) {
+            const int slot = atomicAdd(&s_nlist, 1);
+            if (slot < BP_POLY_LIST) s_list[slot] = j;
+          }
+        }
+        __syncthreads();
+        const int nl = s_nlist < BP_POLY_LIST ? s_nlist : BP_POLY_LIST;
+        const int warp = tid >> 5, lane = tid & 31, nw = T >> 5;
+        for (int q = warp; q < nl; q += nw) {
+          const int j = s_list[q];
+          const int R = sc.nrows[j];
+          for (int e = lane; e < R * 4; e += 32) s_prow[warp][e] = __ldg(sc.rows + (size_t)j * BP_OBS_ROWS * 4 + e);
+          __syncwarp();
+          double y[3];
+          const bool okq = polytope_qp_warp(pmq, s_prow[warp], R, p, y);
+          if (lane == 0) {
+            double d = BP_INF;                          // an empty polytope never constrains the set
+            if (okq) {
+              const double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
+              double w[3];
+              bp_mat3_vec(pm.Q, zz, w);
+              d = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+            }
+            s_dist[j] = d;
+            s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2];
+          }
+          __syncwarp();
+        }
+        __syncthreads();
+        if (tid == 0) s_nlist = 0;
+      }
       lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
       for (unsigned long long mk = alive; mk; mk &= mk - 1) {
         const int j = tid + (__ffsll((long long)mk) - 1) * T;
         double d = s_dist[j];
         int e = 1;
         if (d < 0.0) {
-          if (-d <= thr) {
+          if (!POLY && -d <= thr) {
             double lb[3], ub[3], y[3];
             load_box(sc, j, lb, ub);
             d = closest_on_box(pm, p, lb, ub, y);
@@ -431,6 +577,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
             e = 0;
           }
         }
+        if (!(d < BP_INF)) { alive &= ~(1ull << (__ffsll((long long)mk) - 1)); continue; }   // empty polytope
         if (d < lkey || (d == lkey && e < lexact)) { lkey = d; lidx = j; lexact = e; }
       }
       BP_PPROF_LAP(2);
@@ -472,8 +619,8 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       load_box(sc, j0, l0, u0);
       load_box(sc, j1, l1, u1);
       const double d0 = s_dist[j0], d1 = s_dist[j1];
-      const bool dead0 = j0 == idx || bp_box_min_halfspace(a, bh, l0, u0) >= -1e-4;
-      const bool dead1 = j1 == idx || bp_box_min_halfspace(a, bh, l1, u1) >= -1e-4;
+      const bool dead0 = j0 == idx || (POLY ? poly_min_halfspace(sc, j0, a, bh) : bp_box_min_halfspace(a, bh, l0, u0)) >= -1e-4;
+      const bool dead1 = j1 == idx || (POLY ? poly_min_halfspace(sc, j1, a, bh) : bp_box_min_halfspace(a, bh, l1, u1)) >= -1e-4;
       if (dead0) alive &= ~(1ull << k0);
       else {
         const int e = d0 >= 0.0;
@@ -494,6 +641,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
   *status_out = status;
 }
 
+template <bool POLY>
 __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams pr) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
@@ -545,7 +693,7 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams
   }
 
   int m_cur, status;
-  poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
+  poly_pass_point<POLY>(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
   if (status == BP_OK && m_cur > pr.m_max) status = BP_ROW_OVERFLOW;
   // rows past the last one keep the padding of normalize_set_size (A = 0, b = 10): an earlier,
   // longer pass may have left its rows there
@@ -606,7 +754,7 @@ struct SharedRows {
 // MODE 0: find_set_around_point (:190-240).  MODE 1: find_set_around_line (:242-307) -- the same loop around
 // the midpoint of the segment p0 .. p0 + dp1 with the fixed-rotation MVIE (mvie_socp_fixed_r); no trailing MVIE,
 // and with optimize == 0 one free-centre MVIE after the first pass (:278-282).
-template <int MODE>
+template <int MODE, bool POLY>
 __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
@@ -651,7 +799,7 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     int st;
     {
       BP_PROF_T0();
-      poly_pass_point(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
+      poly_pass_point<POLY>(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
       BP_PROF_ADD(0);
     }
     rows_peak = m_cur > rows_peak ? m_cur : rows_peak;
@@ -2059,8 +2207,47 @@ int bp_scene_create_batch(const double* boxes_host, const int* offsets_host, int
   return 0;
 }
 
+int bp_scene_create_polytopes(const double* rows_host, const int* nrows_host, const double* verts_host,
+                              const int* nverts_host, int n, int vmax, bp_scene** out) {
+  if (!out || n < 1 || vmax < 1 || !rows_host || !nrows_host || !verts_host || !nverts_host)
+    return bp_fail("bp_scene_create_polytopes: bad arguments");
+  // bounding boxes from the vertices: the cheap lower bounds of the lazy closest-point pass
+  double* boxes = (double*)malloc(sizeof(double) * 6 * (size_t)n);
+  if (!boxes) return bp_fail("out of host memory");
+  for (int j = 0; j < n; ++j) {
+    if (nrows_host[j] < 1 || nrows_host[j] > BP_OBS_ROWS || nverts_host[j] < 1 || nverts_host[j] > vmax) {
+      free(boxes);
+      return bp_fail("bp_scene_create_polytopes: an obstacle needs 1..15 rows and 1..vmax vertices");
+    }
+    for (int k = 0; k < 3; ++k) { boxes[6 * j + k] = BP_INF; boxes[6 * j + 3 + k] = -BP_INF; }
+    for (int t = 0; t < nverts_host[j]; ++t)
+      for (int k = 0; k < 3; ++k) {
+        const double v = verts_host[((size_t)j * vmax + t) * 3 + k];
+        if (v < boxes[6 * j + k]) boxes[6 * j + k] = v;
+        if (v > boxes[6 * j + 3 + k]) boxes[6 * j + 3 + k] = v;
+      }
+  }
+  bp_scene* sc = nullptr;
+  int rc = bp_scene_create(boxes, n, 0.0, &sc);
+  free(boxes);
+  if (rc) return rc;
+  cudaError_t e = cudaMalloc(&sc->rows, sizeof(double) * (size_t)n * BP_OBS_ROWS * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&sc->nrows, sizeof(int) * (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc(&sc->verts, sizeof(double) * (size_t)n * vmax * 3);
+  if (e == cudaSuccess) e = cudaMalloc(&sc->nverts, sizeof(int) * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpy(sc->rows, rows_host, sizeof(double) * (size_t)n * BP_OBS_ROWS * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(sc->nrows, nrows_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(sc->verts, verts_host, sizeof(double) * (size_t)n * vmax * 3, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(sc->nverts, nverts_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice);
+  sc->vmax = vmax;
+  if (e != cudaSuccess) { bp_scene_destroy(sc); return bp_fail("bp_scene_create_polytopes", e); }
+  *out = sc;
+  return 0;
+}
+
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream) {
   if (scene && scene->seg_off) return bp_fail("bp_scene_update: not supported for scene batches");
+  if (scene && scene->rows) return bp_fail("bp_scene_update: not supported for polytope scenes (create a new one)");
   if (!scene || n < 0 || (n > 0 && !boxes_host)) return bp_fail("bp_scene_update: bad arguments");
   return scene_upload(scene, boxes_host, n, inflate, (cudaStream_t)stream);
 }
@@ -2068,6 +2255,10 @@ int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inf
 int bp_scene_destroy(bp_scene* scene) {
   if (!scene) return 0;
   if (scene->seg_off) cudaFree(scene->seg_off);
+  if (scene->rows) cudaFree(scene->rows);
+  if (scene->nrows) cudaFree(scene->nrows);
+  if (scene->verts) cudaFree(scene->verts);
+  if (scene->nverts) cudaFree(scene->nverts);
   if (scene->cols) cudaFree(scene->cols);
   free(scene);
   return 0;
@@ -2088,6 +2279,7 @@ int bp_closest_points(const bp_scene* scene, const double* seeds_dev, const doub
 int bp_closest_points_line(const bp_scene* scene, const double* p0_dev, const double* p1_dev, int S,
                            double* x_out_dev, double* phi_out_dev, void* stream) {
   if (!scene || S < 0 || scene->seg_off) return bp_fail("bp_closest_points_line: bad arguments");
+  if (scene->rows) return bp_fail("bp_closest_points_line: polytope scenes are not supported (segment QP is box-only)");
   if (S == 0 || scene->n == 0) return 0;
   dim3 grid((scene->n + 255) / 256, S);
   k_closest_points_line<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(scene), p0_dev, p1_dev, x_out_dev, phi_out_dev);
@@ -2108,8 +2300,14 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
   pr.A = A_dev; pr.b = b_dev; pr.m = m_dev; pr.status = status_dev; pr.m_max = m_max; pr.mode = 0;
   pr.cache_y = poly_cache_y(scene->n);
   size_t smem = poly_smem_bytes(scene->n);
-  if (set_dyn_smem((const void*)k_poly_point, smem)) return 1;
-  k_poly_point<<<S, poly_threads(scene->n), smem, (cudaStream_t)stream>>>(view_of(scene), pr);
+  if (scene->rows) {
+    if (!pr.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    if (set_dyn_smem((const void*)k_poly_point<true>, smem)) return 1;
+    k_poly_point<true><<<S, poly_threads(scene->n), smem, (cudaStream_t)stream>>>(view_of(scene), pr);
+  } else {
+    if (set_dyn_smem((const void*)k_poly_point<false>, smem)) return 1;
+    k_poly_point<false><<<S, poly_threads(scene->n), smem, (cudaStream_t)stream>>>(view_of(scene), pr);
+  }
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -2165,8 +2363,14 @@ int bp_build_sets_around_line(const bp_scene* scene, const double* p0_dev, const
   fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = 0; fp.optimize = optimize;
   fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
   const size_t fsmem = poly_smem_bytes(scene->n);
-  if (set_dyn_smem((const void*)k_iris_fused<1>, fsmem)) return 1;
-  k_iris_fused<1><<<S, 128, fsmem, (cudaStream_t)stream>>>(view_of(scene), fp);
+  if (scene->rows) {
+    if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    if (set_dyn_smem((const void*)k_iris_fused<1, true>, fsmem)) return 1;
+    k_iris_fused<1, true><<<S, 128, fsmem, (cudaStream_t)stream>>>(view_of(scene), fp);
+  } else {
+    if (set_dyn_smem((const void*)k_iris_fused<1, false>, fsmem)) return 1;
+    k_iris_fused<1, false><<<S, 128, fsmem, (cudaStream_t)stream>>>(view_of(scene), fp);
+  }
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -2205,8 +2409,14 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
     fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = fixed_mid; fp.optimize = optimize;
     fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
     const size_t fsmem = poly_smem_bytes(scene->n);
-    if (set_dyn_smem((const void*)k_iris_fused<0>, fsmem)) return 1;
-    k_iris_fused<0><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    if (scene->rows) {
+      if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+      if (set_dyn_smem((const void*)k_iris_fused<0, true>, fsmem)) return 1;
+      k_iris_fused<0, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    } else {
+      if (set_dyn_smem((const void*)k_iris_fused<0, false>, fsmem)) return 1;
+      k_iris_fused<0, false><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    }
     BP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -2223,11 +2433,13 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
   mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st;
   pp.cache_y = poly_cache_y(scene->n);
   size_t smem = poly_smem_bytes(scene->n);
-  if (set_dyn_smem((const void*)k_poly_point, smem)) return 1;
+  if (scene->rows && !pp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+  if (set_dyn_smem(scene->rows ? (const void*)k_poly_point<true> : (const void*)k_poly_point<false>, smem)) return 1;
   const int T = poly_threads(scene->n);
   const int passes = optimize ? max_iter : 1;
   for (int it = 0; it < passes; ++it) {
-    k_poly_point<<<S, T, smem, stream>>>(view_of(scene, seed_scene_dev), pp);
+    if (scene->rows) k_poly_point<true><<<S, T, smem, stream>>>(view_of(scene, seed_scene_dev), pp);
+    else k_poly_point<false><<<S, T, smem, stream>>>(view_of(scene, seed_scene_dev), pp);
     if (!optimize) break;                                 // :214-215
     mp.mode = fixed_mid ? 0 : 1;
     if (launch_mvie(mp, stream)) return 1;
@@ -2262,6 +2474,7 @@ int bp_build_sets_line_ms(const bp_scene* scene, const int* seg_scene_dev, const
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || !ws_min_host || !ws_max_host)
     return bp_fail("bp_build_sets_line: bad arguments");
   if (S == 0) return 0;
+  if (scene->rows) return bp_fail("bp_build_sets_line: polytope scenes are not supported (segment QP is box-only)");
   if (compute_ellipsoid && workspace_bytes < bp_build_sets_workspace_bytes(S))
     return bp_fail("bp_build_sets_line: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -2398,6 +2611,7 @@ int bp_sample_filter(const bp_scene* scene, const int* item_scene_dev, const dou
                      int* first_ok_dev, unsigned char* flags_dev, void* stream) {
   if (!scene || Q < 0 || C < 1 || !cand_dev || !first_ok_dev || (set_off_dev && (m_max < 1 || !A_dev || !b_dev || !m_dev)))
     return bp_fail("bp_sample_filter: bad arguments");
+  if (scene->rows) return bp_fail("bp_sample_filter: polytope scenes are not supported");
   if ((scene->seg_off != nullptr) != (item_scene_dev != nullptr))
     return bp_fail("bp_sample_filter: a scene batch needs item_scene, a single scene must not have it");
   if (Q == 0) return 0;

@@ -80,6 +80,51 @@ class Scene:
             pass
 
 
+class PolytopeScene(Scene):
+    """General convex polytope obstacles resident in HBM: what ConvexSetFinder is handed when the obstacles are not
+    boxes -- obs_sets = [[A (<= 15 rows, zero-padded), b], ...] (already inflated) and obs_points_sets = [vertices
+    (V x 3), ...] (the reference enumerates them with cddlib, util_functions.py:66-79).  Point sets only: the
+    segment QP behind find_set_collision_avoidance is box-only."""
+
+    MAX_ROWS = 15
+
+    def __init__(self, obs_sets, obs_points_sets):
+        _require_cuda()
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p(0)
+        n = len(obs_sets)
+        if n == 0 or len(obs_points_sets) != n:
+            raise ValueError("PolytopeScene needs one vertex array per obstacle set")
+        rows = np.zeros((n, self.MAX_ROWS, 4))
+        rows[:, :, 3] = 10.0
+        nrows = np.zeros(n, np.int32)
+        vmax = max(int(np.asarray(v).reshape(-1, 3).shape[0]) for v in obs_points_sets)
+        verts = np.zeros((n, vmax, 3))
+        nverts = np.zeros(n, np.int32)
+        for j, ((a_set, b_set), v) in enumerate(zip(obs_sets, obs_points_sets)):
+            a_set = np.asarray(a_set, float).reshape(-1, 3)
+            b_set = np.asarray(b_set, float).reshape(-1)
+            nz = np.linalg.norm(a_set, axis=1) > 0
+            k = int(nz.sum())
+            if k > self.MAX_ROWS:
+                raise ValueError(f"obstacle {j} has more than {self.MAX_ROWS} rows")
+            rows[j, :k, :3], rows[j, :k, 3] = a_set[nz], b_set[nz]
+            nrows[j] = k
+            v = np.asarray(v, float).reshape(-1, 3)
+            verts[j, : v.shape[0]] = v
+            nverts[j] = v.shape[0]
+        ip = ctypes.POINTER(ctypes.c_int)
+        torch.cuda.current_device()
+        check(self._lib.bp_scene_create_polytopes(rows.ctypes.data_as(_dp), nrows.ctypes.data_as(ip),
+                                                  verts.ctypes.data_as(_dp), nverts.ctypes.data_as(ip), n, vmax,
+                                                  ctypes.byref(self._h)))
+        self.n = n
+        self.inflate = 0.0
+
+    def update(self, boxes, inflate=None):
+        raise _lib.BpGeoError("PolytopeScene is immutable: create a new one")
+
+
 class SceneBatch(Scene):
     """Several scenes stored back to back in HBM (one per planning query, BASELINE config C3).
     ``boxes_list``: list of [N_k,6] arrays.  Use with build_sets_point / build_sets_line and

@@ -120,3 +120,47 @@ def config_c3_query(i, n_obs=200):
         if np.linalg.norm(pts[0] - pts[1]) >= 0.3:
             break
     return obstacles, inflate, pts[0], pts[1], WORKSPACE_MIN.copy(), WORKSPACE_MAX.copy()
+
+
+def random_polytope_scene(n_obs, rng, size_lo=0.03, size_hi=0.12, max_rows=15, ws_min=WORKSPACE_MIN, ws_max=WORKSPACE_MAX):
+    """n_obs random convex polytope obstacles in the layout ConvexSetFinder takes (what add_obstacle_reps would
+    build for non-box obstacles): obs_sets = [[A (15x3, zero-padded), b (15, padded with 10)], ...] with unit
+    normals, obs_points_sets = [vertices (V x 3), ...].  Each polytope is a random box cut by random planes."""
+    from scipy.spatial import HalfspaceIntersection
+
+    obs_sets, obs_points = [], []
+    box = np.concatenate((np.eye(3), -np.eye(3)))
+    while len(obs_sets) < n_obs:
+        c = rng.uniform(ws_min, ws_max)
+        half = 0.5 * rng.uniform(size_lo, size_hi, 3)
+        n_cut = int(rng.integers(0, max_rows - 6 + 1))
+        cuts = rng.normal(size=(n_cut, 3))
+        cuts /= np.linalg.norm(cuts, axis=1)[:, None]
+        A = np.vstack((box, cuts))
+        b = np.concatenate((c + half, -(c - half), cuts @ c + rng.uniform(0.3, 0.9, n_cut) * (np.abs(cuts) @ half)))
+        hs = HalfspaceIntersection(np.hstack((A, -b[:, None])), c)
+        verts = hs.intersections
+        # keep the rows that support a facet (>= 3 vertices on the plane), like the reference's reduced sets
+        on = np.abs(verts @ A.T - b) < 1e-9
+        keep = on.sum(axis=0) >= 3
+        A, b = A[keep], b[keep]
+        a_pad = np.zeros((max_rows, 3))
+        b_pad = np.full(max_rows, 10.0)
+        a_pad[: A.shape[0]], b_pad[: A.shape[0]] = A, b
+        obs_sets.append([a_pad, b_pad])
+        obs_points.append(np.ascontiguousarray(verts))
+    return obs_sets, obs_points
+
+
+def polytope_free_points(n, obs_sets, margin, rng, ws_min=WORKSPACE_MIN, ws_max=WORKSPACE_MAX):
+    """Uniform points with max(A x - b) >= margin for every polytope."""
+    A = np.stack([s[0] for s in obs_sets])
+    b = np.stack([s[1] for s in obs_sets])
+    out = np.empty((0, 3))
+    while out.shape[0] < n:
+        cand = rng.uniform(ws_min, ws_max, (2 * n, 3))
+        viol = np.einsum("nrk,ck->cnr", A, cand) - b[None]
+        viol[:, np.linalg.norm(A, axis=2) == 0] = -np.inf
+        cand = cand[(viol.max(axis=2) >= margin).all(axis=1)]
+        out = np.vstack((out, cand))
+    return np.ascontiguousarray(out[:n])

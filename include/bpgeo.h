@@ -51,6 +51,14 @@ int bp_scene_create(const double* boxes_host, int n, double inflate, bp_scene** 
  * every seed / segment. */
 int bp_scene_create_batch(const double* boxes_host, const int* offsets_host /*[n_scenes+1]*/, int n_scenes,
                           double inflate, bp_scene** out);
+/* General convex polytope obstacles (util_functions.compute_polytope_vertices / the obs_sets + obs_points_sets
+ * a caller hands to ConvexSetFinder): rows_host [n,15,4] = (a0,a1,a2,b) per row, real rows first, then zero rows
+ * with b = 10 (normalize_set_size padding, util_functions.py:119-133); nrows_host [n]; verts_host [n,vmax,3] with
+ * nverts_host [n] vertices each.  Rows are taken as given (already inflated).  Supported by bp_closest_points,
+ * bp_polyhedron, bp_build_sets_point and bp_build_sets_around_line (at most 3072 obstacles); the segment QP of
+ * bp_build_sets_line / bp_closest_points_line is box-only and fails loudly on such a scene. */
+int bp_scene_create_polytopes(const double* rows_host, const int* nrows_host, const double* verts_host,
+                              const int* nverts_host, int n, int vmax, bp_scene** out);
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream);
 int bp_scene_destroy(bp_scene* scene);
 int bp_scene_size(const bp_scene* scene);

@@ -149,16 +149,18 @@ class ConvexSetFinder:
     def _stack(self):
         A = np.stack([s[0] for s in self.obs_sets])          # (N,15,3)
         b = np.stack([s[1] for s in self.obs_sets])          # (N,15)
-        V = np.stack([np.asarray(v) for v in self.obs_points_sets])   # (N,8,3)
+        # vertices (N,Vmax,3): boxes have 8 each; ragged polytope lists are padded by repeating the first vertex
+        vs = [np.asarray(v, float).reshape(-1, 3) for v in self.obs_points_sets]
+        vmax = max(v.shape[0] for v in vs)
+        V = np.stack([np.vstack((v, np.repeat(v[:1], vmax - v.shape[0], axis=0))) for v in vs])
         return A, b, V
 
     @staticmethod
     def _nonzero_rows(A):
+        """Rows to keep: all obstacles share the padded layout (real rows first, zero rows after); with ragged row
+        counts the zero rows stay in (they are never active and always satisfied, b = 10)."""
         nz = np.linalg.norm(A, axis=2) > 0
-        r = nz.sum(axis=1)
-        if not np.all(r == r[0]) or not np.all(nz[:, : r[0]]):
-            raise NotImplementedError("oracle expects the same row count for every obstacle")
-        return int(r[0])
+        return int(nz.sum(axis=1).max())
 
     # ---- :377-421 ---------------------------------------------------------
     def init_halfspaces(self):

@@ -74,6 +74,30 @@ void hh_box_qp(const double* E, const double* p, const double* lb, const double*
   }
 }
 
+// closest points of n polytopes (rows [n,R,4] = a0 a1 a2 b, padded rows a = 0, b = 10) to p in the metric of
+// E (q_inv): y[n,3], dist[n]; returns the number of empty polytopes
+int hh_polytope_qp(const double* E, const double* p, const double* rows4, int n, int R, double* y, double* dist) {
+  double Q[9], M[9];
+  bp_inv3(E, Q);
+  bp_mat3_ata(Q, M);
+  BpPolyMetric pm;
+  bp_poly_metric_init(M, &pm);
+  int empty = 0;
+  for (int j = 0; j < n; ++j) {
+    struct R4 {
+      const double* r;
+      double a(int i, int k) const { return r[4 * i + k]; }
+      double b(int i) const { return r[4 * i + 3]; }
+    } rows{rows4 + (size_t)j * R * 4};
+    if (!bp_polytope_qp(pm, rows, R, p, y + 3 * j)) { ++empty; dist[j] = -1.0; continue; }
+    double zz[3] = {y[3 * j] - p[0], y[3 * j + 1] - p[1], y[3 * j + 2] - p[2]};
+    double w[3];
+    bp_mat3_vec(Q, zz, w);
+    dist[j] = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  }
+  return empty;
+}
+
 void hh_seg_box(const double* p0, const double* p1, const double* lb, const double* ub, int n, double* x,
                 double* phi) {
   double d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};

@@ -105,12 +105,15 @@ def test_error_behaviour(c1):
     b = np.ones(24)
     with pytest.raises(ValueError):
         gpu.mvie_socp_fixed_mid(A, b, np.zeros(3))
-    # non-box obstacles are refused loudly
+    # non-box obstacles need their vertices (general polytopes, tests/test_gpu_polytopes.py); without them: loud
     import boundplanner_b200 as bp
 
     bad = [[np.vstack((np.eye(3), -np.eye(3), np.ones((1, 3)))), np.ones(7)]]
-    with pytest.raises(NotImplementedError):
-        bp.ConvexSetFinder(bad, [np.zeros((8, 3))], [1, 1, 1], [-1, -1, 0])
+    with pytest.raises(ValueError, match="obs_points_sets"):
+        bp.ConvexSetFinder(bad, [], [1, 1, 1], [-1, -1, 0])
+    sixteen = [[np.vstack((np.eye(3), -np.eye(3), np.ones((10, 3)))), np.ones(16)]]
+    with pytest.raises(ValueError, match="more than 15 rows"):
+        bp.ConvexSetFinder(sixteen, [np.zeros((8, 3))], [1, 1, 1], [-1, -1, 0])
 
 
 def test_scene_update_through_attribute_assignment(c1):

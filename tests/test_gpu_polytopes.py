@@ -1,0 +1,106 @@
+"""GPU: general convex polytope obstacles (obs_sets with up to 15 rows + their vertices, as
+ConvexSetFinder receives them) in the point-set path -- closest points, polyhedron pass, IRIS loop -- against the
+oracle, plus the loud failure of the box-only segment path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import RTOL, assert_rows_close  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def poly_scene():
+    import torch
+
+    assert torch.cuda.is_available()
+    from boundplanner_b200 import geometry as geo, scenes
+    from oracle.convex_set_finder import ConvexSetFinder as OracleFinder
+
+    rng = np.random.default_rng(31)
+    obs_sets, obs_points = scenes.random_polytope_scene(300, rng, 0.04, 0.16)
+    ws_min, ws_max = scenes.WORKSPACE_MIN, scenes.WORKSPACE_MAX
+    seeds = scenes.polytope_free_points(14, obs_sets, 0.03, rng)
+    scene = geo.PolytopeScene(obs_sets, obs_points)
+    ora = OracleFinder(obs_sets, obs_points, list(ws_max), list(ws_min))
+    return geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max
+
+
+def test_polytope_closest_points_match_oracle(poly_scene):
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    rng = np.random.default_rng(1)
+    for trial in range(3):
+        L = np.tril(rng.normal(size=(3, 3))) * 0.1 + np.diag(rng.uniform(0.05, 0.4, 3))
+        E = L @ L.T if trial else 1e-4 * np.eye(3)
+        p = seeds[trial]
+        y, dist = geo.closest_points(scene, p[None], E[None])
+        y, dist = y[0].cpu().numpy(), dist[0].cpu().numpy()
+        yo = ora.compute_set_projs(obs_sets, p, E)
+        do = np.linalg.norm(np.linalg.solve(E, (yo - p).T), axis=0)
+        assert np.abs(y - yo).max() < 1e-7
+        assert (np.abs(dist - do) / do).max() < 1e-7
+
+
+def test_polytope_iris_loop_matches_oracle(poly_scene):
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    out = geo.build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=True, optimize=True)
+    one = geo.build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=True, optimize=False)
+    status, m, iters = out.status.cpu().numpy(), out.m.cpu().numpy(), out.iters.cpu().numpy()
+    A, b, Q, P = out.A.cpu().numpy(), out.b.cpu().numpy(), out.q_ellipse.cpu().numpy(), out.p_mid.cpu().numpy()
+    A1, b1, m1 = one.A.cpu().numpy(), one.b.cpu().numpy(), one.m.cpu().numpy()
+    n_ok = 0
+    for s in range(len(seeds)):
+        # first pass alone (compute_polyhedron around the initial sphere)
+        a_o, b_o, _, _ = ora.find_set_around_point(seeds[s], fixed_mid=True, optimize=False)
+        assert_rows_close(A1[s, : m1[s]], b1[s, : m1[s]], a_o, b_o, f"seed {s}, first pass")
+        try:
+            a_o, b_o, q_o, p_o = ora.find_set_around_point(seeds[s], fixed_mid=True, optimize=True)
+        except (RuntimeError, ValueError):
+            assert status[s] != 0
+            continue
+        assert status[s] == 0 and iters[s] == ora.last_iters, (s, status[s], iters[s], ora.last_iters)
+        assert_rows_close(A[s, : m[s]], b[s, : m[s]], a_o, b_o, f"seed {s}")
+        assert np.abs(Q[s] - q_o).max() <= 1e-5 * np.abs(q_o).max()
+        assert np.abs(P[s] - p_o).max() <= 1e-5
+        n_ok += 1
+    assert n_ok >= 10
+
+
+def test_boxes_as_polytopes_give_the_box_answer(poly_scene):
+    """The same box obstacles through the polytope path (rows + 8 corners) and through the box path."""
+    geo, *_ = poly_scene
+    from boundplanner_b200 import scenes
+    from oracle.obstacles import obstacle_reps
+
+    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(400, 16)
+    obs_sets, pts, _ = obstacle_reps(boxes, inflate)
+    sp = geo.PolytopeScene(obs_sets, pts)
+    sb = geo.Scene(boxes, inflate)
+    op = geo.build_sets_point(sp, seeds, ws_min, ws_max, fixed_mid=True, optimize=True)
+    ob = geo.build_sets_point(sb, seeds, ws_min, ws_max, fixed_mid=True, optimize=True)
+    assert np.array_equal(op.m.cpu().numpy(), ob.m.cpu().numpy())
+    assert np.array_equal(op.iters.cpu().numpy(), ob.iters.cpu().numpy())
+    assert np.abs(op.A.cpu().numpy() - ob.A.cpu().numpy()).max() < 1e-9
+    assert np.abs(op.b.cpu().numpy() - ob.b.cpu().numpy()).max() < 1e-9
+    qp, qb = op.q_ellipse.cpu().numpy(), ob.q_ellipse.cpu().numpy()
+    assert np.abs(qp - qb).max() <= 1e-7 * np.abs(qb).max()
+
+
+def test_dropin_with_polytope_obstacles(poly_scene):
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    import boundplanner_b200 as bp
+
+    gpu = bp.ConvexSetFinder(obs_sets, obs_points, list(ws_max), list(ws_min))
+    A, b, Q, p = gpu.find_set_around_point(seeds[0], fixed_mid=True)
+    Ao, bo, Qo, po = ora.find_set_around_point(seeds[0], fixed_mid=True)
+    assert_rows_close(A, b, Ao, bo, "drop-in polytope set")
+    assert np.abs(Q - Qo).max() <= 1e-5 * np.abs(Qo).max() and np.abs(p - po).max() <= RTOL
+    a_init, b_init = gpu.init_halfspaces()
+    q_inv = np.diag([1e-4] * 3)
+    rows = gpu.compute_polyhedron(q_inv, np.linalg.inv(q_inv), seeds[1], a_init, b_init)
+    rows_o = ora.compute_polyhedron(q_inv, np.linalg.inv(q_inv), seeds[1], a_init, b_init)
+    assert_rows_close(np.array(rows[0]), np.array(rows[1]), np.array(rows_o[0]), np.array(rows_o[1]), "compute_polyhedron")
+    with pytest.raises(NotImplementedError):
+        gpu.find_set_collision_avoidance(seeds[0], seeds[0] + 0.05)
+    with pytest.raises(bp._lib.BpGeoError, match="polytope"):
+        geo.build_sets_line(scene, seeds[:1], seeds[:1] + 0.05, ws_min, ws_max)

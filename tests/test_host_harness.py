@@ -197,3 +197,35 @@ def test_mvie_fixed_r_primitive(host_harness):
     st = host_harness.hh_mvie_fixed_r(dp(BOX.copy()), dp(b), 6, dp(np.zeros(3)), dp(np.eye(3)), ctypes.c_double(0.31),
                                       dp(E), dp(Q), dp(eigs), ctypes.byref(it))
     assert st == 3                      # a_lb larger than the box allows: the reference's SOCP is infeasible
+
+
+def test_polytope_qp_primitive(host_harness):
+    """General-polytope closest points (bp_polytope_qp) vs the oracle's active-set enumeration, ragged row counts."""
+    from boundplanner_b200 import scenes
+
+    rng = np.random.default_rng(17)
+    obs_sets, obs_points = scenes.random_polytope_scene(120, rng)
+    R = 15
+    rows4 = np.ascontiguousarray(np.stack([np.hstack((s[0], s[1][:, None])) for s in obs_sets]))
+    assert len({int((np.linalg.norm(s[0], axis=1) > 0).sum()) for s in obs_sets}) > 3        # ragged
+    worst = 0.0
+    for trial in range(4):
+        p = rng.uniform(-1, 1, 3)
+        p[2] = abs(p[2])
+        L = np.tril(rng.normal(size=(3, 3))) * 0.2 + np.diag(rng.uniform(0.05, 0.6, 3))
+        E = L @ L.T if trial else 1e-4 * np.eye(3)
+        E = np.ascontiguousarray(E)
+        y, dist = np.zeros((120, 3)), np.zeros(120)
+        host_harness.hh_polytope_qp.restype = ctypes.c_int
+        n_empty = host_harness.hh_polytope_qp(dp(E), dp(np.ascontiguousarray(p)), dp(rows4), 120, R, dp(y), dp(dist))
+        assert n_empty == 0
+        A = rows4[:, :, :3]
+        b = rows4[:, :, 3]
+        x = min_norm_point_polytopes(A @ E, b - A @ p)
+        yo = x @ E.T + p
+        do = np.linalg.norm(np.linalg.solve(E, (yo - p).T), axis=0)
+        worst = max(worst, np.abs(y - yo).max(), (np.abs(dist - do) / np.maximum(do, 1e-12)).max())
+        # the points lie in their polytopes and (when p is outside) on their boundary
+        viol = np.einsum("nrk,nk->nr", A, y) - b
+        assert viol.max() < 1e-9
+    assert worst < 1e-7          # (north_star tolerance 1e-6; the oracle's own Gram solves limit the agreement)
