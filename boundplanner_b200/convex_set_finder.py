@@ -13,9 +13,8 @@ Every method is a batch-of-one call into the batched device API in
 ``geometry.py``; use ``find_sets_around_points`` / ``find_sets_collision_avoidance``
 for real batches.  Obstacles are normally the axis-aligned boxes the planner builds
 (A = [I; -I], BoundPlanner.py:126-129); general convex polytopes (<= 15 rows, with
-their vertices in ``obs_points_sets``) are supported by the point-set methods, while
-the segment methods (find_set_collision_avoidance, compute_set_projs_line) raise
-NotImplementedError for them.  There is no CPU fallback.
+their vertices in ``obs_points_sets``) are supported by every method as well.
+There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -150,13 +149,7 @@ class ConvexSetFinder:
         self.proj_time += time.perf_counter() - start
         return out
 
-    def _no_polytope_segments(self):
-        if self._polytopes:
-            raise NotImplementedError("segment closest points / find_set_collision_avoidance handle box obstacles "
-                                      "only; polytope obstacles are supported by the point-set methods")
-
     def compute_set_projs_line(self, obs_sets, p0, p1):
-        self._no_polytope_segments()
         start = time.perf_counter()
         scene = self._scene_for(obs_sets)
         x, phi = geo.closest_points_line(scene, np.asarray(p0, float)[None], np.asarray(p1, float)[None])
@@ -283,7 +276,6 @@ class ConvexSetFinder:
 
     def find_sets_collision_avoidance(self, p0, p1, compute_ellipsoid=False, limit_space=False, e_max=0.3,
                                       m_max=BP_MAX_ROWS):
-        self._no_polytope_segments()
         start = time.perf_counter()
         ws_min, ws_max = self._ws()
         out = geo.build_sets_line(self._scene, p0, p1, ws_min, ws_max, compute_ellipsoid=bool(compute_ellipsoid),

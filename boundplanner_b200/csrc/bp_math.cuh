@@ -414,3 +414,123 @@ BP_HD bool bp_polytope_qp(const BpPolyMetric& pm, const ROWS& rows, int R, const
         }
   return found;
 }
+
+// ---------------------------------------------------------------------------
+// K2p: closest points between the segment p0 + phi d (0 <= phi <= 1) and a GENERAL convex polytope whose offsets
+// are shrunk by `shrink` (b - 0.001, ConvexSetFinder.py:496).  Replaces the same qpOASES solve as K2 (:491-510,
+// problem :52-99) for obstacles that are not boxes.  Exact: at the optimum x is the projection of p(phi) onto the
+// affine hull of its active rows (<= 3) and phi is 0, 1 or the minimiser of the distance between the segment's
+// line and that hull; every (row subset, phi status) is a candidate, the feasible one of least distance wins and,
+// among equal ones, the smallest phi (like bp_seg_box).
+// pm: 0 -> phi = 0, 1 -> phi = 1, 2 -> phi free (kept only when 0 < phi < 1).
+// ---------------------------------------------------------------------------
+template <class ROWS>
+BP_HD bool bp_seg_polytope_candidate(const ROWS& rows, int R, double shrink, const double* p0, const double* d, int i,
+                                     int j, int k, int pm, double* x, double* phi_out, double* obj) {
+  double phi = (double)pm;
+  if (i < 0) {
+    if (pm == 2) return false;
+    x[0] = p0[0] + phi * d[0]; x[1] = p0[1] + phi * d[1]; x[2] = p0[2] + phi * d[2];
+  } else if (k >= 0) {
+    const double a[3] = {rows.a(i, 0), rows.a(i, 1), rows.a(i, 2)};
+    const double c[3] = {rows.a(j, 0), rows.a(j, 1), rows.a(j, 2)};
+    const double e[3] = {rows.a(k, 0), rows.a(k, 1), rows.a(k, 2)};
+    const double n0 = a[1] * c[2] - a[2] * c[1], n1 = a[2] * c[0] - a[0] * c[2], n2 = a[0] * c[1] - a[1] * c[0];
+    const double det = n0 * e[0] + n1 * e[1] + n2 * e[2];
+    const double na = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], nc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double ne = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    if (!(det * det > 1e-24 * na * nc * ne)) return false;
+    const double e0 = c[1] * e[2] - c[2] * e[1], e1 = c[2] * e[0] - c[0] * e[2], e2 = c[0] * e[1] - c[1] * e[0];
+    const double f0 = e[1] * a[2] - e[2] * a[1], f1 = e[2] * a[0] - e[0] * a[2], f2 = e[0] * a[1] - e[1] * a[0];
+    const double ab = rows.b(i) - shrink, cb = rows.b(j) - shrink, eb = rows.b(k) - shrink, id = 1.0 / det;
+    x[0] = (ab * e0 + cb * f0 + eb * n0) * id;
+    x[1] = (ab * e1 + cb * f1 + eb * n1) * id;
+    x[2] = (ab * e2 + cb * f2 + eb * n2) * id;
+    if (pm == 2) {
+      const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      if (!(dd > 0.0)) return false;
+      phi = (d[0] * (x[0] - p0[0]) + d[1] * (x[1] - p0[1]) + d[2] * (x[2] - p0[2])) / dd;
+      if (!(phi > 0.0 && phi < 1.0)) return false;
+    }
+  } else if (j < 0) {
+    const double a[3] = {rows.a(i, 0), rows.a(i, 1), rows.a(i, 2)};
+    const double g = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    if (!(g > 0.0)) return false;
+    const double u = a[0] * p0[0] + a[1] * p0[1] + a[2] * p0[2] - (rows.b(i) - shrink);
+    const double w = a[0] * d[0] + a[1] * d[1] + a[2] * d[2];
+    if (pm == 2) {
+      const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      if (!(w * w > 1e-24 * g * dd)) return false;          // segment parallel to the plane
+      phi = -u / w;                                          // the segment's line crosses the plane
+      if (!(phi > 0.0 && phi < 1.0)) return false;
+    }
+    const double q[3] = {p0[0] + phi * d[0], p0[1] + phi * d[1], p0[2] + phi * d[2]};
+    const double lam = (u + phi * w) / g;
+    x[0] = q[0] - lam * a[0]; x[1] = q[1] - lam * a[1]; x[2] = q[2] - lam * a[2];
+  } else {
+    const double a[3] = {rows.a(i, 0), rows.a(i, 1), rows.a(i, 2)};
+    const double c[3] = {rows.a(j, 0), rows.a(j, 1), rows.a(j, 2)};
+    const double g11 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], g12 = a[0] * c[0] + a[1] * c[1] + a[2] * c[2];
+    const double g22 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double det = g11 * g22 - g12 * g12;
+    if (!(det > 1e-14 * g11 * g22)) return false;
+    const double u1 = a[0] * p0[0] + a[1] * p0[1] + a[2] * p0[2] - (rows.b(i) - shrink);
+    const double u2 = c[0] * p0[0] + c[1] * p0[1] + c[2] * p0[2] - (rows.b(j) - shrink);
+    const double w1 = a[0] * d[0] + a[1] * d[1] + a[2] * d[2], w2 = c[0] * d[0] + c[1] * d[1] + c[2] * d[2];
+    if (pm == 2) {
+      // minimise (u + phi w)^T G^-1 (u + phi w)
+      const double gw1 = (g22 * w1 - g12 * w2) / det, gw2 = (g11 * w2 - g12 * w1) / det;   // G^-1 w
+      const double den = w1 * gw1 + w2 * gw2;
+      const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      if (!(den > 1e-24 * dd)) return false;                 // segment parallel to the edge's normal plane
+      phi = -(u1 * gw1 + u2 * gw2) / den;
+      if (!(phi > 0.0 && phi < 1.0)) return false;
+    }
+    const double r1 = u1 + phi * w1, r2 = u2 + phi * w2;
+    const double l1 = (g22 * r1 - g12 * r2) / det, l2 = (g11 * r2 - g12 * r1) / det;
+    x[0] = p0[0] + phi * d[0] - (l1 * a[0] + l2 * c[0]);
+    x[1] = p0[1] + phi * d[1] - (l1 * a[1] + l2 * c[1]);
+    x[2] = p0[2] + phi * d[2] - (l1 * a[2] + l2 * c[2]);
+  }
+  for (int r = 0; r < R; ++r) {
+    const double q0 = rows.a(r, 0), q1 = rows.a(r, 1), q2 = rows.a(r, 2), br = rows.b(r) - shrink;
+    const double viol = q0 * x[0] + q1 * x[1] + q2 * x[2] - br;
+    const double mag = fabs(q0 * x[0]) + fabs(q1 * x[1]) + fabs(q2 * x[2]) + (fabs(br) > 1.0 ? fabs(br) : 1.0);
+    if (viol > 1e-10 * mag) return false;
+  }
+  const double z0 = p0[0] + phi * d[0] - x[0], z1 = p0[1] + phi * d[1] - x[1], z2 = p0[2] + phi * d[2] - x[2];
+  *obj = z0 * z0 + z1 * z1 + z2 * z2;
+  *phi_out = phi;
+  return true;
+}
+
+// candidate (obj, phi) beats the incumbent: strictly closer, or as close (to rounding) with a smaller phi
+BP_HD bool bp_seg_better(double obj, double phi, double best, double best_phi) {
+  if (obj < best * (1.0 - 1e-12) - 1e-24) return true;
+  return obj <= best * (1.0 + 1e-12) + 1e-24 && phi < best_phi;
+}
+
+// Serial walk (host harness / one thread).  Returns false for an empty polytope.
+template <class ROWS>
+BP_HD bool bp_seg_polytope_qp(const ROWS& rows, int R, double shrink, const double* p0, const double* d, double* x,
+                              double* phi_out, double* dist2_out) {
+  double best = BP_INF, bphi = BP_INF, xc[3], pc, oc;
+  bool found = false;
+#define BP_SEGP_TRY(I, J, K)                                                                         \
+  for (int pm = 0; pm < 3; ++pm)                                                                     \
+    if (bp_seg_polytope_candidate(rows, R, shrink, p0, d, (I), (J), (K), pm, xc, &pc, &oc) &&        \
+        (!found || bp_seg_better(oc, pc, best, bphi))) {                                             \
+      best = oc; bphi = pc; found = true; x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];                  \
+    }
+  BP_SEGP_TRY(-1, -1, -1)
+  for (int i = 0; i < R; ++i) BP_SEGP_TRY(i, -1, -1)
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j) BP_SEGP_TRY(i, j, -1)
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j)
+      for (int k = j + 1; k < R; ++k) BP_SEGP_TRY(i, j, k)
+#undef BP_SEGP_TRY
+  *phi_out = bphi;
+  *dist2_out = best;
+  return found;
+}

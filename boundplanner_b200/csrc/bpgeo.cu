@@ -267,10 +267,19 @@ __global__ void k_closest_points_line(SceneView sc, const double* __restrict__ p
   for (int k = 0; k < 3; ++k) { p0[k] = p0s[(size_t)s * 3 + k]; d[k] = p1s[(size_t)s * 3 + k] - p0[k]; }
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < sc.n; j += gridDim.x * blockDim.x) {
     double lb[3], ub[3], x[3], d2;
+    double phi;
+    if (sc.rows) {                                 // general polytope: serial walk over the candidates
+      GlobalRows4 rows{sc.rows + (size_t)j * BP_OBS_ROWS * 4};
+      if (!bp_seg_polytope_qp(rows, sc.nrows[j], 0.001, p0, d, x, &phi, &d2)) { x[0] = x[1] = x[2] = 0.0; phi = -1.0; }
+      size_t o = (size_t)s * sc.n + j;
+      x_out[3 * o] = x[0]; x_out[3 * o + 1] = x[1]; x_out[3 * o + 2] = x[2];
+      phi_out[o] = phi;
+      continue;
+    }
     load_box(sc, j, lb, ub);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { lb[k] += 0.001; ub[k] -= 0.001; }   // b - 0.001 (:496)
-    double phi = bp_seg_box(p0, d, lb, ub, x, &d2);
+    phi = bp_seg_box(p0, d, lb, ub, x, &d2);
     size_t o = (size_t)s * sc.n + j;
     x_out[3 * o] = x[0]; x_out[3 * o + 1] = x[1]; x_out[3 * o + 2] = x[2];
     phi_out[o] = phi;
@@ -1027,6 +1036,194 @@ __global__ void __launch_bounds__(512) k_poly_line(SceneView sc_all, LineParams 
         s_dist[j] = BP_INF;
       } else if (dd < lmin) {
         lmin = dd; lidx = j;
+      }
+    }
+  }
+  for (int r = m_cur + tid; r < pr.m_max; r += T) {
+    Arow[3 * r] = 0.0; Arow[3 * r + 1] = 0.0; Arow[3 * r + 2] = 0.0;
+    brow[r] = 10.0;
+  }
+  if (tid == 0) {
+    pr.m[s] = m_cur < pr.m_max ? m_cur : pr.m_max;
+    pr.status[s] = m_cur > pr.m_max ? BP_ROW_OVERFLOW : BP_OK;
+    pr.collision[s] = collision;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3'p: find_set_collision_avoidance (:309-375) over GENERAL polytope obstacles.  Same greedy loop as k_poly_line;
+// the closest points come from the segment-polytope QP (bp_seg_polytope_candidate), solved lazily like the point
+// pass: the table starts with the distance from the segment to every obstacle's BOUNDING BOX (a lower bound),
+// and only entries that can still win are refined, each by one warp (candidates dealt to the lanes).
+// Dynamic shared memory: dist[N] | x[3][N] | p_closest[3][N].
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool seg_polytope_qp_warp(const double* rows4, int R, double shrink, const double* p0,
+                                                     const double* d, double* x, double* phi_out, double* dist2) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  SmemRows4 rows{rows4};
+  double best = BP_INF, bphi = BP_INF, xb[3] = {0.0, 0.0, 0.0}, xc[3], pc, oc;
+  int bidx = 0x7fffffff, cnt = 0;
+#define BP_SEGP_TRYW(I, J, K)                                                                                   \
+  for (int pm = 0; pm < 3; ++pm) {                                                                              \
+    if ((cnt & 31) == lane && bp_seg_polytope_candidate(rows, R, shrink, p0, d, (I), (J), (K), pm, xc, &pc, &oc) && \
+        (bidx == 0x7fffffff || bp_seg_better(oc, pc, best, bphi))) {                                            \
+      best = oc; bphi = pc; bidx = cnt; xb[0] = xc[0]; xb[1] = xc[1]; xb[2] = xc[2];                            \
+    }                                                                                                           \
+    ++cnt;                                                                                                      \
+  }
+  BP_SEGP_TRYW(-1, -1, -1)
+  for (int i = 0; i < R; ++i) BP_SEGP_TRYW(i, -1, -1)
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j) BP_SEGP_TRYW(i, j, -1)
+  for (int i = 0; i < R; ++i)
+    for (int j = i + 1; j < R; ++j)
+      for (int k = j + 1; k < R; ++k) BP_SEGP_TRYW(i, j, k)
+#undef BP_SEGP_TRYW
+  const double bmin = warp_min_nonneg(best);
+  if (!(bmin < BP_INF)) return false;
+  // least distance (to rounding), then the smallest phi (quirk Q9), then the first candidate
+  const bool near = best <= bmin * (1.0 + 1e-12) + 1e-24;
+  const double pmin = warp_min_nonneg(near ? (bphi < 0.0 ? 0.0 : bphi) : BP_INF);
+  const unsigned cand = (near && bphi <= pmin) ? (unsigned)bidx : 0xffffffffu;
+  const unsigned widx = __reduce_min_sync(full, cand);
+  const int src = __ffs(__ballot_sync(full, cand == widx)) - 1;
+  x[0] = __shfl_sync(full, xb[0], src);
+  x[1] = __shfl_sync(full, xb[1], src);
+  x[2] = __shfl_sync(full, xb[2], src);
+  *phi_out = __shfl_sync(full, bphi, src);
+  *dist2 = __shfl_sync(full, best, src);
+  return true;
+}
+
+__global__ void __launch_bounds__(512) k_poly_line_p(SceneView sc, LineParams pr) {
+  extern __shared__ double s_dist[];
+  __shared__ double red_val[2][32];
+  __shared__ int red_idx[2][32];
+  __shared__ int s_list[BP_POLY_LIST];
+  __shared__ int s_nlist;
+  __shared__ double s_prow[16][BP_OBS_ROWS * 4];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double* s_x = s_dist + sc.n;                 // [3][N]
+  double* s_pc = s_dist + 4 * (size_t)sc.n;    // [3][N]
+  double p0[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p0[k] = pr.p0[(size_t)s * 3 + k];
+    d[k] = pr.p1[(size_t)s * 3 + k] - p0[k];
+  }
+  double* Arow = pr.A + (size_t)s * pr.m_max * 3;
+  double* brow = pr.b + (size_t)s * pr.m_max;
+  if (tid < 6) {
+    int ax = tid >> 1;
+    double sgn = (tid & 1) ? -1.0 : 1.0;
+    Arow[3 * tid + 0] = ax == 0 ? sgn : 0.0;
+    Arow[3 * tid + 1] = ax == 1 ? sgn : 0.0;
+    Arow[3 * tid + 2] = ax == 2 ? sgn : 0.0;
+    brow[tid] = pr.limit_space ? (sgn * p0[ax] + pr.e_max) : pr.ws_rows[tid];
+  }
+  if (tid == 0) s_nlist = 0;
+  unsigned long long alive = 0ull;
+  double lkey = BP_INF;
+  int lidx = 0x3fffffff, lexact = 0;
+  {
+    int k = 0;
+    for (int j = tid; j < sc.n; j += T, ++k) {
+      double lb[3], ub[3], xb[3], d2;
+      load_box(sc, j, lb, ub);
+      bp_seg_box(p0, d, lb, ub, xb, &d2);                   // distance to the bounding box: a lower bound
+      double bd = sqrt(d2) * (1.0 - 1e-9);
+      if (!(bd > 0.0)) bd = DBL_MIN;
+      s_dist[j] = -bd;
+      alive |= 1ull << k;
+      if (bd < lkey) { lkey = bd; lidx = j; }
+    }
+  }
+  int m_cur = 6, buf = 0, collision = 0;
+  while (true) {
+    double val = lkey;
+    int idx = lidx, exact = lexact;
+    block_argmin_lazy(val, idx, exact, red_val, red_idx, buf);
+    if (!(val < BP_INF)) break;
+    if (!exact) {
+      double lex = BP_INF;
+      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+        const double dv = s_dist[tid + (__ffsll((long long)mk) - 1) * T];
+        if (dv >= 0.0) lex = fmin(lex, dv);
+      }
+      const double ex = block_min_nonneg(lex, red_val, buf);
+      const double thr = fmax(ex < BP_INF ? ex : 0.0, BP_LAZY_GROW * val);
+      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+        const int j = tid + (__ffsll((long long)mk) - 1) * T;
+        const double dv = s_dist[j];
+        if (dv < 0.0 && -dv <= thr) {
+          const int slot = atomicAdd(&s_nlist, 1);
+          if (slot < BP_POLY_LIST) s_list[slot] = j;
+        }
+      }
+      __syncthreads();
+      const int nl = s_nlist < BP_POLY_LIST ? s_nlist : BP_POLY_LIST;
+      const int warp = tid >> 5, lane = tid & 31, nw = T >> 5;
+      for (int q = warp; q < nl; q += nw) {
+        const int j = s_list[q];
+        const int R = sc.nrows[j];
+        for (int e = lane; e < R * 4; e += 32) s_prow[warp][e] = __ldg(sc.rows + (size_t)j * BP_OBS_ROWS * 4 + e);
+        __syncwarp();
+        double x[3], phi, d2;
+        const bool okq = seg_polytope_qp_warp(s_prow[warp], R, 0.001, p0, d, x, &phi, &d2);   // b - 0.001 (:496)
+        if (lane == 0) {
+          s_dist[j] = okq ? sqrt(d2) : BP_INF;               // :327
+          s_x[j] = x[0]; s_x[sc.n + j] = x[1]; s_x[2 * sc.n + j] = x[2];
+          s_pc[j] = p0[0] + phi * d[0]; s_pc[sc.n + j] = p0[1] + phi * d[1]; s_pc[2 * sc.n + j] = p0[2] + phi * d[2];
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      if (tid == 0) s_nlist = 0;
+      lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
+      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+        const int kk = __ffsll((long long)mk) - 1;
+        const int j = tid + kk * T;
+        double dv = s_dist[j];
+        if (!(dv < BP_INF)) { alive &= ~(1ull << kk); continue; }     // empty polytope
+        const int e = dv >= 0.0;
+        dv = fabs(dv);
+        if (dv < lkey || (dv == lkey && e < lexact)) { lkey = dv; lidx = j; lexact = e; }
+      }
+      continue;
+    }
+    double x[3] = {s_x[idx], s_x[sc.n + idx], s_x[2 * sc.n + idx]};
+    double pc[3] = {s_pc[idx], s_pc[sc.n + idx], s_pc[2 * sc.n + idx]};
+    double a[3] = {x[0] - pc[0], x[1] - pc[1], x[2] - pc[2]};
+    double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (nrm < 1e-6) {                                  // line touches an obstacle (:336-345)
+      collision = 1;
+      a[0] = x[0] - p0[0]; a[1] = x[1] - p0[1]; a[2] = x[2] - p0[2];
+      nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      if (nrm < 1e-6) {
+        a[0] = d[0]; a[1] = d[1]; a[2] = d[2];
+        nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      }
+    }
+    a[0] /= nrm; a[1] /= nrm; a[2] /= nrm;
+    double bh = (a[0] * x[0] + a[1] * x[1] + a[2] * x[2]) - 0.001;    // :347
+    if (tid == 0 && m_cur < pr.m_max) {
+      Arow[3 * m_cur + 0] = a[0]; Arow[3 * m_cur + 1] = a[1]; Arow[3 * m_cur + 2] = a[2];
+      brow[m_cur] = bh;
+    }
+    ++m_cur;
+    lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
+    for (unsigned long long mk = alive; mk; mk &= mk - 1) {
+      const int kk = __ffsll((long long)mk) - 1;
+      const int j = tid + kk * T;
+      if (j == idx || poly_min_halfspace(sc, j, a, bh) >= -1e-4) {   // unshrunk vertices (:352-357)
+        alive &= ~(1ull << kk);
+      } else {
+        double dv = s_dist[j];
+        const int e = dv >= 0.0;
+        dv = fabs(dv);
+        if (dv < lkey || (dv == lkey && e < lexact)) { lkey = dv; lidx = j; lexact = e; }
       }
     }
   }
@@ -2279,7 +2476,6 @@ int bp_closest_points(const bp_scene* scene, const double* seeds_dev, const doub
 int bp_closest_points_line(const bp_scene* scene, const double* p0_dev, const double* p1_dev, int S,
                            double* x_out_dev, double* phi_out_dev, void* stream) {
   if (!scene || S < 0 || scene->seg_off) return bp_fail("bp_closest_points_line: bad arguments");
-  if (scene->rows) return bp_fail("bp_closest_points_line: polytope scenes are not supported (segment QP is box-only)");
   if (S == 0 || scene->n == 0) return 0;
   dim3 grid((scene->n + 255) / 256, S);
   k_closest_points_line<<<grid, 256, 0, (cudaStream_t)stream>>>(view_of(scene), p0_dev, p1_dev, x_out_dev, phi_out_dev);
@@ -2474,7 +2670,6 @@ int bp_build_sets_line_ms(const bp_scene* scene, const int* seg_scene_dev, const
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || !ws_min_host || !ws_max_host)
     return bp_fail("bp_build_sets_line: bad arguments");
   if (S == 0) return 0;
-  if (scene->rows) return bp_fail("bp_build_sets_line: polytope scenes are not supported (segment QP is box-only)");
   if (compute_ellipsoid && workspace_bytes < bp_build_sets_workspace_bytes(S))
     return bp_fail("bp_build_sets_line: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -2483,9 +2678,16 @@ int bp_build_sets_line_ms(const bp_scene* scene, const int* seg_scene_dev, const
   lp.p0 = p0_dev; lp.p1 = p1_dev; lp.limit_space = limit_space; lp.e_max = e_max;
   for (int i = 0; i < 3; ++i) { lp.ws_rows[2 * i] = ws_max_host[i]; lp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
   lp.A = A_dev; lp.b = b_dev; lp.m = m_dev; lp.status = status_dev; lp.collision = collision_dev; lp.m_max = m_max;
-  size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
-  if (set_dyn_smem((const void*)k_poly_line, smem)) return 1;
-  k_poly_line<<<S, poly_threads(scene->n), smem, stream>>>(view_of(scene, seg_scene_dev), lp);
+  if (scene->rows) {                                     // general polytopes: dist | x[3] | p_closest[3] per obstacle
+    const size_t psmem = sizeof(double) * 7 * (size_t)scene->n;
+    if (scene->n > 3072) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    if (set_dyn_smem((const void*)k_poly_line_p, psmem)) return 1;
+    k_poly_line_p<<<S, poly_threads(scene->n), psmem, stream>>>(view_of(scene), lp);
+  } else {
+    size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
+    if (set_dyn_smem((const void*)k_poly_line, smem)) return 1;
+    k_poly_line<<<S, poly_threads(scene->n), smem, stream>>>(view_of(scene, seg_scene_dev), lp);
+  }
   if (compute_ellipsoid) {
     SeedState* st = (SeedState*)workspace_dev;
     k_state_init_line<<<(S + 127) / 128, 128, 0, stream>>>(st, p0_dev, status_dev, S);

@@ -83,8 +83,7 @@ class Scene:
 class PolytopeScene(Scene):
     """General convex polytope obstacles resident in HBM: what ConvexSetFinder is handed when the obstacles are not
     boxes -- obs_sets = [[A (<= 15 rows, zero-padded), b], ...] (already inflated) and obs_points_sets = [vertices
-    (V x 3), ...] (the reference enumerates them with cddlib, util_functions.py:66-79).  Point sets only: the
-    segment QP behind find_set_collision_avoidance is box-only."""
+    (V x 3), ...] (the reference enumerates them with cddlib, util_functions.py:66-79).  At most 3072 obstacles."""
 
     MAX_ROWS = 15
 

@@ -127,6 +127,74 @@ def closest_points_segment_boxes(lb, ub, p0, p1):
     return x_out, phi_out
 
 
+def closest_points_segment_polytopes(A, b, p0, p1):
+    """min ||p0 + phi (p1-p0) - x||^2, A[n] x <= b[n], 0 <= phi <= 1 for N polytopes (A: (N,r,3) with zero rows as
+    padding, b already shrunk) -- the QP of ConvexSetFinder.py:52-99 for obstacles that are not boxes.
+    Exact: x is the projection of p(phi) onto the affine hull of its active rows (<= 3), phi is 0, 1 or the
+    minimiser of the line-to-hull distance; enumerate, keep the feasible candidates, take the least distance and
+    among equal ones the smallest phi (quirk Q9).  Returns x (N,3), phi (N,)."""
+    N, r, _ = A.shape
+    d = p1 - p0
+    dd = float(d @ d)
+    best = np.full(N, np.inf)
+    bphi = np.full(N, np.inf)
+    xbest = np.zeros((N, 3))
+    scale = np.maximum(1.0, np.abs(b))
+
+    def consider(x, phi, ok):
+        viol = np.einsum("nrj,nj->nr", A, x) - b
+        mag = np.einsum("nrj,nj->nr", np.abs(A), np.abs(x)) + scale
+        feas = ok & np.all(viol <= 1e-10 * mag, axis=1)
+        q = p0[None] + phi[:, None] * d[None]
+        obj = np.sum((q - x) ** 2, axis=1)
+        better = feas & ((obj < best * (1 - 1e-12) - 1e-24) | ((obj <= best * (1 + 1e-12) + 1e-24) & (phi < bphi)))
+        best[better] = obj[better]
+        bphi[better] = phi[better]
+        xbest[better] = x[better]
+
+    ones = np.ones(N, bool)
+    for fixed in (0.0, 1.0):                               # no active row: x = p(phi)
+        consider(np.repeat((p0 + fixed * d)[None], N, axis=0), np.full(N, fixed), ones)
+    for S in _active_sets(r):
+        As = A[:, S, :]                                      # (N,k,3)
+        bs = b[:, S]
+        nrm = np.prod(np.einsum("nkj,nkj->nk", As, As), axis=1)
+        if len(S) == 3:
+            det = np.linalg.det(As)
+            ok = det * det > 1e-24 * nrm
+            if not np.any(ok):
+                continue
+            v = np.zeros((N, 3))
+            v[ok] = np.linalg.solve(As[ok], bs[ok][..., None])[..., 0]
+            for fixed in (0.0, 1.0):
+                consider(v, np.full(N, fixed), ok)
+            if dd > 0:
+                phi = (v - p0[None]) @ d / dd
+                consider(v, phi, ok & (phi > 0) & (phi < 1))
+            continue
+        gram = As @ As.transpose(0, 2, 1)
+        det = np.linalg.det(gram)
+        ok = det > 1e-14 * nrm
+        if not np.any(ok):
+            continue
+        ginv = np.zeros_like(gram)
+        ginv[ok] = np.linalg.inv(gram[ok])
+        u = np.einsum("nkj,j->nk", As, p0) - bs               # A_S p0 - b_S
+        w = np.einsum("nkj,j->nk", As, d)
+        gw = np.einsum("nkl,nl->nk", ginv, w)
+        den = np.einsum("nk,nk->n", w, gw)
+        free_ok = ok & (den > 1e-24 * dd)
+        phi_free = np.where(free_ok, -np.einsum("nk,nk->n", u, gw) / np.where(free_ok, den, 1.0), 0.0)
+        for phi, okc in ((np.zeros(N), ok), (np.ones(N), ok), (phi_free, free_ok & (phi_free > 0) & (phi_free < 1))):
+            rres = u + phi[:, None] * w
+            lam = np.einsum("nkl,nl->nk", ginv, rres)
+            x = p0[None] + phi[:, None] * d[None] - np.einsum("nkj,nk->nj", As, lam)
+            consider(x, phi, okc)
+    if not np.all(np.isfinite(best)):
+        raise RuntimeError("segment QP infeasible (empty obstacle)")
+    return xbest, bphi
+
+
 class ConvexSetFinder:
     """Oracle twin of the reference class (same constructor / method names)."""
 
@@ -214,7 +282,13 @@ class ConvexSetFinder:
         b = np.stack([s[1] for s in obs_sets])
         box = np.concatenate((np.eye(3), -np.eye(3)))
         if self._nonzero_rows(A) != 6 or not np.all(A[:, :6, :] == box[None]):
-            raise NotImplementedError("oracle line QP handles box obstacles (A=[I;-I])")
+            # general polytopes: shrink every real row (the padded ones keep 0 x <= 10)
+            r = self._nonzero_rows(A)
+            real = np.linalg.norm(A[:, :r, :], axis=2) > 0
+            x, phi = closest_points_segment_polytopes(A[:, :r, :], b[:, :r] - 0.001 * real, np.asarray(p0, float),
+                                                      np.asarray(p1, float))
+            self.proj_time += time.perf_counter() - start
+            return x, phi
         ub = b[:, :3] - 0.001                                # b - 0.001 (:496)
         lb = -(b[:, 3:6] - 0.001)
         x, phi = closest_points_segment_boxes(lb, ub, np.asarray(p0, float), np.asarray(p1, float))

@@ -98,6 +98,22 @@ int hh_polytope_qp(const double* E, const double* p, const double* rows4, int n,
   return empty;
 }
 
+// closest points between the segment p0..p1 and n polytopes (rows4 as above), offsets shrunk by `shrink`
+int hh_seg_polytope(const double* p0, const double* p1, const double* rows4, int n, int R, double shrink, double* x,
+                    double* phi, double* dist2) {
+  double d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+  int empty = 0;
+  for (int j = 0; j < n; ++j) {
+    struct R4 {
+      const double* r;
+      double a(int i, int k) const { return r[4 * i + k]; }
+      double b(int i) const { return r[4 * i + 3]; }
+    } rows{rows4 + (size_t)j * R * 4};
+    if (!bp_seg_polytope_qp(rows, R, shrink, p0, d, x + 3 * j, phi + j, dist2 + j)) ++empty;
+  }
+  return empty;
+}
+
 void hh_seg_box(const double* p0, const double* p1, const double* lb, const double* ub, int n, double* x,
                 double* phi) {
   double d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};

@@ -1,6 +1,6 @@
 """GPU: general convex polytope obstacles (obs_sets with up to 15 rows + their vertices, as
 ConvexSetFinder receives them) in the point-set path -- closest points, polyhedron pass, IRIS loop -- against the
-oracle, plus the loud failure of the box-only segment path."""
+oracle, and the segment path (closest points to a segment, find_set_collision_avoidance)."""
 import numpy as np
 import pytest
 
@@ -100,7 +100,41 @@ def test_dropin_with_polytope_obstacles(poly_scene):
     rows = gpu.compute_polyhedron(q_inv, np.linalg.inv(q_inv), seeds[1], a_init, b_init)
     rows_o = ora.compute_polyhedron(q_inv, np.linalg.inv(q_inv), seeds[1], a_init, b_init)
     assert_rows_close(np.array(rows[0]), np.array(rows[1]), np.array(rows_o[0]), np.array(rows_o[1]), "compute_polyhedron")
-    with pytest.raises(NotImplementedError):
-        gpu.find_set_collision_avoidance(seeds[0], seeds[0] + 0.05)
-    with pytest.raises(bp._lib.BpGeoError, match="polytope"):
-        geo.build_sets_line(scene, seeds[:1], seeds[:1] + 0.05, ws_min, ws_max)
+    # BoundMPC's call (BoundMPC.py:486-488) and the planner's (BoundPlanner.py:387-389) on polytope obstacles
+    for k, kw in enumerate((dict(limit_space=True, e_max=0.7), dict(compute_ellipsoid=True))):
+        p0, p1 = seeds[2 + k], seeds[2 + k] + np.array([0.03, -0.02, 0.04])
+        got = gpu.find_set_collision_avoidance(p0, p1, **kw)
+        want = ora.find_set_collision_avoidance(p0, p1, **kw)
+        assert got[-1] == want[-1]
+        assert_rows_close(got[0], got[1], want[0], want[1], "line set over polytopes")
+        if "compute_ellipsoid" in kw:
+            assert np.abs(got[2] - want[2]).max() <= 1e-5 * np.abs(want[2]).max()
+            assert np.abs(got[3] - want[3]).max() <= 1e-5
+
+
+def test_polytope_segment_closest_points_and_line_sets(poly_scene):
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    rng = np.random.default_rng(5)
+    p0 = seeds.copy()
+    d = rng.normal(size=p0.shape)
+    d *= (rng.uniform(0.02, 0.25, (p0.shape[0], 1)) / np.linalg.norm(d, axis=1)[:, None])
+    d[1] = [0.0, 0.0, 0.05]                                  # the planner's l_ee (axis-aligned)
+    p1 = p0 + d
+    x, phi = geo.closest_points_line(scene, p0[:4], p1[:4])
+    x, phi = x.cpu().numpy(), phi.cpu().numpy()
+    for s in range(4):
+        xo, phio = ora.compute_set_projs_line(obs_sets, p0[s], p1[s])
+        do = np.linalg.norm(p0[s] + phio[:, None] * d[s] - xo, axis=1)
+        dg = np.linalg.norm(p0[s] + phi[s][:, None] * d[s] - x[s], axis=1)
+        assert np.abs(dg - do).max() < 1e-9
+        assert np.abs(phi[s] - phio).max() < 1e-7 and np.abs(x[s] - xo).max() < 1e-7
+    out = geo.build_sets_line(scene, p0, p1, ws_min, ws_max, compute_ellipsoid=False)
+    A, b, m = out.A.cpu().numpy(), out.b.cpu().numpy(), out.m.cpu().numpy()
+    coll = out.collision.cpu().numpy()
+    n_coll = 0
+    for s in range(p0.shape[0]):
+        a_o, b_o, c_o = ora.find_set_collision_avoidance(p0[s], p1[s])
+        assert bool(coll[s]) == bool(c_o)
+        n_coll += bool(c_o)
+        if not c_o:                                           # touching segments: the fallback normals are not unique
+            assert_rows_close(A[s, : m[s]], b[s, : m[s]], a_o, b_o, f"segment {s}")

@@ -229,3 +229,63 @@ def test_polytope_qp_primitive(host_harness):
         viol = np.einsum("nrk,nk->nr", A, y) - b
         assert viol.max() < 1e-9
     assert worst < 1e-7          # (north_star tolerance 1e-6; the oracle's own Gram solves limit the agreement)
+
+
+def test_segment_polytope_primitive(host_harness):
+    """Segment-polytope closest points (bp_seg_polytope_qp): boxes given as polytopes reproduce the box oracle
+    (incl. the smallest-phi rule, quirk Q9); random polytopes agree with an SLSQP solve of the reference's QP
+    (ConvexSetFinder.py:52-99)."""
+    from scipy.optimize import minimize
+
+    from boundplanner_b200 import scenes
+
+    host_harness.hh_seg_polytope.restype = ctypes.c_int
+    rng = np.random.default_rng(23)
+    # (1) boxes as polytopes
+    N = 200
+    lb = rng.uniform(-1, 1, (N, 3))
+    ub = lb + rng.uniform(0.02, 0.3, (N, 3))
+    rows4 = np.zeros((N, 15, 4))
+    rows4[:, :, 3] = 10.0
+    rows4[:, :3, :3] = np.eye(3)
+    rows4[:, 3:6, :3] = -np.eye(3)
+    rows4[:, :3, 3] = ub
+    rows4[:, 3:6, 3] = -lb
+    rows4 = np.ascontiguousarray(rows4)
+    for trial in range(5):
+        p0 = rng.uniform(-1, 1, 3)
+        p1 = p0 + rng.normal(size=3) * rng.uniform(0.05, 0.8)
+        if trial == 3:
+            p1 = p0 + np.array([0.0, 0.0, 0.4])            # axis-aligned: non-unique minimisers are common
+        if trial == 4:
+            p0 = 0.5 * (lb[0] + ub[0]); p1 = p0 + np.array([0.5, 0.1, 0.0])    # starts inside box 0
+        p0 = np.ascontiguousarray(p0); p1 = np.ascontiguousarray(p1)
+        x, phi, d2 = np.zeros((N, 3)), np.zeros(N), np.zeros(N)
+        assert host_harness.hh_seg_polytope(dp(p0), dp(p1), dp(rows4), N, 15, ctypes.c_double(0.001), dp(x), dp(phi),
+                                            dp(d2)) == 0
+        xo, phio = closest_points_segment_boxes(lb + 0.001, ub - 0.001, p0, p1)
+        do2 = np.sum((p0 + phio[:, None] * (p1 - p0) - xo) ** 2, axis=1)
+        assert np.abs(d2 - do2).max() < 1e-12
+        assert np.abs(phi - phio).max() < 1e-9
+        assert np.abs(x - xo).max() < 1e-9
+    # (2) random polytopes vs SLSQP on the QP itself
+    obs_sets, _ = scenes.random_polytope_scene(12, rng, 0.1, 0.5)
+    rows4 = np.ascontiguousarray(np.stack([np.hstack((s[0], s[1][:, None])) for s in obs_sets]))
+    p0 = np.ascontiguousarray(rng.uniform(-1, 1, 3)); p1 = np.ascontiguousarray(p0 + rng.normal(size=3) * 0.5)
+    n = len(obs_sets)
+    x, phi, d2 = np.zeros((n, 3)), np.zeros(n), np.zeros(n)
+    assert host_harness.hh_seg_polytope(dp(p0), dp(p1), dp(rows4), n, 15, ctypes.c_double(0.001), dp(x), dp(phi),
+                                        dp(d2)) == 0
+    for j, (A, b) in enumerate(obs_sets):
+        nz = np.linalg.norm(A, axis=1) > 0
+        A, b = A[nz], b[nz] - 0.001
+        assert np.max(A @ x[j] - b) < 1e-9 and -1e-12 <= phi[j] <= 1 + 1e-12
+        fun = lambda z: np.sum((p0 + z[3] * (p1 - p0) - z[:3]) ** 2)
+        cons = [{"type": "ineq", "fun": lambda z, A=A, b=b: b - A @ z[:3]}]
+        best = np.inf
+        for z3 in (0.0, 0.5, 1.0):
+            res = minimize(fun, np.concatenate((x[j] + 1e-3, [z3])), constraints=cons, bounds=[(None, None)] * 3 + [(0, 1)],
+                           method="SLSQP", options={"ftol": 1e-14, "maxiter": 300})
+            if res.success:
+                best = min(best, res.fun)
+        assert d2[j] <= best + 1e-9 and abs(d2[j] - best) < 1e-7 * max(1.0, best)
