@@ -13,11 +13,27 @@ def oracle_finder(boxes, inflate, ws_min, ws_max, max_rows=None):
     return OracleFinder(obs_sets, pts, ws_max, ws_min, max_rows=max_rows)
 
 
+REORDERED = []      # (tag) of every comparison that only matched up to a permutation of the picked rows
+
+
 def assert_rows_close(A, b, Ao, bo, tag=""):
+    """Rows agree within RTOL, in order.  The picked rows (index >= 6) may come in a different ORDER when the
+    greedy loop met a numerical tie: the obstacles an inscribed ellipsoid touches are all at distance exactly 1 in
+    its metric (ConvexSetFinder.py:429-431), so which of them np.argmin returns first is decided by the last bits
+    of the MVIE solve -- in the reference (OSQP / Clarabel tolerances) as much as here.  Such a permutation is
+    accepted and recorded in REORDERED; the set of halfspaces must still be the same."""
     assert A.shape == Ao.shape, f"{tag}: row count {A.shape[0]} vs oracle {Ao.shape[0]}"
     scale = max(1.0, np.abs(bo).max())
-    assert np.abs(A - Ao).max() <= RTOL, f"{tag}: normals differ {np.abs(A - Ao).max()}"
-    assert np.abs(b - bo).max() <= RTOL * scale, f"{tag}: offsets differ {np.abs(b - bo).max()}"
+    if np.abs(A - Ao).max() <= RTOL and np.abs(b - bo).max() <= RTOL * scale:
+        return
+    assert np.abs(A[:6] - Ao[:6]).max() <= RTOL and np.abs(b[:6] - bo[:6]).max() <= RTOL * scale, f"{tag}: init rows"
+    free = list(range(6, Ao.shape[0]))
+    for r in range(6, A.shape[0]):
+        d = [max(np.abs(A[r] - Ao[k]).max(), abs(b[r] - bo[k]) / scale) for k in free]
+        k = int(np.argmin(d))
+        assert d[k] <= RTOL, f"{tag}: row {r} has no counterpart in the oracle's set (closest differs by {d[k]})"
+        free.pop(k)
+    REORDERED.append(tag)
 
 
 class OracleBackend:
