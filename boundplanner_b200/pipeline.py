@@ -23,9 +23,27 @@ class SetGraphPipeline:
         self.kw = dict(fixed_mid=fixed_mid, optimize=optimize, max_iter=max_iter)
         self.tol = tol
         self.seeds_dev = torch.zeros((self.S, 3), dtype=torch.float64, device="cuda")
-        self.batch = geo.alloc_set_batch(self.S, m_max)
-        self.pair_buf = geo.alloc_pair_buffers(self.S)
-        self.bits = self.pair_buf[0]
+        # every result of a step lives in ONE device buffer (A | b | q_ellipse | p_mid | m | status | adjacency bits),
+        # so that the end-to-end path copies it back with a single D2H transfer instead of seven
+        S, words = self.S, (self.S + 31) // 32
+        n64 = [S * m_max * 3, S * m_max, S * 9, S * 3]
+        n32 = [S, S, S * words]
+        self._out_dev = torch.zeros((sum(n64) * 8 + sum(n32) * 4,), dtype=torch.uint8, device="cuda")
+        v64 = self._out_dev[: sum(n64) * 8].view(torch.float64)
+        v32 = self._out_dev[sum(n64) * 8:].view(torch.int32)
+        o64 = [0, n64[0], n64[0] + n64[1], n64[0] + n64[1] + n64[2]]
+        A = v64[o64[0]: o64[0] + n64[0]].view(S, m_max, 3)
+        b = v64[o64[1]: o64[1] + n64[1]].view(S, m_max)
+        q = v64[o64[2]: o64[2] + n64[2]].view(S, 3, 3)
+        p = v64[o64[3]: o64[3] + n64[3]].view(S, 3)
+        b.fill_(10.0)                                   # normalize_set_size padding
+        m = v32[:S]
+        status = v32[S: 2 * S]
+        self.bits = v32[2 * S:].view(S, words)
+        own = geo.alloc_set_batch(self.S, m_max)        # iters / rows_peak / loop workspace
+        self.batch = geo.SetBatch(A, b, m, q, p, status, iters=own.iters, rows_peak=own.rows_peak, work=own.work)
+        self.pair_buf = (self.bits, geo.alloc_pair_buffers(self.S)[1])
+        self._views = (A, b, m, q, p, status, self.bits)
         self._host = None
         self._graph = None
         self._stream = torch.cuda.Stream()
@@ -59,14 +77,16 @@ class SetGraphPipeline:
         """End-to-end step from pinned host seeds [S,3]: H2D, step, D2H of every result
         (A, b, m, q_ellipse, p_mid, status, adjacency bits) into pinned host buffers."""
         if self._host is None:
-            srcs = (self.batch.A, self.batch.b, self.batch.m, self.batch.q_ellipse, self.batch.p_mid,
-                    self.batch.status, self.bits)
-            self._host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in srcs]
-            self._srcs = srcs
+            self._out_host = torch.empty(self._out_dev.shape, dtype=torch.uint8, pin_memory=True)
+            # host views with the layout of the device buffer
+            host = []
+            for t in self._views:
+                off = t.data_ptr() - self._out_dev.data_ptr()
+                host.append(self._out_host[off: off + t.numel() * t.element_size()].view(t.dtype).view(t.shape))
+            self._host = host
         self.seeds_dev.copy_(seeds_host_pinned, non_blocking=True)
         self.run_device()
-        for h, d in zip(self._host, self._srcs):
-            h.copy_(d, non_blocking=True)
+        self._out_host.copy_(self._out_dev, non_blocking=True)      # one D2H transfer for all results
         torch.cuda.current_stream().synchronize()
         return self._host
 
