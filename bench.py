@@ -279,12 +279,35 @@ def run_gpu(args):
     # ---- end to end through the public API with host buffers
     for _ in range(2):
         step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        res = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_depth = 1
+    if pipe is not None and os.environ.get("BPGEO_E2E_DEPTH", "2") != "1":
+        # two pipeline objects used round-robin: every step still copies its seeds in and all its results out, but
+        # the D2H of step k (copy stream) overlaps step k+1 and the host does not synchronize per step
+        from boundplanner_b200.pipeline import PipelinedSetGraph
+
+        e2e_depth = 2
+        ps = PipelinedSetGraph(scene, N_SEEDS, ws_min, ws_max, depth=e2e_depth, fixed_mid=True, optimize=True, tol=TOL)
+        for _ in range(4):
+            ps.take()
+            ps.put(seeds_host)
+        ps.drain()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            got = ps.take()                      # results of step k - 2, delivered in pinned host memory
+            if got is not None:
+                res = got
+            ps.put(seeds_host)
+        res = ps.drain()[-1]
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    else:
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            res = step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
     h2d = seeds_host.numel() * 8
     d2h = sum(t.numel() * t.element_size() for t in res)
 
@@ -331,7 +354,7 @@ def run_gpu(args):
                        / max(n_pairs, 1)},
             "pair_checks_per_sec": n_pairs * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h, "steps_in_flight": e2e_depth},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": prof["roofline"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),

@@ -90,6 +90,75 @@ class SetGraphPipeline:
         torch.cuda.current_stream().synchronize()
         return self._host
 
+    # ---- asynchronous form: submit() enqueues H2D + step + D2H and returns at once, wait() delivers the results ----
+    def submit(self, seeds_host_pinned, copy_stream=None):
+        """Enqueue one end-to-end step.  The D2H transfer goes to `copy_stream` (behind an event), so that the next
+        step of ANOTHER pipeline object can start while this one's results travel back."""
+        if self._host is None:
+            self.run(seeds_host_pinned)                               # allocates the pinned mirror (synchronous once)
+        cur = torch.cuda.current_stream()
+        self.seeds_dev.copy_(seeds_host_pinned, non_blocking=True)
+        self.run_device()
+        if copy_stream is None:
+            self._out_host.copy_(self._out_dev, non_blocking=True)
+            self._done = torch.cuda.Event()
+            self._done.record(cur)
+        else:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                self._out_host.copy_(self._out_dev, non_blocking=True)
+                self._done = torch.cuda.Event()
+                self._done.record(copy_stream)
+            # the next step on `cur` overwrites the device buffers: it has to wait for this copy
+            self._copy_done_for_compute = self._done
+
+    def wait(self):
+        """Block until the results of the last submit() are in the pinned host buffers; returns them."""
+        self._done.synchronize()
+        return self._host
+
+
+class PipelinedSetGraph:
+    """`depth` SetGraphPipeline objects used round-robin: while the results of step k travel back to the host on a
+    copy stream, step k+1 already runs on the compute stream (its own buffers).  Every step still copies its seeds
+    in and ALL its results out; only the host no longer idles on a synchronize per step."""
+
+    def __init__(self, scene, n_seeds, ws_min, ws_max, depth=2, **kw):
+        self.pipes = [SetGraphPipeline(scene, n_seeds, ws_min, ws_max, **kw) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream()
+        self._k = 0
+        self._busy = [False] * depth
+
+    def take(self):
+        """Results (pinned host views) of the step that used the next slot `depth` submissions ago, or None.  They
+        stay valid until the following put(): consume them first."""
+        i = self._k % len(self.pipes)
+        if not self._busy[i]:
+            return None
+        self._busy[i] = False
+        return self.pipes[i].wait()             # the slot's D2H has long finished: its buffers may be reused now
+
+    def put(self, seeds_host_pinned):
+        i = self._k % len(self.pipes)
+        if self._busy[i]:
+            raise RuntimeError("take() the slot's results before reusing it")
+        self.pipes[i].submit(seeds_host_pinned, self.copy_stream)
+        self._busy[i] = True
+        self._k += 1
+
+    def drain(self):
+        """Results of the steps still in flight, oldest first."""
+        out = []
+        n = len(self.pipes)
+        for j in range(n):
+            i = (self._k + j) % n
+            if self._busy[i]:
+                out.append(self.pipes[i].wait())
+                self._busy[i] = False
+        return out
+
 
 class ShardedSetGraphPipeline:
     """Multi-GPU step (one process per GPU, NCCL): every rank builds its S_loc seeds (CUDA graph 1),

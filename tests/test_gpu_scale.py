@@ -163,3 +163,31 @@ def test_maximum_scene_size_and_loud_failure(geo):
     too_big = geo.Scene(scenes.random_box_scene(30000, rng, 0.004, 0.012), 0.0)
     with pytest.raises(_lib.BpGeoError, match="too large"):
         geo.build_sets_point(too_big, seeds, scenes.WORKSPACE_MIN, scenes.WORKSPACE_MAX)
+
+
+def test_pipelined_end_to_end_equals_synchronous(geo):
+    """PipelinedSetGraph (two steps in flight, D2H on a copy stream) delivers the same results as run()."""
+    import torch
+
+    from boundplanner_b200 import scenes
+    from boundplanner_b200.pipeline import PipelinedSetGraph, SetGraphPipeline
+
+    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(1000, 64)
+    sc = geo.Scene(boxes, inflate)
+    rng = np.random.default_rng(9)
+    batches = [scenes.free_points(64, boxes, inflate, rng) for _ in range(5)]
+    hosts = [torch.as_tensor(b).pin_memory() for b in batches]
+    ref = SetGraphPipeline(sc, 64, ws_min, ws_max, fixed_mid=True, optimize=True)
+    want = [[t.clone() for t in ref.run(h)] for h in hosts]
+    ps = PipelinedSetGraph(sc, 64, ws_min, ws_max, depth=2, fixed_mid=True, optimize=True)
+    got = []
+    for h in hosts:
+        r = ps.take()
+        if r is not None:
+            got.append([t.clone() for t in r])
+        ps.put(h)
+    got += [[t.clone() for t in r] for r in ps.drain()]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert torch.equal(a, b)
