@@ -242,13 +242,20 @@ def run_gpu(args):
         bits, _ = bpd.sharded_adjacency(out.A, out.b, out.m, pair_fn, TOL)
         return out, bits
 
+    e2e_host = []
+
     def step_e2e():
         if pipe is not None:
             return pipe.run(seeds_host)                              # H2D seeds, graph replay, D2H results
         sd = seeds_host.cuda(non_blocking=True)                      # H2D of the step's inputs
         out, bits = step_device(sd)
-        res = [t.cpu() for t in (out.A, out.b, out.m, out.q_ellipse, out.p_mid, out.status, bits)]   # D2H
-        return res
+        srcs = (out.A, out.b, out.m, out.q_ellipse, out.p_mid, out.status, bits)
+        if not e2e_host:                                             # pinned mirrors, allocated once
+            e2e_host.extend(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in srcs)
+        for h, t in zip(e2e_host, srcs):                             # D2H of every result, one synchronize
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return e2e_host
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
 
