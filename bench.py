@@ -95,12 +95,17 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle port of the reference's Python path
 # ----------------------------------------------------------------------------
 def _oracle_worker(args):
-    boxes, inflate, ws_min, ws_max, seeds = args
+    boxes, inflate, ws_min, ws_max, seeds = args[:5]
+    per_obstacle_loop = len(args) > 5 and args[5]
     from oracle.convex_set_finder import ConvexSetFinder
     from oracle.obstacles import obstacle_reps
 
     obs_sets, pts, _ = obstacle_reps(boxes, inflate)
     f = ConvexSetFinder(obs_sets, pts, ws_max, ws_min, max_rows=None)
+    if per_obstacle_loop:
+        # the reference's own loop structure: one closest-point QP solve per obstacle and pass
+        # (ConvexSetFinder.py:468-486), instead of the oracle's NumPy batch over all obstacles
+        f.compute_set_projs = f.compute_set_projs_loop
     sets = []
     for p in seeds:
         try:
@@ -378,6 +383,10 @@ def run_gpu(args):
                 "value": ns / t, "unit": UNIT, "cores": 1, "kind": "port",
                 "sample": f"first {n_cpu} of the {N_SEEDS} C2 seeds + their {npairs} pair checks, vectorised NumPy "
                           "oracle (stronger than the reference's per-obstacle solver loop), 1 core"}
+            # the same port with the reference's loop structure (one QP solve per obstacle and pass), 2 seeds
+            t0 = time.perf_counter()
+            n_loop = len(_oracle_worker((boxes, inflate, ws_min, ws_max, seeds0[:2], True)))
+            line["cpu_baseline"]["per_obstacle_loop_sets_per_sec"] = n_loop / (time.perf_counter() - t0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
