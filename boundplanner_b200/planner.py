@@ -34,11 +34,18 @@ bookkeeping then runs in the reference's order.
 """
 from __future__ import annotations
 
+import math
+
 import networkx as nx
 import numpy as np
 from scipy.spatial.transform import Rotation as R
 
 REFERENCE_MAX_ROWS = 20
+
+try:                                   # np.linalg.det minus ~35 us of argument checking per call
+    _det = np.linalg._umath_linalg.det
+except AttributeError:                 # pragma: no cover
+    _det = np.linalg.det
 
 
 def _set_errors(status, rows):
@@ -111,6 +118,7 @@ class SetSequencePlanner:
         # row (+-e_k) the reference's A x - b is exactly x_k - ub_k / lb_k - x_k, padded rows give -10
         ob_b = np.array([ob[1][:6] for ob in self.obs_sets]).reshape(-1, 6)
         self._ub, self._lb = ob_b[:, :3], -ob_b[:, 3:]
+        self._b6 = np.ascontiguousarray(ob_b)                 # b of the rows [I; -I]: A x - b = [x; -x] - b6
 
     # ---- known sets, stacked (vectorised forms of the per-node loops of :472-476 and :505-512) ----
     def _nodes_reset(self):
@@ -145,14 +153,17 @@ class SetSequencePlanner:
     def _in_collision(self, sample):
         if self._ub.shape[0] == 0:
             return False
-        viol = np.maximum(sample - self._ub, self._lb - sample).max(axis=1)
-        return bool((viol < 1e-3).any())
+        s6 = np.concatenate((sample, -sample))                # x - ub and lb - x = (-x) - (-lb), exactly
+        return bool(((s6 - self._b6).max(axis=1) < 1e-3).any())
 
     # ---- :789-896 -----------------------------------------------------------
     def _add_edges(self, id_new, graph, inter_graph, end, start):
         connected = False
-        set_new = graph.nodes[id_new]["cset"]
-        others = [(vid, vdata) for vid, vdata in graph.nodes.items() if vid != id_new]
+        # (graph._node / inter_graph._node are networkx's own node -> attribute dicts: same objects the NodeView
+        # hands out, without the view indirection on every access of this doubly nested loop)
+        gnodes, inodes = graph._node, inter_graph._node
+        set_new = gnodes[id_new]["cset"]
+        others = [(vid, vdata) for vid, vdata in gnodes.items() if vid != id_new]
         if not others:
             return connected
         res = yield ("edges", [v["cset"] for _, v in others], set_new, 0.01,
@@ -169,15 +180,24 @@ class SetSequencePlanner:
             inter_graph.add_node(self.id_inter, cset=set_inter, id0=vid, id1=id_new, conn_to_start=False,
                                  conn_to_end=False, p_proj=None, p_via=via, fits=fits)
             self.nr_inter_set += 2
-            me = inter_graph.nodes[self.id_inter]
-            for eid, edata in list(inter_graph.nodes.items()):
+            me = inodes[self.id_inter]
+            # the reference walks ALL intersection nodes in insertion order and keeps those that share a set with the
+            # new one (:827-841); an index set -> its intersection nodes gives the same nodes in the same order
+            # (intersection ids grow with insertion)
+            by_node = self._inter_by_node
+            by_node.setdefault(vid, []).append(self.id_inter)
+            if id_new != vid:
+                by_node.setdefault(id_new, []).append(self.id_inter)
+            cand = by_node[vid] if id_new == vid else sorted(set(by_node[vid]) | set(by_node[id_new]))
+            for eid in cand:
+                edata = inodes[eid]
                 v0, v1 = edata["id0"], edata["id1"]
                 cond1 = v0 == vid or v1 == vid
                 cond2 = v0 == id_new or v1 == id_new
                 if cond1:
                     size = vdata["size"]
                 elif cond2:
-                    size = graph.nodes[id_new]["size"]
+                    size = gnodes[id_new]["size"]
                 if self.id_inter != eid and (cond1 or cond2):
                     self.nr_edges += 2
                     p_proj = edata["p_proj"]
@@ -185,7 +205,8 @@ class SetSequencePlanner:
                         p_proj = end
                     if me["p_proj"] is None:
                         me["p_proj"] = yield ("project", set_inter[0], set_inter[1], np.array(p_proj, float))
-                    dist = np.linalg.norm(me["p_proj"] - p_proj)
+                    dvec = me["p_proj"] - p_proj
+                    dist = math.sqrt(float(dvec.dot(dvec)))            # == np.linalg.norm of a 1-D vector
                     conn_to_start = me["conn_to_start"] or edata["conn_to_start"]
                     conn_to_end = me["conn_to_end"] or edata["conn_to_end"]
                     me["conn_to_start"] = conn_to_start
@@ -193,7 +214,7 @@ class SetSequencePlanner:
                     edata["conn_to_start"] = conn_to_start
                     edata["conn_to_end"] = conn_to_end
                     connected = bool(conn_to_start and conn_to_end)          # last edge wins (quirk Q6)
-                    c_size = np.tanh(0.25 - np.cbrt(size))
+                    c_size = float(np.tanh(0.25 - np.cbrt(size)))
                     cost = dist * (1 + self.w_size * c_size) + self.w_bias
                     if not fits:
                         cost += self.c_fit
@@ -263,6 +284,7 @@ class SetSequencePlanner:
         graph, inter_graph = nx.Graph(), nx.Graph()
         self.nr_sets = self.nr_edges = self.nr_inter_set = 0
         self._nodes_reset()
+        self._inter_by_node = {}
 
         a_set, b_set, q_start, p_mid_start, a_red, b_red = yield ("set_point", start, True, True)     # :278-283
         collision = False
@@ -274,11 +296,12 @@ class SetSequencePlanner:
         set_start = [a_set, b_set]
         self.id_inter = 0
         self.id_graph = 0
-        graph.add_node(0, cset=set_start, size=1 / np.linalg.det(q_start), q_ellipse=q_start, p_mid=p_mid_start,
+        graph.add_node(0, cset=set_start, size=1 / float(_det(q_start)), q_ellipse=q_start, p_mid=p_mid_start,
                        a_set=np.array(a_set), b_set=np.array(b_set))
         self._nodes_add(a_set, b_set, q_start, p_mid_start)
         inter_graph.add_node(0, cset=set_start, id0=0, id1=0, conn_to_start=True, conn_to_end=False, p_proj=start,
                              p_via=np.concatenate((start, [0.0])), fits=True)
+        self._inter_by_node.setdefault(0, []).append(0)
         self.nr_sets += 1
         connected = yield from self._add_edges(0, graph, inter_graph, end, start)
         if np.max(a_set @ end - b_set) < 1e-8 and np.max(a_set @ (end + self.l_ee_end) - b_set) < 1e-8:   # :361-375
@@ -288,11 +311,12 @@ class SetSequencePlanner:
         set_end = [a_set, b_set]
         self.id_graph += 1
         self.id_inter += 1
-        graph.add_node(1, cset=set_end, size=1 / np.linalg.det(q_end), q_ellipse=q_end, p_mid=p_mid_end,
+        graph.add_node(1, cset=set_end, size=1 / float(_det(q_end)), q_ellipse=q_end, p_mid=p_mid_end,
                        a_set=np.array(a_set), b_set=np.array(b_set))
         self._nodes_add(a_set, b_set, q_end, p_mid_end)
         inter_graph.add_node(1, cset=set_end, id0=1, id1=1, conn_to_start=False, conn_to_end=True, p_proj=end,
                              p_via=np.concatenate((end, [1.0])), fits=True)
+        self._inter_by_node.setdefault(1, []).append(1)
         self.nr_sets += 1
         conn = yield from self._add_edges(1, graph, inter_graph, end, start)
         connected = conn or connected
@@ -336,7 +360,7 @@ class SetSequencePlanner:
                 dvertex = self._min_node_distance(q_ellipse, p_mid)
                 if dvertex > 0.01:
                     self.id_graph += 1
-                    graph.add_node(self.id_graph, cset=[a_set, b_set], size=1 / np.linalg.det(q_ellipse),
+                    graph.add_node(self.id_graph, cset=[a_set, b_set], size=1 / float(_det(q_ellipse)),
                                    q_ellipse=q_ellipse, p_mid=p_mid, a_set=np.array(a_set), b_set=np.array(b_set))
                     self._nodes_add(a_set, b_set, q_ellipse, p_mid)
                     self.nr_sets += 1
