@@ -2119,7 +2119,9 @@ __global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const d
       }
     }
     __syncthreads();
-    if (!flags && s_first < 0x7fffffff) break;       // (with flags every candidate is classified)
+    const int found = s_first;
+    __syncthreads();                                 // nobody updates s_first for the next group before all have read it
+    if (!flags && found < 0x7fffffff) break;         // (with flags every candidate is classified)
   }
   if (threadIdx.x == 0) first_ok[q] = s_first < 0x7fffffff ? s_first : -1;
 }

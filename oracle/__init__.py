@@ -12,7 +12,12 @@ reference (Thieso/BoundPlanner, pure Python) runs on its hot path:
 * ``casadi_blob``       -- decoder / VM for the reference's *.ca FK functions
 * ``reduce_ineqs``      -- bound_planner/utils/util_functions.py:82-88 (cddlib)
 * ``planner_graph``     -- BoundPlanner.check_intersection / projection QP
-                           (BoundPlanner.py:745-772, :842-864)
+                           (BoundPlanner.py:745-772, :842-864) and the planner loop's
+                           rejection / duplicate / shortest-path steps (:459-478,
+                           :505-512, :434 -- the latter is networkx itself)
+  (``convex_set_finder`` also covers find_set_around_line / mvie_socp_fixed_r,
+  :242-307 / :564-588, and general polytope obstacles: ragged row / vertex counts,
+  ``closest_points_segment_polytopes`` for the segment QP of :52-99)
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 / ``--impl reference`` legs may import it, and only as the *checker* or the
