@@ -2,11 +2,14 @@
 
 One "step" of the hot path (BASELINE.json configs[1]): S seeds -> S convex sets
 (find_set_around_point) -> all-pairs intersection graph (set_intersection at
-tol 0.01).  The 16 kernel launches of a step are captured once into a CUDA
-graph; a step is then one H2D copy of the seeds, one graph launch and the D2H
-copies of the results, with no per-step allocation and no Python between
-kernels.  Single GPU; the multi-GPU path (boundplanner_b200/distributed.py)
-runs the same kernels eagerly around its NCCL collectives.
+tol 0.01).  The kernel launches of a step (k_iris_fused, k_set_aabb, k_pair_filter,
+k_pair_lp) are captured once into a CUDA graph; a step is then one H2D copy of the
+seeds, one graph launch and one D2H copy of the results, with no per-step allocation
+and no Python between kernels.
+
+SetGraphPipeline / PipelinedSetGraph: one GPU (the latter keeps two steps in flight).
+PeerSetGraphPipeline: multi-GPU, sets and adjacency rows exchanged by peer stores over
+NVLink inside one CUDA graph per step.  ShardedSetGraphPipeline: the NCCL all-gather variant.
 """
 from __future__ import annotations
 
