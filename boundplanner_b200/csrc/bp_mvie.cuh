@@ -113,7 +113,10 @@ BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx) {
 // Out: L[6] (tril packed), d[3] centre.  Returns a BP_* status.
 template <int NV, class ROWS>
 BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout, double* dout, int* iters_out,
-                        const double* L0 = nullptr, double t0 = 1.0) {
+                        const double* L0 = nullptr, double t0 = 1.0, const double* x_start = nullptr,
+                        double t_stop = 0.0) {
+  // x_start (NV entries, strictly feasible) with t0: continue the path from that point (bp_mvie_pd.cuh);
+  // t_stop > 0: return after the centring of the first stage with t >= t_stop.
   constexpr int NH = NV * (NV + 1) / 2;
   double x[NV];
   // strictly feasible start: ball of half the inradius around c0
@@ -156,8 +159,15 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
     }
   }
 
+  if (x_start) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x[k] = x_start[k];
+    t = t0;
+  }
+
   const double nu = 2.0 * m + 4.0;
   const double t_final = nu / BP_MVIE_GAP_TOL;
+  if (t > t_final) t = t_final;
   int iters = 0;
   int status = BP_OK;
   double xc_prev[NV];           // previous centre x(t_prev), for the secant predictor
@@ -297,6 +307,7 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
       if (!centred) status = BP_MVIE_NOT_CONVERGED;
       break;
     }
+    if (t_stop > 0.0 && t >= t_stop) break;
     // next barrier parameter; near the optimum the central path is linear in
     // tau = 1/t, so start the next centering from the secant extrapolation of
     // the last two centres (kept only if strictly feasible).

@@ -6,6 +6,7 @@
 #include "../boundplanner_b200/csrc/bp_math.cuh"
 #include "../boundplanner_b200/csrc/bp_mvie.cuh"
 #include "../boundplanner_b200/csrc/bp_mvie_fixed_r.cuh"
+#include "../boundplanner_b200/csrc/bp_mvie_pd.cuh"
 #include "../boundplanner_b200/csrc/bp_lp.cuh"
 #include "../boundplanner_b200/csrc/bp_fk.cuh"
 
@@ -38,6 +39,22 @@ int hh_mvie_ws(const double* A, const double* b, int m, int free_centre, const d
   double Q[9], det;
   bp_shape_from_L(L, E, Q, &det);
   for (int k = 0; k < 6; ++k) Lout[k] = L[k];
+  centre[0] = d[0]; centre[1] = d[1]; centre[2] = d[2];
+  return st;
+}
+
+// hybrid barrier / primal-dual MVIE (bp_mvie_pd.cuh, the specification of the next solver); phase_iters[3] =
+// Newton iterations of the barrier centring, the primal-dual phase and the final barrier stages
+int hh_mvie_pd(const double* A, const double* b, int m, int free_centre, const double* c0, double* E, double* Q,
+               double* centre, int* iters, int* phase_iters) {
+  HostRows rows{A, b};
+  double L[6], d[3];
+  BpQ4 z[48];                                  // BP_MAX_ROWS of include/bpgeo.h
+  if (m > 48) return BP_ROW_OVERFLOW;
+  int st = free_centre ? bp_mvie_pd_solve<9>(rows, m, c0, L, d, iters, z, phase_iters)
+                       : bp_mvie_pd_solve<6>(rows, m, c0, L, d, iters, z, phase_iters);
+  double det;
+  bp_shape_from_L(L, E, Q, &det);
   centre[0] = d[0]; centre[1] = d[1]; centre[2] = d[2];
   return st;
 }

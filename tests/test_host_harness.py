@@ -289,3 +289,39 @@ def test_segment_polytope_primitive(host_harness):
             if res.success:
                 best = min(best, res.fun)
         assert d2[j] <= best + 1e-9 and abs(d2[j] - best) < 1e-7 * max(1.0, best)
+
+
+def test_mvie_primal_dual_specification(host_harness):
+    """bp_mvie_pd.cuh (barrier centre -> primal-dual -> final barrier stages, the specification of the next MVIE
+    kernel) against the barrier solver and the oracle: same ellipsoid, fewer Newton iterations."""
+    rng = np.random.default_rng(3)
+    it_pd, it_bar, worst, worst_o = [], [], 0.0, 0.0
+    for _ in range(25):
+        k = rng.integers(3, 20)
+        c = rng.uniform(-0.5, 0.5, 3)
+        c[2] += 0.6
+        An = rng.normal(size=(k, 3))
+        An /= np.linalg.norm(An, axis=1)[:, None]
+        A = np.ascontiguousarray(np.vstack((BOX, An)))
+        b = np.concatenate((np.array([1, 1, 1.2, 1, 1, 0.0]), An @ c + rng.uniform(0.005, 0.4, k)))
+        if np.min(b - A @ c) <= 1e-3:
+            continue
+        # padded rows (A = 0, b = 10) carry no cone
+        Ap = np.ascontiguousarray(np.vstack((A, np.zeros((2, 3)))))
+        bp_ = np.concatenate((b, [10.0, 10.0]))
+        for free in (0, 1):
+            E, Q, cen, it = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), ctypes.c_int()
+            ph = (ctypes.c_int * 3)()
+            st = host_harness.hh_mvie_pd(dp(Ap), dp(bp_), Ap.shape[0], free, dp(c), dp(E), dp(Q), dp(cen), ctypes.byref(it),
+                                         ph)
+            assert st == 0
+            E0, Q0, cen0, it0 = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), ctypes.c_int()
+            assert host_harness.hh_mvie(dp(A), dp(b), A.shape[0], free, dp(c), dp(E0), dp(Q0), dp(cen0), ctypes.byref(it0)) == 0
+            Eo, co = omvie.mvie_free(A, b, p_hint=c) if free else omvie.mvie_fixed_mid(A, b, c)
+            worst = max(worst, np.abs(E - E0).max() / np.abs(E0).max(), np.abs(cen - cen0).max())
+            worst_o = max(worst_o, np.abs(E - Eo).max() / np.abs(Eo).max(), np.abs(cen - co).max())
+            assert ph[1] < 30                      # the primal-dual phase converged (no fall-back to the barrier path)
+            it_pd.append(it.value)
+            it_bar.append(it0.value)
+    assert worst < 1e-10 and worst_o < 1e-9        # both end with the same barrier stages
+    assert np.mean(it_pd) < 0.85 * np.mean(it_bar)
