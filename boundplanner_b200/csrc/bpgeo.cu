@@ -2101,7 +2101,13 @@ __global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const d
         double lb[3], ub[3];
         load_box(sc, j, lb, ub);
         // rows +-e_k of the inflated box: A x - b = x_k - ub_k, lb_k - x_k (padded rows give -10)
-        const double v = fmax(fmax(fmax(x0 - ub[0], lb[0] - x0), fmax(x1 - ub[1], lb[1] - x1)), fmax(x2 - ub[2], lb[2] - x2));
+        double v = fmax(fmax(fmax(x0 - ub[0], lb[0] - x0), fmax(x1 - ub[1], lb[1] - x1)), fmax(x2 - ub[2], lb[2] - x2));
+        if (sc.rows && v < 1e-3) {                  // general polytope: inside its bounding box -> walk its rows
+          const double* r4 = sc.rows + (size_t)j * BP_OBS_ROWS * 4;
+          v = -10.0;                                // the padded rows' A x - b (only matters for an obstacle without rows)
+          for (int r = 0; r < sc.nrows[j]; ++r)
+            v = fmax(v, (__ldg(r4 + 4 * r) * x0 + __ldg(r4 + 4 * r + 1) * x1 + __ldg(r4 + 4 * r + 2) * x2) - __ldg(r4 + 4 * r + 3));
+        }
         coll |= v < 1e-3;
       }
       for (int t = s0 + lane; t < s1; t += 32) {
@@ -2815,7 +2821,6 @@ int bp_sample_filter(const bp_scene* scene, const int* item_scene_dev, const dou
                      int* first_ok_dev, unsigned char* flags_dev, void* stream) {
   if (!scene || Q < 0 || C < 1 || !cand_dev || !first_ok_dev || (set_off_dev && (m_max < 1 || !A_dev || !b_dev || !m_dev)))
     return bp_fail("bp_sample_filter: bad arguments");
-  if (scene->rows) return bp_fail("bp_sample_filter: polytope scenes are not supported");
   if ((scene->seg_off != nullptr) != (item_scene_dev != nullptr))
     return bp_fail("bp_sample_filter: a scene batch needs item_scene, a single scene must not have it");
   if (Q == 0) return 0;

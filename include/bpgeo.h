@@ -56,7 +56,7 @@ int bp_scene_create_batch(const double* boxes_host, const int* offsets_host /*[n
  * with b = 10 (normalize_set_size padding, util_functions.py:119-133); nrows_host [n]; verts_host [n,vmax,3] with
  * nverts_host [n] vertices each.  Rows are taken as given (already inflated).  Supported by bp_closest_points(_line),
  * bp_polyhedron, bp_build_sets_point, bp_build_sets_around_line and bp_build_sets_line (at most 3072 obstacles);
- * scene batches and bp_sample_filter take boxes only. */
+ * scene batches take boxes only. */
 int bp_scene_create_polytopes(const double* rows_host, const int* nrows_host, const double* verts_host,
                               const int* nverts_host, int n, int vmax, bp_scene** out);
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream);

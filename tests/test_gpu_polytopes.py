@@ -138,3 +138,29 @@ def test_polytope_segment_closest_points_and_line_sets(poly_scene):
         n_coll += bool(c_o)
         if not c_o:                                           # touching segments: the fallback normals are not unique
             assert_rows_close(A[s, : m[s]], b[s, : m[s]], a_o, b_o, f"segment {s}")
+
+
+def test_sample_filter_over_polytope_obstacles(poly_scene):
+    """K11 on a polytope scene: the reference's rejection test max(A x - b) < 1e-3 over the obstacle's own rows."""
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    from oracle.planner_graph import first_free_sample, sample_flags
+
+    rng = np.random.default_rng(77)
+    cand = rng.uniform(ws_min, ws_max, (2, 400, 3))
+    # candidates just outside a face (inside / outside the 1 mm margin) and at obstacle centroids
+    A0, b0 = obs_sets[0]
+    on_face = obs_points[0][np.abs(obs_points[0] @ A0[0] - b0[0]) < 1e-9]
+    face_mid = on_face.mean(axis=0)
+    cand[0, 0] = face_mid + 5e-4 * A0[0]
+    cand[0, 1] = face_mid + 5e-3 * A0[0]
+    for k in range(20):
+        cand[1, k] = obs_points[3 * k].mean(axis=0)
+    first, flags = geo.sample_filter(scene, cand, want_flags=True)
+    first, flags = first.cpu().numpy(), flags.cpu().numpy()
+    n_coll = 0
+    for q in range(2):
+        ref = [sample_flags(obs_sets, [], c)[0] for c in cand[q]]
+        assert [bool(f & 1) for f in flags[q]] == ref
+        assert first[q] == first_free_sample(obs_sets, [], cand[q])
+        n_coll += sum(ref)
+    assert n_coll > 10 and bool(flags[0, 0] & 1) and not bool(flags[0, 1] & 1)
