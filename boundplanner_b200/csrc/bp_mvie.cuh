@@ -44,7 +44,9 @@
 #endif
 #define BP_MVIE_OUTER_MAX 48
 #define BP_MVIE_INNER_MAX 40
+#ifndef BP_MVIE_GAP_TOL
 #define BP_MVIE_GAP_TOL 1e-11
+#endif
 
 // LDL^T solve of an NV x NV SPD system, H stored as packed lower triangle
 // (index r*(r+1)/2 + c).  Returns false when a pivot is not positive.
