@@ -64,8 +64,19 @@ BP_HD void bp_fix_b(BpFrame& f) {
 
 // q[7] -> p_ee[3], p_col[7*3] (joint_3..joint_7 origins, link4_col_link,
 // end_effector_col_link), optional T_ee[16] (row-major 4x4), optional
-// jac[6*7] (row-major; rows 0-2 linear, 3-5 angular).
-BP_HD void bp_fk_iiwa14(const double* q, double* p_ee, double* p_col, double* T_ee, double* jac) {
+// jac[6*7] (row-major; rows 0-2 linear, 3-5 angular), optional djac[6*7] = d/dt jac for the joint
+// velocities dq[7] (djacobian_fk, RobotModel.py:233-251: pin.getFrameJacobianTimeVariation,
+// LOCAL_WORLD_ALIGNED): with z_k, o_k the axis / origin of joint k,
+//   dz_k = w_k x z_k, w_k = sum_{i<k} z_i dq_i;  do_k = sum_{i<k} dq_i z_i x (o_k - o_i);
+//   v_ee = sum_i dq_i z_i x (p_ee - o_i);  djac[:3,k] = dz_k x (p_ee - o_k) + z_k x (v_ee - do_k);  djac[3:,k] = dz_k.
+BP_HD void bp_cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+BP_HD void bp_fk_iiwa14(const double* q, double* p_ee, double* p_col, double* T_ee, double* jac,
+                        const double* dq = nullptr, double* djac = nullptr) {
   BpFrame f;
   f.X[0] = 1; f.X[1] = 0; f.X[2] = 0;
   f.Y[0] = 0; f.Y[1] = 1; f.Y[2] = 0;
@@ -140,6 +151,36 @@ BP_HD void bp_fk_iiwa14(const double* q, double* p_ee, double* p_col, double* T_
       jac[3 * 7 + j] = zax[j][0];
       jac[4 * 7 + j] = zax[j][1];
       jac[5 * 7 + j] = zax[j][2];
+    }
+  }
+  if (djac && dq) {
+    double v_ee[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < 7; ++i) {
+      const double r[3] = {pe[0] - org[i][0], pe[1] - org[i][1], pe[2] - org[i][2]};
+      double c[3];
+      bp_cross3(zax[i], r, c);
+      for (int k = 0; k < 3; ++k) v_ee[k] += dq[i] * c[k];
+    }
+    double w[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < 7; ++j) {
+      double dz[3], dob[3] = {0.0, 0.0, 0.0};
+      bp_cross3(w, zax[j], dz);
+      for (int i = 0; i < j; ++i) {
+        const double r[3] = {org[j][0] - org[i][0], org[j][1] - org[i][1], org[j][2] - org[i][2]};
+        double c[3];
+        bp_cross3(zax[i], r, c);
+        for (int k = 0; k < 3; ++k) dob[k] += dq[i] * c[k];
+      }
+      const double r[3] = {pe[0] - org[j][0], pe[1] - org[j][1], pe[2] - org[j][2]};
+      const double dv[3] = {v_ee[0] - dob[0], v_ee[1] - dob[1], v_ee[2] - dob[2]};
+      double c1[3], c2[3];
+      bp_cross3(dz, r, c1);
+      bp_cross3(zax[j], dv, c2);
+      for (int k = 0; k < 3; ++k) {
+        djac[k * 7 + j] = c1[k] + c2[k];
+        djac[(3 + k) * 7 + j] = dz[k];
+        w[k] += zax[j][k] * dq[j];
+      }
     }
   }
 }

@@ -2068,6 +2068,36 @@ __global__ void __launch_bounds__(FK_T) k_fk(const double* __restrict__ q, int B
   }
 }
 
+// K7b: RobotModel.forward_kinematics (RobotModel.py:70-77): pose, Jacobian and its time derivative for
+// (q, dq) pairs, one thread per configuration.  The MPC loop calls this once or twice per step on single
+// configurations (MPCNode.py:118, util_functions.py:57), so the outputs (16 + 42 + 42 doubles) are staged through
+// shared memory only for coalesced stores; no bulk copies.
+__global__ void __launch_bounds__(32) k_fk_kin(const double* __restrict__ q, const double* __restrict__ dq, int B,
+                                               double* __restrict__ T_ee, double* __restrict__ jac,
+                                               double* __restrict__ djac) {
+  __shared__ double s_out[32 * 101];             // odd row stride: conflict-free per-thread rows
+  const int base = blockIdx.x * 32;
+  const int nb = min(32, B - base);
+  if ((int)threadIdx.x < nb) {
+    double qq[7], dd[7], pe[3], pc[21], T[16], J[42], dJ[42];
+    const size_t i = (size_t)(base + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { qq[k] = q[i * 7 + k]; dd[k] = dq ? dq[i * 7 + k] : 0.0; }
+    bp_fk_iiwa14(qq, pe, pc, T, J, dd, dJ);
+    double* o = s_out + threadIdx.x * 101;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = T[k];
+#pragma unroll
+    for (int k = 0; k < 42; ++k) { o[16 + k] = J[k]; o[58 + k] = dJ[k]; }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * 16; e += 32) T_ee[(size_t)base * 16 + e] = s_out[(e / 16) * 101 + e % 16];
+  for (int e = threadIdx.x; e < nb * 42; e += 32) {
+    jac[(size_t)base * 42 + e] = s_out[(e / 42) * 101 + 16 + e % 42];
+    if (djac) djac[(size_t)base * 42 + e] = s_out[(e / 42) * 101 + 58 + e % 42];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K11-K13: the planner loop's own tests, batched over queries.
 //   k_sample_filter   the rejection loop of plan_convex_set_path (BoundPlanner.py:459-478): candidate points of a
@@ -2892,6 +2922,15 @@ int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev
   if (T_ee_dev) return launch_fk<true, false>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
   if (jac_dev) return launch_fk<false, true>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
   return launch_fk<false, false>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
+}
+
+int bp_fk_iiwa14_kin(const double* q_dev, const double* dq_dev, int B, double* T_ee_dev, double* jac_dev,
+                     double* djac_dev, void* stream) {
+  if (B < 0 || !q_dev || !T_ee_dev || !jac_dev || (djac_dev && !dq_dev)) return bp_fail("bp_fk_iiwa14_kin: bad arguments");
+  if (B == 0) return 0;
+  k_fk_kin<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(q_dev, dq_dev, B, T_ee_dev, jac_dev, djac_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -539,3 +539,19 @@ def fk_iiwa14(q, want_pose=False, want_jacobian=False):
     J = torch.empty((B, 6, 7), dtype=torch.float64, device="cuda") if want_jacobian else None
     check(lib.bp_fk_iiwa14(_ptr(q), B, _ptr(p_ee), _ptr(p_col), _ptr(T), _ptr(J), _stream()))
     return p_ee, p_col, T, J
+
+
+def fk_kinematics(q, dq=None):
+    """RobotModel.forward_kinematics (RobotModel.py:70-77) for B (q, dq) pairs: returns (T_ee [B,4,4],
+    jac [B,6,7], djac [B,6,7] | None) -- hom_transform_endeffector, jacobian_fk and djacobian_fk (:233-251)."""
+    lib = _lib.load()
+    q = _dev(q).reshape(-1, 7)
+    B = q.shape[0]
+    dq = None if dq is None else _dev(dq).reshape(-1, 7)
+    if dq is not None and dq.shape[0] != B:
+        raise ValueError("q and dq must hold the same number of configurations")
+    T = torch.empty((B, 4, 4), dtype=torch.float64, device="cuda")
+    J = torch.empty((B, 6, 7), dtype=torch.float64, device="cuda")
+    dJ = torch.empty((B, 6, 7), dtype=torch.float64, device="cuda") if dq is not None else None
+    check(lib.bp_fk_iiwa14_kin(_ptr(q), _ptr(dq), B, _ptr(T), _ptr(J), _ptr(dJ), _stream()))
+    return T, J, dJ

@@ -3,8 +3,10 @@
 
 Only the kinematic queries the MPC loop makes on NumPy inputs are mirrored
 (BoundMPC.py:480-481, MPCNode.py:38,118): ``fk_pos``, ``fk_pos_col``, ``fk``,
-``hom_transform_endeffector``, ``jacobian_fk``, plus batched forms.  The
-symbolic CasADi branch (used inside the OCP) stays in the reference.
+``hom_transform_endeffector``, ``jacobian_fk``, ``djacobian_fk``,
+``forward_kinematics(q, dq)`` (:70-77), ``velocity_ee`` / ``acceleration_ee`` /
+``omega_ee`` (:253-267), plus batched forms.  The symbolic CasADi branch (used
+inside the OCP) stays in the reference.
 """
 from __future__ import annotations
 
@@ -65,6 +67,33 @@ class RobotModel:
 
     def jacobian_fk(self, q):
         return geo.fk_iiwa14(self._numeric(q), want_jacobian=True)[3][0].cpu().numpy()
+
+    def djacobian_fk(self, q, dq):
+        """RobotModel.py:233-251: time variation of the LOCAL_WORLD_ALIGNED frame Jacobian along dq."""
+        dq = np.ascontiguousarray(dq, dtype=np.float64).reshape(1, 7)
+        return geo.fk_kinematics(self._numeric(q), dq)[2][0].cpu().numpy()
+
+    def forward_kinematics(self, q, dq):
+        """RobotModel.py:70-77 -> (p_robot [p, rotvec], jac_ee [6,7], djac_ee [6,7]); one kernel launch and one
+        D2H copy (the reference makes three Pinocchio passes)."""
+        dq = np.ascontiguousarray(dq, dtype=np.float64).reshape(1, 7)
+        T, J, dJ = geo.fk_kinematics(self._numeric(q), dq)
+        h = T[0].cpu().numpy()
+        m = np.zeros(6)
+        m[:3] = h[:3, 3]
+        m[3:] = R.from_matrix(h[:3, :3]).as_rotvec()
+        return m, J[0].cpu().numpy(), dJ[0].cpu().numpy()
+
+    @staticmethod
+    def forward_kinematics_batch(q, dq):
+        """q, dq [B,7] -> (T_ee [B,4,4], jac [B,6,7], djac [B,6,7]) CUDA tensors."""
+        return geo.fk_kinematics(q, dq)
+
+    def acceleration_ee(self, q, dq, ddq):
+        """RobotModel.py:258-262"""
+        dq = np.ascontiguousarray(dq, dtype=np.float64).reshape(7)
+        T, J, dJ = geo.fk_kinematics(self._numeric(q), dq.reshape(1, 7))
+        return dJ[0].cpu().numpy() @ dq + J[0].cpu().numpy() @ np.asarray(ddq, dtype=np.float64).reshape(7)
 
     def velocity_ee(self, q, dq):
         return (self.jacobian_fk(q) @ dq)[:3]

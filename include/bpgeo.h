@@ -246,6 +246,12 @@ int bp_scatter_rows_peers(const unsigned int* rows_dev, int rows, int words, int
 int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev, double* T_ee_dev, double* jac_dev,
                  void* stream);
 
+/* RobotModel.forward_kinematics(q, dq) (RobotModel.py:70-77; callers MPCNode.py:38,118, util_functions.py:57),
+ * jacobian_fk (:213-231) and djacobian_fk (:233-251, pin.getFrameJacobianTimeVariation, LOCAL_WORLD_ALIGNED) for
+ * B (q, dq) pairs: T_ee[B,4,4], jac[B,6,7], djac[B,6,7] (= d/dt jac along dq; NULL with dq_dev NULL: skip). */
+int bp_fk_iiwa14_kin(const double* q_dev, const double* dq_dev, int B, double* T_ee_dev, double* jac_dev,
+                     double* djac_dev, void* stream);
+
 /* ---- diagnostics: FP64 pipe probe (roofline denominator in bench.py) ------------
  * Launches blocks x threads threads, each running `chains` (1, 4 or 8)
  * independent chains of `iters` dependent DFMAs; out_dev: [blocks*threads]. */

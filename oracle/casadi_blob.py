@@ -48,6 +48,28 @@ _BINARY = {
 }
 
 
+class _Dual:
+    """value + tangent (forward-mode AD over the smooth operations the FK programs use)"""
+    __slots__ = ("v", "t")
+
+    def __init__(self, v, t):
+        self.v, self.t = v, t
+
+
+_DUAL_UNARY = {
+    OP_ASSIGN: lambda x: x, OP_NEG: lambda x: _Dual(-x.v, -x.t), OP_SQ: lambda x: _Dual(x.v * x.v, 2.0 * x.v * x.t),
+    OP_TWICE: lambda x: _Dual(2.0 * x.v, 2.0 * x.t), OP_SIN: lambda x: _Dual(math.sin(x.v), math.cos(x.v) * x.t),
+    OP_COS: lambda x: _Dual(math.cos(x.v), -math.sin(x.v) * x.t),
+    OP_SQRT: lambda x: _Dual(math.sqrt(x.v), 0.5 * x.t / math.sqrt(x.v)),
+    OP_INV: lambda x: _Dual(1.0 / x.v, -x.t / (x.v * x.v)),
+}
+_DUAL_BINARY = {
+    OP_ADD: lambda x, y: _Dual(x.v + y.v, x.t + y.t), OP_SUB: lambda x, y: _Dual(x.v - y.v, x.t - y.t),
+    OP_MUL: lambda x, y: _Dual(x.v * y.v, x.t * y.v + x.v * y.t),
+    OP_DIV: lambda x, y: _Dual(x.v / y.v, (x.t - x.v / y.v * y.t) / y.v),
+}
+
+
 def decode_bytes(text):
     text = text.strip()
     return bytes(((ord(text[2 * i]) - 97) | ((ord(text[2 * i + 1]) - 97) << 4)) for i in range(len(text) // 2))
@@ -179,6 +201,46 @@ class SXFunctionBlob:
             else:
                 return False
         return outs == sum(n_out_nz)
+
+    def jvp(self, args, dargs):
+        """Forward-mode directional derivative of the program: returns (value, d value / d args . dargs) as
+        dense outputs.  Used to pin djacobian_fk (RobotModel.py:233-251; the reference ships no djacobian.ca)
+        to the time derivative of the reference's own jacobian.ca: dJ/dt = sum_k dJ/dq_k dq_k."""
+        ins = [[_Dual(float(v), float(t)) for v, t in zip(np.asarray(a, float).reshape(-1),
+                                                          np.asarray(d, float).reshape(-1))]
+               for a, d in zip(args, dargs)]
+        val = self._run(ins, _Dual(0.0, 0.0))
+        vals = [np.vectorize(lambda e: e.v, otypes=[float])(m) for m in val]
+        tans = [np.vectorize(lambda e: e.t, otypes=[float])(m) for m in val]
+        return (vals[0], tans[0]) if len(vals) == 1 else (vals, tans)
+
+    def _run(self, ins, zero):
+        w = [zero] * self.worksize
+        outs = [[zero] * len(sp[3]) for sp in self.sp_out]
+        for op, i0, rest in self.prog:
+            if op == OP_CONST:
+                w[i0] = _Dual(struct.unpack("<d", rest)[0], 0.0)
+                continue
+            i1, i2 = struct.unpack("<ii", rest)
+            if op == OP_INPUT:
+                w[i0] = ins[i1][i2]
+            elif op == OP_OUTPUT:
+                outs[i0][i2] = w[i1]
+            elif op in _DUAL_UNARY:
+                w[i0] = _DUAL_UNARY[op](w[i1])
+            elif op in _DUAL_BINARY:
+                w[i0] = _DUAL_BINARY[op](w[i1], w[i2])
+            else:
+                raise NotImplementedError(f"jvp: operation code {op}")
+        res = []
+        for (nrow, ncol, colind, row), nz in zip(self.sp_out, outs):
+            m = np.empty((nrow, ncol), dtype=object)
+            m[:] = zero
+            for c in range(ncol):
+                for k in range(colind[c], colind[c + 1]):
+                    m[row[k], c] = nz[k]
+            res.append(m)
+        return res
 
     def __call__(self, *args):
         ins = [np.asarray(a, float).reshape(-1) for a in args]

@@ -117,3 +117,37 @@ def jacobian_fk(q):
         jac[:3, k] = np.cross(z, p_ee - fr[k][:3, 3])
         jac[3:, k] = z
     return jac
+
+
+def djacobian_fk(q, dq):
+    """Time derivative of the LOCAL_WORLD_ALIGNED frame Jacobian for joint velocities dq
+    (RobotModel.py:233-251, pin.getFrameJacobianTimeVariation): with z_k, o_k the axis / origin of joint k,
+        d/dt z_k = w_k x z_k,            w_k  = sum_{i<k} z_i dq_i      (angular velocity of the parent link)
+        d/dt o_k = sum_{i<k} dq_i z_i x (o_k - o_i),   v_ee = sum_i dq_i z_i x (p_ee - o_i)
+        dJ[:3,k] = dz_k x (p_ee - o_k) + z_k x (v_ee - do_k),   dJ[3:,k] = dz_k.
+    The reference ships no djacobian.ca; this is pinned to the directional derivative of its jacobian.ca
+    (tests/golden/fk_reference_blobs.npz, key djacobian)."""
+    fr = joint_frames(q)
+    p_ee = fk_pos(q)
+    z = [f[:3, 2] for f in fr]
+    o = [f[:3, 3] for f in fr]
+    v_ee = sum(dq[i] * np.cross(z[i], p_ee - o[i]) for i in range(7))
+    dj = np.zeros((6, 7))
+    w = np.zeros(3)
+    for k in range(7):
+        dz = np.cross(w, z[k])
+        do = sum((dq[i] * np.cross(z[i], o[k] - o[i]) for i in range(k)), np.zeros(3))
+        dj[:3, k] = np.cross(dz, p_ee - o[k]) + np.cross(z[k], v_ee - do)
+        dj[3:, k] = dz
+        w = w + z[k] * dq[k]
+    return dj
+
+
+def forward_kinematics(q, dq):
+    """RobotModel.py:70-77 -> (fk(q), jacobian_fk(q), djacobian_fk(q, dq))"""
+    return fk(q), jacobian_fk(q), djacobian_fk(q, dq)
+
+
+def acceleration_ee(q, dq, ddq):
+    """RobotModel.py:258-262"""
+    return djacobian_fk(q, dq) @ dq + jacobian_fk(q) @ ddq

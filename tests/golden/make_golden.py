@@ -10,7 +10,8 @@ fk_golden.npz       iiwa14 FK at fixed configurations.  Source: the ORACLE
 fk_reference_blobs.npz  The reference's OWN serialized CasADi functions (bound_planner/RobotModel/
                     fk_pos.ca, fk_pos_col_{0..5}.ca, hom_trans.ca, jacobian.ca -- what RobotModel.py:158,179,
                     209,229 load) evaluated at 64 configurations by oracle/casadi_blob.py (a CasADi-free
-                    decoder + SX virtual machine).  Reference-generated golden vectors: they pin the FK oracle
+                    decoder + SX virtual machine); djacobian = the directional derivative of jacobian.ca
+                    along dq (forward-mode AD through the same program).  Reference-generated golden vectors: they pin the FK oracle
                     and the FK kernel.  Needs /root/reference (this container only).
 c1_sets_golden.npz  The first two convex sets the reference's example plan builds
                     (boundplanner_example.py:89-92 -> BoundPlanner.py:278-294,
@@ -55,7 +56,12 @@ def main():
         f_col = [SXFunctionBlob(ref_dir + f"fk_pos_col_{i}.ca") for i in range(6)]
         f_hom = SXFunctionBlob(ref_dir + "hom_trans.ca")
         f_jac = SXFunctionBlob(ref_dir + "jacobian.ca")
-        np.savez(os.path.join(HERE, "fk_reference_blobs.npz"), q=qg,
+        # djacobian_fk (RobotModel.py:233-251): the reference ships no djacobian.ca; the golden value is the exact
+        # directional derivative (forward-mode AD through the SX program) of its own jacobian.ca along dq
+        dqg = np.random.default_rng(4321).uniform(-2.0, 2.0, (64, 7))
+        dqg[0] = 0.0
+        djac = np.array([f_jac.jvp([x], [v])[1] for x, v in zip(qg, dqg)])
+        np.savez(os.path.join(HERE, "fk_reference_blobs.npz"), q=qg, dq=dqg, djacobian=djac,
                  fk_pos=np.array([f_pos(x).ravel() for x in qg]),
                  fk_pos_col=np.array([[f(x).ravel() for f in f_col] for x in qg]),
                  hom_trans=np.array([f_hom(x) for x in qg]),

@@ -158,6 +158,13 @@ void hh_fk(const double* q, int n, double* p_ee, double* p_col, double* T_ee, do
                  jac ? jac + 42 * i : nullptr);
 }
 
+void hh_fk_kin(const double* q, const double* dq, int n, double* T_ee, double* jac, double* djac) {
+  for (int i = 0; i < n; ++i) {
+    double pe[3], pc[21];
+    bp_fk_iiwa14(q + 7 * i, pe, pc, T_ee + 16 * i, jac + 42 * i, dq + 7 * i, djac + 42 * i);
+  }
+}
+
 double hh_min_eig(const double* A) { return bp_sym3_min_eig(A); }
 
 }  // extern "C"

@@ -197,3 +197,40 @@ def test_against_committed_golden_fixtures(c1):
     assert np.abs(p_col.cpu().numpy() - fk["p_col"]).max() < 1e-12
     assert np.abs(T.cpu().numpy() - fk["T_ee"]).max() < 1e-12
     assert np.abs(J.cpu().numpy() - fk["jac"]).max() < 1e-12
+
+
+def test_forward_kinematics_call_shapes_of_the_mpc_loop():
+    """RobotModel.forward_kinematics / djacobian_fk / acceleration_ee (RobotModel.py:70-77, 233-262) through the
+    shim with the call shapes of MPCNode.py:38,118 and util_functions.py:57-62 (integrate_joint), pinned to the
+    reference's jacobian.ca differentiated along dq."""
+    import boundplanner_b200 as bp
+    from oracle import fk_iiwa14 as ofk
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_reference_blobs.npz"))
+    model = bp.RobotModel()
+    q0 = np.array([0, 0, 0, -np.pi / 2, 0, np.pi / 2, 0.0])           # boundplanner_with_mpc_example.py:20-26
+    p0, _, _ = model.forward_kinematics(q0, q0)                       # MPCNode.py:38
+    assert np.abs(p0 - ofk.fk(q0)).max() < 1e-12
+    for i in (1, 5, 17, 40):
+        q, dq = ref["q"][i], ref["dq"][i]
+        p_lie, jac_fk, djac_fk = model.forward_kinematics(q, dq)      # MPCNode.py:118
+        assert p_lie.shape == (6,) and jac_fk.shape == (6, 7) and djac_fk.shape == (6, 7)
+        assert np.abs(p_lie - ofk.fk(q)).max() < 1e-12
+        assert np.abs(jac_fk - ref["jacobian"][i]).max() < 1e-12
+        assert np.abs(djac_fk - ref["djacobian"][i]).max() < 1e-12
+        assert np.abs(model.djacobian_fk(q, dq) - ref["djacobian"][i]).max() < 1e-12
+        ddq = 0.1 * dq[::-1]
+        an = djac_fk @ dq + jac_fk @ ddq                               # util_functions.py:61
+        assert np.abs(model.acceleration_ee(q, dq, ddq) - an).max() < 1e-12
+        assert np.abs(model.acceleration_ee(q, dq, ddq) - ofk.acceleration_ee(q, dq, ddq)).max() < 1e-12
+        vn = np.concatenate((model.velocity_ee(q, dq), model.omega_ee(q, dq)))   # util_functions.py:60
+        assert np.abs(vn - ref["jacobian"][i] @ dq).max() < 1e-12
+    # batched form, ragged tile (B not a multiple of the CTA size)
+    T, J, dJ = bp.RobotModel.forward_kinematics_batch(ref["q"], ref["dq"])
+    assert np.abs(T.cpu().numpy() - ref["hom_trans"]).max() < 1e-12
+    assert np.abs(J.cpu().numpy() - ref["jacobian"]).max() < 1e-12
+    assert np.abs(dJ.cpu().numpy() - ref["djacobian"]).max() < 1e-12
+    qq = np.tile(ref["q"], (3, 1))[:150]
+    dd = np.tile(ref["dq"], (3, 1))[:150]
+    _, _, dJ2 = bp.RobotModel.forward_kinematics_batch(qq, dd)
+    assert np.array_equal(dJ2.cpu().numpy()[:64], dJ.cpu().numpy()) and np.array_equal(dJ2.cpu().numpy()[128:150], dJ.cpu().numpy()[:22])

@@ -2,6 +2,7 @@
 tests/host_harness.cpp, against the oracle.  This is the exact code the kernels run
 (the warp-cooperative kernels follow the same algorithm, constants and row order)."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -123,6 +124,24 @@ def test_fk_primitive(host_harness):
         assert np.abs(pc[i] - ofk.fk_pos_col_all(q[i])).max() < 1e-12
         assert np.abs(T[i] - ofk.hom_transform_endeffector(q[i])).max() < 1e-12
         assert np.abs(J[i] - ofk.jacobian_fk(q[i])).max() < 1e-12
+
+
+def test_fk_jacobian_time_variation_primitive(host_harness):
+    """djacobian_fk (RobotModel.py:233-251) of the device code (host build) vs the oracle and vs the reference's
+    jacobian.ca differentiated along dq (golden)."""
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_reference_blobs.npz"))
+    q, dq = np.ascontiguousarray(ref["q"]), np.ascontiguousarray(ref["dq"])
+    n = q.shape[0]
+    T, J, dJ = np.zeros((n, 4, 4)), np.zeros((n, 6, 7)), np.zeros((n, 6, 7))
+    host_harness.hh_fk_kin(dp(q), dp(dq), n, dp(T), dp(J), dp(dJ))
+    assert np.abs(J - ref["jacobian"]).max() < 1e-12 and np.abs(T - ref["hom_trans"]).max() < 1e-12
+    assert np.abs(dJ - ref["djacobian"]).max() < 1e-12
+    for i in range(0, n, 7):
+        assert np.abs(dJ[i] - ofk.djacobian_fk(q[i], dq[i])).max() < 1e-12
+    # finite-difference cross-check of the oracle formula
+    h = 1e-6
+    fd = (ofk.jacobian_fk(q[3] + h * dq[3]) - ofk.jacobian_fk(q[3] - h * dq[3])) / (2 * h)
+    assert np.abs(fd - dJ[3]).max() < 1e-8
 
 
 def test_min_eig_primitive(host_harness):
