@@ -8,8 +8,8 @@ c2_graph_golden.npz  config C2 of BASELINE.json in full: the ORACLE's convex set
                      adjacency from the reference's own scipy.optimize.linprog call (BoundPlanner.py:774-798, tol
                      0.01) on those sets, plus the exact margin s* of every pair HiGHS answers within 1e-5 of the
                      decision boundary (near ties, see oracle/set_graph.py).
-c4_sets_golden.npz   config C4: the oracle's sets for 96 of the 2048 seeds (every 21st + the last) and the
-                     adjacency among them.
+c4_sets_golden.npz   config C4: the oracle's sets for 258 of the 2048 seeds (every 8th + seeds 700, 2047) and the
+                     adjacency among them (33 153 pairs).
 Source of every number: the oracle (oracle/convex_set_finder.py, a restatement of the reference whose QP / SOCP
 solvers are not installable here) and, for the adjacency, the reference's verbatim HiGHS call.
 """
@@ -127,7 +127,7 @@ def main():
     if "c4" in which:
         t0 = time.time()
         boxes, inflate, seeds, ws_min, ws_max = scenes.config_c4()
-        sel = np.unique(np.concatenate((np.arange(0, 2048, 21), [700, 2047])))[:96]
+        sel = np.unique(np.concatenate((np.arange(0, 2048, 8), [700, 2047])))
         res = build_all(boxes, inflate, ws_min, ws_max, seeds[sel], cores)
         d = pack(res)
         sets = [[r[1], r[2]] for r in res]
