@@ -37,9 +37,7 @@ def boxes_from_obs_sets(obs_sets):
         a_set = np.asarray(a_set, float)
         b_set = np.asarray(b_set, float)
         if a_set.shape[0] < 6 or not np.array_equal(a_set[:6], _BOX) or np.any(a_set[6:] != 0.0):
-            raise NotImplementedError(
-                "boundplanner_b200.ConvexSetFinder handles the box obstacles BoundPlanner.make_box builds "
-                "(A = [I; -I]); general polytope obstacles are not implemented")
+            raise NotImplementedError("not an axis-aligned box (A = [I; -I], BoundPlanner.make_box): general polytope")
         boxes[k, :3] = -b_set[3:6]
         boxes[k, 3:] = b_set[:3]
     return boxes
@@ -60,14 +58,19 @@ class ConvexSetFinder:
         # strict_rows=True reproduces the reference's ValueError on sets with more than 20 rows
         self.strict_rows = strict_rows
         self.verbose = False
-        self._scene = None
+        self._scene_obj = None
+        self._scene_dirty = True
         self._polytopes = False
         self._obs_sets = []
         self._obs_points_sets = []
+        self.obs_sets = obs_sets
         self.obs_points_sets = obs_points_sets
-        self.obs_sets = obs_sets                      # uploads the scene
+        self._scene                                   # upload the scene now: a missing GPU fails here
 
-    # add_obstacle_reps(update=True) ASSIGNS these attributes (BoundPlanner.py:150-152)
+    # add_obstacle_reps(update=True) ASSIGNS these two attributes, obs_sets first and obs_points_sets second
+    # (BoundPlanner.py:150-152).  Both setters only mark the device scene stale; it is (re)built on first use, from
+    # whatever pair of lists is current then -- so the order of the two assignments does not matter, and a polytope
+    # update never keeps the old vertex lists.
     @property
     def obs_sets(self):
         return self._obs_sets
@@ -75,21 +78,7 @@ class ConvexSetFinder:
     @obs_sets.setter
     def obs_sets(self, value):
         self._obs_sets = list(value).copy()
-        try:
-            boxes = boxes_from_obs_sets(self._obs_sets)
-        except NotImplementedError:
-            # general polytopes: rows + the vertices of obs_points_sets (assigned first by add_obstacle_reps, :150-151)
-            if len(self._obs_points_sets) != len(self._obs_sets):
-                raise ValueError("polytope obstacles need obs_points_sets (one vertex array per obstacle) "
-                                 "to be assigned before obs_sets") from None
-            self._scene = geo.PolytopeScene(self._obs_sets, self._obs_points_sets)
-            self._polytopes = True
-            return
-        self._polytopes = False
-        if self._scene is None or isinstance(self._scene, geo.PolytopeScene):
-            self._scene = geo.Scene(boxes, 0.0)       # obs_sets are already inflated (:141)
-        else:
-            self._scene.update(boxes, 0.0)
+        self._scene_dirty = True
 
     @property
     def obs_points_sets(self):
@@ -97,8 +86,31 @@ class ConvexSetFinder:
 
     @obs_points_sets.setter
     def obs_points_sets(self, value):
-        # vertices are implied by the boxes (8 corners); kept for attribute compatibility
+        # for boxes the vertices are implied (8 corners); polytope scenes take their vertex lists from here
         self._obs_points_sets = list(value).copy() if value is not None else []
+        self._scene_dirty = True
+
+    @property
+    def _scene(self):
+        if not self._scene_dirty:
+            return self._scene_obj
+        try:
+            boxes = boxes_from_obs_sets(self._obs_sets)
+        except NotImplementedError:
+            # general polytopes: the rows of obs_sets + the vertices of obs_points_sets
+            if len(self._obs_points_sets) != len(self._obs_sets):
+                raise ValueError(f"polytope obstacles need one vertex array per obstacle: {len(self._obs_sets)} "
+                                 f"obs_sets but {len(self._obs_points_sets)} obs_points_sets") from None
+            self._scene_obj = geo.PolytopeScene(self._obs_sets, self._obs_points_sets)
+            self._polytopes = True
+        else:
+            self._polytopes = False
+            if self._scene_obj is None or isinstance(self._scene_obj, geo.PolytopeScene):
+                self._scene_obj = geo.Scene(boxes, 0.0)       # obs_sets are already inflated (:141)
+            else:
+                self._scene_obj.update(boxes, 0.0)
+        self._scene_dirty = False
+        return self._scene_obj
 
     # ---- errors ----------------------------------------------------------
     def _raise_for_status(self, status, m=None):

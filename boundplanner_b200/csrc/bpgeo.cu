@@ -2132,7 +2132,10 @@ __global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const d
         load_box(sc, j, lb, ub);
         // rows +-e_k of the inflated box: A x - b = x_k - ub_k, lb_k - x_k (padded rows give -10)
         double v = fmax(fmax(fmax(x0 - ub[0], lb[0] - x0), fmax(x1 - ub[1], lb[1] - x1)), fmax(x2 - ub[2], lb[2] - x2));
-        if (sc.rows && v < 1e-3) {                  // general polytope: inside its bounding box -> walk its rows
+        if (sc.rows) {
+          // general polytope: the reference's test is max(A x - b) < 1e-3 over the obstacle's own rows (:467-471).
+          // No bounding-box gate: near a sharp vertex or edge that region reaches 1e-3 / sin(theta / 2) beyond the
+          // polytope, i.e. outside any fixed growth of the vertex bounding box
           const double* r4 = sc.rows + (size_t)j * BP_OBS_ROWS * 4;
           v = -10.0;                                // the padded rows' A x - b (only matters for an obstacle without rows)
           for (int r = 0; r < sc.nrows[j]; ++r)

@@ -100,6 +100,12 @@ class SetGraphPipeline:
         if self._host is None:
             self.run(seeds_host_pinned)                               # allocates the pinned mirror (synchronous once)
         cur = torch.cuda.current_stream()
+        # a previous submit()'s D2H on the copy stream may still be reading the device buffers this step overwrites
+        # (and the pinned mirror): order this step behind it
+        pending = getattr(self, "_copy_done_for_compute", None)
+        if pending is not None:
+            cur.wait_event(pending)
+            self._copy_done_for_compute = None
         self.seeds_dev.copy_(seeds_host_pinned, non_blocking=True)
         self.run_device()
         if copy_stream is None:

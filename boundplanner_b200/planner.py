@@ -424,6 +424,22 @@ class BatchedGpuExecutor:
             A[k, :n], b[k, :n], m[k] = s[0], s[1], n
         return torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(), torch.as_tensor(m).cuda()
 
+    @staticmethod
+    def _row_limit_error(req):
+        from ._lib import BP_MAX_ROWS
+
+        kind = req[0]
+        worst = 0
+        if kind in ("edges", "intersect_many"):
+            worst = max((s[0].shape[0] + req[2][0].shape[0] for s in req[1]), default=0)
+        elif kind == "fit_many":
+            worst = max((a.shape[0] for a, _, _ in req[1]), default=0)
+        elif kind == "project":
+            worst = np.asarray(req[1]).shape[0]
+        if worst > BP_MAX_ROWS:
+            return ValueError(f"'{kind}' request with {worst} rows exceeds the kernels' {BP_MAX_ROWS}-row sets")
+        return None
+
     # -- one round ----------------------------------------------------------------
     def execute(self, pending):
         """pending: {qid: request}.  Returns {qid: result | Exception}."""
@@ -431,6 +447,13 @@ class BatchedGpuExecutor:
         out = {}
         by_kind = {}
         for qid, req in pending.items():
+            # a request whose sets exceed the kernels' row capacity fails for ITS query only (the other queries of
+            # the lock-step batch go on): pair / fit kernels take m_i + m_j <= BP_MAX_ROWS rows, the projection
+            # one packed set of <= BP_MAX_ROWS rows
+            err = self._row_limit_error(req)
+            if err is not None:
+                out[qid] = err
+                continue
             by_kind.setdefault(req[0], []).append(qid)
 
         for (fixed_mid, optimize) in ((True, True), (True, False), (False, True), (False, False)):

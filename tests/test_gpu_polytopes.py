@@ -164,3 +164,30 @@ def test_sample_filter_over_polytope_obstacles(poly_scene):
         assert first[q] == first_free_sample(obs_sets, [], cand[q])
         n_coll += sum(ref)
     assert n_coll > 10 and bool(flags[0, 0] & 1) and not bool(flags[0, 1] & 1)
+
+
+def test_polytope_scene_update_in_the_reference_assignment_order(poly_scene):
+    """add_obstacle_reps(update=True) assigns set_finder.obs_sets FIRST and obs_points_sets second
+    (BoundPlanner.py:150-152).  A polytope update -- same obstacle count with moved obstacles, and a changed
+    count -- must use the NEW vertex lists (vertex test of ConvexSetFinder.py:449-451)."""
+    import boundplanner_b200 as bp
+    from boundplanner_b200 import scenes
+    from oracle.convex_set_finder import ConvexSetFinder as OracleFinder
+
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    gpu = bp.ConvexSetFinder(obs_sets, obs_points, list(ws_max), list(ws_min), strict_rows=False)
+    rng = np.random.default_rng(21)
+    for n_new in (len(obs_sets), len(obs_sets) // 2):
+        sets2, pts2 = scenes.random_polytope_scene(n_new, rng)
+        gpu.obs_sets = sets2                       # reference order: rows first ...
+        gpu.obs_points_sets = pts2                 # ... vertices second
+        ora2 = OracleFinder(sets2, pts2, list(ws_max), list(ws_min), max_rows=None)
+        pts = scenes.polytope_free_points(3, sets2, 0.02, rng)
+        for p in pts:
+            A, b, Q, c = gpu.find_set_around_point(p, fixed_mid=True)
+            Ao, bo, Qo, co = ora2.find_set_around_point(p, fixed_mid=True)
+            assert_rows_close(A, b, Ao, bo, f"polytope update to {n_new} obstacles")
+    # a polytope scene with a stale vertex list of the wrong length fails loudly at first use
+    gpu.obs_sets = obs_sets
+    with pytest.raises(ValueError, match="one vertex array per obstacle"):
+        gpu.find_set_around_point(seeds[0], fixed_mid=True)
