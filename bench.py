@@ -9,15 +9,26 @@ that hot path over the seed batch.  Metric: convex sets built per second
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL): every rank builds its
-own 256 seeds over the replicated scene (weak scaling), the halfspace tensors
-are all-gathered and the pair matrix is split in balanced row blocks.
+N > 1 is launched by torchrun (one rank per GPU): every rank builds its own 256
+seeds over the replicated scene (weak scaling), the sets are exchanged by peer
+stores over NVLink and the global pair matrix is split in balanced row blocks.
+
+Besides the headline line's contract keys (value, e2e, roofline, cpu_baseline,
+clocks, gpu_launches) the line carries
+  stages_ms   per-stage device time of one step (max over ranks at N > 1)
+  saturated   the same set build with 2048 seeds in one launch (chip filled)
+  c3 / c4 / c5  the other BASELINE configs: batched planning queries (queries/s,
+              p50/p95 latency over ALL queries), the 10k-obstacle / 2048-seed graph
+              (strong scaling over the ranks), the MPC step geometry (us per step)
+  adjacency_equals_single_rank   (N > 1) the exchanged global graph re-tested by
+              rank 0 alone, outside the timed region
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -34,7 +45,16 @@ N_SEEDS = 256           # per GPU
 TOL = 0.01
 METRIC = "convex_sets_built_per_sec"
 UNIT = "sets/s"
-WORKLOAD = "C2: 1000 random box obstacles (edge U[0.02,0.08], inflate 0.01), 256 seeds/GPU, IRIS loop fixed_mid + all-pairs set graph tol 0.01"
+WORKLOAD = ("C2: 1000 random box obstacles (edge U[0.02,0.08], inflate 0.01), 256 seeds/GPU, IRIS loop fixed_mid + "
+            "all-pairs set graph tol 0.01")
+PAIRS_PER_SET = (N_SEEDS - 1) / 2.0        # 32 640 pairs / 256 sets on one GPU
+
+
+def config_dict(world):
+    """the same dict in both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "n_obstacles": N_OBS, "seeds_per_gpu": N_SEEDS,
+            "pairs_per_set": PAIRS_PER_SET if world == 1 else (N_SEEDS * world - 1) / 2.0,
+            "l2": "flushed between timed steps (256 MiB fill)"}
 
 
 # ----------------------------------------------------------------------------
@@ -92,87 +112,132 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference's Python path
+# CPU arm: the oracle port of the reference's Python path on a persistent process pool
 # ----------------------------------------------------------------------------
-def _oracle_worker(args):
-    boxes, inflate, ws_min, ws_max, seeds = args[:5]
-    per_obstacle_loop = len(args) > 5 and args[5]
+_FINDER = None
+
+
+def _pool_init(boxes, inflate, ws_min, ws_max):
+    """runs once in every worker: the scene is ingested here, outside any timed region"""
+    global _FINDER
     from oracle.convex_set_finder import ConvexSetFinder
     from oracle.obstacles import obstacle_reps
 
     obs_sets, pts, _ = obstacle_reps(boxes, inflate)
-    f = ConvexSetFinder(obs_sets, pts, ws_max, ws_min, max_rows=None)
-    if per_obstacle_loop:
-        # the reference's own loop structure: one closest-point QP solve per obstacle and pass
-        # (ConvexSetFinder.py:468-486), instead of the oracle's NumPy batch over all obstacles
-        f.compute_set_projs = f.compute_set_projs_loop
-    sets = []
-    for p in seeds:
-        try:
-            A, b, _, _ = f.find_set_around_point(p, fixed_mid=True, optimize=True)
-            sets.append([A, b])
-        except RuntimeError:
-            pass
-    return sets
+    _FINDER = ConvexSetFinder(obs_sets, pts, ws_max, ws_min, max_rows=None)
 
 
-def cpu_sample(boxes, inflate, ws_min, ws_max, seeds, cores):
-    """Build len(seeds) sets with the oracle on `cores` processes and test all their
-    pairs with the reference's linprog call; returns (seconds, n_sets, n_pairs)."""
+def _pool_build(seed):
+    """find_set_around_point (ConvexSetFinder.py:190-240) for one seed; None when the reference would raise"""
+    try:
+        A, b, _, _ = _FINDER.find_set_around_point(seed, fixed_mid=True, optimize=True)
+        return [A, b]
+    except (RuntimeError, ValueError):
+        return None
+
+
+def _pool_pairs(chunk):
+    """the reference's set_intersection call (BoundPlanner.py:774-787) for a chunk of set pairs"""
     from oracle.set_graph import set_intersection
 
-    t0 = time.perf_counter()
-    if cores == 1:
-        sets = _oracle_worker((boxes, inflate, ws_min, ws_max, seeds))
-    else:
+    return [bool(set_intersection(s1, s2, TOL)[2]) for s1, s2 in chunk]
+
+
+class CpuArm:
+    """The reference's CPU path (oracle port: vectorised NumPy closest points + barrier MVIE, SciPy/HiGHS pair
+    LPs) over `cores` persistent worker processes.  One step = `n_seeds` sets built + the GPU arm's ratio of
+    pair checks per set (127.5 at one GPU), against the sets built before."""
+
+    def __init__(self, cores):
         import multiprocessing as mp
 
-        chunks = [seeds[i::cores] for i in range(cores)]
-        with mp.get_context("fork").Pool(cores) as pool:
-            parts = pool.map(_oracle_worker, [(boxes, inflate, ws_min, ws_max, c) for c in chunks if len(c)])
-        sets = [s for p in parts for s in p]
-    npairs = 0
-    for i in range(len(sets)):
-        for j in range(i):
-            set_intersection(sets[i], sets[j], TOL)
-            npairs += 1
-    return time.perf_counter() - t0, len(seeds), npairs
+        from boundplanner_b200 import scenes
+
+        self.cores = cores
+        self.boxes, self.inflate, self.seeds, self.ws_min, self.ws_max = scenes.config_c2(N_OBS, N_SEEDS)
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_pool_init,
+                                                initargs=(self.boxes, self.inflate, self.ws_min, self.ws_max)) if cores > 1 else None
+        if self.pool is None:
+            _pool_init(self.boxes, self.inflate, self.ws_min, self.ws_max)
+        self.sets = []              # every set built so far (pair partners)
+        self.cursor = 0
+
+    def step(self, n_seeds):
+        """returns (seconds, sets built, pair checks)"""
+        sel = [self.seeds[(self.cursor + k) % N_SEEDS] for k in range(n_seeds)]
+        self.cursor += n_seeds
+        t0 = time.perf_counter()
+        built = self.pool.map(_pool_build, sel, chunksize=1) if self.pool else [_pool_build(s) for s in sel]
+        built = [s for s in built if s is not None]
+        want = int(round(len(built) * PAIRS_PER_SET))
+        pairs = []
+        partners = self.sets + built
+        for a, s in enumerate(built):                # newest sets first, like add_edges walks the graph's nodes
+            me = len(self.sets) + a
+            for j in range(me - 1, -1, -1):
+                if len(pairs) >= (a + 1) * want // max(len(built), 1):
+                    break
+                pairs.append((s, partners[j]))
+        if self.pool:
+            n_chunks = self.cores * 4
+            chunks = [pairs[k::n_chunks] for k in range(n_chunks) if pairs[k::n_chunks]]
+            res = self.pool.map(_pool_pairs, chunks, chunksize=1)
+        else:
+            res = [_pool_pairs(pairs)]
+        dt = time.perf_counter() - t0
+        self.sets.extend(built)
+        return dt, len(built), sum(len(r) for r in res)
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The true
-    reference cannot run here (casadi/cvxpy/cdd absent, no network), so this is
-    the oracle port (kind "port"), split over all host cores, on a bounded sample
-    of the same workload per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from boundplanner_b200 import scenes
-
-    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(N_OBS, N_SEEDS)
-    cores = os.cpu_count() or 1
-    cores = min(cores, 32)
-    per_step = max(cores * 2, 8)
-    for _ in range(args.warmup):
-        cpu_sample(boxes, inflate, ws_min, ws_max, seeds[: max(2, cores)], cores)
-    tot_t, tot_sets, tot_pairs = 0.0, 0, 0
-    for k in range(args.steps):
-        sel = seeds[(k * per_step) % N_SEEDS: (k * per_step) % N_SEEDS + per_step]
-        t, ns, npairs = cpu_sample(boxes, inflate, ws_min, ws_max, sel, cores)
+def cpu_measure(cores, n_seeds, steps, warmup, partner_sets=None):
+    arm = CpuArm(cores)
+    # partners for the pair checks: enough sets that the first timed step already finds 127.5 per new set
+    # (untimed: sets handed in by the caller, else built here)
+    need = int(PAIRS_PER_SET) + 1
+    if partner_sets:
+        arm.sets.extend(partner_sets[:need])
+    while len(arm.sets) < need:
+        arm.step(min(n_seeds, need))
+    for _ in range(warmup):
+        arm.step(n_seeds)
+    tot_t = tot_sets = tot_pairs = 0
+    for _ in range(steps):
+        t, ns, npairs = arm.step(n_seeds)
         tot_t += t
         tot_sets += ns
         tot_pairs += npairs
+    arm.close()
+    return tot_t, tot_sets, tot_pairs
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The true reference cannot run here
+    (casadi / cvxpy / cdd / pinocchio absent, no network), so this is the oracle port (kind "port") on all host
+    cores, a bounded sample of the same workload per step: 2 seeds per core + 127.5 pair checks per set."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(os.cpu_count() or 1, 32)
+    per_step = 2 * cores
+    tot_t, tot_sets, tot_pairs = cpu_measure(cores, per_step, args.steps, min(args.warmup, 2))
     value = tot_sets / tot_t
+    sample = (f"{per_step} of the {N_SEEDS} C2 seeds + {int(round(per_step * PAIRS_PER_SET))} pair checks per step "
+              f"(the GPU arm's {PAIRS_PER_SET} pairs per set), oracle port (vectorised NumPy + barrier MVIE, "
+              f"scipy linprog/HiGHS per pair) on a persistent pool of {cores} processes; scene ingest and pool "
+              "start outside the timed region")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{per_step} seeds + their pair checks per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} of the {N_SEEDS} C2 seeds per step, vectorised NumPy oracle "
-                                   f"(oracle/convex_set_finder.py) over {cores} processes + scipy linprog per pair"},
+        "config": config_dict(1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "pair_checks_per_sec": tot_pairs / tot_t,
+        "pair_checks_per_sec": tot_pairs / tot_t, "sets_timed": tot_sets, "pairs_timed": tot_pairs,
     }
     print(json.dumps(line))
 
@@ -211,7 +276,7 @@ def run_gpu(args):
         return geo.pair_feasible(A, b, m, tol, r0, r1)
 
     # single GPU: static buffers + one CUDA graph per step (boundplanner_b200/pipeline.py);
-    # multi GPU: the same kernels eagerly around the NCCL all-gathers
+    # multi GPU: one CUDA graph per rank with the exchange by peer stores (or the NCCL all-gather pipeline)
     pipe = None
     if world == 1 and not args.no_cuda_graph:
         from boundplanner_b200.pipeline import SetGraphPipeline
@@ -220,12 +285,10 @@ def run_gpu(args):
         pipe.seeds_dev.copy_(seeds_dev)
 
     spipe = None
+    peer_note = None
     if world > 1 and not args.no_cuda_graph:
         from boundplanner_b200.pipeline import PeerSetGraphPipeline, ShardedSetGraphPipeline
 
-        # exchange by peer stores over NVLink (symmetric memory) in one CUDA graph per step; BPGEO_PEER=0 or a
-        # box without peer mappings -> the NCCL all-gather pipeline
-        peer_note = None
         if os.environ.get("BPGEO_PEER", "1") != "0":
             try:
                 spipe = PeerSetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
@@ -235,6 +298,7 @@ def run_gpu(args):
         if spipe is None:
             spipe = ShardedSetGraphPipeline(scene, N_SEEDS, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
         spipe.seeds_dev.copy_(seeds_dev)
+    is_peer = type(spipe).__name__ == "PeerSetGraphPipeline"
 
     def step_device(seeds_d):
         if pipe is not None:
@@ -269,7 +333,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         out, bits = step_device(seeds_dev)
     barrier()
 
@@ -323,8 +388,46 @@ def run_gpu(args):
     h2d = seeds_host.numel() * 8
     d2h = sum(t.numel() * t.element_size() for t in res)
 
+    # ---- per-stage breakdown of one step (eager launches, CUDA events between the stages; outside the timed region)
+    stages = None
+    if pipe is not None or is_peer:
+        stages = (pipe or spipe).stage_times(reps=7)
+        if world > 1:
+            keys = sorted(stages)
+            tt = torch.tensor([stages[k] for k in keys], dtype=torch.float64, device="cuda")
+            tmax, tmin = tt.clone(), tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            stages = {k: {"max": tmax[i].item(), "min": tmin[i].item()} for i, k in enumerate(keys)}
+
+    # ---- N > 1: the exchanged global graph, re-tested by rank 0 alone from the global set tables
+    adj_equal = None
+    if world > 1 and spipe is not None:
+        gbits = spipe.adjacency_bits().clone()
+        if is_peer:
+            Ag, bg, mg = spipe.Ag, spipe.bg, spipe.mg
+        else:
+            Ag, bg, mg = spipe.Ag, spipe.bg, spipe.mg
+        if rank == 0:
+            single = geo.pair_feasible(Ag, bg, mg, TOL)
+            adj_equal = bool(torch.equal(single, gbits))
+        # every rank's local sets are what the global table holds at its slot
+        own = torch.equal(Ag[rank * N_SEEDS: (rank + 1) * N_SEEDS], out.A)
+        flag = torch.tensor([1.0 if own else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            adj_equal = adj_equal and bool(flag.item() == 1.0)
+
     # ---- per-kernel timing of the dominant kernels (roofline), CUDA events on the launch stream
-    prof = kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch)
+    prof = kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch) if rank == 0 else None
+
+    # ---- the other BASELINE configs (outside the headline's timed region)
+    extras = {}
+    if not args.no_extras:
+        extras["c3"] = bench_c3(args, world, rank, dist, torch)
+        extras["c4"] = bench_c4(args, world, rank, dist, torch, geo, scenes)
+        if rank == 0:
+            extras["c5"] = bench_c5(torch, geo, scenes)
 
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -334,10 +437,10 @@ def run_gpu(args):
     mrows = out.m.cpu().numpy()
     n_pairs = S_total * (S_total - 1) // 2
     value = S_total * args.steps / (dev_ms * 1e-3)
-    fused = os.environ.get("BPGEO_FUSED", "1") != "0" and N_OBS <= 4096
+    fused = os.environ.get("BPGEO_FUSED", "1") != "0"
     # fused: k_iris_fused + aabb + filter + lp;  else state_init, 5x(poly,mvie), final mvie, export, aabb+filter+lp
     launches_per_step = (1 + 3) if fused else (1 + 5 * 2 + 1 + 1 + 3)
-    if type(spipe).__name__ == "PeerSetGraphPipeline":
+    if is_peer:
         launches_per_step += 2                      # the two peer-scatter kernels (barriers are torch's)
     if rank == 0:
         peaks = {}
@@ -346,98 +449,266 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        which = "measured" if "hbm_gbs" in peaks else "fallback"
+        launch = ("one CUDA graph per step" if pipe is not None else
+                  ("one CUDA graph per step; sets and adjacency rows exchanged by peer stores over NVLink + two "
+                   "signal-pad barriers (no NCCL on the data path)"
+                   + ("" if getattr(spipe, "_graph", None) is not None else " [eager: capture refused]"))
+                  if is_peer else
+                  "two CUDA graphs + two NCCL all-gathers per step" if spipe is not None else "eager launches")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_obstacles": N_OBS, "seeds_per_gpu": N_SEEDS, "pairs": n_pairs,
-                       "l2": "flushed between timed steps (256 MiB fill)",
-                       "launch": ("one CUDA graph per step" if pipe is not None else
-                                  ("one CUDA graph per step; sets and adjacency rows exchanged by peer stores over "
-                                   "NVLink + two signal-pad barriers (no NCCL on the data path)"
-                                   + ("" if getattr(spipe, "_graph", None) is not None else " [eager: capture refused]"))
-                                  if type(spipe).__name__ == "PeerSetGraphPipeline" else
-                                  "two CUDA graphs + two NCCL all-gathers per step" if spipe is not None else
-                                  "eager launches"),
-                       "frac_sets_over_20_rows": float((mrows > 20).mean()),
-                       "frac_status_ok": float((status == 0).mean()),
-                       "adjacency_density": float(geo.unpack_adjacency(
-                           spipe.adjacency_bits() if spipe is not None else bits, S_total).sum().item())
-                       / max(n_pairs, 1)},
+            "config": config_dict(world),
+            "run": {"pairs": n_pairs, "launch": launch, "peer_note": peer_note,
+                    "frac_sets_over_20_rows": float((mrows > 20).mean()),
+                    "frac_status_ok": float((status == 0).mean()),
+                    "adjacency_density": float(geo.unpack_adjacency(
+                        spipe.adjacency_bits() if spipe is not None else bits, S_total).sum().item())
+                    / max(n_pairs, 1)},
             "pair_checks_per_sec": n_pairs * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps_in_flight": e2e_depth},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": prof["roofline"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),
-            "roofline_fk": prof["roofline_fk"](hbm_peak, "measured" if "hbm_gbs" in peaks else "fallback"),
+            "stages_ms": stages,
+            "roofline": prof["roofline"](),
+            "roofline_fk": prof["roofline_fk"](hbm_peak, which),
+            "saturated": prof["saturated"],
             "kernels": prof["kernels"],
         }
+        if adj_equal is not None:
+            line["adjacency_equals_single_rank"] = adj_equal
+        line.update(extras)
         if world == 1 and not args.no_plan_latency:
             line["plan_latency"] = plan_latency(not args.no_cpu_baseline)
-        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only): the reference arm's routine
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = 24
-            t, ns, npairs = cpu_sample(boxes, inflate, ws_min, ws_max, seeds0[:n_cpu], 1)
+            cores = min(os.cpu_count() or 1, 32)
+            per_step = 2 * cores
+            gsets = [[a.copy(), b.copy()] for a, b in out.to_sets()]      # pair partners (untimed)
+            t, ns, npairs = cpu_measure(cores, per_step, 6, 1, gsets)
             line["cpu_baseline"] = {
-                "value": ns / t, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"first {n_cpu} of the {N_SEEDS} C2 seeds + their {npairs} pair checks, vectorised NumPy "
-                          "oracle (stronger than the reference's per-obstacle solver loop), 1 core"}
-            # the same port with the reference's loop structure (one QP solve per obstacle and pass), 2 seeds
-            t0 = time.perf_counter()
-            n_loop = len(_oracle_worker((boxes, inflate, ws_min, ws_max, seeds0[:2], True)))
-            line["cpu_baseline"]["per_obstacle_loop_sets_per_sec"] = n_loop / (time.perf_counter() - t0)
+                "value": ns / t, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"6 steps of {per_step} C2 seeds + {int(round(per_step * PAIRS_PER_SET))} pair checks each "
+                          f"({ns} sets, {npairs} pairs), oracle port on a persistent pool of {cores} processes "
+                          "(the routine of --impl reference)"}
+            t1, ns1, np1 = cpu_measure(1, 6, 1, 0, gsets)
+            line["cpu_baseline"]["one_core_sets_per_sec"] = ns1 / t1
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------
+# C3: batched planning queries (BASELINE configs[2]) -- queries sharded over the ranks, no communication
+# ----------------------------------------------------------------------------
+def bench_c3(args, world, rank, dist, torch):
+    from scipy.spatial.transform import Rotation as R
+
+    from boundplanner_b200 import scenes
+    from boundplanner_b200.planner import plan_batch
+
+    nq = args.c3_queries
+    r0 = R.from_euler("XYZ", [0, 90, 0], degrees=True).as_matrix()
+    ids = list(range(rank * nq, (rank + 1) * nq))
+    queries = []
+    for i in ids:
+        ob, infl, st, en, wmin, wmax = scenes.config_c3_query(i)
+        queries.append(dict(obstacles=ob, start=st, end=en, r0=r0, r1=r0))
+    wmin, wmax = list(wmin), list(wmax)
+    plan_batch(queries[:8], 0.01, wmax, wmin, rng_seeds=ids[:8])          # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    results, stats = plan_batch(queries, 0.01, wmax, wmin, rng_seeds=ids)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    lat = np.asarray(stats["finish_s"]) * 1e3
+    ok = np.array([not isinstance(r, Exception) for r in results])
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+        lat_all = [torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(lat_all, torch.as_tensor(lat, device="cuda"))
+        lat = torch.cat(lat_all).cpu().numpy()
+        okc = torch.tensor([float(ok.sum())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(okc)
+        n_ok = int(okc.item())
+    else:
+        n_ok = int(ok.sum())
+    return {"what": "C3: independent planning queries over 200-obstacle scenes, plan_convex_set_path up to the planned "
+                    "set sequence, lock-step batched kernel calls; queries sharded over the ranks",
+            "queries_per_gpu": nq, "queries": nq * world, "plan_queries_per_sec": nq * world / dt, "seconds": dt,
+            "latency_ms_p50": float(np.percentile(lat, 50)), "latency_ms_p95": float(np.percentile(lat, 95)),
+            "latency_over": "all queries incl. the reference's error exits (completion time inside the lock-step batch)",
+            "success_fraction": n_ok / (nq * world), "rounds_rank0": stats["rounds"],
+            "kernel_batches_rank0": stats["kernel_batches"]}
+
+
+# ----------------------------------------------------------------------------
+# C4: 10k obstacles, 2048 seeds, full intersection graph (BASELINE configs[3]); strong scaling over the ranks
+# ----------------------------------------------------------------------------
+def bench_c4(args, world, rank, dist, torch, geo, scenes):
+    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c4()
+    S = seeds.shape[0]
+    scene = geo.Scene(boxes, inflate)
+    reps = 5
+    if world == 1:
+        from boundplanner_b200.pipeline import SetGraphPipeline
+
+        pipe = SetGraphPipeline(scene, S, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
+        pipe.seeds_dev.copy_(torch.as_tensor(seeds).cuda())
+        run = pipe.run_device
+        st_fn = pipe.stage_times
+        mode = "one CUDA graph"
+    else:
+        from boundplanner_b200.pipeline import PeerSetGraphPipeline
+
+        s_loc = S // world
+        pipe = PeerSetGraphPipeline(scene, s_loc, ws_min, ws_max, fixed_mid=True, optimize=True, tol=TOL)
+        pipe.seeds_dev.copy_(torch.as_tensor(seeds[rank * s_loc: (rank + 1) * s_loc]).cuda())
+        run = pipe.run_device
+        st_fn = pipe.stage_times
+        mode = "one CUDA graph per rank, peer stores over NVLink"
+    for _ in range(3):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = statistics.median(ts)
+    stages = st_fn(reps=3)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+        keys = sorted(stages)
+        sv = torch.tensor([stages[k] for k in keys], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sv, op=dist.ReduceOp.MAX)
+        stages = {k: sv[i].item() for i, k in enumerate(keys)}
+        bits = pipe.adjacency_bits()
+        status = pipe.batch.status
+        mrows = pipe.batch.m
+    else:
+        bits = pipe.bits
+        status = pipe.batch.status
+        mrows = pipe.batch.m
+    n_pairs = S * (S - 1) // 2
+    edges = int(geo.unpack_adjacency(bits, S).sum().item())
+    return {"what": "C4: 10 000 obstacles (shelf plates + clutter), 2048 seeds, full 2 096 128-pair graph; the seeds are "
+                    "split over the ranks (strong scaling), sets exchanged into the global graph",
+            "n_obstacles": int(boxes.shape[0]), "seeds": S, "ms_per_step": ms, "sets_per_sec": S / (ms * 1e-3),
+            "pair_checks_per_sec": n_pairs / (ms * 1e-3), "stages_ms": stages, "launch": mode,
+            "edges": edges, "frac_status_ok_rank0": float((status == 0).double().mean().item()),
+            "frac_over_20_rows_rank0": float((mrows > 20).double().mean().item())}
+
+
+# ----------------------------------------------------------------------------
+# C5: the geometry of one MPC step (BASELINE configs[4]): 12 FK evaluations + 6 line sets (BoundMPC.py:480-496)
+# plus the loop's own forward_kinematics(q, dq) (MPCNode.py:118)
+# ----------------------------------------------------------------------------
+def bench_c5(torch, geo, scenes):
+    import boundplanner_b200 as bp
+    from boundplanner_b200 import mpc_geometry
+
+    boxes, ws_min, ws_max, _ = scenes.example_scene()
+    scene = geo.Scene(boxes, 0.0)                                   # obs_size_increase = 0.0 in the MPC (BoundMPC.py:265)
+    q_a = np.array([0, 0, 0, -np.pi / 2, 0, np.pi / 2, 0.0])        # boundplanner_with_mpc_example.py:20-26
+    q_b = q_a + np.array([0.6, 0.4, -0.3, 0.5, 0.2, -0.4, 0.3])
+    n = 200
+    traj = [q_a + (q_b - q_a) * 0.5 * (1 - np.cos(np.pi * k / (n - 1))) for k in range(n + 10)]
+    model = bp.RobotModel()
+    for k in range(5):
+        mpc_geometry.collision_sets(scene, traj[k], traj[k + 10], ws_min, ws_max)
+        model.forward_kinematics(traj[k], traj[k + 1] - traj[k])
+    torch.cuda.synchronize()
+    lat = []
+    for k in range(n):
+        t0 = time.perf_counter()
+        p_lie, jac, djac = model.forward_kinematics(traj[k], (traj[k + 1] - traj[k]) / 0.1)       # MPCNode.py:118
+        a_sets, b_sets, coll = mpc_geometry.collision_sets(scene, traj[k], traj[k + 10], ws_min, ws_max)
+        lat.append((time.perf_counter() - t0) * 1e6)
+    # the same geometry for a whole horizon sweep in one batch (T = 200 (q0, qf) pairs): device-side rate
+    q0 = np.array(traj[:n])
+    qf = np.array(traj[10: n + 10])
+    mpc_geometry.collision_sets(scene, q0, qf, ws_min, ws_max)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        mpc_geometry.collision_sets(scene, q0, qf, ws_min, ws_max)
+    torch.cuda.synchronize()
+    batched_us = (time.perf_counter() - t0) / 5 / n * 1e6
+    return {"what": "C5: geometry of one MPC step through the drop-in API from host arrays -- forward_kinematics(q, dq) "
+                    "+ 12 FK evaluations + 6 find_set_collision_avoidance(limit_space=True, e_max=0.7) over the 12 "
+                    "example obstacles, results back on the host",
+            "steps": n, "us_per_mpc_step_p50": float(np.percentile(lat, 50)),
+            "us_per_mpc_step_p95": float(np.percentile(lat, 95)),
+            "us_per_mpc_step_batched_200": batched_us}
 
 
 def plan_latency(with_cpu):
     """p50 plan latency (BASELINE.json metric, third part): SetSequencePlanner.plan_set_sequence -- the
-    reference's plan_convex_set_path up to the planned set sequence -- on the C1 example and on the
-    C3-style queries that plan successfully, every primitive a batch-of-one kernel call."""
-    import statistics
-
+    reference's plan_convex_set_path up to the planned set sequence -- one query at a time (every primitive a
+    batch-of-one kernel call) on the C1 example and on the first 24 C3 queries, failures included."""
     from scipy.spatial.transform import Rotation as R
 
     from boundplanner_b200 import scenes
-    from boundplanner_b200.planner import SetSequencePlanner
+    from boundplanner_b200.planner import GpuBackend, SetSequencePlanner
 
     r0 = R.from_euler("XYZ", [0, 90, 0], degrees=True).as_matrix()
 
     def cases():
         boxes, ws_min, ws_max, inflate = scenes.example_scene()
         yield "C1", boxes, inflate, np.array([0.3, 0.0, 0.7]), np.array([0.45, -0.5, 0.2]), ws_min, ws_max, 0
-        for i in (0, 7, 8, 11):
+        for i in range(24):
             ob, infl, st, en, wmin, wmax = scenes.config_c3_query(i)
             yield f"C3[{i}]", ob, infl, st, en, wmin, wmax, i
 
-    def run(backend_factory, names=None):
+    def run(backend_factory, names=None, reps=2):
         lat = {}
         for name, ob, infl, st, en, wmin, wmax, seed in cases():
             if names is not None and name not in names:
                 continue
             backend = backend_factory(ob, infl, list(wmax), list(wmin))
-            for rep in range(3 if names is None else 1):
+            for rep in range(reps):
                 planner = SetSequencePlanner(ob, infl, list(wmax), list(wmin), backend=backend,
                                              rng=np.random.default_rng(seed))
                 t0 = time.perf_counter()
-                res = planner.plan_set_sequence(st.copy(), en.copy(), r0, r0)
-                lat[name] = (time.perf_counter() - t0) * 1e3, len(res["set_ids"]), res["graph"].number_of_nodes()
+                try:
+                    res = planner.plan_set_sequence(st.copy(), en.copy(), r0, r0)
+                    info = (len(res["set_ids"]), res["graph"].number_of_nodes(), True)
+                except (RuntimeError, ValueError):
+                    info = (0, 0, False)
+                lat[name] = ((time.perf_counter() - t0) * 1e3,) + info
         return lat
-
-    from boundplanner_b200.planner import GpuBackend
 
     gpu = run(GpuBackend)
     vals = sorted(v[0] for v in gpu.values())
-    out = {"unit": "ms", "p50": statistics.median(vals), "max": vals[-1],
-           "queries": {k: {"ms": v[0], "sets_in_sequence": v[1], "sets_built": v[2]} for k, v in gpu.items()},
+    vals_ok = sorted(v[0] for v in gpu.values() if v[3])
+    out = {"unit": "ms", "p50": statistics.median(vals), "p95": float(np.percentile(vals, 95)), "max": vals[-1],
+           "p50_successful": statistics.median(vals_ok) if vals_ok else None,
+           "queries": len(vals), "success_fraction": len(vals_ok) / len(vals),
+           "c1_ms": gpu["C1"][0],
            "what": "plan_convex_set_path up to the planned set sequence (no final Ipopt NLP), host loop + "
-                   "batch-of-one kernel calls"}
+                   "batch-of-one kernel calls; C1 + the first 24 C3 queries, the reference's error exits included"}
     if with_cpu:
         from tests.util import OracleBackend
 
-        cpu = run(OracleBackend, names=("C1", "C3[7]"))
+        cpu = run(OracleBackend, names=("C1", "C3[7]"), reps=1)
         out["cpu_port_ms"] = {k: v[0] for k, v in cpu.items()}
     return out
 
@@ -446,9 +717,8 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
     """Time the kernels of one step in isolation (CUDA events on the launch stream,
     several back-to-back launches per measurement) and build the roofline entries."""
     import ctypes
-    import statistics
 
-    from boundplanner_b200 import _lib
+    from boundplanner_b200 import _lib, scenes
     from boundplanner_b200.robot_model import Q_LIM_UPPER
 
     def timeit(fn, reps=5, inner=4):
@@ -496,6 +766,27 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
                      reps=3, inner=1)
     fp64_peak_tflops = 296 * 256 * 8 * iters * 2 / (t_probe * 1e-3) / 1e12
 
+    def algorithmic_flops(n_seeds, passes, rows, n_fm, n_free):
+        # SURVEY 8(d) per-unit figures: per (seed, obstacle, pass) closest-point QP 1.1 kflop + 64 flop per picked
+        # row and obstacle (exclusion test); per Newton iteration of an MVIE m*200 + 250 flop
+        picks = max(rows - 6.0, 0.0)
+        return n_seeds * (passes * N * (1100.0 + 64.0 * picks) + (passes * n_fm + n_free) * (rows * 200.0 + 250.0))
+
+    # the chip filled: the same set build with 2048 seeds (8 x the headline batch) in ONE launch
+    S_sat = 2048
+    seeds_sat = scenes.free_points(S_sat, scenes.config_c2(N_OBS, 8)[0], 0.01, np.random.default_rng(7), ws_min, ws_max)
+    seeds_sat_dev = torch.as_tensor(seeds_sat).cuda()
+    sb_sat = geo.alloc_set_batch(S_sat)
+    t_sat = timeit(lambda: geo.build_sets_point(scene, seeds_sat_dev, ws_min, ws_max, fixed_mid=True, optimize=True,
+                                                out=sb_sat), reps=5, inner=2)
+    passes_sat = float(torch.clamp(sb_sat.iters.double(), max=5).mean().item())
+    rows_sat = float(sb_sat.m.double().mean().item())
+    flops_sat = algorithmic_flops(S_sat, passes_sat, rows_sat, newton_fm, newton_free)
+    saturated = {"what": "k_iris_fused on the C2 scene with 2048 seeds in one launch (all SMs occupied)",
+                 "seeds": S_sat, "ms": t_sat, "sets_per_sec": S_sat / (t_sat * 1e-3),
+                 "fp64_tflops_algorithmic": flops_sat / (t_sat * 1e-3) / 1e12,
+                 "frac_of_fp64_peak": flops_sat / (t_sat * 1e-3) / 1e12 / fp64_peak_tflops}
+
     # K7 FK micro-benchmark (C5): B = 2^20 configurations, inputs larger than L2 are flushed between runs
     B = 1 << 20
     lim = torch.as_tensor(Q_LIM_UPPER, device="cuda")
@@ -520,41 +811,34 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
         "newton_iters_free": newton_free, "mean_rows": m_mean, "fp64_peak_tflops_measured": fp64_peak_tflops,
     }
 
-    def roofline(hbm_peak, which):
-        # dominant kernel of the step: the set build (k_iris_fused: one launch = the whole IRIS loop of S seeds;
-        # with BPGEO_FUSED=0 the same work is the (k_poly_point, k_mvie) launch sequence).
-        # Algorithmic bytes per launch: seeds in, the scene once, one padded set + ellipsoid
-        # out per seed.  Algorithmic flops: passes x [N x (1.1 kflop QP + 64 flop x picked rows)] per seed for
-        # the polyhedron passes + Newton iterations x (m x 200 + 250) flop for the MVIEs (passes + 1 per seed).
-        # (SURVEY 8d's per-unit figures; the kernel itself solves far fewer QPs than N per pass -- lazy lower
-        # bounds -- so this is the reference algorithm's work per second, not executed instructions.)
-        picks = max(m_mean - 6.0, 0.0)
+    def roofline():
+        # Dominant kernel of the step: the set build (k_iris_fused: one launch = the whole IRIS loop of S seeds).
+        # set build and pair LP are bound by the FP64 CUDA-core pipe, not by HBM (operands live in
+        # shared memory / L2).  achieved = ALGORITHMIC flops per launch (the reference algorithm's work: N
+        # closest-point QPs per pass although the kernel's lazy bounds skip most of them) / measured duration;
+        # peak = this GPU's FP64 pipe measured by a DFMA probe in this run (MEASURED_PEAKS.json has no FP64 entry).
+        flops = algorithmic_flops(S, passes_mean, m_mean, newton_fm, newton_free)
+        ach = flops / (t_build * 1e-3) / 1e12
         bytes_alg = S * 24 + N * 48 + S * (m_mean * 32 + 12 * 8 + 12)
-        flops = S * (passes_mean * N * (1100.0 + 64.0 * picks)
-                     + (passes_mean * newton_fm + newton_free) * (m_mean * 200.0 + 250.0))
-        dur = t_build
-        ach = bytes_alg / (dur * 1e-3) / 1e9
         return {"kernel": "k_iris_fused (set build: whole find_set_around_point loop, one CTA per seed)",
-                "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": 191744, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_final2_iris_fused.txt",
-                "peak_source": which,
-                "note": "latency-bound fp64 kernel: 256 independent chains of ~5 x (polyhedron pass + ~35 dependent "
-                        "Newton iterations); it moves only its compulsory bytes (operands live in L2 / shared "
-                        "memory), so the HBM fraction is tiny by construction -- see fp64 below, and roofline_fk "
-                        "for the HBM-bound kernel of the path",
-                "fp64": {"achieved_gflops": flops / (dur * 1e-3) / 1e9, "peak_gflops": fp64_peak_tflops * 1e3,
-                         "frac": flops / (dur * 1e-3) / 1e12 / fp64_peak_tflops}}
+                "bound": "fp64", "achieved": ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                "frac": ach / fp64_peak_tflops, "traffic": 191744,
+                "traffic_source": "ncu dram__bytes_read+write per launch (profiles/): compulsory bytes only "
+                                  f"(algorithmic bytes {int(bytes_alg)})",
+                "peak_source": "bp_probe_fp64: independent DFMA chains on all SMs, measured in this run",
+                "algorithmic_gflop_per_launch": flops / 1e9, "launch_ms": t_build,
+                "note": "latency-bound at 256 seeds (one CTA per seed, 256 CTAs on 148 SMs); `saturated` gives the "
+                        "same kernel with the chip filled; roofline_fk is the HBM-bound kernel of the path"}
 
     def roofline_fk(hbm_peak, which):
         ach = fk_bytes / (t_fk * 1e-3) / 1e9
         return {"kernel": "k_fk<false,false> (B = 2^20 configurations, 248 B each)", "bound": "hbm", "achieved": ach,
                 "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 201795328,
                 "traffic_source": "ncu dram__bytes_read+write per launch (below the 260 MB algorithmic bytes: part "
-                                  "of the output is still dirty in the 126 MB L2 at kernel end), "
-                                  "profiles/r01_ncu_final2_pair_fk.txt",
+                                  "of the output is still dirty in the 126 MB L2 at kernel end), profiles/",
                 "peak_source": which, "poses_per_sec": B / (t_fk * 1e-3)}
 
-    return {"kernels": kernels, "roofline": roofline, "roofline_fk": roofline_fk}
+    return {"kernels": kernels, "roofline": roofline, "roofline_fk": roofline_fk, "saturated": saturated}
 
 
 def main():
@@ -563,9 +847,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--c3-queries", type=int, default=128, help="C3 planning queries per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plan-latency", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C4 / C5 measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

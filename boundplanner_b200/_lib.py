@@ -56,6 +56,8 @@ SIGNATURES = {
     "bp_pair_workspace_bytes": (_sz, [_i, _i]),
     "bp_set_aabb": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "bp_pair_feasible": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bp_pair_feasible_stages": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp,
+                                    _c.POINTER(_c.c_float)]),
     "bp_reduce_ineqs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_check_fit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _dp, _i, _d, _vp, _vp, _vp]),
     "bp_project_points": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),

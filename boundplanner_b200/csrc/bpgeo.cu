@@ -2758,9 +2758,10 @@ int bp_set_aabb(const double* A_dev, const double* b_dev, const int* m_dev, int 
   return 0;
 }
 
-int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
-                     int row_begin, int row_end, unsigned int* adj_bits_dev, double* x_feas_dev,
-                     const double* aabb_in_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+static int pair_feasible_impl(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                              int row_begin, int row_end, unsigned int* adj_bits_dev, double* x_feas_dev,
+                              const double* aabb_in_dev, void* workspace_dev, size_t workspace_bytes, void* stream_,
+                              cudaEvent_t* ev) {
   if (S < 0 || row_begin < 0 || row_end > S || row_begin > row_end || m_max < 1 || m_max > BP_MAX_ROWS)
     return bp_fail("bp_pair_feasible: bad arguments");
   if (row_end == row_begin) return 0;
@@ -2773,10 +2774,13 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   const int words = (S + 31) / 32;
   BP_CUDA(cudaMemsetAsync(adj_bits_dev, 0, sizeof(unsigned int) * (size_t)rows * words, stream));
   BP_CUDA(cudaMemsetAsync(count, 0, 16, stream));
+  if (ev) BP_CUDA(cudaEventRecord(ev[0], stream));
   if (aabb_in_dev) aabb = const_cast<double*>(aabb_in_dev);      // boxes computed elsewhere (e.g. all-gathered)
   else k_set_aabb<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb);
+  if (ev) BP_CUDA(cudaEventRecord(ev[1], stream));
   dim3 grid((S + 31) / 32, (rows + 7) / 8);
   k_pair_filter<<<grid, 256, 0, stream>>>(aabb, S, row_begin, row_end, list, count);
+  if (ev) BP_CUDA(cudaEventRecord(ev[2], stream));
   int nsm = 148;
   {
     int dev = 0;
@@ -2788,8 +2792,34 @@ int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev,
   if (ctas < 1) ctas = 1;
   k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count, adj_bits_dev,
                                                        x_feas_dev);
+  if (ev) BP_CUDA(cudaEventRecord(ev[3], stream));
   BP_CUDA(cudaGetLastError());
   return 0;
+}
+
+int bp_pair_feasible(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                     int row_begin, int row_end, unsigned int* adj_bits_dev, double* x_feas_dev,
+                     const double* aabb_in_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  return pair_feasible_impl(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, row_end, adj_bits_dev, x_feas_dev, aabb_in_dev,
+                            workspace_dev, workspace_bytes, stream_, nullptr);
+}
+
+int bp_pair_feasible_stages(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                            int row_begin, int row_end, unsigned int* adj_bits_dev, const double* aabb_in_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream_, float* ms_host) {
+  if (!ms_host) return bp_fail("bp_pair_feasible_stages: bad arguments");
+  ms_host[0] = ms_host[1] = ms_host[2] = 0.f;
+  if (row_end <= row_begin) return 0;
+  cudaEvent_t ev[4];
+  for (int k = 0; k < 4; ++k) BP_CUDA(cudaEventCreate(&ev[k]));
+  int rc = pair_feasible_impl(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, row_end, adj_bits_dev, nullptr, aabb_in_dev,
+                              workspace_dev, workspace_bytes, stream_, ev);
+  if (rc == 0) {
+    BP_CUDA(cudaEventSynchronize(ev[3]));
+    for (int k = 0; k < 3; ++k) BP_CUDA(cudaEventElapsedTime(&ms_host[k], ev[k], ev[k + 1]));
+  }
+  for (int k = 0; k < 4; ++k) cudaEventDestroy(ev[k]);
+  return rc;
 }
 
 int bp_pairs_feasible_list(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,

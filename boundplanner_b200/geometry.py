@@ -382,6 +382,22 @@ def pair_feasible(A, b, m, tol=0.01, row_begin=0, row_end=None, want_points=Fals
     return bits
 
 
+def pair_feasible_stages(A, b, m, tol=0.01, row_begin=0, row_end=None, out=None, aabb=None):
+    """Diagnostics: pair_feasible with CUDA events between its kernels; synchronises and returns
+    {"aabb": ms, "filter": ms, "lp": ms} (aabb = 0 when the boxes are given)."""
+    lib = _lib.load()
+    S, m_max = A.shape[0], A.shape[1]
+    if row_end is None:
+        row_end = S
+    if out is None:
+        out = alloc_pair_buffers(S, row_end - row_begin)
+    bits, work = out
+    ms = (ctypes.c_float * 3)()
+    check(lib.bp_pair_feasible_stages(_ptr(A), _ptr(b), _ptr(m), S, m_max, float(tol), int(row_begin), int(row_end),
+                                      _ptr(bits), _ptr(aabb), _ptr(work), work.numel(), _stream(), ms))
+    return {"aabb": float(ms[0]), "filter": float(ms[1]), "lp": float(ms[2])}
+
+
 def reduce_ineqs(A, b, m):
     """reduce_ineqs (util_functions.py:82-88) for S sets: returns (A_red, b_red, m_red, keep [S,m_max] bool)."""
     lib = _lib.load()

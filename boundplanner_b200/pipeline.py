@@ -68,6 +68,23 @@ class SetGraphPipeline:
             self._enqueue()
         self._graph = g
 
+    def stage_times(self, reps=5):
+        """Per-stage device time of one step in ms (median of `reps` eager steps, CUDA events between the kernels on
+        the launch stream): k_iris_fused | k_set_aabb | k_pair_filter | k_pair_lp."""
+        import statistics
+
+        acc = {"build": [], "aabb": [], "filter": [], "lp": []}
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
+            e1.record()
+            st = geo.pair_feasible_stages(self.batch.A, self.batch.b, self.batch.m, self.tol, out=self.pair_buf)
+            acc["build"].append(e0.elapsed_time(e1))
+            for k, v in st.items():
+                acc[k].append(v)
+        return {k: statistics.median(v) for k, v in acc.items()}
+
     def run_device(self):
         """Inputs already in self.seeds_dev; enqueue one step on the current stream."""
         if self._graph is not None:
@@ -340,6 +357,54 @@ class PeerSetGraphPipeline:
             geo.check(lib.bp_scatter_rows_peers(geo._ptr(bits), rows, self.words, self.r0, geo._ptr(self.peer_base),
                                                 self.world, self.off_bits, st))
         self.hdl.barrier(channel=1)
+
+    def stage_times(self, reps=5):
+        """Per-stage device time of one step on THIS rank in ms (median of `reps` eager steps with CUDA events
+        between the stages).  barrier0 = waiting for the slowest rank's sets, barrier1 = for its adjacency rows."""
+        import statistics
+
+        names = ["build", "aabb", "scatter_sets", "barrier0", "filter", "lp", "scatter_rows", "barrier1"]
+        acc = {k: [] for k in names}
+        lib, st = self._lib, geo._stream()
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            self.hdl.barrier(channel=0)                  # start the ranks together, like back-to-back steps do
+            ev[0].record()
+            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
+            ev[1].record()
+            geo.set_aabb(self.batch.A, self.batch.b, self.batch.m, out=self.aabb_loc)
+            ev[2].record()
+            geo.check(lib.bp_scatter_sets_peers(geo._ptr(self.batch.A), geo._ptr(self.batch.b), geo._ptr(self.batch.m),
+                                                geo._ptr(self.aabb_loc), self.S_loc, self.m_max, self.rank * self.S_loc,
+                                                geo._ptr(self.peer_base), self.world, self.off_A, self.off_b,
+                                                self.off_m, self.off_aabb, st))
+            ev[3].record()
+            self.hdl.barrier(channel=0)
+            ev[4].record()
+            rows = self.r1 - self.r0
+            pst = {"filter": 0.0, "lp": 0.0}
+            bits = self.pair_buf[0][:max(rows, 0)]
+            if rows > 0:
+                pst = geo.pair_feasible_stages(self.Ag, self.bg, self.mg, self.tol, self.r0, self.r1,
+                                               out=(bits, self.pair_buf[1]), aabb=self.aabb_g)
+            ev[5].record()
+            if rows > 0:
+                geo.check(lib.bp_scatter_rows_peers(geo._ptr(bits), rows, self.words, self.r0, geo._ptr(self.peer_base),
+                                                    self.world, self.off_bits, st))
+            ev[6].record()
+            self.hdl.barrier(channel=1)
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            torch.cuda.synchronize()
+            acc["build"].append(ev[0].elapsed_time(ev[1]))
+            acc["aabb"].append(ev[1].elapsed_time(ev[2]))
+            acc["scatter_sets"].append(ev[2].elapsed_time(ev[3]))
+            acc["barrier0"].append(ev[3].elapsed_time(ev[4]))
+            acc["filter"].append(pst["filter"])
+            acc["lp"].append(pst["lp"])
+            acc["scatter_rows"].append(ev[5].elapsed_time(ev[6]))
+            acc["barrier1"].append(ev[6].elapsed_time(end))
+        return {k: statistics.median(v) for k, v in acc.items()}
 
     def _capture(self):
         self._stream.wait_stream(torch.cuda.current_stream())

@@ -584,7 +584,11 @@ def plan_batch(queries, obs_size_increase=0.01, workspace_max=(1.0, 1.0, 1.2), w
     if executor is None:
         executor = BatchedGpuExecutor([q["obstacles"] for q in queries], obs_size_increase, workspace_max,
                                       workspace_min)
+    import time
+
+    t_start = time.perf_counter()
     planners, gens, pending, results = [], {}, {}, [None] * len(queries)
+    finish = [0.0] * len(queries)              # seconds after the start of the batch at which query i was answered
     for i, q in enumerate(queries):
         pl = SetSequencePlanner(q["obstacles"], obs_size_increase, workspace_max, workspace_min,
                                 rng=np.random.default_rng(rng_seeds[i] if rng_seeds is not None else None))
@@ -594,8 +598,10 @@ def plan_batch(queries, obs_size_increase=0.01, workspace_max=(1.0, 1.0, 1.2), w
             pending[i] = next(gens[i])
         except StopIteration as stop:
             results[i] = stop.value
+            finish[i] = time.perf_counter() - t_start
         except (RuntimeError, ValueError) as e:
             results[i] = e
+            finish[i] = time.perf_counter() - t_start
     rounds = 0
     while pending:
         rounds += 1
@@ -606,7 +612,9 @@ def plan_batch(queries, obs_size_increase=0.01, workspace_max=(1.0, 1.0, 1.2), w
                 nxt[i] = gens[i].throw(ans) if isinstance(ans, Exception) else gens[i].send(ans)
             except StopIteration as stop:
                 results[i] = stop.value
+                finish[i] = time.perf_counter() - t_start
             except (RuntimeError, ValueError) as e:
                 results[i] = e
+                finish[i] = time.perf_counter() - t_start
         pending = nxt
-    return results, {"rounds": rounds, "kernel_batches": executor.calls}
+    return results, {"rounds": rounds, "kernel_batches": executor.calls, "finish_s": finish}

@@ -170,6 +170,12 @@ int bp_pair_feasible(const double* A_dev /*[S,m_max,3]*/, const double* b_dev /*
                      const double* aabb_in_dev /* NULL or [S,6] from bp_set_aabb */,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Diagnostics (bench.py's per-stage breakdown): the same launches as bp_pair_feasible with CUDA events between
+ * them; synchronises and writes ms_host[3] = { k_set_aabb (0 when aabb_in_dev is given), k_pair_filter, k_pair_lp }. */
+int bp_pair_feasible_stages(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,
+                            int row_begin, int row_end, unsigned int* adj_bits_dev, const double* aabb_in_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream, float* ms_host);
+
 /* The same test over an explicit list of pairs (i, j) (pairs_dev [P,2] int32): result[P] = 1/0,
  * x_feas[P,3] (or NULL).  Workspace: 6*S doubles. */
 int bp_pairs_feasible_list(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, double tol,

@@ -1,5 +1,7 @@
 """GPU: the reference-facing drop-in classes behave like the reference's (as
 restated by the oracle) on the C1 example scene (boundplanner_example.py:19-92)."""
+import os
+
 import numpy as np
 import pytest
 
