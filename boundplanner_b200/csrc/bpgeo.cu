@@ -650,6 +650,258 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
   *status_out = status;
 }
 
+// ---------------------------------------------------------------------------
+// compute_polyhedron pass for BOX scenes, "shell" form (same picks, same rows as poly_pass_point<false>):
+//   A  every thread writes a cheap lower bound (squared, pass metric) of its obstacles' distances: key2[j];
+//   B  the obstacles whose bound does not exceed thr = max(smallest exact distance known, GROW x smallest bound)
+//      move into the SHELL (<= BP_SHELL slots in shared memory) and get their exact closest-point QP, one per
+//      thread in parallel;
+//   C  warp 0 alone runs the reference's greedy loop (ConvexSetFinder.py:431-458) over the shell while its
+//      nearest entry is within thr -- every obstacle outside the shell is farther than thr, so the pick is the
+//      global argmin (ties -> lowest obstacle index, quirk Q11): warp argmin by redux.sync, halfspace, vertex
+//      test of the shell entries (boxes kept in the shell) -- no block barrier per pick;
+//   D  all threads apply the new halfspaces to the obstacles outside the shell (vertex test, :447-458) and
+//      recompute the smallest remaining bound; back to B until nothing is left.
+// A pass costs 2-3 rounds of four barriers instead of two barriers per pick and per refinement round.
+// Shell overflow (more than BP_SHELL obstacles within thr, e.g. a degenerate metric) -> *fallback = 1 and the
+// caller reruns the pass with poly_pass_point.
+// ---------------------------------------------------------------------------
+#define BP_SHELL 128
+struct ShellMem {
+  double dist[BP_SHELL];               // exact distance (:429); +inf = free slot
+  double y[3][BP_SHELL];               // closest point on the obstacle
+  double lb[3][BP_SHELL], ub[3][BP_SHELL];
+  double pick[BP_MAX_ROWS][4];         // halfspaces picked since the last sweep over the obstacles outside the shell
+  double exmin;                        // smallest exact distance left in the shell
+  int idx[BP_SHELL];                   // obstacle index of a slot
+  int free_list[BP_SHELL];             // free slots
+  int new_list[BP_SHELL];              // slots filled in this round (exact QP pending)
+  int n_free, cnt, n_pick, m_cur, status, pad_;
+};
+
+template <int AW>
+__device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassMetric& pm, const double* p,
+                                                double* s_key, ShellMem* sh, double (*red_val)[32], double* Arow,
+                                                double* brow, int m_max, int* m_out, int* status_out, int* fallback) {
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  BP_PPROF_MARK();
+  PassBound pb;
+  pass_bound_init(pm, &pb);
+  unsigned long long alive[AW];
+#pragma unroll
+  for (int w = 0; w < AW; ++w) alive[w] = 0ull;
+  // ---- A: squared lower bounds of every obstacle (entry k of this thread is obstacle tid + k T)
+  double lmin2 = BP_INF;
+  {
+    int k = 0;
+    for (int j = tid; j < sc.n; j += T, ++k) {
+      double lb[3], ub[3];
+      load_box(sc, j, lb, ub);
+      const double d0 = fmax(fmax(lb[0] - p[0], p[0] - ub[0]), 0.0);
+      const double d1 = fmax(fmax(lb[1] - p[1], p[1] - ub[1]), 0.0);
+      const double d2 = fmax(fmax(lb[2] - p[2], p[2] - ub[2]), 0.0);
+      const double q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2;
+      const double b2 = fmax(fmax(pb.c[0] * q0, pb.c[1] * q1), fmax(pb.c[2] * q2, pb.lmin * ((q0 + q1) + q2)));
+      s_key[j] = b2;
+      alive[k >> 6] |= 1ull << (k & 63);
+      lmin2 = fmin(lmin2, b2);
+    }
+  }
+  for (int e = tid; e < BP_SHELL; e += T) { sh->dist[e] = BP_INF; sh->free_list[e] = e; }
+  if (tid == 0) { sh->n_free = BP_SHELL; sh->cnt = 0; sh->n_pick = 0; sh->m_cur = 6; sh->status = BP_OK; sh->exmin = BP_INF; }
+  int buf = 0;
+  int m_cur = 6, status = BP_OK;
+  BP_PPROF_LAP(0);
+  while (true) {
+    // smallest bound outside the shell (the barrier inside also publishes the shell state written by warp 0)
+    const double bmin2 = block_min_nonneg(lmin2, red_val, buf);
+    const double exmin = sh->exmin;
+    if (!(bmin2 < BP_INF) && !(exmin < BP_INF)) break;                 // no obstacle left
+    double thr = BP_INF, thr2 = BP_INF;
+    if (bmin2 < BP_INF) {
+      thr = fmax(exmin < BP_INF ? exmin : 0.0, BP_LAZY_GROW * sqrt(bmin2));
+      thr2 = thr * thr;
+    }
+    // ---- B: move the obstacles within thr into the shell
+    const int n_free = sh->n_free;
+    unsigned long long taken[AW];
+#pragma unroll
+    for (int w = 0; w < AW; ++w) taken[w] = 0ull;
+    bool over = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (bmin2 < BP_INF) {
+#pragma unroll
+        for (int w = 0; w < AW; ++w) {
+          taken[w] = 0ull;
+          for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+            const int k = __ffsll((long long)mk) - 1;
+            const int j = tid + (k + 64 * w) * T;
+            if (s_key[j] <= thr2) {
+              const int slot = atomicAdd(&sh->cnt, 1);
+              if (slot < n_free) { const int ph = sh->free_list[slot]; sh->idx[ph] = j; sh->new_list[slot] = ph; }
+              taken[w] |= 1ull << k;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      over = sh->cnt > n_free;
+      if (!over) break;
+      __syncthreads();                                   // everybody has read cnt
+      if (tid == 0) sh->cnt = 0;
+      // too many obstacles within GROW x the smallest bound: take only what the next pick needs
+      thr = fmax(exmin < BP_INF ? exmin : 0.0, sqrt(bmin2));
+      thr2 = fmax(thr * thr, bmin2);
+      __syncthreads();
+    }
+    if (over) { *fallback = 1; return; }
+    const int n_new = sh->cnt;
+#pragma unroll
+    for (int w = 0; w < AW; ++w) alive[w] &= ~taken[w];
+    // exact closest points of the new shell entries
+    for (int e = tid; e < n_new; e += T) {
+      const int ph = sh->new_list[e];
+      const int j = sh->idx[ph];
+      double lb[3], ub[3], y[3];
+      load_box(sc, j, lb, ub);
+      const double d = closest_on_box(pm, p, lb, ub, y);
+      sh->dist[ph] = d;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { sh->y[c][ph] = y[c]; sh->lb[c][ph] = lb[c]; sh->ub[c][ph] = ub[c]; }
+    }
+    __syncthreads();
+    BP_PPROF_LAP(2);
+    // ---- C: greedy picks over the shell, warp 0
+    if (warp == 0) {
+      double d[BP_SHELL / 32];
+      int id[BP_SHELL / 32];
+#pragma unroll
+      for (int q = 0; q < BP_SHELL / 32; ++q) { d[q] = sh->dist[lane + 32 * q]; id[q] = sh->idx[lane + 32 * q]; }
+      int m = m_cur, npick = 0, st = BP_OK;
+      while (npick < BP_MAX_ROWS) {
+        double lv = d[0];
+        int li = id[0], lq = 0;
+#pragma unroll
+        for (int q = 1; q < BP_SHELL / 32; ++q)
+          if (d[q] < lv || (d[q] == lv && id[q] < li)) { lv = d[q]; li = id[q]; lq = q; }
+        // warp argmin of non-negative doubles: order of the bit patterns, then the obstacle index
+        const unsigned hi = (unsigned)__double2hiint(lv);
+        const unsigned mh = __reduce_min_sync(full, hi);
+        const unsigned lo = hi == mh ? (unsigned)__double2loint(lv) : 0xffffffffu;
+        const unsigned ml = __reduce_min_sync(full, lo);
+        const bool cand = hi == mh && lo == ml && lv < BP_INF;
+        const unsigned mc = __reduce_min_sync(full, cand ? (unsigned)li : 0xffffffffu);
+        const double val = __hiloint2double((int)mh, (int)ml);
+        if (!(val < BP_INF) || !(val <= thr)) break;            // shell exhausted / the rest needs a wider shell
+        BP_PPROF_COUNT(5);
+        if (val < 0.99) { st = BP_ELLIPSE_VIOLATION; break; }   // :433-438
+        const int src = __ffs(__ballot_sync(full, cand && (unsigned)li == mc)) - 1;
+        const int e = __shfl_sync(full, lane + 32 * lq, src);
+        const double y[3] = {sh->y[0][e], sh->y[1][e], sh->y[2][e]};
+        double zz[3] = {y[0] - p[0], y[1] - p[1], y[2] - p[2]};
+        double a[3];
+        bp_mat3_vec(pm.G, zz, a);
+        a[0] *= 2.0; a[1] *= 2.0; a[2] *= 2.0;           // 2 (Q Q^T)(cp - p)   (:440)
+        double bh = a[0] * y[0] + a[1] * y[1] + a[2] * y[2];
+        double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        a[0] /= nrm; a[1] /= nrm; a[2] /= nrm; bh /= nrm;
+        if (lane == 0) {
+          if (m < m_max) { Arow[3 * m + 0] = a[0]; Arow[3 * m + 1] = a[1]; Arow[3 * m + 2] = a[2]; brow[m] = bh; }
+          sh->pick[npick][0] = a[0]; sh->pick[npick][1] = a[1]; sh->pick[npick][2] = a[2]; sh->pick[npick][3] = bh;
+        }
+        ++m; ++npick;
+        // delete the winner and every shell obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458)
+#pragma unroll
+        for (int q = 0; q < BP_SHELL / 32; ++q) {
+          if (d[q] < BP_INF) {
+            const int s = lane + 32 * q;
+            const double l3[3] = {sh->lb[0][s], sh->lb[1][s], sh->lb[2][s]};
+            const double u3[3] = {sh->ub[0][s], sh->ub[1][s], sh->ub[2][s]};
+            if ((unsigned)id[q] == mc || bp_box_min_halfspace(a, bh, l3, u3) >= -1e-4) d[q] = BP_INF;
+          }
+        }
+      }
+      // shell bookkeeping for the next round: free slots, smallest exact distance left
+      int nf = 0;
+      double ex = BP_INF;
+#pragma unroll
+      for (int q = 0; q < BP_SHELL / 32; ++q) {
+        const bool fr = !(d[q] < BP_INF);
+        const unsigned bal = __ballot_sync(full, fr);
+        if (fr) { sh->free_list[nf + __popc(bal & ((1u << lane) - 1u))] = lane + 32 * q; sh->dist[lane + 32 * q] = BP_INF; }
+        else ex = fmin(ex, d[q]);
+        nf += __popc(bal);
+      }
+      ex = warp_min_nonneg(ex);
+      if (lane == 0) { sh->n_free = nf; sh->cnt = 0; sh->n_pick = npick; sh->m_cur = m; sh->status = st; sh->exmin = ex; }
+    }
+    __syncthreads();
+    BP_PPROF_LAP(3);
+    m_cur = sh->m_cur;
+    status = sh->status;
+    if (status != BP_OK) break;
+    // ---- D: the new halfspaces against the obstacles outside the shell
+    const int npk = sh->n_pick;
+    lmin2 = BP_INF;
+#pragma unroll
+    for (int w = 0; w < AW; ++w) {
+      for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+        const int k = __ffsll((long long)mk) - 1;
+        const int j = tid + (k + 64 * w) * T;
+        bool dead = false;
+        if (npk > 0) {
+          double lb[3], ub[3];
+          load_box(sc, j, lb, ub);
+          for (int t = 0; t < npk; ++t) {
+            const double a[3] = {sh->pick[t][0], sh->pick[t][1], sh->pick[t][2]};
+            dead = dead || bp_box_min_halfspace(a, sh->pick[t][3], lb, ub) >= -1e-4;
+          }
+        }
+        if (dead) alive[w] &= ~(1ull << k);
+        else lmin2 = fmin(lmin2, s_key[j]);
+      }
+    }
+    BP_PPROF_LAP(4);
+  }
+  *m_out = m_cur;
+  *status_out = status;
+}
+
+// (arguments by value: taking the address of the caller's metric / scene view would move them to local memory
+// on the hot path as well)
+struct PassResult { int m, status; };
+__device__ __noinline__ PassResult poly_pass_point_fallback(SceneView sc, PassMetric pm, Vec3 p, double* s_dist,
+                                                            double (*red_val)[32], int (*red_idx)[32], double* Arow,
+                                                            double* brow, int m_max) {
+  PassResult r;
+  poly_pass_point<false>(sc, pm, p.v, s_dist, 0, red_val, red_idx, Arow, brow, m_max, &r.m, &r.status);
+  return r;
+}
+
+// one compute_polyhedron pass of this CTA's seed: box scenes take the shell form (AW words of alive bits per
+// thread: N <= 64 AW blockDim.x), polytope scenes the lazy per-pick form
+template <bool POLY, int AW>
+__device__ __forceinline__ void poly_pass(const SceneView& sc, int n_max, const PassMetric& pm, const double* p,
+                                          double* s_dist, int cache_y, double (*red_val)[32], int (*red_idx)[32],
+                                          double* Arow, double* brow, int m_max, int* m_out, int* status_out) {
+  if (POLY) {
+    poly_pass_point<true>(sc, pm, p, s_dist, cache_y, red_val, red_idx, Arow, brow, m_max, m_out, status_out);
+  } else {
+    ShellMem* sh = (ShellMem*)(s_dist + ((n_max + 1) & ~1));
+    int fb = 0;
+    poly_pass_shell<AW>(sc, pm, p, s_dist, sh, red_val, Arow, brow, m_max, m_out, status_out, &fb);
+    if (fb) {                                  // (block-uniform) shell overflow: the per-pick form, from scratch
+      __syncthreads();
+      Vec3 pv;
+      pv.v[0] = p[0]; pv.v[1] = p[1]; pv.v[2] = p[2];
+      const PassResult r = poly_pass_point_fallback(sc, pm, pv, s_dist, red_val, red_idx, Arow, brow, m_max);
+      *m_out = r.m;
+      *status_out = r.status;
+    }
+  }
+}
+
 template <bool POLY>
 __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams pr) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
@@ -702,7 +954,7 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams
   }
 
   int m_cur, status;
-  poly_pass_point<POLY>(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
+  poly_pass<POLY, 1>(sc, sc_all.n, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
   if (status == BP_OK && m_cur > pr.m_max) status = BP_ROW_OVERFLOW;
   // rows past the last one keep the padding of normalize_set_size (A = 0, b = 10): an earlier,
   // longer pass may have left its rows there
@@ -763,7 +1015,7 @@ struct SharedRows {
 // MODE 0: find_set_around_point (:190-240).  MODE 1: find_set_around_line (:242-307) -- the same loop around
 // the midpoint of the segment p0 .. p0 + dp1 with the fixed-rotation MVIE (mvie_socp_fixed_r); no trailing MVIE,
 // and with optimize == 0 one free-centre MVIE after the first pass (:278-282).
-template <int MODE, bool POLY>
+template <int MODE, bool POLY, int AW = 1>
 __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ double s_dist[];
@@ -808,7 +1060,7 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     int st;
     {
       BP_PROF_T0();
-      poly_pass_point<POLY>(sc, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
+      poly_pass<POLY, AW>(sc, sc_all.n, pm, p, s_dist, pr.cache_y, red_val, red_idx, sA, sb, pr.m_max, &m_cur, &st);
       BP_PROF_ADD(0);
     }
     rows_peak = m_cur > rows_peak ? m_cur : rows_peak;
@@ -2305,9 +2557,11 @@ static int launch_fk(const double* q, int B, double* p_ee, double* p_col, double
 
 // closest points are cached in shared memory while dist[N] + y[3][N] stays within 96 KB per CTA
 static int poly_cache_y(int n) { return (size_t)n * 32 <= 96 * 1024; }
-static size_t poly_smem_bytes(int n) {
+// polytope scenes: dist[N] (+ y[3][N] while that fits); box scenes: key2[N] + the shell (poly_pass_shell)
+static size_t poly_smem_bytes(int n, bool polytopes) {
   if (n < 1) n = 1;
-  return sizeof(double) * (size_t)n * (poly_cache_y(n) ? 4 : 1);
+  if (polytopes) return sizeof(double) * (size_t)n * (poly_cache_y(n) ? 4 : 1);
+  return sizeof(double) * (size_t)((n + 1) & ~1) + sizeof(ShellMem);
 }
 // fused per-seed kernel for small / medium scenes; BPGEO_FUSED=0 forces the launch sequence
 static bool use_fused_iris(int n) {
@@ -2316,7 +2570,7 @@ static bool use_fused_iris(int n) {
     const char* e = getenv("BPGEO_FUSED");
     env = (e && e[0] == '0') ? 0 : 1;
   }
-  return env == 1 && n <= 4096;
+  return env == 1 && n <= 16384;            // 128 threads x 2 words of alive bits
 }
 static int poly_threads(int n) { return n <= 256 ? 128 : (n <= 4096 ? 256 : 512); }
 
@@ -2536,7 +2790,7 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
   pr.seeds = seeds_dev; pr.q_ellipse = q_ellipse_dev; pr.init_rows = init_rows_dev;
   pr.A = A_dev; pr.b = b_dev; pr.m = m_dev; pr.status = status_dev; pr.m_max = m_max; pr.mode = 0;
   pr.cache_y = poly_cache_y(scene->n);
-  size_t smem = poly_smem_bytes(scene->n);
+  size_t smem = poly_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows) {
     if (!pr.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
     if (set_dyn_smem((const void*)k_poly_point<true>, smem)) return 1;
@@ -2599,7 +2853,7 @@ int bp_build_sets_around_line(const bp_scene* scene, const double* p0_dev, const
   fp.status = status_dev; fp.iters = iters_dev; fp.rows_peak = rows_peak_dev;
   fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = 0; fp.optimize = optimize;
   fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
-  const size_t fsmem = poly_smem_bytes(scene->n);
+  const size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows) {
     if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
     if (set_dyn_smem((const void*)k_iris_fused<1, true>, fsmem)) return 1;
@@ -2645,14 +2899,17 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
     fp.status = status_dev; fp.iters = iters_dev; fp.rows_peak = rows_peak_dev;
     fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = fixed_mid; fp.optimize = optimize;
     fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
-    const size_t fsmem = poly_smem_bytes(scene->n);
+    const size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
     if (scene->rows) {
       if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
       if (set_dyn_smem((const void*)k_iris_fused<0, true>, fsmem)) return 1;
       k_iris_fused<0, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
-    } else {
+    } else if (scene->n <= 64 * 128) {
       if (set_dyn_smem((const void*)k_iris_fused<0, false>, fsmem)) return 1;
       k_iris_fused<0, false><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    } else {                                   // two words of alive bits per thread: N <= 16384
+      if (set_dyn_smem((const void*)k_iris_fused<0, false, 2>, fsmem)) return 1;
+      k_iris_fused<0, false, 2><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     }
     BP_CUDA(cudaGetLastError());
     return 0;
@@ -2669,7 +2926,7 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
   memset(&mp, 0, sizeof(mp));
   mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st;
   pp.cache_y = poly_cache_y(scene->n);
-  size_t smem = poly_smem_bytes(scene->n);
+  size_t smem = poly_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows && !pp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
   if (set_dyn_smem(scene->rows ? (const void*)k_poly_point<true> : (const void*)k_poly_point<false>, smem)) return 1;
   const int T = poly_threads(scene->n);
