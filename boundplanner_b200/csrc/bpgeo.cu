@@ -373,7 +373,12 @@ __device__ __forceinline__ void pass_bound_init(const PassMetric& pm, PassBound*
   double M[9], Mi[9];
   bp_mat3_ata(pm.Q, M);
   const double det = bp_inv3(M, Mi);
-  const double lm = bp_sym3_min_eig(M);
+  // lambda_min(M) = 1 / lambda_max(M^-1) >= 1 / ||M^-1||_F: a valid (at most sqrt(3) times weaker) bound without the
+  // trigonometric eigenvalue solve, which cost every thread ~2.5 k cycles per pass
+  double fro = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) fro += Mi[k] * Mi[k];
+  const double lm = det > 0.0 ? 1.0 / sqrt(fro) : 0.0;
   // eta = 1e-3 covers the rounding of the inverse / eigenvalue up to cond(M) ~ 1e12; the bound only decides
   // WHICH closest-point QPs are solved, never a result
   const double keep = 1.0 - 1e-3;
@@ -461,7 +466,7 @@ __device__ __forceinline__ double poly_min_halfspace(const SceneView& sc, int j,
 // POLY: the obstacles are general polytopes (sc.rows != NULL): the bounds come from their bounding boxes, the exact
 // closest points from warp-cooperative QPs over a shared work list, the vertex test walks their vertex lists;
 // needs cache_y.
-template <bool POLY>
+template <bool POLY, int AW = 1>
 __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassMetric& pm, const double* p,
                                                 double* s_dist, int cache_y, double (*red_val)[32],
                                                 int (*red_idx)[32], double* Arow,
@@ -481,9 +486,11 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
   BP_PPROF_MARK();
   PassBound pb;
   pass_bound_init(pm, &pb);
-  // Entry k of this thread is obstacle j = tid + k T (k < 64: N <= 64 T, see poly_threads); `alive` has a bit
-  // per entry that no picked halfspace has cut off yet, so the scans below touch live entries only.
-  unsigned long long alive = 0ull;
+  // Entry k of this thread is obstacle j = tid + k T (k < 64 AW: N <= 64 AW T); `alive` has a bit per entry that
+  // no picked halfspace has cut off yet, so the scans below touch live entries only.
+  unsigned long long alive[AW];
+#pragma unroll
+  for (int w = 0; w < AW; ++w) alive[w] = 0ull;
   // phase 1: lower bounds (stored negated); a zero bound (p inside the box's slabs) is refined on the spot
   double lkey = BP_INF;
   int lidx = 0x3fffffff, lexact = 0;
@@ -504,7 +511,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       } else {
         s_dist[j] = -bd;
       }
-      alive |= 1ull << k;
+      alive[k >> 6] |= 1ull << (k & 63);
       if (bd < lkey || (bd == lkey && ex < lexact)) { lkey = bd; lidx = j; lexact = ex; }
     }
   }
@@ -527,16 +534,20 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       // number of refinement rounds (one QP latency + one barrier each) small, everything within
       // BP_LAZY_GROW x the smallest bound: the next picks come from that shell
       double lex = BP_INF;
-      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
-        const double d = s_dist[tid + (__ffsll((long long)mk) - 1) * T];
-        if (d >= 0.0) lex = fmin(lex, d);
-      }
+#pragma unroll
+      for (int w = 0; w < AW; ++w)
+        for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+          const double d = s_dist[tid + (__ffsll((long long)mk) - 1 + 64 * w) * T];
+          if (d >= 0.0) lex = fmin(lex, d);
+        }
       const double ex = block_min_nonneg(lex, red_val, buf);
       const double thr = fmax(ex < BP_INF ? ex : 0.0, BP_LAZY_GROW * val);
       if (POLY) {
         // work list of the obstacles to refine (what does not fit waits for the next round)
-        for (unsigned long long mk = alive; mk; mk &= mk - 1) {
-          const int j = tid + (__ffsll((long long)mk) - 1) * T;
+#pragma unroll
+        for (int w = 0; w < AW; ++w)
+        for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+          const int j = tid + (__ffsll((long long)mk) - 1 + 64 * w) * T;
           const double d = s_dist[j];
           if (d < 0.0 && -d <= thr) {
             const int slot = atomicAdd(&s_nlist, 1);
@@ -570,8 +581,10 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
         if (tid == 0) s_nlist = 0;
       }
       lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
-      for (unsigned long long mk = alive; mk; mk &= mk - 1) {
-        const int j = tid + (__ffsll((long long)mk) - 1) * T;
+#pragma unroll
+      for (int w = 0; w < AW; ++w)
+      for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+        const int j = tid + (__ffsll((long long)mk) - 1 + 64 * w) * T;
         double d = s_dist[j];
         int e = 1;
         if (d < 0.0) {
@@ -586,7 +599,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
             e = 0;
           }
         }
-        if (!(d < BP_INF)) { alive &= ~(1ull << (__ffsll((long long)mk) - 1)); continue; }   // empty polytope
+        if (!(d < BP_INF)) { alive[w] &= ~(1ull << (__ffsll((long long)mk) - 1)); continue; }   // empty polytope
         if (d < lkey || (d == lkey && e < lexact)) { lkey = d; lidx = j; lexact = e; }
       }
       BP_PPROF_LAP(2);
@@ -618,26 +631,28 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
     // delete the winner and every obstacle whose 8 vertices satisfy a.v - b >= -1e-4  (:447-458); live entries
     // are taken two at a time so that their box loads are in flight together
     lkey = BP_INF; lidx = 0x3fffffff; lexact = 0;
-    for (unsigned long long mk = alive; mk;) {
+#pragma unroll
+    for (int w = 0; w < AW; ++w)
+    for (unsigned long long mk = alive[w]; mk;) {
       const int k0 = __ffsll((long long)mk) - 1;
       mk &= mk - 1;
       const int k1 = mk ? __ffsll((long long)mk) - 1 : k0;
       mk &= mk - 1;                               // (0 & anything stays 0)
-      const int j0 = tid + k0 * T, j1 = tid + k1 * T;
+      const int j0 = tid + (k0 + 64 * w) * T, j1 = tid + (k1 + 64 * w) * T;
       double l0[3], u0[3], l1[3], u1[3];
       load_box(sc, j0, l0, u0);
       load_box(sc, j1, l1, u1);
       const double d0 = s_dist[j0], d1 = s_dist[j1];
       const bool dead0 = j0 == idx || (POLY ? poly_min_halfspace(sc, j0, a, bh) : bp_box_min_halfspace(a, bh, l0, u0)) >= -1e-4;
       const bool dead1 = j1 == idx || (POLY ? poly_min_halfspace(sc, j1, a, bh) : bp_box_min_halfspace(a, bh, l1, u1)) >= -1e-4;
-      if (dead0) alive &= ~(1ull << k0);
+      if (dead0) alive[w] &= ~(1ull << k0);
       else {
         const int e = d0 >= 0.0;
         const double d = fabs(d0);
         if (d < lkey || (d == lkey && e < lexact)) { lkey = d; lidx = j0; lexact = e; }
       }
       if (k1 != k0) {
-        if (dead1) alive &= ~(1ull << k1);
+        if (dead1) alive[w] &= ~(1ull << k1);
         else {
           const int e = d1 >= 0.0;
           const double d = fabs(d1);
@@ -666,6 +681,30 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
 // Shell overflow (more than BP_SHELL obstacles within thr, e.g. a degenerate metric) -> *fallback = 1 and the
 // caller reruns the pass with poly_pass_point.
 // ---------------------------------------------------------------------------
+// squared lower bound of the pass-metric distance from p to a box (see box_dist_bound)
+__device__ __forceinline__ double box_bound2(const PassBound& pb, const double* p, const double* lb, const double* ub) {
+  const double d0 = fmax(fmax(lb[0] - p[0], p[0] - ub[0]), 0.0);
+  const double d1 = fmax(fmax(lb[1] - p[1], p[1] - ub[1]), 0.0);
+  const double d2 = fmax(fmax(lb[2] - p[2], p[2] - ub[2]), 0.0);
+  const double q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2;
+  return fmax(fmax(pb.c[0] * q0, pb.c[1] * q1), fmax(pb.c[2] * q2, pb.lmin * ((q0 + q1) + q2)));
+}
+// smallest value (>= 0, +inf allowed) and the sum of an int over the block
+__device__ __forceinline__ double block_min_count(double v, int& cnt, double (*red_val)[32], int (*red_cnt)[32],
+                                                  int& buf) {
+  v = warp_min_nonneg(v);
+  const int c = __reduce_add_sync(0xffffffffu, cnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red_val[buf][warp] = v; red_cnt[buf][warp] = c; }
+  __syncthreads();
+  double bv = red_val[buf][0];
+  int bc = red_cnt[buf][0];
+  for (int w = 1; w < nw; ++w) { bv = fmin(bv, red_val[buf][w]); bc += red_cnt[buf][w]; }
+  buf ^= 1;
+  cnt = bc;
+  return bv;
+}
+
 #define BP_SHELL 128
 struct ShellMem {
   double dist[BP_SHELL];               // exact distance (:429); +inf = free slot
@@ -681,8 +720,9 @@ struct ShellMem {
 
 template <int AW>
 __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassMetric& pm, const double* p,
-                                                double* s_key, ShellMem* sh, double (*red_val)[32], double* Arow,
-                                                double* brow, int m_max, int* m_out, int* status_out, int* fallback) {
+                                                double* s_key, ShellMem* sh, double (*red_val)[32],
+                                                int (*red_idx)[32], double* Arow, double* brow, int m_max, int* m_out,
+                                                int* status_out, int* fallback) {
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
   BP_PPROF_MARK();
@@ -693,19 +733,27 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
   for (int w = 0; w < AW; ++w) alive[w] = 0ull;
   // ---- A: squared lower bounds of every obstacle (entry k of this thread is obstacle tid + k T)
   double lmin2 = BP_INF;
+  int n_alive = 0;
   {
+    // two obstacles per trip: their loads and the two short dependency chains overlap
     int k = 0;
-    for (int j = tid; j < sc.n; j += T, ++k) {
-      double lb[3], ub[3];
-      load_box(sc, j, lb, ub);
-      const double d0 = fmax(fmax(lb[0] - p[0], p[0] - ub[0]), 0.0);
-      const double d1 = fmax(fmax(lb[1] - p[1], p[1] - ub[1]), 0.0);
-      const double d2 = fmax(fmax(lb[2] - p[2], p[2] - ub[2]), 0.0);
-      const double q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2;
-      const double b2 = fmax(fmax(pb.c[0] * q0, pb.c[1] * q1), fmax(pb.c[2] * q2, pb.lmin * ((q0 + q1) + q2)));
-      s_key[j] = b2;
+    for (int j = tid; j < sc.n; j += 2 * T, k += 2) {
+      const int j1 = j + T;
+      const bool two = j1 < sc.n;
+      double la[3], ua[3], lc[3], uc[3];
+      load_box(sc, j, la, ua);
+      load_box(sc, two ? j1 : j, lc, uc);
+      const double ba = box_bound2(pb, p, la, ua), bc = box_bound2(pb, p, lc, uc);
+      s_key[j] = ba;
       alive[k >> 6] |= 1ull << (k & 63);
-      lmin2 = fmin(lmin2, b2);
+      lmin2 = fmin(lmin2, ba);
+      ++n_alive;
+      if (two) {
+        s_key[j1] = bc;
+        alive[(k + 1) >> 6] |= 1ull << ((k + 1) & 63);
+        lmin2 = fmin(lmin2, bc);
+        ++n_alive;
+      }
     }
   }
   for (int e = tid; e < BP_SHELL; e += T) { sh->dist[e] = BP_INF; sh->free_list[e] = e; }
@@ -715,16 +763,19 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
   BP_PPROF_LAP(0);
   while (true) {
     // smallest bound outside the shell (the barrier inside also publishes the shell state written by warp 0)
-    const double bmin2 = block_min_nonneg(lmin2, red_val, buf);
+    int n_out = n_alive;
+    const double bmin2 = block_min_count(lmin2, n_out, red_val, red_idx, buf);
     const double exmin = sh->exmin;
     if (!(bmin2 < BP_INF) && !(exmin < BP_INF)) break;                 // no obstacle left
+    BP_PPROF_COUNT(6);
+    // ---- B: move the obstacles within thr into the shell; once everything left outside fits, take it all
+    // (one more round ends the pass)
+    const int n_free = sh->n_free;
     double thr = BP_INF, thr2 = BP_INF;
-    if (bmin2 < BP_INF) {
+    if (bmin2 < BP_INF && n_out > n_free) {
       thr = fmax(exmin < BP_INF ? exmin : 0.0, BP_LAZY_GROW * sqrt(bmin2));
       thr2 = thr * thr;
     }
-    // ---- B: move the obstacles within thr into the shell
-    const int n_free = sh->n_free;
     unsigned long long taken[AW];
 #pragma unroll
     for (int w = 0; w < AW; ++w) taken[w] = 0ull;
@@ -757,6 +808,9 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
     }
     if (over) { *fallback = 1; return; }
     const int n_new = sh->cnt;
+#ifdef BPGEO_PROFILE
+    if (tid == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + 7] += n_new;
+#endif
 #pragma unroll
     for (int w = 0; w < AW; ++w) alive[w] &= ~taken[w];
     // exact closest points of the new shell entries
@@ -804,8 +858,8 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
         bp_mat3_vec(pm.G, zz, a);
         a[0] *= 2.0; a[1] *= 2.0; a[2] *= 2.0;           // 2 (Q Q^T)(cp - p)   (:440)
         double bh = a[0] * y[0] + a[1] * y[1] + a[2] * y[2];
-        double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-        a[0] /= nrm; a[1] /= nrm; a[2] /= nrm; bh /= nrm;
+        const double inrm = rsqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);   // a / ||a||, b / ||a||  (:441-444)
+        a[0] *= inrm; a[1] *= inrm; a[2] *= inrm; bh *= inrm;
         if (lane == 0) {
           if (m < m_max) { Arow[3 * m + 0] = a[0]; Arow[3 * m + 1] = a[1]; Arow[3 * m + 2] = a[2]; brow[m] = bh; }
           sh->pick[npick][0] = a[0]; sh->pick[npick][1] = a[1]; sh->pick[npick][2] = a[2]; sh->pick[npick][3] = bh;
@@ -844,6 +898,7 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
     // ---- D: the new halfspaces against the obstacles outside the shell
     const int npk = sh->n_pick;
     lmin2 = BP_INF;
+    n_alive = 0;
 #pragma unroll
     for (int w = 0; w < AW; ++w) {
       for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
@@ -859,7 +914,7 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
           }
         }
         if (dead) alive[w] &= ~(1ull << k);
-        else lmin2 = fmin(lmin2, s_key[j]);
+        else { lmin2 = fmin(lmin2, s_key[j]); ++n_alive; }
       }
     }
     BP_PPROF_LAP(4);
@@ -871,11 +926,14 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
 // (arguments by value: taking the address of the caller's metric / scene view would move them to local memory
 // on the hot path as well)
 struct PassResult { int m, status; };
+__device__ unsigned long long g_shell_fallbacks;     // passes that overflowed the shell (bp_debug_counters)
+template <int AW>
 __device__ __noinline__ PassResult poly_pass_point_fallback(SceneView sc, PassMetric pm, Vec3 p, double* s_dist,
                                                             double (*red_val)[32], int (*red_idx)[32], double* Arow,
                                                             double* brow, int m_max) {
   PassResult r;
-  poly_pass_point<false>(sc, pm, p.v, s_dist, 0, red_val, red_idx, Arow, brow, m_max, &r.m, &r.status);
+  if (threadIdx.x == 0) atomicAdd(&g_shell_fallbacks, 1ull);
+  poly_pass_point<false, AW>(sc, pm, p.v, s_dist, 0, red_val, red_idx, Arow, brow, m_max, &r.m, &r.status);
   return r;
 }
 
@@ -890,12 +948,12 @@ __device__ __forceinline__ void poly_pass(const SceneView& sc, int n_max, const 
   } else {
     ShellMem* sh = (ShellMem*)(s_dist + ((n_max + 1) & ~1));
     int fb = 0;
-    poly_pass_shell<AW>(sc, pm, p, s_dist, sh, red_val, Arow, brow, m_max, m_out, status_out, &fb);
+    poly_pass_shell<AW>(sc, pm, p, s_dist, sh, red_val, red_idx, Arow, brow, m_max, m_out, status_out, &fb);
     if (fb) {                                  // (block-uniform) shell overflow: the per-pick form, from scratch
       __syncthreads();
       Vec3 pv;
       pv.v[0] = p[0]; pv.v[1] = p[1]; pv.v[2] = p[2];
-      const PassResult r = poly_pass_point_fallback(sc, pm, pv, s_dist, red_val, red_idx, Arow, brow, m_max);
+      const PassResult r = poly_pass_point_fallback<AW>(sc, pm, pv, s_dist, red_val, red_idx, Arow, brow, m_max);
       *m_out = r.m;
       *status_out = r.status;
     }
@@ -3212,6 +3270,19 @@ int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev
   if (T_ee_dev) return launch_fk<true, false>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
   if (jac_dev) return launch_fk<false, true>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
   return launch_fk<false, false>(q_dev, B, p_ee_dev, p_col_dev, T_ee_dev, jac_dev, use_tma, st);
+}
+
+int bp_debug_counters(unsigned long long* out_host, int n, int reset) {
+  if (!out_host || n < 1) return bp_fail("bp_debug_counters: bad arguments");
+  unsigned long long v = 0ull;
+  BP_CUDA(cudaMemcpyFromSymbol(&v, g_shell_fallbacks, sizeof(v)));
+  out_host[0] = v;
+  for (int k = 1; k < n; ++k) out_host[k] = 0ull;
+  if (reset) {
+    v = 0ull;
+    BP_CUDA(cudaMemcpyToSymbol(g_shell_fallbacks, &v, sizeof(v)));
+  }
+  return 0;
 }
 
 int bp_fk_iiwa14_kin(const double* q_dev, const double* dq_dev, int B, double* T_ee_dev, double* jac_dev,

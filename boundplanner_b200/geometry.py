@@ -571,3 +571,11 @@ def fk_kinematics(q, dq=None):
     dJ = torch.empty((B, 6, 7), dtype=torch.float64, device="cuda") if dq is not None else None
     check(lib.bp_fk_iiwa14_kin(_ptr(q), _ptr(dq), B, _ptr(T), _ptr(J), _ptr(dJ), _stream()))
     return T, J, dJ
+
+
+def debug_counters(reset=False):
+    """{"shell_fallbacks": polyhedron passes redone in the per-pick form because the closest-point shell overflowed}"""
+    lib = _lib.load()
+    buf = (ctypes.c_ulonglong * 4)()
+    check(lib.bp_debug_counters(buf, 4, int(bool(reset))))
+    return {"shell_fallbacks": int(buf[0])}

@@ -258,6 +258,10 @@ int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev
 int bp_fk_iiwa14_kin(const double* q_dev, const double* dq_dev, int B, double* T_ee_dev, double* jac_dev,
                      double* djac_dev, void* stream);
 
+/* Diagnostics: out_host[0] = polyhedron passes (since the last reset) that overflowed the closest-point shell of
+ * the box-scene pass and were redone in the per-pick form; further entries reserved (0).  Synchronises the device. */
+int bp_debug_counters(unsigned long long* out_host, int n, int reset);
+
 /* ---- diagnostics: FP64 pipe probe (roofline denominator in bench.py) ------------
  * Launches blocks x threads threads, each running `chains` (1, 4 or 8)
  * independent chains of `iters` dependent DFMAs; out_dev: [blocks*threads]. */
