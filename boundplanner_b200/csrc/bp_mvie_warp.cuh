@@ -72,10 +72,18 @@ __device__ __forceinline__ double bp_warp_prod(double v) {
   return v;
 }
 
-// A, b: global rows of this set; scratch: BP_MVIE_SCRATCH_DOUBLES doubles of shared memory private to the warp.
-template <int NV>
-__device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restrict__ b, int m, const double* c0,
-                            double* scratch, double* Lout, double* dout, int* iters_out) {
+// A, b: rows of this set; scratch: BP_MVIE_SCRATCH_DOUBLES doubles of shared memory private to the warp.
+// RPL = rows per lane: 1 while m <= 32 (every set the reference can build: its buffers hold 20 rows), else 2.
+struct BpMvieOut {
+  double L[6], d[3];
+  int status, iters;
+};
+
+template <int NV, int RPL>
+__device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict__ A, const double* __restrict__ b,
+                                                       int m, double c00, double c01, double c02, double* scratch) {
+  const double c0[3] = {c00, c01, c02};
+  BpMvieOut res;
   constexpr int NH = NV * (NV + 1) / 2;
   constexpr int W = BP_MVIE_W(NV);
   constexpr int NOUT = NH + NV + 6;
@@ -85,10 +93,10 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
   double* OUT = scratch + BP_MAX_ROWS * 17;     // [64]
 
   // rows owned by this lane
-  double ra[2][3], rb[2];
-  bool rv[2];
+  double ra[RPL][3], rb[RPL];
+  bool rv[RPL];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < RPL; ++q) {
     const int i = lane + 32 * q;
     rv[q] = i < m;
     ra[q][0] = ra[q][1] = ra[q][2] = 0.0;
@@ -110,7 +118,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
   // strictly feasible start: ball of half the inradius around c0
   double r = BP_INF;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < RPL; ++q) {
     if (rv[q]) {
       double s = rb[q] - (ra[q][0] * c0[0] + ra[q][1] * c0[1] + ra[q][2] * c0[2]);
       double nrm = sqrt(ra[q][0] * ra[q][0] + ra[q][1] * ra[q][1] + ra[q][2] * ra[q][2]);
@@ -119,7 +127,14 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
     }
   }
   r = bp_warp_min(r);
-  if (!(r > 0.0) || !(r < BP_INF)) return BP_MVIE_NO_INTERIOR;
+  if (!(r > 0.0) || !(r < BP_INF)) {
+    res.status = BP_MVIE_NO_INTERIOR;
+    res.iters = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) res.L[k] = 0.0;
+    res.d[0] = c0[0]; res.d[1] = c0[1]; res.d[2] = c0[2];
+    return res;
+  }
   r *= 0.5;
   double x[NV];
   x[0] = r; x[1] = 0.0; x[2] = r; x[3] = 0.0; x[4] = 0.0; x[5] = r;
@@ -144,9 +159,9 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
       BP_MPROF_MARK();
       if (NV == 9) { cen[0] = x[6]; cen[1] = x[7]; cen[2] = x[8]; }
       // ---- per-row barrier pieces -> feature rows
-      double rs[2], ru[2][3], rpsi[2], rtw[2];
+      double rs[RPL], ru[RPL][3], rpsi[RPL], rtw[RPL];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < RPL; ++q) {
         const double a0 = ra[q][0], a1 = ra[q][1], a2 = ra[q][2];
         const double s = rb[q] - (a0 * cen[0] + a1 * cen[1] + a2 * cen[2]);
         const double u0 = x[0] * a0 + x[1] * a1 + x[3] * a2;
@@ -231,9 +246,9 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
       // ---- line search: psi(x + alpha dx) = psi + alpha B1 + alpha^2 A2 per row
       double dcn[3] = {0.0, 0.0, 0.0};
       if (NV == 9) { dcn[0] = dx[6]; dcn[1] = dx[7]; dcn[2] = dx[8]; }
-      double rds[2], rB1[2], rA2[2];
+      double rds[RPL], rB1[RPL], rA2[RPL];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < RPL; ++q) {
         const double a0 = ra[q][0], a1 = ra[q][1], a2 = ra[q][2];
         const double ds = -(a0 * dcn[0] + a1 * dcn[1] + a2 * dcn[2]);
         const double e0 = dx[0] * a0 + dx[1] * a1 + dx[3] * a2;
@@ -250,7 +265,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         bool ok = (x[0] + alpha * dx[0] > 0.0) && (x[2] + alpha * dx[2] > 0.0) && (x[5] + alpha * dx[5] > 0.0);
         double prod = 1.0;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < RPL; ++q) {
           if (rv[q]) {
             const double rel = alpha * (rB1[q] + alpha * rA2[q]) * (0.5 * rtw[q]);     // / psi
             if (!(rs[q] + alpha * rds[q] > 0.0) || !(rel > -1.0)) ok = false;
@@ -307,7 +322,7 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
         double cp[3] = {cen[0], cen[1], cen[2]};
         if (NV == 9) { cp[0] = xp[6]; cp[1] = xp[7]; cp[2] = xp[8]; }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < RPL; ++q) {
           if (rv[q]) {
             const double a0 = ra[q][0], a1 = ra[q][1], a2 = ra[q][2];
             const double s = rb[q] - (a0 * cp[0] + a1 * cp[1] + a2 * cp[2]);
@@ -331,9 +346,30 @@ __device__ int bp_mvie_warp(const double* __restrict__ A, const double* __restri
   }
 done:
 #pragma unroll
-  for (int k = 0; k < 6; ++k) Lout[k] = x[k];
-  if (NV == 9) { dout[0] = x[6]; dout[1] = x[7]; dout[2] = x[8]; }
-  else { dout[0] = c0[0]; dout[1] = c0[1]; dout[2] = c0[2]; }
-  if (iters_out) *iters_out = iters;
-  return status;
+  for (int k = 0; k < 6; ++k) res.L[k] = x[k];
+  if (NV == 9) { res.d[0] = x[6]; res.d[1] = x[7]; res.d[2] = x[8]; }
+  else { res.d[0] = c0[0]; res.d[1] = c0[1]; res.d[2] = c0[2]; }
+  res.iters = iters;
+  res.status = status;
+  return res;
+}
+
+// One copy of the solver per kernel and NV (the Newton loop is ~30 KB of SASS: inlining it at every call site
+// of the fused kernel tripled that): all call sites share this function.
+template <int NV>
+__device__ __noinline__ BpMvieOut bp_mvie_warp_fn(const double* A, const double* b, int m, double c00, double c01,
+                                                  double c02, double* scratch) {
+  if (m <= 32) return bp_mvie_warp_impl<NV, 1>(A, b, m, c00, c01, c02, scratch);
+  return bp_mvie_warp_impl<NV, 2>(A, b, m, c00, c01, c02, scratch);
+}
+
+template <int NV>
+__device__ __forceinline__ int bp_mvie_warp(const double* A, const double* b, int m, const double* c0, double* scratch,
+                                            double* Lout, double* dout, int* iters_out) {
+  const BpMvieOut o = bp_mvie_warp_fn<NV>(A, b, m, c0[0], c0[1], c0[2], scratch);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Lout[k] = o.L[k];
+  dout[0] = o.d[0]; dout[1] = o.d[1]; dout[2] = o.d[2];
+  if (iters_out) *iters_out = o.iters;
+  return o.status;
 }

@@ -310,6 +310,7 @@ struct PolyParams {
   int mode;
   int max_iter;
   int cache_y;               // closest points kept in shared memory (y[3][N] after dist[N])
+  int shell;                 // box scene whose key table + shell fit in shared memory: poly_pass_shell
   int row_cap;               // > 0: stop a seed whose pass produced more rows (reference: 20, quirk Q5)
 };
 
@@ -1012,7 +1013,10 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams
   }
 
   int m_cur, status;
-  poly_pass<POLY, 1>(sc, sc_all.n, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
+  if (POLY || pr.shell)
+    poly_pass<POLY, 1>(sc, sc_all.n, pm, p, s_dist, pr.cache_y, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
+  else     // the largest scenes: only the distance table fits in shared memory
+    poly_pass_point<false, 1>(sc, pm, p, s_dist, 0, red_val, red_idx, Arow, brow, pr.m_max, &m_cur, &status);
   if (status == BP_OK && m_cur > pr.m_max) status = BP_ROW_OVERFLOW;
   // rows past the last one keep the padding of normalize_set_size (A = 0, b = 10): an earlier,
   // longer pass may have left its rows there
@@ -1073,6 +1077,8 @@ struct SharedRows {
 // MODE 0: find_set_around_point (:190-240).  MODE 1: find_set_around_line (:242-307) -- the same loop around
 // the midpoint of the segment p0 .. p0 + dp1 with the fixed-rotation MVIE (mvie_socp_fixed_r); no trailing MVIE,
 // and with optimize == 0 one free-centre MVIE after the first pass (:278-282).
+__device__ unsigned g_sm_slot[256];     // CTAs started per SM (only its parity is used, never reset)
+
 template <int MODE, bool POLY, int AW = 1>
 __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
@@ -1081,9 +1087,22 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
   __shared__ int red_idx[2][32];
   __shared__ double sA[BP_MAX_ROWS * 3], sb[BP_MAX_ROWS];
   __shared__ double scratch[BP_MVIE_SCRATCH_DOUBLES];
+  __shared__ double scratch2[MODE == 0 ? BP_MVIE_SCRATCH_DOUBLES : 1];   // the concurrent trailing solve (below)
   __shared__ double c_Q[9], c_p[3], c_det;
-  __shared__ int c_status, c_small;
+  __shared__ double f_Q[9], f_p[3];
+  __shared__ int c_status, c_small, f_status, c_mw;
   const int s = blockIdx.x, tid = threadIdx.x;
+  // The MVIE is a one-warp solve.  Two CTAs share an SM, and a warp's scheduler (SM sub-partition) is its index
+  // mod 4: the CTAs of an SM take their slot from a per-SM counter so that their solver warps -- primary 2 slot,
+  // the concurrent trailing solve 2 slot + 1 -- sit on four different sub-partitions and never share an FP64 pipe.
+  if (tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    c_mw = (int)((atomicAdd(&g_sm_slot[smid & 255u], 1u) & 1u) << 1);
+  }
+  __syncthreads();
+  const int warp_id = tid >> 5, mw = c_mw, mw2 = c_mw + 1;
+  bool have_final = false;
   double Q[9] = {1e4, 0, 0, 0, 1e4, 0, 0, 0, 1e4};          // q_ellipse = diag(1/1e-4) (:192-194)
   double p[3] = {pr.seeds[3 * (size_t)s], pr.seeds[3 * (size_t)s + 1], pr.seeds[3 * (size_t)s + 2]};
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -1170,14 +1189,18 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
       continue;
     }
     det_old = det;                                            // :217
-    __syncthreads();                                          // thread 0 has written the picked rows
-    if (tid < 32) {
+    __syncthreads();                                          // the picked rows are in shared memory
+    // Pass max_iter is the last one whatever its MVIE returns (:204-207), and the trailing free-centre solve
+    // (:235-238) depends only on this pass's rows and the seed: it runs NOW on a second warp, next to the
+    // fixed-centre solve, instead of after it.
+    const bool spec_final = MODE == 0 && pr.fixed_mid && k == pr.max_iter;
+    if (warp_id == mw) {
       double L[6], d[3];
       BP_PROF_T0();
       const int ms = pr.fixed_mid ? bp_mvie_warp<6>(sA, sb, m_cur, p, scratch, L, d, nullptr)
                                   : bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
       BP_PROF_ADD(1);
-      if (tid == 0) {
+      if ((tid & 31) == 0) {
         double E[9], Qn[9], dq;
         bp_shape_from_L(L, E, Qn, &dq);
 #pragma unroll
@@ -1187,7 +1210,21 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
         c_status = ms;
         c_small = (ms == BP_OK && bp_sym3_min_eig(E) < 1e-3) ? 1 : 0;   // :232-233
       }
+    } else if (spec_final && warp_id == mw2) {
+      double L[6], d[3];
+      BP_PROF_T0();
+      const int ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch2, L, d, nullptr);
+      BP_PROF_ADD(2);
+      if ((tid & 31) == 0) {
+        double E[9], Qn[9], dq;
+        bp_shape_from_L(L, E, Qn, &dq);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) f_Q[q] = Qn[q];
+        f_p[0] = d[0]; f_p[1] = d[1]; f_p[2] = d[2];
+        f_status = ms;
+      }
     }
+    have_final = spec_final;
     __syncthreads();
     if (c_status != BP_OK) { status = c_status; break; }
 #pragma unroll
@@ -1200,42 +1237,42 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     // (running this solve speculatively on an idle warp next to every pass's fixed-centre solve was measured
     // slower: the two solves slow each other down by ~20 % and the pass then waits for the longer one)
     __syncthreads();
-    if (tid < 32) {
+    if (!have_final && warp_id == mw) {
       double L[6], d[3];
       BP_PROF_T0();
       const int ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch, L, d, nullptr);
       BP_PROF_ADD(2);
-      if (tid == 0) {
+      if ((tid & 31) == 0) {
         double E[9], Qn[9], dq;
         bp_shape_from_L(L, E, Qn, &dq);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) c_Q[q] = Qn[q];
-        c_p[0] = d[0]; c_p[1] = d[1]; c_p[2] = d[2];
-        c_status = ms;
+        for (int q = 0; q < 9; ++q) f_Q[q] = Qn[q];
+        f_p[0] = d[0]; f_p[1] = d[1]; f_p[2] = d[2];
+        f_status = ms;
       }
     }
     __syncthreads();
-    if (c_status != BP_OK) status = c_status;
+    if (f_status != BP_OK) status = f_status;
     else {
 #pragma unroll
-      for (int q = 0; q < 9; ++q) Q[q] = c_Q[q];
-      p[0] = c_p[0]; p[1] = c_p[1]; p[2] = c_p[2];
+      for (int q = 0; q < 9; ++q) Q[q] = f_Q[q];
+      p[0] = f_p[0]; p[1] = f_p[1]; p[2] = f_p[2];
     }
   }
   __syncthreads();
   // outputs: rows padded like normalize_set_size (A = 0, b = 10)
-  const int mw = m_cur < pr.m_max ? m_cur : pr.m_max;
+  const int m_out = m_cur < pr.m_max ? m_cur : pr.m_max;
   double* Arow = pr.A + (size_t)s * pr.m_max * 3;
   double* brow = pr.b + (size_t)s * pr.m_max;
   for (int r = tid; r < pr.m_max; r += blockDim.x) {
-    const bool live = r < mw;
+    const bool live = r < m_out;
     Arow[3 * r] = live ? sA[3 * r] : 0.0;
     Arow[3 * r + 1] = live ? sA[3 * r + 1] : 0.0;
     Arow[3 * r + 2] = live ? sA[3 * r + 2] : 0.0;
     brow[r] = live ? sb[r] : 10.0;
   }
   if (tid == 0) {
-    pr.m[s] = mw;
+    pr.m[s] = m_out;
 #pragma unroll
     for (int q = 0; q < 9; ++q) pr.q_ellipse[(size_t)s * 9 + q] = Q[q];
     pr.p_mid[3 * (size_t)s] = p[0]; pr.p_mid[3 * (size_t)s + 1] = p[1]; pr.p_mid[3 * (size_t)s + 2] = p[2];
@@ -2621,6 +2658,12 @@ static size_t poly_smem_bytes(int n, bool polytopes) {
   if (polytopes) return sizeof(double) * (size_t)n * (poly_cache_y(n) ? 4 : 1);
   return sizeof(double) * (size_t)((n + 1) & ~1) + sizeof(ShellMem);
 }
+// k_poly_point on box scenes: the shell form while key table + shell fit next to 1 KB of static shared memory
+static bool poly_point_shell(int n) { return poly_smem_bytes(n, false) + 1024 <= 227 * 1024; }
+static size_t poly_point_smem_bytes(int n, bool polytopes) {
+  if (polytopes || poly_point_shell(n)) return poly_smem_bytes(n, polytopes);
+  return sizeof(double) * (size_t)n;
+}
 // fused per-seed kernel for small / medium scenes; BPGEO_FUSED=0 forces the launch sequence
 static bool use_fused_iris(int n) {
   static int env = -1;
@@ -2645,7 +2688,9 @@ static int set_dyn_smem(const void* fn, size_t bytes) {
              "N <= %zu)", bytes, (size_t)fa.sharedSizeBytes, optin, ((size_t)optin - fa.sharedSizeBytes) / sizeof(double));
     return 1;
   }
-  if (bytes > 48 * 1024) BP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // (the 48 KB default limit counts static + dynamic shared memory)
+  if (bytes + fa.sharedSizeBytes > 48 * 1024)
+    BP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
 
@@ -2848,7 +2893,8 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
   pr.seeds = seeds_dev; pr.q_ellipse = q_ellipse_dev; pr.init_rows = init_rows_dev;
   pr.A = A_dev; pr.b = b_dev; pr.m = m_dev; pr.status = status_dev; pr.m_max = m_max; pr.mode = 0;
   pr.cache_y = poly_cache_y(scene->n);
-  size_t smem = poly_smem_bytes(scene->n, scene->rows != nullptr);
+  pr.shell = !scene->rows && poly_point_shell(scene->n);
+  size_t smem = poly_point_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows) {
     if (!pr.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
     if (set_dyn_smem((const void*)k_poly_point<true>, smem)) return 1;
@@ -2984,7 +3030,8 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
   memset(&mp, 0, sizeof(mp));
   mp.A = A_dev; mp.b = b_dev; mp.m = m_dev; mp.S = S; mp.m_max = m_max; mp.state = st;
   pp.cache_y = poly_cache_y(scene->n);
-  size_t smem = poly_smem_bytes(scene->n, scene->rows != nullptr);
+  pp.shell = !scene->rows && poly_point_shell(scene->n);
+  size_t smem = poly_point_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows && !pp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
   if (set_dyn_smem(scene->rows ? (const void*)k_poly_point<true> : (const void*)k_poly_point<false>, smem)) return 1;
   const int T = poly_threads(scene->n);

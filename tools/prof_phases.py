@@ -42,6 +42,11 @@ for s in k:
     print(f"seed {s}: passes {it[s]} poly {buf[s, 0]} mvie {buf[s, 1]} final {buf[s, 2]} sum {tot[s]} "
           f"({tot[s] / 1.965e3:.0f} us at 1965 MHz) rows {int(out.m[s])}")
 print("per pass: poly", (buf[:, 0] / np.minimum(it, 5)).mean(), "mvie6", (buf[:, 1] / np.minimum(it, 5)).mean())
+lib.bp_prof_read_poly(pbuf.ctypes.data_as(ctypes.c_void_p), S, 0)
+print("polyhedron pass of those seeds (cycles over all passes: bounds | collect+QP | picks | sweep; picks, rounds, QPs):")
+for s in k:
+    r = pbuf[s]
+    print(f"  seed {s}: {r[0]} | {r[2]} | {r[3]} | {r[4]}; picks {r[5]} rounds {r[6]} qps {r[7]}")
 
 lib.bp_prof_read_mvie(mbuf.ctypes.data_as(ctypes.c_void_p), S, 1)
 names = ["rows", "dots+H", "ldl", "linesearch", "predictor", "newton", "armijo", "backtracks"]
@@ -54,11 +59,12 @@ print(f"  newton iterations per seed {mbuf[:, 5].mean():.1f}, armijo evals per i
 
 lib.bp_prof_read_poly(pbuf.ctypes.data_as(ctypes.c_void_p), S, 1)
 npass = np.minimum(it, 5).sum()
-pn = ["phase 1 (bounds)", "block argmin", "refine rounds", "halfspace", "delete scan"]
+pn = ["A bounds", "(unused)", "B collect + QPs", "C picks (warp 0)", "D sweep"]
 print("polyhedron pass, cycles per pass (thread 0's view):")
 for k in range(5):
     print(f"  {pn[k]:18s} {pbuf[:, k].sum() / npass:8.0f}")
-print(f"  picks per pass {pbuf[:, 5].sum() / npass:.1f}, refine rounds per pass {pbuf[:, 6].sum() / npass:.1f}")
+print(f"  picks per pass {pbuf[:, 5].sum() / npass:.1f}, rounds per pass {pbuf[:, 6].sum() / npass:.1f}, "
+      f"exact QPs per pass {pbuf[:, 7].sum() / npass:.1f}")
 
 # pair LP statistics on the same sets
 qbuf = np.zeros(128, dtype=np.int64)
