@@ -717,6 +717,7 @@ struct ShellMem {
   int free_list[BP_SHELL];             // free slots
   int new_list[BP_SHELL];              // slots filled in this round (exact QP pending)
   int n_free, cnt, n_pick, m_cur, status, pad_;
+  int hist[4][16];                     // per-warp counts of the obstacles within four candidate thresholds
 };
 
 template <int AW>
@@ -774,8 +775,35 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
     const int n_free = sh->n_free;
     double thr = BP_INF, thr2 = BP_INF;
     if (bmin2 < BP_INF && n_out > n_free) {
-      thr = fmax(exmin < BP_INF ? exmin : 0.0, BP_LAZY_GROW * sqrt(bmin2));
-      thr2 = thr * thr;
+      // Every round costs one closest-point QP latency however few QPs it solves, so the shell is filled as far
+      // as it goes: the widest of the thresholds GROW x {1, 2, 4, 8} x (smallest bound) that still fits.
+      const double bmin = sqrt(bmin2), floor_ = exmin < BP_INF ? exmin : 0.0;
+      double cand[4], cand2[4];
+      int c4[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { cand[g] = fmax(floor_, (BP_LAZY_GROW * (1 << g)) * bmin); cand2[g] = cand[g] * cand[g]; }
+#pragma unroll
+      for (int w = 0; w < AW; ++w)
+        for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+          const double key = s_key[tid + (__ffsll((long long)mk) - 1 + 64 * w) * T];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) c4[g] += key <= cand2[g];
+        }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = __reduce_add_sync(full, c4[g]);
+        if (lane == 0) sh->hist[g][warp] = c;
+      }
+      __syncthreads();
+      int pick_g = 0;
+#pragma unroll
+      for (int g = 1; g < 4; ++g) {
+        int tot = 0;
+        for (int w = 0; w < (T >> 5); ++w) tot += sh->hist[g][w];
+        if (tot <= n_free) pick_g = g;
+      }
+      thr = cand[pick_g];
+      thr2 = cand2[pick_g];
     }
     unsigned long long taken[AW];
 #pragma unroll
