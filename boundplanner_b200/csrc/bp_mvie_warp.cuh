@@ -21,13 +21,18 @@
 // the per-lane row writes spread over the shared-memory banks
 #ifdef BPGEO_PROFILE
 __device__ long long g_prof_mvie[8 * 65536];   // [cta][rows, dots, ldl, linesearch, predictor, newton iters, armijo evals, backtracks]
-#define BP_MPROF_MARK() long long mprof_t_ = clock64()
-#define BP_MPROF_LAP(slot) { const long long now_ = clock64(); if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof_mvie[8 * blockIdx.x + (slot)] += now_ - mprof_t_; mprof_t_ = now_; }
-#define BP_MPROF_COUNT(slot) { if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof_mvie[8 * blockIdx.x + (slot)] += 1; }
+// (accumulated in registers, written once per solve: a global read-modify-write per lap would cost ~600 cycles)
+#define BP_MPROF_INIT() long long mprof_t_ = 0; long long mprof_a_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define BP_MPROF_MARK() mprof_t_ = clock64()
+#define BP_MPROF_LAP(slot) { const long long now_ = clock64(); mprof_a_[slot] += now_ - mprof_t_; mprof_t_ = now_; }
+#define BP_MPROF_COUNT(slot) { mprof_a_[slot] += 1; }
+#define BP_MPROF_FLUSH() { if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) { for (int q_ = 0; q_ < 8; ++q_) atomicAdd((unsigned long long*)&g_prof_mvie[8 * blockIdx.x + q_], (unsigned long long)mprof_a_[q_]); } }
 #else
+#define BP_MPROF_INIT()
 #define BP_MPROF_MARK()
 #define BP_MPROF_LAP(slot)
 #define BP_MPROF_COUNT(slot)
+#define BP_MPROF_FLUSH()
 #endif
 
 #define BP_MVIE_W(NV) ((((NV) + 7) & 1) ? ((NV) + 7) : ((NV) + 8))
@@ -84,6 +89,7 @@ __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict_
                                                        int m, double c00, double c01, double c02, double* scratch) {
   const double c0[3] = {c00, c01, c02};
   BpMvieOut res;
+  BP_MPROF_INIT();
   constexpr int NH = NV * (NV + 1) / 2;
   constexpr int W = BP_MVIE_W(NV);
   constexpr int NOUT = NH + NV + 6;
@@ -345,6 +351,7 @@ __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict_
     t = t_next;
   }
 done:
+  BP_MPROF_FLUSH();
 #pragma unroll
   for (int k = 0; k < 6; ++k) res.L[k] = x[k];
   if (NV == 9) { res.d[0] = x[6]; res.d[1] = x[7]; res.d[2] = x[8]; }

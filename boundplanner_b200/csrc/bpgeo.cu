@@ -127,9 +127,12 @@ struct Vec3 { double v[3]; };
 __device__ long long g_prof[4 * 65536];   // [seed][poly cycles, mvie cycles, passes, total]
 __device__ long long g_prof_pair[128];        // [0..63] histogram of Newton iterations per LP (bucket = iters / 2), [64] LPs, [65] sum of iterations, [66] max warp cycles, [67] answers 1
 __device__ long long g_prof_poly[8 * 65536];   // [cta][phase1, argmin, refine, halfspace, delete scan, picks, refine rounds, qps of thread 0]
-#define BP_PPROF_MARK() long long pprof_t_ = clock64()
-#define BP_PPROF_LAP(slot) { const long long now_ = clock64(); if (threadIdx.x == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + (slot)] += now_ - pprof_t_; pprof_t_ = now_; }
-#define BP_PPROF_COUNT(slot) { if (threadIdx.x == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + (slot)] += 1; }
+// (accumulated in registers and written once per pass: a global read-modify-write per lap costs ~600 cycles)
+#define BP_PPROF_MARK() long long pprof_t_ = clock64(); long long pprof_a_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define BP_PPROF_LAP(slot) { const long long now_ = clock64(); pprof_a_[slot] += now_ - pprof_t_; pprof_t_ = now_; }
+#define BP_PPROF_COUNT(slot) { pprof_a_[slot] += 1; }
+#define BP_PPROF_ADDN(slot, n) { pprof_a_[slot] += (n); }
+#define BP_PPROF_FLUSH() { if (threadIdx.x == 0 && blockIdx.x < 65536) { for (int q_ = 0; q_ < 8; ++q_) g_prof_poly[8 * blockIdx.x + q_] += pprof_a_[q_]; } }
 #define BP_PROF_T0() const long long prof_t0_ = clock64()
 #define BP_PROF_ADD(slot) if ((threadIdx.x & 31) == 0 && blockIdx.x < 65536) g_prof[4 * blockIdx.x + (slot)] += clock64() - prof_t0_
 #else
@@ -138,6 +141,8 @@ __device__ long long g_prof_poly[8 * 65536];   // [cta][phase1, argmin, refine, 
 #define BP_PPROF_MARK()
 #define BP_PPROF_LAP(slot)
 #define BP_PPROF_COUNT(slot)
+#define BP_PPROF_ADDN(slot, n)
+#define BP_PPROF_FLUSH()
 #endif
 
 
@@ -525,7 +530,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
   while (true) {
     double val = lkey;
     int idx = lidx, exact = lexact;
-    BP_PPROF_LAP(buf == 0 && m_cur == 6 ? 0 : 4);
+    if (buf == 0 && m_cur == 6) { BP_PPROF_LAP(0); } else { BP_PPROF_LAP(4); }
     block_argmin_lazy(val, idx, exact, red_val, red_idx, buf);
     BP_PPROF_LAP(1);
     if (!(val < BP_INF)) break;                      // no obstacle left
@@ -662,6 +667,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
       }
     }
   }
+  BP_PPROF_FLUSH();
   *m_out = m_cur;
   *status_out = status;
 }
@@ -777,33 +783,42 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
     if (bmin2 < BP_INF && n_out > n_free) {
       // Every round costs one closest-point QP latency however few QPs it solves, so the shell is filled as far
       // as it goes: the widest of the thresholds GROW x {1, 2, 4, 8} x (smallest bound) that still fits.
+      // (a dense neighbourhood where not even GROW x fits gets a second, finer ladder below GROW x)
       const double bmin = sqrt(bmin2), floor_ = exmin < BP_INF ? exmin : 0.0;
-      double cand[4], cand2[4];
-      int c4[4] = {0, 0, 0, 0};
+      for (int level = 0; level < 2; ++level) {
+        double cand[4], cand2[4];
+        int c4[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int g = 0; g < 4; ++g) { cand[g] = fmax(floor_, (BP_LAZY_GROW * (1 << g)) * bmin); cand2[g] = cand[g] * cand[g]; }
-#pragma unroll
-      for (int w = 0; w < AW; ++w)
-        for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
-          const double key = s_key[tid + (__ffsll((long long)mk) - 1 + 64 * w) * T];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) c4[g] += key <= cand2[g];
+        for (int g = 0; g < 4; ++g) {
+          const double f = level == 0 ? BP_LAZY_GROW * (1 << g) : 1.0 + (BP_LAZY_GROW - 1.0) * (0.1 + 0.2 * g);
+          cand[g] = fmax(floor_, f * bmin);
+          cand2[g] = cand[g] * cand[g];
         }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = __reduce_add_sync(full, c4[g]);
-        if (lane == 0) sh->hist[g][warp] = c;
-      }
-      __syncthreads();
-      int pick_g = 0;
+        for (int w = 0; w < AW; ++w)
+          for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
+            const double key = s_key[tid + (__ffsll((long long)mk) - 1 + 64 * w) * T];
 #pragma unroll
-      for (int g = 1; g < 4; ++g) {
-        int tot = 0;
-        for (int w = 0; w < (T >> 5); ++w) tot += sh->hist[g][w];
-        if (tot <= n_free) pick_g = g;
+            for (int g = 0; g < 4; ++g) c4[g] += key <= cand2[g];
+          }
+        if (level == 1) __syncthreads();                 // the level-0 counts have been read by everybody
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c = __reduce_add_sync(full, c4[g]);
+          if (lane == 0) sh->hist[g][warp] = c;
+        }
+        __syncthreads();
+        int pick_g = -1;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          int tot = 0;
+          for (int w = 0; w < (T >> 5); ++w) tot += sh->hist[g][w];
+          if (tot <= n_free) pick_g = g;
+        }
+        thr = cand[pick_g < 0 ? 0 : pick_g];
+        thr2 = cand2[pick_g < 0 ? 0 : pick_g];
+        if (pick_g >= 0) break;                          // (else: the finer ladder; after it the retry below)
       }
-      thr = cand[pick_g];
-      thr2 = cand2[pick_g];
     }
     unsigned long long taken[AW];
 #pragma unroll
@@ -835,11 +850,9 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
       thr2 = fmax(thr * thr, bmin2);
       __syncthreads();
     }
-    if (over) { *fallback = 1; return; }
+    if (over) { BP_PPROF_FLUSH(); *fallback = 1; return; }
     const int n_new = sh->cnt;
-#ifdef BPGEO_PROFILE
-    if (tid == 0 && blockIdx.x < 65536) g_prof_poly[8 * blockIdx.x + 7] += n_new;
-#endif
+    BP_PPROF_ADDN(7, n_new);
 #pragma unroll
     for (int w = 0; w < AW; ++w) alive[w] &= ~taken[w];
     // exact closest points of the new shell entries
@@ -937,9 +950,14 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
         if (npk > 0) {
           double lb[3], ub[3];
           load_box(sc, j, lb, ub);
-          for (int t = 0; t < npk; ++t) {
-            const double a[3] = {sh->pick[t][0], sh->pick[t][1], sh->pick[t][2]};
-            dead = dead || bp_box_min_halfspace(a, sh->pick[t][3], lb, ub) >= -1e-4;
+          for (int t = 0; t < npk && !dead; ++t) {
+            // min over the 8 vertices of a.v - b: by monotone rounding min(a lb, a ub) == a * (a >= 0 ? lb : ub),
+            // the same bits as bp_box_min_halfspace with half the FP64 instructions
+            const double a0 = sh->pick[t][0], a1 = sh->pick[t][1], a2 = sh->pick[t][2];
+            const double t0 = a0 * (a0 >= 0.0 ? lb[0] : ub[0]);
+            const double t1 = a1 * (a1 >= 0.0 ? lb[1] : ub[1]);
+            const double t2 = a2 * (a2 >= 0.0 ? lb[2] : ub[2]);
+            dead = (((t0 + t1) + t2) - sh->pick[t][3]) >= -1e-4;
           }
         }
         if (dead) alive[w] &= ~(1ull << k);
@@ -948,6 +966,7 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
     }
     BP_PPROF_LAP(4);
   }
+  BP_PPROF_FLUSH();
   *m_out = m_cur;
   *status_out = status;
 }
@@ -1120,6 +1139,9 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
   __shared__ double f_Q[9], f_p[3];
   __shared__ int c_status, c_small, f_status, c_mw;
   const int s = blockIdx.x, tid = threadIdx.x;
+#ifdef BPGEO_PROFILE
+  const long long prof_k0_ = clock64();
+#endif
   // The MVIE is a one-warp solve.  Two CTAs share an SM, and a warp's scheduler (SM sub-partition) is its index
   // mod 4: the CTAs of an SM take their slot from a per-SM counter so that their solver warps -- primary 2 slot,
   // the concurrent trailing solve 2 slot + 1 -- sit on four different sub-partitions and never share an FP64 pipe.
@@ -1307,6 +1329,9 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     pr.status[s] = status;
     if (pr.iters) pr.iters[s] = k;
     if (pr.rows_peak) pr.rows_peak[s] = rows_peak;
+#ifdef BPGEO_PROFILE
+    if (blockIdx.x < 65536) g_prof[4 * blockIdx.x + 3] = clock64() - prof_k0_;
+#endif
   }
 }
 

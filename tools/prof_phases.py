@@ -35,12 +35,13 @@ torch.cuda.synchronize()
 lib.bp_prof_read(buf.ctypes.data_as(ctypes.c_void_p), S, 1)
 it = out.iters.cpu().numpy()
 tot = buf[:, :3].sum(1)
+print(f"slowest CTA {buf[:, 3].max()} cycles ({buf[:, 3].max() / 1.965e3:.0f} us at 1965 MHz), mean {buf[:, 3].mean():.0f}")
 print(f"kernel {ev0.elapsed_time(ev1) * 1e3:.0f} us; per seed cycles (poly, mvie-in-loop, mvie-final): "
       f"mean {buf[:, 0].mean():.0f} {buf[:, 1].mean():.0f} {buf[:, 2].mean():.0f}")
-k = np.argsort(-tot)[:8]
+k = np.argsort(-buf[:, 3])[:8]
 for s in k:
     print(f"seed {s}: passes {it[s]} poly {buf[s, 0]} mvie {buf[s, 1]} final {buf[s, 2]} sum {tot[s]} "
-          f"({tot[s] / 1.965e3:.0f} us at 1965 MHz) rows {int(out.m[s])}")
+          f"CTA total {buf[s, 3]} ({buf[s, 3] / 1.965e3:.0f} us at 1965 MHz) rows {int(out.m[s])}")
 print("per pass: poly", (buf[:, 0] / np.minimum(it, 5)).mean(), "mvie6", (buf[:, 1] / np.minimum(it, 5)).mean())
 lib.bp_prof_read_poly(pbuf.ctypes.data_as(ctypes.c_void_p), S, 0)
 print("polyhedron pass of those seeds (cycles over all passes: bounds | collect+QP | picks | sweep; picks, rounds, QPs):")
