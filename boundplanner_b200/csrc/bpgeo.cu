@@ -723,7 +723,7 @@ struct ShellMem {
   int free_list[BP_SHELL];             // free slots
   int new_list[BP_SHELL];              // slots filled in this round (exact QP pending)
   int n_free, cnt, n_pick, m_cur, status, pad_;
-  int hist[4][16];                     // per-warp counts of the obstacles within four candidate thresholds
+  int hist[8][16];                     // per-warp counts of the obstacles within the candidate thresholds
 };
 
 template <int AW>
@@ -786,31 +786,34 @@ __device__ __forceinline__ void poly_pass_shell(const SceneView& sc, const PassM
       // (a dense neighbourhood where not even GROW x fits gets a second, finer ladder below GROW x)
       const double bmin = sqrt(bmin2), floor_ = exmin < BP_INF ? exmin : 0.0;
       for (int level = 0; level < 2; ++level) {
-        double cand[4], cand2[4];
-        int c4[4] = {0, 0, 0, 0};
+        // level 0: GROW x 1.4^g (the count grows about cubically with the radius: a ladder this fine fills the
+        // shell to more than a third); level 1: eight steps between 1 x and GROW x
+        double cand[8], cand2[8];
+        int c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double f = level == 0 ? BP_LAZY_GROW : 1.0 + (BP_LAZY_GROW - 1.0) * 0.06;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const double f = level == 0 ? BP_LAZY_GROW * (1 << g) : 1.0 + (BP_LAZY_GROW - 1.0) * (0.1 + 0.2 * g);
+        for (int g = 0; g < 8; ++g) {
           cand[g] = fmax(floor_, f * bmin);
           cand2[g] = cand[g] * cand[g];
+          f = level == 0 ? f * 1.4 : f + (BP_LAZY_GROW - 1.0) * 0.12;
         }
 #pragma unroll
         for (int w = 0; w < AW; ++w)
           for (unsigned long long mk = alive[w]; mk; mk &= mk - 1) {
             const double key = s_key[tid + (__ffsll((long long)mk) - 1 + 64 * w) * T];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) c4[g] += key <= cand2[g];
+            for (int g = 0; g < 8; ++g) c8[g] += key <= cand2[g];
           }
         if (level == 1) __syncthreads();                 // the level-0 counts have been read by everybody
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = __reduce_add_sync(full, c4[g]);
+        for (int g = 0; g < 8; ++g) {
+          const int c = __reduce_add_sync(full, c8[g]);
           if (lane == 0) sh->hist[g][warp] = c;
         }
         __syncthreads();
         int pick_g = -1;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 8; ++g) {
           int tot = 0;
           for (int w = 0; w < (T >> 5); ++w) tot += sh->hist[g][w];
           if (tot <= n_free) pick_g = g;
