@@ -438,10 +438,11 @@ def run_gpu(args):
     n_pairs = S_total * (S_total - 1) // 2
     value = S_total * args.steps / (dev_ms * 1e-3)
     fused = os.environ.get("BPGEO_FUSED", "1") != "0"
-    # fused: k_iris_fused + aabb + filter + lp;  else state_init, 5x(poly,mvie), final mvie, export, aabb+filter+lp
-    launches_per_step = (1 + 3) if fused else (1 + 5 * 2 + 1 + 1 + 3)
+    # fused: k_iris_fused (boxes and peer stores in its epilogue) + filter + lp;  else state_init, 5x(poly,mvie),
+    # final mvie, export, aabb + filter + lp
+    launches_per_step = (1 + 2) if fused else (1 + 5 * 2 + 1 + 1 + 3)
     if is_peer:
-        launches_per_step += 2                      # the two peer-scatter kernels (barriers are torch's)
+        launches_per_step += 1 if fused else 2      # the adjacency-row scatter (+ the set scatter when not fused)
     if rank == 0:
         peaks = {}
         try:

@@ -48,6 +48,8 @@ SIGNATURES = {
                                  _i, _vp, _sz, _vp]),
     "bp_build_sets_point_ms": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _i, _vp, _sz, _vp]),
+    "bp_build_sets_point_x": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _i, _vp, _vp, _i, _i, _sz, _sz, _sz, _sz, _vp, _sz, _vp]),
     "bp_build_sets_line_ms": (_i, [_vp, _vp, _vp, _vp, _i, _dp, _dp, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _sz, _vp]),
     "bp_pairs_feasible_list": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

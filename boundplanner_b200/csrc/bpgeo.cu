@@ -1094,7 +1094,88 @@ __global__ void __launch_bounds__(512) k_poly_point(SceneView sc_all, PolyParams
 // for the slowest MVIE of the whole batch, and the rows never leave shared memory between the phases.
 // Used for scenes whose distance table leaves room for two CTAs per SM (N <= 4096).
 // ---------------------------------------------------------------------------
+// Exact axis-aligned bounding box of the polytope {A x <= b} (ms rows) by vertex enumeration over all row
+// triples, by the 128 threads of a CTA; rows may live in global or shared memory.  out6 = lo[3] | hi[3]
+// (-inf / +inf when no vertex is found: unbounded or empty description -- never reject on such a set).
+// Used by k_set_aabb and by the epilogue of the fused set build (same code, same bits).
+#define BP_AABB_EPS 1e-9
+__device__ __forceinline__ void cta_set_aabb(const double* As, const double* bs, int ms, double (*red)[6],
+                                             double* out6) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double lo[3] = {BP_INF, BP_INF, BP_INF}, hi[3] = {-BP_INF, -BP_INF, -BP_INF};
+  // all row triples (i < j < k), flattened over the threads so that every thread walks the same number of
+  // candidates (the nested-loop version ran at 8.7 active threads/warp)
+  const int ntrip = ms * (ms - 1) * (ms - 2) / 6;
+  for (int t = threadIdx.x; t < ntrip; t += 128) {
+    int i = 0, rem = t;
+    for (;;) { const int c = (ms - 1 - i) * (ms - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
+    int j = i + 1;
+    for (;;) { const int c = ms - 1 - j; if (rem < c) break; rem -= c; ++j; }
+    const int k = j + 1 + rem;
+    const double a0 = As[3 * i], a1 = As[3 * i + 1], a2 = As[3 * i + 2], ab = bs[i];
+    const double c0 = As[3 * j], c1 = As[3 * j + 1], c2 = As[3 * j + 2], cb = bs[j];
+    const double d0 = As[3 * k], d1 = As[3 * k + 1], d2 = As[3 * k + 2], db = bs[k];
+    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;      // a x c
+    const double det = n0 * d0 + n1 * d1 + n2 * d2;
+    const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
+    if (!(fabs(det) > 1e-12 * scale)) continue;
+    // v = (ab (c x d) + cb (d x a) + db (a x c)) / det
+    const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
+    const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
+    const double id = 1.0 / det;
+    const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
+    const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
+    const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
+    bool inside = true;
+    for (int r = 0; r < ms; ++r) {
+      const double q0 = As[3 * r], q1 = As[3 * r + 1], q2 = As[3 * r + 2];
+      const double viol = q0 * v0 + q1 * v1 + q2 * v2 - bs[r];
+      if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
+    }
+    if (inside) {
+      lo[0] = fmin(lo[0], v0); hi[0] = fmax(hi[0], v0);
+      lo[1] = fmin(lo[1], v1); hi[1] = fmax(hi[1], v1);
+      lo[2] = fmin(lo[2], v2); hi[2] = fmax(hi[2], v2);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], red[w][k]); hi[k] = fmax(hi[k], red[w][3 + k]); }
+    }
+    const bool none = !(lo[0] <= hi[0]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      out6[k] = none ? -BP_INF : lo[k];
+      out6[3 + k] = none ? BP_INF : hi[k];
+    }
+  }
+}
+
+// where the owner of a set also delivers it (multi-GPU exchange by peer stores)
+struct PeerTables {
+  const unsigned long long* base;   // device array [world]: base address of every rank's symmetric allocation
+  int world, slot0;                 // this rank's sets go to rows slot0 .. slot0 + S - 1 of the global tables
+  size_t off_A, off_b, off_m, off_aabb;
+};
+
 struct FusedParams {
+  double* aabb;              // [S,6] or NULL: exact bounding box of every finished set (what k_set_aabb computes)
+  PeerTables peers;          // peers.world > 0: finished sets and boxes are also stored into every rank's tables
   const double* seeds;       // [S,3] seeds (MODE 0) / segment starts p0 (MODE 1)
   const double* dp1;         // [S,3] segment vectors (MODE 1)
   double ws_rows[6];
@@ -1332,10 +1413,33 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     pr.status[s] = status;
     if (pr.iters) pr.iters[s] = k;
     if (pr.rows_peak) pr.rows_peak[s] = rows_peak;
-#ifdef BPGEO_PROFILE
-    if (blockIdx.x < 65536) g_prof[4 * blockIdx.x + 3] = clock64() - prof_k0_;
-#endif
   }
+  if (MODE == 0 && (pr.aabb || pr.peers.world > 0)) {
+    // Epilogue: the set's exact bounding box (the pair filter's input) while its rows are still in shared memory,
+    // and -- multi-GPU -- the owner's stores of rows, row count and box straight into every rank's global tables
+    // over NVLink: no separate box / scatter kernels, and a finished seed's stores overlap the seeds still running.
+    __shared__ double e_red[4][6], e_box[6];
+    for (int r = m_out + tid; r < pr.m_max; r += blockDim.x) {          // padding, as written to A / b above
+      sA[3 * r] = 0.0; sA[3 * r + 1] = 0.0; sA[3 * r + 2] = 0.0; sb[r] = 10.0;
+    }
+    __syncthreads();
+    cta_set_aabb(sA, sb, m_out, e_red, e_box);
+    __syncthreads();
+    if (pr.aabb && tid < 6) pr.aabb[(size_t)s * 6 + tid] = e_box[tid];
+    const int g = pr.peers.slot0 + s;
+    for (int r = 0; r < pr.peers.world; ++r) {
+      char* base = (char*)pr.peers.base[r];
+      double* Ad = (double*)(base + pr.peers.off_A) + (size_t)g * pr.m_max * 3;
+      double* bd = (double*)(base + pr.peers.off_b) + (size_t)g * pr.m_max;
+      for (int e = tid; e < 3 * pr.m_max; e += blockDim.x) Ad[e] = sA[e];
+      for (int e = tid; e < pr.m_max; e += blockDim.x) bd[e] = sb[e];
+      if (tid < 6) ((double*)(base + pr.peers.off_aabb))[(size_t)g * 6 + tid] = e_box[tid];
+      if (tid == 6) ((int*)(base + pr.peers.off_m))[g] = m_out;
+    }
+  }
+#ifdef BPGEO_PROFILE
+  if (tid == 0 && blockIdx.x < 65536) g_prof[4 * blockIdx.x + 3] = clock64() - prof_k0_;
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -1813,81 +1917,14 @@ __global__ void k_state_init_line(SeedState* st, const double* __restrict__ p0, 
 // the LP, every 0 from the LP or from a rigorous box separation.
 // ---------------------------------------------------------------------------
 
-#define BP_AABB_EPS 1e-9
 #define BP_LP_T0_SCALE 8.0
 
 __global__ void __launch_bounds__(128) k_set_aabb(const double* __restrict__ A, const double* __restrict__ b,
                                                   const int* __restrict__ m, int S, int m_max,
                                                   double* __restrict__ aabb) {
   __shared__ double red[4][6];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = blockIdx.x;                     // one 128-thread CTA per set
-  const double* As = A + (size_t)s * m_max * 3;
-  const double* bs = b + (size_t)s * m_max;
-  const int ms = m[s];
-  double lo[3] = {BP_INF, BP_INF, BP_INF}, hi[3] = {-BP_INF, -BP_INF, -BP_INF};
-  // all row triples (i < j < k), flattened over the lanes so that every lane walks
-  // the same number of candidates (the nested-loop version ran at 8.7 active threads/warp)
-  const int ntrip = ms * (ms - 1) * (ms - 2) / 6;
-  for (int t = threadIdx.x; t < ntrip; t += 128) {
-    int i = 0, rem = t;
-    for (;;) { const int c = (ms - 1 - i) * (ms - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
-    int j = i + 1;
-    for (;;) { const int c = ms - 1 - j; if (rem < c) break; rem -= c; ++j; }
-    const int k = j + 1 + rem;
-    const double a0 = __ldg(As + 3 * i), a1 = __ldg(As + 3 * i + 1), a2 = __ldg(As + 3 * i + 2), ab = __ldg(bs + i);
-    const double c0 = __ldg(As + 3 * j), c1 = __ldg(As + 3 * j + 1), c2 = __ldg(As + 3 * j + 2), cb = __ldg(bs + j);
-    const double d0 = __ldg(As + 3 * k), d1 = __ldg(As + 3 * k + 1), d2 = __ldg(As + 3 * k + 2), db = __ldg(bs + k);
-    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;      // a x c
-    const double det = n0 * d0 + n1 * d1 + n2 * d2;
-    const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
-    if (!(fabs(det) > 1e-12 * scale)) continue;
-    // v = (ab (c x d) + cb (d x a) + db (a x c)) / det
-    const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
-    const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
-    const double id = 1.0 / det;
-    const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
-    const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
-    const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
-    bool inside = true;
-    for (int r = 0; r < ms; ++r) {
-      const double q0 = __ldg(As + 3 * r), q1 = __ldg(As + 3 * r + 1), q2 = __ldg(As + 3 * r + 2);
-      const double viol = q0 * v0 + q1 * v1 + q2 * v2 - __ldg(bs + r);
-      if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
-    }
-    if (inside) {
-      lo[0] = fmin(lo[0], v0); hi[0] = fmax(hi[0], v0);
-      lo[1] = fmin(lo[1], v1); hi[1] = fmax(hi[1], v1);
-      lo[2] = fmin(lo[2], v2); hi[2] = fmax(hi[2], v2);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
-      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 1; w < 4; ++w) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], red[w][k]); hi[k] = fmax(hi[k], red[w][3 + k]); }
-    }
-    // no vertex found (unbounded or empty description): never reject on this set
-    const bool none = !(lo[0] <= hi[0]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      aabb[(size_t)s * 6 + k] = none ? -BP_INF : lo[k];
-      aabb[(size_t)s * 6 + 3 + k] = none ? BP_INF : hi[k];
-    }
-  }
+  cta_set_aabb(A + (size_t)s * m_max * 3, b + (size_t)s * m_max, m[s], red, aabb + (size_t)s * 6);
 }
 
 // Block = 8 rows i x 32 columns j.
@@ -3043,6 +3080,21 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
                            int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
                            double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
                            void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  return bp_build_sets_point_x(scene, seed_scene_dev, seeds_dev, S, ws_min_host, ws_max_host, fixed_mid, optimize,
+                               max_iter, m_max, A_dev, b_dev, m_dev, q_ellipse_dev, p_mid_dev, status_dev, iters_dev,
+                               rows_peak_dev, row_cap, nullptr, nullptr, 0, 0, 0, 0, 0, 0, workspace_dev,
+                               workspace_bytes, stream_);
+}
+
+int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, const double* seeds_dev, int S,
+                          const double* ws_min_host, const double* ws_max_host, int fixed_mid, int optimize,
+                          int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                          double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                          double* aabb_dev, const unsigned long long* peer_base_dev, int world, int slot0,
+                          size_t off_A, size_t off_b, size_t off_m, size_t off_aabb, void* workspace_dev,
+                          size_t workspace_bytes, void* stream_) {
+  if (world < 0 || slot0 < 0 || (world > 0 && !peer_base_dev))
+    return bp_fail("bp_build_sets_point_x: bad peer arguments");
   if (scene && ((scene->seg_off != nullptr) != (seed_scene_dev != nullptr)))
     return bp_fail("bp_build_sets_point: a scene batch needs seed_scene, a single scene must not have it");
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || max_iter < 1 || !ws_min_host || !ws_max_host)
@@ -3059,6 +3111,9 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
     fp.status = status_dev; fp.iters = iters_dev; fp.rows_peak = rows_peak_dev;
     fp.m_max = m_max; fp.max_iter = max_iter; fp.fixed_mid = fixed_mid; fp.optimize = optimize;
     fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
+    fp.aabb = aabb_dev;
+    fp.peers.base = peer_base_dev; fp.peers.world = world; fp.peers.slot0 = slot0;
+    fp.peers.off_A = off_A; fp.peers.off_b = off_b; fp.peers.off_m = off_m; fp.peers.off_aabb = off_aabb;
     const size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
     if (scene->rows) {
       if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
@@ -3105,6 +3160,12 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
   }
   k_state_export<<<(S + 127) / 128, 128, 0, stream>>>(st, S, optimize ? max_iter : 1 << 30, q_ellipse_dev, p_mid_dev, status_dev, iters_dev,
                                                       rows_peak_dev);
+  // the launch-sequence path delivers boxes / peer copies with the stand-alone kernels
+  if (world > 0 && !aabb_dev) return bp_fail("bp_build_sets_point_x: the launch-sequence path needs aabb_dev for the peer stores");
+  if (aabb_dev) k_set_aabb<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, aabb_dev);
+  if (world > 0)
+    k_scatter_sets_peers<<<S, 128, 0, stream>>>(A_dev, b_dev, m_dev, aabb_dev, m_max, slot0, peer_base_dev, world, off_A,
+                                                off_b, off_m, off_aabb);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -191,10 +191,13 @@ def alloc_set_batch(S, m_max=BP_MAX_ROWS):
 
 
 def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS,
-                     row_cap=0, out=None, item_scene=None):
+                     row_cap=0, out=None, item_scene=None, aabb=None, peers=None):
     """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds.
     row_cap=20 reproduces the reference's failure on passes with more than 20 rows (status 5).
-    out: a batch from alloc_set_batch to write into (no allocation, CUDA-graph capturable)."""
+    out: a batch from alloc_set_batch to write into (no allocation, CUDA-graph capturable).
+    aabb: [S,6] tensor that receives every set's exact bounding box from the kernel's epilogue.
+    peers: dict(base=int64 tensor [world] of mapped base addresses, world, slot0, off_A, off_b, off_m, off_aabb):
+    the sets are also stored into every rank's global tables (multi-GPU exchange by peer stores)."""
     lib = _lib.load()
     seeds = _dev(seeds).reshape(-1, 3)
     S = seeds.shape[0]
@@ -208,10 +211,13 @@ def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=Tru
     amax, pmax = _host3(ws_max)
     if item_scene is not None:
         item_scene = _dev(item_scene, torch.int32).reshape(S)
-    check(lib.bp_build_sets_point_ms(scene._h, _ptr(item_scene), _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)),
-                                     int(bool(optimize)), int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m),
-                                     _ptr(q), _ptr(p), _ptr(status), _ptr(iters), _ptr(peak), int(row_cap),
-                                     _ptr(work), wbytes, _stream()))
+    pk = peers or {}
+    check(lib.bp_build_sets_point_x(scene._h, _ptr(item_scene), _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)),
+                                    int(bool(optimize)), int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m),
+                                    _ptr(q), _ptr(p), _ptr(status), _ptr(iters), _ptr(peak), int(row_cap),
+                                    _ptr(aabb), _ptr(pk.get("base")), int(pk.get("world", 0)), int(pk.get("slot0", 0)),
+                                    int(pk.get("off_A", 0)), int(pk.get("off_b", 0)), int(pk.get("off_m", 0)),
+                                    int(pk.get("off_aabb", 0)), _ptr(work), wbytes, _stream()))
     del amin, amax
     return out
 

@@ -46,6 +46,7 @@ class SetGraphPipeline:
         own = geo.alloc_set_batch(self.S, m_max)        # iters / rows_peak / loop workspace
         self.batch = geo.SetBatch(A, b, m, q, p, status, iters=own.iters, rows_peak=own.rows_peak, work=own.work)
         self.pair_buf = (self.bits, geo.alloc_pair_buffers(self.S)[1])
+        self.aabb = torch.empty((self.S, 6), dtype=torch.float64, device="cuda")   # written by the build's epilogue
         self._views = (A, b, m, q, p, status, self.bits)
         self._host = None
         self._graph = None
@@ -54,8 +55,9 @@ class SetGraphPipeline:
             self._capture()
 
     def _enqueue(self):
-        geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
-        geo.pair_feasible(self.batch.A, self.batch.b, self.batch.m, self.tol, out=self.pair_buf)
+        geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb,
+                             **self.kw)
+        geo.pair_feasible(self.batch.A, self.batch.b, self.batch.m, self.tol, out=self.pair_buf, aabb=self.aabb)
 
     def _capture(self):
         self._stream.wait_stream(torch.cuda.current_stream())
@@ -70,16 +72,19 @@ class SetGraphPipeline:
 
     def stage_times(self, reps=5):
         """Per-stage device time of one step in ms (median of `reps` eager steps, CUDA events between the kernels on
-        the launch stream): k_iris_fused | k_set_aabb | k_pair_filter | k_pair_lp."""
+        the launch stream): k_iris_fused (with the bounding boxes from its epilogue; "aabb" is 0 then) |
+        k_pair_filter | k_pair_lp."""
         import statistics
 
         acc = {"build": [], "aabb": [], "filter": [], "lp": []}
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
+            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb,
+                                 **self.kw)
             e1.record()
-            st = geo.pair_feasible_stages(self.batch.A, self.batch.b, self.batch.m, self.tol, out=self.pair_buf)
+            st = geo.pair_feasible_stages(self.batch.A, self.batch.b, self.batch.m, self.tol, out=self.pair_buf,
+                                          aabb=self.aabb)
             acc["build"].append(e0.elapsed_time(e1))
             for k, v in st.items():
                 acc[k].append(v)
@@ -282,9 +287,9 @@ class PeerSetGraphPipeline:
     process) holding the global tables  A[S,m_max,3] | b[S,m_max] | aabb[S,6] | m[S] | adjacency[S,words].
     A step is ONE CUDA graph per rank:
 
-      k_iris_fused (own S_loc seeds) -> k_set_aabb -> k_scatter_sets_peers: the owner writes its sets into
-      the tables of every rank through the peers' mapped addresses (no pack / all-gather / unpack)
-      -> signal-pad barrier -> pair kernels on the own row block of the global pair matrix, reading the
+      k_iris_fused (own S_loc seeds; its epilogue computes each finished set's bounding box and stores rows,
+      row count and box into the tables of EVERY rank through the peers' mapped addresses -- no pack /
+      all-gather / unpack, no separate box / scatter kernels) -> signal-pad barrier -> pair kernels on the own row block of the global pair matrix, reading the
       local tables -> k_scatter_rows_peers: the adjacency rows go to every rank -> signal-pad barrier.
 
     The second barrier also protects the tables: no rank starts the next step's scatter before every rank
@@ -340,14 +345,16 @@ class PeerSetGraphPipeline:
         self._graph = None
         self._capture()
 
+    def _peers(self):
+        return dict(base=self.peer_base, world=self.world, slot0=self.rank * self.S_loc, off_A=self.off_A,
+                    off_b=self.off_b, off_m=self.off_m, off_aabb=self.off_aabb)
+
     def _enqueue(self):
         lib, st = self._lib, geo._stream()
-        geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
-        geo.set_aabb(self.batch.A, self.batch.b, self.batch.m, out=self.aabb_loc)
-        geo.check(lib.bp_scatter_sets_peers(geo._ptr(self.batch.A), geo._ptr(self.batch.b), geo._ptr(self.batch.m),
-                                            geo._ptr(self.aabb_loc), self.S_loc, self.m_max, self.rank * self.S_loc,
-                                            geo._ptr(self.peer_base), self.world, self.off_A, self.off_b, self.off_m,
-                                            self.off_aabb, st))
+        # the owner's stores of every finished set (rows, row count, bounding box) into all ranks' tables happen in
+        # the epilogue of the set-build kernel: no separate box / scatter launches
+        geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb_loc,
+                             peers=self._peers(), **self.kw)
         self.hdl.barrier(channel=0)
         rows = self.r1 - self.r0
         if rows > 0:
@@ -370,14 +377,10 @@ class PeerSetGraphPipeline:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             self.hdl.barrier(channel=0)                  # start the ranks together, like back-to-back steps do
             ev[0].record()
-            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, **self.kw)
+            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch,
+                                 aabb=self.aabb_loc, peers=self._peers(), **self.kw)
             ev[1].record()
-            geo.set_aabb(self.batch.A, self.batch.b, self.batch.m, out=self.aabb_loc)
-            ev[2].record()
-            geo.check(lib.bp_scatter_sets_peers(geo._ptr(self.batch.A), geo._ptr(self.batch.b), geo._ptr(self.batch.m),
-                                                geo._ptr(self.aabb_loc), self.S_loc, self.m_max, self.rank * self.S_loc,
-                                                geo._ptr(self.peer_base), self.world, self.off_A, self.off_b,
-                                                self.off_m, self.off_aabb, st))
+            ev[2].record()                               # (boxes and peer stores: epilogue of the build kernel)
             ev[3].record()
             self.hdl.barrier(channel=0)
             ev[4].record()

@@ -125,6 +125,21 @@ int bp_build_sets_point_ms(const bp_scene* scene, const int* seed_scene_dev, con
                            double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
                            void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* The same with two optional deliveries from the kernel's epilogue (rows still in shared memory):
+ *   aabb_dev [S,6]    the exact bounding box of every finished set (what bp_set_aabb computes) -- hand it to
+ *                     bp_pair_feasible as aabb_in_dev;
+ *   peer tables       world > 0: rows, row count and box of set s are also stored into the global tables
+ *                     A[S_glob,m_max,3] | b | m | aabb of EVERY rank at row slot0 + s through peer_base_dev[world]
+ *                     (see bp_scatter_sets_peers); the caller synchronises the ranks afterwards.
+ * Replaces find_set_around_point (ConvexSetFinder.py:190-240) + the exchange step of SURVEY 8e. */
+int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, const double* seeds_dev, int S,
+                          const double* ws_min_host, const double* ws_max_host, int fixed_mid, int optimize,
+                          int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                          double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                          double* aabb_dev, const unsigned long long* peer_base_dev, int world, int slot0,
+                          size_t off_A, size_t off_b, size_t off_m, size_t off_aabb, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
 /* Replaces ConvexSetFinder.find_set_around_line (:242-307) for S segments p0 .. p0 + dp1: the IRIS loop around
  * the segment midpoint with the fixed-rotation MVIE (not called by the reference planner on main,
  * BoundPlanner.py:378-380, but part of ConvexSetFinder's surface).  optimize == 0: one pass + one free-centre
