@@ -73,6 +73,7 @@ struct SceneView {
   int vmax;
   const int* seg_off;     // scene batch: obstacle range of scene k is [seg_off[k], seg_off[k+1])
   const int* item_seg;    // scene index of every seed / segment (device, [S]) when seg_off != NULL
+  int staged;             // lb / ub point into shared memory (stage_scene)
 };
 
 static SceneView view_of(const bp_scene* s) {
@@ -85,6 +86,7 @@ static SceneView view_of(const bp_scene* s) {
   v.rows = s->rows; v.nrows = s->nrows; v.verts = s->verts; v.nverts = s->nverts; v.vmax = s->vmax;
   v.seg_off = s->seg_off;
   v.item_seg = nullptr;
+  v.staged = 0;
   return v;
 }
 
@@ -106,6 +108,7 @@ __device__ __forceinline__ SceneView scene_of_item(const SceneView& sc, int item
   v.rows = nullptr; v.nrows = nullptr; v.verts = nullptr; v.nverts = nullptr; v.vmax = 0;   // batches hold boxes
   v.seg_off = nullptr;
   v.item_seg = nullptr;
+  v.staged = 0;
   return v;
 }
 
@@ -149,12 +152,76 @@ __device__ long long g_prof_poly[8 * 65536];   // [cta][phase1, argmin, refine, 
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
 __device__ __forceinline__ void load_box(const SceneView& sc, int j, double* lb, double* ub) {
+  if (sc.staged) {                      // columns staged in shared memory (stage_scene): plain loads
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    lb[k] = __ldg(sc.lb[k] + j);
-    ub[k] = __ldg(sc.ub[k] + j);
+    for (int k = 0; k < 3; ++k) { lb[k] = sc.lb[k][j]; ub[k] = sc.ub[k][j]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lb[k] = __ldg(sc.lb[k] + j);
+      ub[k] = __ldg(sc.ub[k] + j);
+    }
   }
+}
+
+// Stage the six scene columns of this CTA's scene in shared memory with TMA bulk copies (cp.async.bulk, one
+// elected thread, mbarrier completion): every later box read of the polyhedron passes (bounds, sweeps, exact
+// QPs: ~4 N reads per pass) is then a shared-memory load instead of an L1/L2 access.  dst: 6 * ncap doubles,
+// ncap = n rounded up to even (16-byte bulk granularity).  All threads call it; returns the staged view.
+__device__ __forceinline__ SceneView stage_scene(const SceneView& sc, double* dst, uint64_t* bar) {
+  const int ncap = (sc.n + 1) & ~1;
+  const uint32_t bytes = (uint32_t)ncap * 8u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(6u * bytes) : "memory");
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(dst + (size_t)k * ncap)), "l"(sc.lb[k]), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(dst + (size_t)(3 + k) * ncap)), "l"(sc.ub[k]), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    }
+  }
+  __syncthreads();                      // the barrier is initialised before anybody waits on it
+  mbar_wait(bar, 0);
+  SceneView v = sc;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { v.lb[k] = dst + (size_t)k * ncap; v.ub[k] = dst + (size_t)(3 + k) * ncap; }
+  v.staged = 1;
+  return v;
 }
 
 // (value, index) argmin across the block; ties -> smallest index (np.argmin, quirk Q11).
@@ -1188,6 +1255,7 @@ struct FusedParams {
   int* iters;
   int* rows_peak;
   int m_max, max_iter, fixed_mid, optimize, row_cap, cache_y;
+  int stage;                 // box scene: stage the scene columns in shared memory (TMA) after key table + shell
 };
 
 struct GlobalRows {
@@ -1212,13 +1280,19 @@ __device__ unsigned g_sm_slot[256];     // CTAs started per SM (only its parity 
 
 template <int MODE, bool POLY, int AW = 1>
 __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
-  const SceneView sc = scene_of_item(sc_all, blockIdx.x);
-  extern __shared__ double s_dist[];
+  SceneView sc = scene_of_item(sc_all, blockIdx.x);
+  extern __shared__ __align__(16) double s_dist[];
   __shared__ double red_val[2][32];
   __shared__ int red_idx[2][32];
   __shared__ double sA[BP_MAX_ROWS * 3], sb[BP_MAX_ROWS];
   __shared__ double scratch[BP_MVIE_SCRATCH_DOUBLES];
   __shared__ double scratch2[MODE == 0 ? BP_MVIE_SCRATCH_DOUBLES : 1];   // the concurrent trailing solve (below)
+  __shared__ __align__(8) uint64_t stage_bar;
+  if (!POLY && pr.stage && (((uintptr_t)sc.lb[0] | (uintptr_t)sc.lb[1]) & 15) == 0) {
+    // (a segment of a scene batch that starts at an odd obstacle index is not 16-byte aligned: global loads then)
+    double* s_scene = s_dist + ((sc_all.n + 1) & ~1) + 2 * ((sizeof(ShellMem) + 15) / 16);
+    sc = stage_scene(sc, s_scene, &stage_bar);
+  }
   __shared__ double c_Q[9], c_p[3], c_det;
   __shared__ double f_Q[9], f_p[3];
   __shared__ int c_status, c_small, f_status, c_mw;
@@ -2413,37 +2487,6 @@ __global__ void __launch_bounds__(256) k_project(const double* __restrict__ A, c
 // ---------------------------------------------------------------------------
 #define FK_T 128
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-}
-
 template <bool POSE, bool JAC>
 __global__ void __launch_bounds__(FK_T) k_fk(const double* __restrict__ q, int B, double* __restrict__ p_ee,
                                              double* __restrict__ p_col, double* __restrict__ T_ee,
@@ -3114,7 +3157,15 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
     fp.aabb = aabb_dev;
     fp.peers.base = peer_base_dev; fp.peers.world = world; fp.peers.slot0 = slot0;
     fp.peers.off_A = off_A; fp.peers.off_b = off_b; fp.peers.off_m = off_m; fp.peers.off_aabb = off_aabb;
-    const size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
+    size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
+    // box scenes small enough for two CTAs per SM: the scene columns are staged in shared memory by TMA
+    // (BPGEO_STAGE=0 keeps the global / L1 loads: the A/B switch of profiles/r02_stage_ab.txt)
+    {
+      static int env = -1;
+      if (env < 0) { const char* e = getenv("BPGEO_STAGE"); env = (e && e[0] == '0') ? 0 : 1; }
+      const size_t staged = 16 * ((sizeof(ShellMem) + 15) / 16) + sizeof(double) * (size_t)((scene->n + 1) & ~1) * 7;
+      if (env && !scene->rows && staged + 20 * 1024 <= 110 * 1024) { fp.stage = 1; fsmem = staged; }
+    }
     if (scene->rows) {
       if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
       if (set_dyn_smem((const void*)k_iris_fused<0, true>, fsmem)) return 1;
