@@ -21,6 +21,7 @@ STATUS_ROW_OVERFLOW = 2
 STATUS_MVIE_NO_INTERIOR = 3
 STATUS_MVIE_NOT_CONVERGED = 4
 STATUS_ROW_CAP = 5
+STATUS_NOT_A_POLYTOPE = 6
 
 _c = ctypes
 _vp, _i, _d, _sz = _c.c_void_p, _c.c_int, _c.c_double, _c.c_size_t
@@ -69,6 +70,7 @@ SIGNATURES = {
     "bp_scatter_sets_peers": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _sz, _sz, _sz, _sz, _vp]),
     "bp_scatter_rows_peers": (_i, [_vp, _i, _i, _i, _vp, _i, _sz, _vp]),
     "bp_fk_iiwa14": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "bp_polytope_vertices": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "bp_debug_counters": (_i, [_c.POINTER(_c.c_ulonglong), _i, _i]),
     "bp_fk_iiwa14_kin": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_probe_fp64": (_i, [_i, _i, _i, _i, _vp, _vp]),

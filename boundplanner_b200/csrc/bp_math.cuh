@@ -24,6 +24,7 @@ enum {
   BP_MVIE_NO_INTERIOR = 3,    // centre / hint not strictly inside the polytope
   BP_MVIE_NOT_CONVERGED = 4,
   BP_ROW_CAP = 5,             // more rows than the caller's row_cap (reference MVIE buffers: 20 rows, quirk Q5)
+  BP_NOT_A_POLYTOPE = 6,      // bp_polytope_vertices: unbounded or empty (util_functions.py:76 raises ValueError)
 };
 
 // ---------------------------------------------------------------------------

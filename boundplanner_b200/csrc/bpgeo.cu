@@ -2087,19 +2087,29 @@ __device__ __forceinline__ bool bp_pair_margin_reject(const double* __restrict__
   return __any_sync(full, apart);
 }
 
-__global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
+// MINB = CTAs per SM the register allocation is held to: 2 (122 registers, no spills) is fastest while the LPs of
+// a call fit the resident warps about once (latency-bound: 1.7 k LPs on C2); 3 (80 registers, a few spills) wins
+// when a rank has many LPs per resident warp (throughput-bound: the 8-GPU graph, C4).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
                                                  const int* __restrict__ m, int S, int m_max, double tol,
                                                  int row_begin, const double* __restrict__ aabb,
                                                  const int2* __restrict__ list,
-                                                 const unsigned int* __restrict__ count,
+                                                 unsigned int* __restrict__ count,
                                                  unsigned int* __restrict__ adj, double* __restrict__ x_feas) {
   __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int words = (S + 31) >> 5;
-  const unsigned int n = *count;
-  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned int p = warp; p < n; p += nwarps) {       // one warp per surviving pair
+  const unsigned int n = count[0];
+  // One warp per surviving pair, taken from a shared cursor (count[1], zeroed with the list count): the grid holds
+  // exactly the CTAs that are resident at once, and a warp that drew short LPs takes more of them.  (A strided
+  // static split over a larger grid ran in waves, each paying the latency of its slowest LPs: 0.29 ms instead of
+  // 0.1 ms for the 13.6 k LPs of a rank of the 8-GPU graph.)
+  for (;;) {
+    unsigned int p = 0;
+    if (lane == 0) p = atomicAdd(count + 1, 1u);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= n) break;
     const int2 pr = list[p];
     if (bp_pair_margin_reject(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x], aabb + (size_t)pr.x * 6,
                               A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], aabb + (size_t)pr.y * 6,
@@ -2312,6 +2322,122 @@ __global__ void __launch_bounds__(128) k_reduce_rows(const double* __restrict__ 
     if (keep_out) for (int r = ms; r < m_max; ++r) keep_out[(size_t)s * m_max + r] = 0;
     m_out[s] = k;
     if (status) status[s] = overflow ? BP_ROW_OVERFLOW : BP_OK;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Vertex enumeration of polytopes {A x <= b}: replaces compute_polytope_vertices
+// (bound_planner/utils/util_functions.py:66-79; cddlib double description) -- what add_obstacle_reps needs to
+// turn obstacle halfspace sets into the vertex lists of obs_points_sets (BoundPlanner.py:142).  One 128-thread
+// CTA per set: every row triple gives a candidate point (as in k_set_aabb / k_reduce_rows); the feasible ones are
+// kept, coinciding candidates (more than three planes through a vertex) merged, and the vertices written in the
+// order of their first triple (deterministic).  status: BP_OK, BP_NOT_A_POLYTOPE (the recession cone
+// {d : A d <= 0} is not {0}: the reference raises ValueError("Polyhedron is not a polytope")), BP_ROW_OVERFLOW
+// (more than vmax vertices).
+// ---------------------------------------------------------------------------
+#define BP_VERT_MERGE 1e-9
+__global__ void __launch_bounds__(128) k_polytope_vertices(const double* __restrict__ A, const double* __restrict__ b,
+                                                           const int* __restrict__ m, int m_max, int vmax,
+                                                           double* __restrict__ V, int* __restrict__ nv_out,
+                                                           int* __restrict__ status) {
+  __shared__ double sA[BP_MAX_ROWS * 3], sb[BP_MAX_ROWS];
+  __shared__ double sv[BP_RED_VMAX * 3];
+  __shared__ int st[BP_RED_VMAX];                   // triple index of every stored candidate
+  __shared__ unsigned char dup[BP_RED_VMAX];
+  __shared__ int nverts, unbounded, anypair;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int ms = m[s];
+  for (int e = tid; e < ms * 3; e += 128) sA[e] = A[(size_t)s * m_max * 3 + e];
+  for (int e = tid; e < ms; e += 128) sb[e] = b[(size_t)s * m_max + e];
+  if (tid == 0) { nverts = 0; unbounded = 0; anypair = 0; }
+  __syncthreads();
+  // bounded?  a direction of the recession cone, if there is one, can be taken along +-(a_i x a_j)
+  for (int t = tid; t < ms * ms; t += 128) {
+    const int i = t / ms, j = t % ms;
+    if (j <= i) continue;
+    double d0 = sA[3 * i + 1] * sA[3 * j + 2] - sA[3 * i + 2] * sA[3 * j + 1];
+    double d1 = sA[3 * i + 2] * sA[3 * j] - sA[3 * i] * sA[3 * j + 2];
+    double d2 = sA[3 * i] * sA[3 * j + 1] - sA[3 * i + 1] * sA[3 * j];
+    const double dn = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    const double ni = sqrt(sA[3 * i] * sA[3 * i] + sA[3 * i + 1] * sA[3 * i + 1] + sA[3 * i + 2] * sA[3 * i + 2]);
+    const double nj = sqrt(sA[3 * j] * sA[3 * j] + sA[3 * j + 1] * sA[3 * j + 1] + sA[3 * j + 2] * sA[3 * j + 2]);
+    if (!(dn > 1e-12 * ni * nj)) continue;          // parallel (or zero) rows
+    anypair = 1;
+    d0 /= dn; d1 /= dn; d2 /= dn;
+    double mx = -BP_INF, mn = BP_INF;
+    for (int r = 0; r < ms; ++r) {
+      const double rn = sqrt(sA[3 * r] * sA[3 * r] + sA[3 * r + 1] * sA[3 * r + 1] + sA[3 * r + 2] * sA[3 * r + 2]);
+      if (!(rn > 0.0)) continue;
+      const double v = (sA[3 * r] * d0 + sA[3 * r + 1] * d1 + sA[3 * r + 2] * d2) / rn;
+      mx = fmax(mx, v); mn = fmin(mn, v);
+    }
+    if (mx <= 1e-12 || mn >= -1e-12) unbounded = 1;   // A d <= 0 for d or for -d
+  }
+  const int ntrip = ms * (ms - 1) * (ms - 2) / 6;
+  for (int t = tid; t < ntrip; t += 128) {
+    int i = 0, rem = t;
+    for (;;) { const int c = (ms - 1 - i) * (ms - 2 - i) / 2; if (rem < c) break; rem -= c; ++i; }
+    int j = i + 1;
+    for (;;) { const int c = ms - 1 - j; if (rem < c) break; rem -= c; ++j; }
+    const int k = j + 1 + rem;
+    const double a0 = sA[3 * i], a1 = sA[3 * i + 1], a2 = sA[3 * i + 2], ab = sb[i];
+    const double c0 = sA[3 * j], c1 = sA[3 * j + 1], c2 = sA[3 * j + 2], cb = sb[j];
+    const double d0 = sA[3 * k], d1 = sA[3 * k + 1], d2 = sA[3 * k + 2], db = sb[k];
+    const double n0 = a1 * c2 - a2 * c1, n1 = a2 * c0 - a0 * c2, n2 = a0 * c1 - a1 * c0;
+    const double det = n0 * d0 + n1 * d1 + n2 * d2;
+    const double scale = (fabs(n0) + fabs(n1) + fabs(n2)) * (fabs(d0) + fabs(d1) + fabs(d2));
+    if (!(fabs(det) > 1e-12 * scale)) continue;
+    const double e0 = c1 * d2 - c2 * d1, e1 = c2 * d0 - c0 * d2, e2 = c0 * d1 - c1 * d0;
+    const double f0 = d1 * a2 - d2 * a1, f1 = d2 * a0 - d0 * a2, f2 = d0 * a1 - d1 * a0;
+    const double id = 1.0 / det;
+    const double v0 = (ab * e0 + cb * f0 + db * n0) * id;
+    const double v1 = (ab * e1 + cb * f1 + db * n1) * id;
+    const double v2 = (ab * e2 + cb * f2 + db * n2) * id;
+    bool inside = true;
+    for (int r = 0; r < ms; ++r) {
+      const double q0 = sA[3 * r], q1 = sA[3 * r + 1], q2 = sA[3 * r + 2];
+      const double viol = q0 * v0 + q1 * v1 + q2 * v2 - sb[r];
+      if (viol > BP_AABB_EPS * (1.0 + fabs(q0 * v0) + fabs(q1 * v1) + fabs(q2 * v2))) inside = false;
+    }
+    if (inside) {
+      const int slot = atomicAdd(&nverts, 1);
+      if (slot < BP_RED_VMAX) { sv[3 * slot] = v0; sv[3 * slot + 1] = v1; sv[3 * slot + 2] = v2; st[slot] = t; }
+    }
+  }
+  __syncthreads();
+  const int nc = nverts < BP_RED_VMAX ? nverts : BP_RED_VMAX;
+  // a candidate is a duplicate when a candidate of a smaller triple index lies at the same point
+  for (int v = tid; v < nc; v += 128) {
+    bool d = false;
+    const double scl = 1.0 + fabs(sv[3 * v]) + fabs(sv[3 * v + 1]) + fabs(sv[3 * v + 2]);
+    for (int u = 0; u < nc && !d; ++u)
+      if (st[u] < st[v] && fabs(sv[3 * u] - sv[3 * v]) + fabs(sv[3 * u + 1] - sv[3 * v + 1]) +
+                               fabs(sv[3 * u + 2] - sv[3 * v + 2]) <= BP_VERT_MERGE * scl)
+        d = true;
+    dup[v] = d ? 1 : 0;
+  }
+  __syncthreads();
+  __shared__ int n_unique;
+  if (tid == 0) n_unique = 0;
+  __syncthreads();
+  for (int v = tid; v < nc; v += 128) {
+    if (dup[v]) continue;
+    int rank = 0;
+    for (int u = 0; u < nc; ++u) rank += (!dup[u] && st[u] < st[v]) ? 1 : 0;
+    atomicAdd(&n_unique, 1);
+    if (rank < vmax) {
+      double* o = V + ((size_t)s * vmax + rank) * 3;
+      o[0] = sv[3 * v]; o[1] = sv[3 * v + 1]; o[2] = sv[3 * v + 2];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int nu = n_unique;
+    nv_out[s] = nu < vmax ? nu : vmax;
+    int stt = BP_OK;
+    if (unbounded || !anypair || nu == 0) stt = BP_NOT_A_POLYTOPE;
+    else if (nverts > BP_RED_VMAX || nu > vmax) stt = BP_ROW_OVERFLOW;
+    status[s] = stt;
   }
 }
 
@@ -3318,10 +3444,27 @@ static int pair_feasible_impl(const double* A_dev, const double* b_dev, const in
   }
   const long long max_pairs = (long long)rows * S;
   long long ctas = (max_pairs + 7) / 8;              // 8 warps per CTA, one pair per warp per trip
-  if (ctas > (long long)nsm * 8) ctas = (long long)nsm * 8;
+  static int lp_ctas_per_sm[2] = {0, 0};             // resident CTAs per SM of the two variants
+  static int lp_env = -1;                            // BPGEO_LP_MINB = 2 / 3 forces a variant (A/B measurements)
+  if (lp_ctas_per_sm[0] == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_lp<2>, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    lp_ctas_per_sm[0] = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_lp<3>, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    lp_ctas_per_sm[1] = nb;
+    const char* e = getenv("BPGEO_LP_MINB");
+    lp_env = e ? atoi(e) : 0;
+  }
+  // about 5 % of the box-overlapping pairs reach the LP: many pairs per resident warp -> the denser variant
+  const int dense = lp_env == 3 || (lp_env != 2 && max_pairs > 200000) ? 1 : 0;
+  if (ctas > (long long)nsm * lp_ctas_per_sm[dense]) ctas = (long long)nsm * lp_ctas_per_sm[dense];
   if (ctas < 1) ctas = 1;
-  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count, adj_bits_dev,
-                                                       x_feas_dev);
+  if (dense)
+    k_pair_lp<3><<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count,
+                                               adj_bits_dev, x_feas_dev);
+  else
+    k_pair_lp<2><<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count,
+                                               adj_bits_dev, x_feas_dev);
   if (ev) BP_CUDA(cudaEventRecord(ev[3], stream));
   BP_CUDA(cudaGetLastError());
   return 0;
@@ -3374,6 +3517,16 @@ int bp_reduce_ineqs(const double* A_dev, const double* b_dev, const int* m_dev, 
     return bp_fail("bp_reduce_ineqs: bad arguments");
   k_reduce_rows<<<S, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, A_out_dev, b_out_dev, m_out_dev,
                                                       keep_out_dev, status_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_polytope_vertices(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, int vmax,
+                         double* V_dev, int* nv_dev, int* status_dev, void* stream) {
+  if (S < 0 || m_max < 1 || m_max > BP_MAX_ROWS || vmax < 1 || !V_dev || !nv_dev || !status_dev)
+    return bp_fail("bp_polytope_vertices: bad arguments");
+  if (S == 0) return 0;
+  k_polytope_vertices<<<S, 128, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, vmax, V_dev, nv_dev, status_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -87,11 +87,16 @@ class PolytopeScene(Scene):
 
     MAX_ROWS = 15
 
-    def __init__(self, obs_sets, obs_points_sets):
+    def __init__(self, obs_sets, obs_points_sets=None):
         _require_cuda()
         self._lib = _lib.load()
         self._h = ctypes.c_void_p(0)
         n = len(obs_sets)
+        if obs_points_sets is None and n > 0:
+            # no vertex lists given: enumerate them on the device (compute_polytope_vertices, util_functions.py:66-79)
+            from .utils import obstacle_points_sets
+
+            obs_points_sets = obstacle_points_sets(obs_sets)
         if n == 0 or len(obs_points_sets) != n:
             raise ValueError("PolytopeScene needs one vertex array per obstacle set")
         rows = np.zeros((n, self.MAX_ROWS, 4))
@@ -585,3 +590,19 @@ def debug_counters(reset=False):
     buf = (ctypes.c_ulonglong * 4)()
     check(lib.bp_debug_counters(buf, 4, int(bool(reset))))
     return {"shell_fallbacks": int(buf[0])}
+
+
+def polytope_vertices(A, b, m, vmax=64):
+    """compute_polytope_vertices (util_functions.py:66-79) for S polytopes {A x <= b}: returns (V [S,vmax,3],
+    nv [S], status [S]); status 6 = not a polytope (unbounded / empty), 2 = more than vmax vertices."""
+    lib = _lib.load()
+    A = _dev(A)
+    S, m_max = A.shape[0], A.shape[1]
+    b = _dev(b).reshape(S, m_max)
+    m = _dev(m, torch.int32).reshape(S)
+    V = torch.zeros((S, vmax, 3), dtype=torch.float64, device="cuda")
+    nv = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    status = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    check(lib.bp_polytope_vertices(_ptr(A), _ptr(b), _ptr(m), S, m_max, int(vmax), _ptr(V), _ptr(nv), _ptr(status),
+                                   _stream()))
+    return V, nv, status

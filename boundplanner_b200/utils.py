@@ -34,3 +34,36 @@ def reduce_ineqs(a_set, b_set):
 def reduce_ineqs_batch(batch):
     """Device path: geometry.SetBatch -> (A_red, b_red, m_red, keep) CUDA tensors."""
     return geo.reduce_ineqs(batch.A, batch.b, batch.m)[:4]
+
+
+def compute_polytope_vertices(a_set, b_set, vmax=64):
+    """Same signature and return as the reference (util_functions.py:66-79): the list of vertices of
+    {x : a_set x <= b_set}; ValueError("Polyhedron is not a polytope") for an unbounded (or empty) set.
+    The order of the vertices is the kernel's (first row triple through each vertex), not cddlib's; every caller in
+    the reference treats the list as a set (obstacle vertex tests ConvexSetFinder.py:449-451, plotting)."""
+    from ._lib import STATUS_NOT_A_POLYTOPE, STATUS_ROW_OVERFLOW
+
+    A, b, m = pack_sets([[np.asarray(a_set, float), np.asarray(b_set, float).reshape(-1)]])
+    V, nv, status = geo.polytope_vertices(A, b, m, vmax=vmax)
+    st = int(status.item())
+    if st == STATUS_NOT_A_POLYTOPE:
+        raise ValueError("Polyhedron is not a polytope")
+    if st == STATUS_ROW_OVERFLOW:
+        raise ValueError(f"polytope has more than {vmax} vertices")
+    v = V[0, : int(nv.item())].cpu().numpy()
+    return [v[i].copy() for i in range(v.shape[0])]
+
+
+def obstacle_points_sets(obs_sets, vmax=64):
+    """Vertex lists of a whole list of obstacle sets in one launch (what add_obstacle_reps builds per obstacle with
+    cddlib, BoundPlanner.py:142): [[A, b], ...] -> [vertices (V x 3), ...]."""
+    from ._lib import STATUS_OK
+
+    A, b, m = pack_sets([[np.asarray(s[0], float), np.asarray(s[1], float).reshape(-1)] for s in obs_sets])
+    V, nv, status = geo.polytope_vertices(A, b, m, vmax=vmax)
+    V, nv, status = V.cpu().numpy(), nv.cpu().numpy(), status.cpu().numpy()
+    if (status != STATUS_OK).any():
+        bad = int(np.where(status != STATUS_OK)[0][0])
+        raise ValueError(f"obstacle {bad}: " + ("Polyhedron is not a polytope" if status[bad] == 6
+                                                else f"more than {vmax} vertices"))
+    return [V[j, : nv[j]].copy() for j in range(len(obs_sets))]

@@ -23,7 +23,8 @@
  *   - Per-item status codes (int32, one per seed / segment):
  *       BP_OK 0, BP_ELLIPSE_VIOLATION 1 (ConvexSetFinder.py:433-438 RuntimeError),
  *       BP_ROW_OVERFLOW 2 (more than m_max rows), BP_MVIE_NO_INTERIOR 3,
- *       BP_MVIE_NOT_CONVERGED 4, BP_ROW_CAP 5 (more rows than row_cap in an IRIS pass).
+ *       BP_MVIE_NOT_CONVERGED 4, BP_ROW_CAP 5 (more rows than row_cap in an IRIS pass),
+ *       BP_NOT_A_POLYTOPE 6 (bp_polytope_vertices: unbounded / empty set).
  *   - There is NO CPU fallback: every compute entry point needs a CUDA device.
  */
 #ifndef BPGEO_H
@@ -272,6 +273,12 @@ int bp_fk_iiwa14(const double* q_dev, int B, double* p_ee_dev, double* p_col_dev
  * B (q, dq) pairs: T_ee[B,4,4], jac[B,6,7], djac[B,6,7] (= d/dt jac along dq; NULL with dq_dev NULL: skip). */
 int bp_fk_iiwa14_kin(const double* q_dev, const double* dq_dev, int B, double* T_ee_dev, double* jac_dev,
                      double* djac_dev, void* stream);
+
+/* compute_polytope_vertices (bound_planner/utils/util_functions.py:66-79, cddlib): vertices of S polytopes
+ * {A x <= b}: V[S,vmax,3] (first nv[s] rows valid, deterministic order), status[s] = BP_OK, BP_NOT_A_POLYTOPE (the
+ * reference raises ValueError("Polyhedron is not a polytope")) or BP_ROW_OVERFLOW (more than vmax vertices). */
+int bp_polytope_vertices(const double* A_dev, const double* b_dev, const int* m_dev, int S, int m_max, int vmax,
+                         double* V_dev, int* nv_dev, int* status_dev, void* stream);
 
 /* Diagnostics: out_host[0] = polyhedron passes (since the last reset) that overflowed the closest-point shell of
  * the box-scene pass and were redone in the per-pick form; further entries reserved (0).  Synchronises the device. */

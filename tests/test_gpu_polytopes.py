@@ -191,3 +191,32 @@ def test_polytope_scene_update_in_the_reference_assignment_order(poly_scene):
     gpu.obs_sets = obs_sets
     with pytest.raises(ValueError, match="one vertex array per obstacle"):
         gpu.find_set_around_point(seeds[0], fixed_mid=True)
+
+
+def test_compute_polytope_vertices_on_device(poly_scene):
+    """compute_polytope_vertices (util_functions.py:66-79) on the GPU: the same vertex SET as the scene generator's
+    qhull enumeration, the reference's ValueError for an unbounded set, and a PolytopeScene built without vertex
+    lists gives the same sets as one built with them."""
+    import boundplanner_b200 as bp
+    from boundplanner_b200 import utils
+
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    got = utils.obstacle_points_sets(obs_sets)
+    for j, (g, want) in enumerate(zip(got, obs_points)):
+        assert g.shape == want.shape, f"obstacle {j}: {g.shape[0]} vertices, expected {want.shape[0]}"
+        d = np.linalg.norm(g[:, None, :] - want[None, :, :], axis=2)
+        assert d.min(axis=1).max() < 1e-9 and d.min(axis=0).max() < 1e-9
+    # a unit cube: 8 vertices, each met by exactly three planes; a cube with a redundant plane through a vertex
+    box = np.vstack((np.eye(3), -np.eye(3)))
+    v = np.array(bp.compute_polytope_vertices(box, np.array([1, 1, 1, 0, 0, 0.0])))
+    assert v.shape == (8, 3) and set(map(tuple, np.round(v, 12))) == {(x, y, z) for x in (0, 1) for y in (0, 1) for z in (0, 1)}
+    touch = np.vstack((box, [[1, 1, 1]])) 
+    v = np.array(bp.compute_polytope_vertices(touch, np.array([1, 1, 1, 0, 0, 0, 3.0])))
+    assert v.shape == (8, 3)                                  # four planes through (1,1,1): still one vertex
+    with pytest.raises(ValueError, match="not a polytope"):
+        bp.compute_polytope_vertices(box[:5], np.array([1, 1, 1, 0, 0.0]))      # open towards -z
+    auto = geo.PolytopeScene(obs_sets)                        # vertices enumerated on the device
+    a = geo.build_sets_point(auto, seeds[:6], ws_min, ws_max, fixed_mid=True)
+    w = geo.build_sets_point(scene, seeds[:6], ws_min, ws_max, fixed_mid=True)
+    assert np.array_equal(a.m.cpu().numpy(), w.m.cpu().numpy())
+    assert np.abs(a.A.cpu().numpy() - w.A.cpu().numpy()).max() < 1e-9
