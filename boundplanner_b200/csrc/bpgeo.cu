@@ -2087,11 +2087,9 @@ __device__ __forceinline__ bool bp_pair_margin_reject(const double* __restrict__
   return __any_sync(full, apart);
 }
 
-// MINB = CTAs per SM the register allocation is held to: 2 (122 registers, no spills) is fastest while the LPs of
-// a call fit the resident warps about once (latency-bound: 1.7 k LPs on C2); 3 (80 registers, a few spills) wins
-// when a rank has many LPs per resident warp (throughput-bound: the 8-GPU graph, C4).
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
+// (122 registers: two CTAs per SM.  Holding the allocation to 80 registers for three CTAs per SM spills and was
+// measured slower on both the 1.7 k LPs of C2 (0.064 vs 0.055 ms) and the ~10 k LPs of C4 (0.113 vs 0.109 ms).)
+__global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, const double* __restrict__ b,
                                                  const int* __restrict__ m, int S, int m_max, double tol,
                                                  int row_begin, const double* __restrict__ aabb,
                                                  const int2* __restrict__ list,
@@ -3444,27 +3442,16 @@ static int pair_feasible_impl(const double* A_dev, const double* b_dev, const in
   }
   const long long max_pairs = (long long)rows * S;
   long long ctas = (max_pairs + 7) / 8;              // 8 warps per CTA, one pair per warp per trip
-  static int lp_ctas_per_sm[2] = {0, 0};             // resident CTAs per SM of the two variants
-  static int lp_env = -1;                            // BPGEO_LP_MINB = 2 / 3 forces a variant (A/B measurements)
-  if (lp_ctas_per_sm[0] == 0) {
+  static int lp_ctas_per_sm = 0;                     // resident CTAs per SM (registers / shared memory)
+  if (lp_ctas_per_sm == 0) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_lp<2>, 256, 0) != cudaSuccess || nb < 1) nb = 1;
-    lp_ctas_per_sm[0] = nb;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_lp<3>, 256, 0) != cudaSuccess || nb < 1) nb = 1;
-    lp_ctas_per_sm[1] = nb;
-    const char* e = getenv("BPGEO_LP_MINB");
-    lp_env = e ? atoi(e) : 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_lp, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    lp_ctas_per_sm = nb;
   }
-  // about 5 % of the box-overlapping pairs reach the LP: many pairs per resident warp -> the denser variant
-  const int dense = lp_env == 3 || (lp_env != 2 && max_pairs > 200000) ? 1 : 0;
-  if (ctas > (long long)nsm * lp_ctas_per_sm[dense]) ctas = (long long)nsm * lp_ctas_per_sm[dense];
+  if (ctas > (long long)nsm * lp_ctas_per_sm) ctas = (long long)nsm * lp_ctas_per_sm;
   if (ctas < 1) ctas = 1;
-  if (dense)
-    k_pair_lp<3><<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count,
-                                               adj_bits_dev, x_feas_dev);
-  else
-    k_pair_lp<2><<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count,
-                                               adj_bits_dev, x_feas_dev);
+  k_pair_lp<<<(int)ctas, 256, 0, stream>>>(A_dev, b_dev, m_dev, S, m_max, tol, row_begin, aabb, list, count, adj_bits_dev,
+                                           x_feas_dev);
   if (ev) BP_CUDA(cudaEventRecord(ev[3], stream));
   BP_CUDA(cudaGetLastError());
   return 0;
