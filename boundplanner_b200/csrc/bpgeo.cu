@@ -2719,7 +2719,8 @@ __global__ void __launch_bounds__(32) k_fk_kin(const double* __restrict__ q, con
 __global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const double* __restrict__ cand, int C,
                                                        const double* __restrict__ A, const double* __restrict__ b,
                                                        const int* __restrict__ m, int m_max,
-                                                       const int* __restrict__ set_off, int* __restrict__ first_ok,
+                                                       const int* __restrict__ set_off,
+                                                       const int* __restrict__ set_cnt, int* __restrict__ first_ok,
                                                        unsigned char* __restrict__ flags) {
   const SceneView sc = scene_of_item(sc_all, blockIdx.x);
   __shared__ int s_first;
@@ -2727,7 +2728,8 @@ __global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const d
   const unsigned full = 0xffffffffu;
   if (threadIdx.x == 0) s_first = 0x7fffffff;
   __syncthreads();
-  const int s0 = set_off ? set_off[q] : 0, s1 = set_off ? set_off[q + 1] : 0;
+  // known sets of query q: rows set_off[q] .. set_off[q+1]-1, or (set_cnt given) set_off[q] .. set_off[q]+set_cnt[q]-1
+  const int s0 = set_off ? set_off[q] : 0, s1 = set_off ? (set_cnt ? s0 + set_cnt[q] : set_off[q + 1]) : 0;
   for (int base = 0; base < C; base += 4) {
     const int c = base + warp;
     if (c < C) {
@@ -2775,12 +2777,14 @@ __global__ void __launch_bounds__(128) k_sample_filter(SceneView sc_all, const d
 __global__ void __launch_bounds__(32) k_dedupe_dist(const double* __restrict__ q_new, const double* __restrict__ p_new,
                                                     const double* __restrict__ q_nodes,
                                                     const double* __restrict__ p_nodes,
-                                                    const int* __restrict__ node_off, double* __restrict__ dmin,
+                                                    const int* __restrict__ node_off,
+                                                    const int* __restrict__ node_cnt, double* __restrict__ dmin,
                                                     int* __restrict__ argmin) {
   const int i = blockIdx.x, lane = threadIdx.x;
   double best = BP_INF;
   int bidx = 0x7fffffff;
-  for (int v = node_off[i] + lane; v < node_off[i + 1]; v += 32) {
+  const int v_end = node_cnt ? node_off[i] + node_cnt[i] : node_off[i + 1];
+  for (int v = node_off[i] + lane; v < v_end; v += 32) {
     double sq = 0.0, sp = 0.0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) { const double d = q_new[(size_t)i * 9 + k] - q_nodes[(size_t)v * 9 + k]; sq += d * d; }
@@ -3558,7 +3562,22 @@ int bp_sample_filter(const bp_scene* scene, const int* item_scene_dev, const dou
     return bp_fail("bp_sample_filter: a scene batch needs item_scene, a single scene must not have it");
   if (Q == 0) return 0;
   k_sample_filter<<<Q, 128, 0, (cudaStream_t)stream>>>(view_of(scene, item_scene_dev), cand_dev, C, A_dev, b_dev, m_dev,
-                                                       m_max, set_off_dev, first_ok_dev, flags_dev);
+                                                       m_max, set_off_dev, nullptr, first_ok_dev, flags_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_sample_filter_tables(const bp_scene* scene, const int* item_scene_dev, const double* cand_dev, int Q, int C,
+                            const double* A_dev, const double* b_dev, const int* m_dev, int m_max,
+                            const int* set_begin_dev, const int* set_count_dev, int* first_ok_dev, void* stream) {
+  if (!scene || Q < 0 || C < 1 || !cand_dev || !first_ok_dev || m_max < 1 || !A_dev || !b_dev || !m_dev ||
+      !set_begin_dev || !set_count_dev)
+    return bp_fail("bp_sample_filter_tables: bad arguments");
+  if ((scene->seg_off != nullptr) != (item_scene_dev != nullptr))
+    return bp_fail("bp_sample_filter_tables: a scene batch needs item_scene, a single scene must not have it");
+  if (Q == 0) return 0;
+  k_sample_filter<<<Q, 128, 0, (cudaStream_t)stream>>>(view_of(scene, item_scene_dev), cand_dev, C, A_dev, b_dev, m_dev,
+                                                       m_max, set_begin_dev, set_count_dev, first_ok_dev, nullptr);
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -3569,7 +3588,19 @@ int bp_dedupe_distance(const double* q_new_dev, const double* p_new_dev, int P, 
   if (P < 0 || !q_new_dev || !p_new_dev || !node_off_dev || !dmin_dev) return bp_fail("bp_dedupe_distance: bad arguments");
   if (P == 0) return 0;
   k_dedupe_dist<<<P, 32, 0, (cudaStream_t)stream>>>(q_new_dev, p_new_dev, q_nodes_dev, p_nodes_dev, node_off_dev,
-                                                    dmin_dev, argmin_dev);
+                                                    nullptr, dmin_dev, argmin_dev);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_dedupe_distance_tables(const double* q_new_dev, const double* p_new_dev, int P, const double* q_nodes_dev,
+                              const double* p_nodes_dev, const int* node_begin_dev, const int* node_count_dev,
+                              double* dmin_dev, int* argmin_dev, void* stream) {
+  if (P < 0 || !q_new_dev || !p_new_dev || !node_begin_dev || !node_count_dev || !dmin_dev)
+    return bp_fail("bp_dedupe_distance_tables: bad arguments");
+  if (P == 0) return 0;
+  k_dedupe_dist<<<P, 32, 0, (cudaStream_t)stream>>>(q_new_dev, p_new_dev, q_nodes_dev, p_nodes_dev, node_begin_dev,
+                                                    node_count_dev, dmin_dev, argmin_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

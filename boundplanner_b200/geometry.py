@@ -606,3 +606,34 @@ def polytope_vertices(A, b, m, vmax=64):
     check(lib.bp_polytope_vertices(_ptr(A), _ptr(b), _ptr(m), S, m_max, int(vmax), _ptr(V), _ptr(nv), _ptr(status),
                                    _stream()))
     return V, nv, status
+
+
+def sample_filter_tables(scene, cand, A, b, m, set_begin, set_count, item_scene=None):
+    """K11 over device-resident per-query tables: the known sets of query q are rows set_begin[q] ..
+    set_begin[q] + set_count[q] - 1 of (A, b, m).  Returns first_ok [Q] int32 (-1: no candidate accepted)."""
+    lib = _lib.load()
+    cand = _dev(cand)
+    Q, C = cand.shape[0], cand.shape[1]
+    first = torch.empty((Q,), dtype=torch.int32, device="cuda")
+    set_begin = _dev(set_begin, torch.int32).reshape(Q)
+    set_count = _dev(set_count, torch.int32).reshape(Q)
+    if item_scene is not None:
+        item_scene = _dev(item_scene, torch.int32).reshape(Q)
+    check(lib.bp_sample_filter_tables(scene._h, _ptr(item_scene), _ptr(cand), Q, C, _ptr(A), _ptr(b), _ptr(m),
+                                      int(A.shape[1]), _ptr(set_begin), _ptr(set_count), _ptr(first), _stream()))
+    return first
+
+
+def dedupe_distance_tables(q_new, p_new, q_nodes, p_nodes, node_begin, node_count):
+    """K12 over device-resident node tables (see bp_dedupe_distance_tables): (dmin [P], argmin [P])."""
+    lib = _lib.load()
+    q_new = _dev(q_new).reshape(-1, 9)
+    P = q_new.shape[0]
+    p_new = _dev(p_new).reshape(P, 3)
+    node_begin = _dev(node_begin, torch.int32).reshape(P)
+    node_count = _dev(node_count, torch.int32).reshape(P)
+    dmin = torch.empty((P,), dtype=torch.float64, device="cuda")
+    arg = torch.empty((P,), dtype=torch.int32, device="cuda")
+    check(lib.bp_dedupe_distance_tables(_ptr(q_new), _ptr(p_new), P, _ptr(q_nodes), _ptr(p_nodes), _ptr(node_begin),
+                                        _ptr(node_count), _ptr(dmin), _ptr(arg), _stream()))
+    return dmin, arg

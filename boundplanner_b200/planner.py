@@ -22,6 +22,13 @@ primitives and receives their results:
                                            every existing set + check_intersection of every hit (one device round:
                                            the fit check starts from the LP's point and never leaves the GPU)
   ("project", A, b, x_d)                -> x                                         projection QP of add_edges
+  with ``device_loop`` (backends that keep every query's known sets and node ellipsoids in device tables):
+  ("sample_set", cand[C,3], optimize, planner) -> (first, (A, b, q, p, A_red, b_red, dvertex) | Exception)
+                                           the rejection loop of :459-478 over C pre-drawn candidates (first accepted
+                                           one, in draw order), find_set_around_point at it, reduce_ineqs and the
+                                           duplicate-set distance of :505-512 -- one device round, nothing on the host
+  ("set_point", p, fixed_mid, optimize, planner) -> (..., dvertex)                   the same for a given point
+  ("shortest_path", inter_graph)        -> [node ids]                                nx.shortest_path(..., 0, 1) (:434)
 
 Drivers: ``plan_set_sequence`` answers every request at once through a backend
 (batch-of-one kernel calls; the parity tests plug the oracle in here), and
@@ -65,6 +72,8 @@ class GpuBackend:
     """Answers planner requests one at a time: a batch of one through the same executor the lock-step driver
     uses, so every request is one chain of kernels on the device and one read-back."""
 
+    device_loop = True       # sampling / duplicate test / shortest path on the device (K11-K13)
+
     def __init__(self, obstacles, obs_size_increase, workspace_max, workspace_min):
         self.obs_sets = obstacle_sets(obstacles, obs_size_increase)
         self._bx = BatchedGpuExecutor([np.asarray(obstacles, float).reshape(-1, 6)], obs_size_increase, workspace_max,
@@ -91,7 +100,11 @@ def obstacle_sets(obstacles, obs_size_increase):
 
 class SetSequencePlanner:
     def __init__(self, obstacles=(), obs_size_increase=0.08, workspace_max=(1.0, 1.0, 1.2),
-                 workspace_min=(-1.0, -1.0, 0.0), backend=None, rng=None, obs_sets=None):
+                 workspace_min=(-1.0, -1.0, 0.0), backend=None, rng=None, obs_sets=None, device_loop=None):
+        # device_loop: sampling / duplicate test / shortest path answered by the backend's kernels (K11-K13)
+        # instead of the host loops below; default: whatever the backend offers
+        self.device_loop = bool(getattr(backend, "device_loop", False)) if device_loop is None else bool(device_loop)
+        self.sample_chunk = 32               # candidates drawn ahead per sampling request
         self.obs_size_increase = obs_size_increase
         self.workspace_max = list(workspace_max)
         self.workspace_min = list(workspace_min)
@@ -155,6 +168,31 @@ class SetSequencePlanner:
             return False
         s6 = np.concatenate((sample, -sample))                # x - ub and lb - x = (-x) - (-lb), exactly
         return bool(((s6 - self._b6).max(axis=1) < 1e-3).any())
+
+    # ---- :459-478 on the device ---------------------------------------------------
+    def _sample_set_on_device(self, optimize):
+        """The rejection loop with the candidates drawn ahead in chunks: the backend returns the first accepted
+        candidate of a chunk (draw order) together with the convex set built around it.  Afterwards the generator is
+        rewound to exactly the number of draws the reference's one-at-a-time loop would have consumed
+        (rng.uniform(lo, hi, (n, 3)) is n successive rng.uniform(lo, hi, 3) draws of the same bit stream)."""
+        lo, hi = self.workspace_min, self.workspace_max
+        state = self.rng.bit_generator.state
+        drawn, n, first, cand, payload = 0, 0, -1, None, None
+        while drawn < self.max_samples + 1:
+            c = min(self.sample_chunk, self.max_samples + 1 - drawn)
+            cand = self.rng.uniform(lo, hi, (c, 3))
+            first, payload = yield ("sample_set", cand, optimize, self)
+            if first >= 0:
+                n = drawn + first + 1
+                break
+            drawn += c
+            n = drawn
+        self.rng.bit_generator.state = state
+        if n:
+            self.rng.uniform(lo, hi, (n, 3))
+        if first < 0 or n >= self.max_samples:                    # :477-478
+            raise RuntimeError("(PosPath) Could not find collision-free sample")
+        return cand[first].copy(), payload
 
     # ---- :789-896 -----------------------------------------------------------
     def _add_edges(self, id_new, graph, inter_graph, end, start):
@@ -326,8 +364,12 @@ class SetSequencePlanner:
         p_via_old = None
         path = None
         while True:                                               # :430-534
+            pre_answers = None
             if connected:
-                path = nx.shortest_path(inter_graph, 0, 1, weight="weight")
+                if self.device_loop:
+                    path = yield ("shortest_path", inter_graph)
+                else:
+                    path = nx.shortest_path(inter_graph, 0, 1, weight="weight")
                 p_via, p_via_list, sets_via, seq_via = self.compute_via_points(path, start, end, graph, inter_graph)
                 if p_via_old is not None and p_via_old.shape == p_via.shape and \
                         np.linalg.norm(p_via_old - p_via) < 1e-4:
@@ -336,6 +378,12 @@ class SetSequencePlanner:
                 p_via_old = np.copy(p_via)
             elif not sampled_first and first_sample is not None:
                 samples = [first_sample]
+            elif self.device_loop:
+                sample, pre = yield from self._sample_set_on_device(not (nr_samples + 1 >= self.nr_optimized))
+                samples, pre_answers = [sample], [pre]
+                nr_samples += 1
+                if nr_samples > self.max_iters:
+                    raise RuntimeError("(PosPath) Exceeded max iterations")
             else:
                 in_collision = in_safe = True
                 nr_sampled = 0
@@ -351,13 +399,21 @@ class SetSequencePlanner:
                 nr_samples += 1
                 if nr_samples > self.max_iters:
                     raise RuntimeError("(PosPath) Exceeded max iterations")
-            for sample in samples:
+            for si, sample in enumerate(samples):
                 j += 1
                 optimize = not (nr_samples >= self.nr_optimized)
                 # fixed_mid = (via_sample or (not sampled_first),) is a 1-tuple: always truthy (quirk Q3)
-                _, _, q_ellipse, p_mid, a_set, b_set = yield ("set_point", np.asarray(sample, float), True, optimize)
+                if pre_answers is not None:
+                    ans = pre_answers[si]                  # built in the sampling round
+                    if isinstance(ans, Exception):
+                        raise ans
+                elif self.device_loop:
+                    ans = yield ("set_point", np.asarray(sample, float), True, optimize, self)
+                else:
+                    ans = yield ("set_point", np.asarray(sample, float), True, optimize)
+                _, _, q_ellipse, p_mid, a_set, b_set = ans[:6]
                 sampled_first = True
-                dvertex = self._min_node_distance(q_ellipse, p_mid)
+                dvertex = ans[6] if len(ans) > 6 else self._min_node_distance(q_ellipse, p_mid)
                 if dvertex > 0.01:
                     self.id_graph += 1
                     graph.add_node(self.id_graph, cset=[a_set, b_set], size=1 / float(_det(q_ellipse)),
@@ -392,7 +448,16 @@ class SetSequencePlanner:
 # Batched driver (BASELINE config C3): many independent queries, one scene each, in lock step
 # ---------------------------------------------------------------------------------------------
 class BatchedGpuExecutor:
-    """Answers the pending requests of many queries with one batched kernel call per primitive."""
+    """Answers the pending requests of many queries with one batched kernel call per primitive.
+
+    Every query's known sets (rows of its graph nodes) and node ellipsoids live in fixed-size blocks of device
+    tables, extended when a request shows that the query's planner has added nodes: the sampling rejection test
+    (K11), the duplicate-set distance (K12) and the shortest path (K13) then run on the device in the same round as
+    the set build they belong to (``device_loop``)."""
+
+    device_loop = True
+    MAX_NODES = 64           # graph nodes per query the tables hold (2 + 20 samples + via-point re-samples)
+    NODE_ROWS = 24           # rows per reduced node set (the reference's sets have at most 20)
 
     def __init__(self, obstacles_list, obs_size_increase, workspace_max, workspace_min):
         from . import geometry as geo
@@ -402,6 +467,70 @@ class BatchedGpuExecutor:
         self.ws_min = np.asarray(workspace_min, float)
         self.ws_max = np.asarray(workspace_max, float)
         self.calls = 0
+        self._n_queries = len(obstacles_list)
+        self._tab = None
+
+    # -- device tables of the queries' graph nodes -------------------------------------
+    def _tables(self):
+        import torch
+
+        if self._tab is None:
+            n = self._n_queries * self.MAX_NODES
+            self._tab = dict(
+                A=torch.zeros((n, self.NODE_ROWS, 3), dtype=torch.float64, device="cuda"),
+                b=torch.full((n, self.NODE_ROWS), 10.0, dtype=torch.float64, device="cuda"),
+                m=torch.zeros((n,), dtype=torch.int32, device="cuda"),
+                q=torch.zeros((n, 9), dtype=torch.float64, device="cuda"),
+                p=torch.zeros((n, 3), dtype=torch.float64, device="cuda"),
+                count=torch.zeros((self._n_queries,), dtype=torch.int32, device="cuda"),
+                begin=(torch.arange(self._n_queries, dtype=torch.int32, device="cuda") * self.MAX_NODES),
+                count_host=np.zeros(self._n_queries, np.int64), owner=[None] * self._n_queries)
+        return self._tab
+
+    def _sync_tables(self, items):
+        """items: [(qid, planner)].  Upload the nodes the planners have added since the last round (one H2D copy per
+        table for the whole round).  Returns {qid: ValueError} for queries the tables cannot hold."""
+        import torch
+
+        tab = self._tables()
+        slots, rows_a, rows_b, ms, qs, ps, bad = [], [], [], [], [], [], {}
+        for q, pl in items:
+            if tab["owner"][q] is not pl:                 # a new planner object on this slot: its table starts empty
+                tab["owner"][q] = pl
+                tab["count_host"][q] = 0
+            have, n = int(tab["count_host"][q]), len(pl._row_start)
+            if n > self.MAX_NODES:
+                bad[q] = ValueError(f"more than {self.MAX_NODES} graph nodes in one query")
+                continue
+            starts = pl._row_start + [pl._rows_a.shape[0]]
+            for k in range(have, n):
+                r0, r1 = starts[k], starts[k + 1]
+                if r1 - r0 > self.NODE_ROWS:
+                    bad[q] = ValueError(f"graph node with more than {self.NODE_ROWS} rows")
+                    break
+                a = np.zeros((self.NODE_ROWS, 3))
+                bb = np.full(self.NODE_ROWS, 10.0)
+                a[: r1 - r0], bb[: r1 - r0] = pl._rows_a[r0:r1], pl._rows_b[r0:r1]
+                slots.append(q * self.MAX_NODES + k)
+                rows_a.append(a); rows_b.append(bb); ms.append(r1 - r0)
+                qs.append(pl._node_q[k]); ps.append(pl._node_p[k])
+            if q not in bad:
+                tab["count_host"][q] = n
+        if slots:
+            idx = torch.as_tensor(np.asarray(slots, np.int64)).cuda()
+            tab["A"].index_copy_(0, idx, torch.as_tensor(np.asarray(rows_a)).cuda())
+            tab["b"].index_copy_(0, idx, torch.as_tensor(np.asarray(rows_b)).cuda())
+            tab["m"].index_copy_(0, idx, torch.as_tensor(np.asarray(ms, np.int32)).cuda())
+            tab["q"].index_copy_(0, idx, torch.as_tensor(np.asarray(qs)).cuda())
+            tab["p"].index_copy_(0, idx, torch.as_tensor(np.asarray(ps)).cuda())
+            tab["count"].copy_(torch.as_tensor(tab["count_host"].astype(np.int32)))
+        return bad
+
+    def _dvertex(self, batch, qi):
+        """K12 against the queries' node tables: min ||Q - Q_v||_F + ||p - p_v|| (inf without nodes)."""
+        tab = self._tables()
+        return self.geo.dedupe_distance_tables(batch.q_ellipse, batch.p_mid, tab["q"], tab["p"],
+                                               tab["begin"][qi], tab["count"][qi])[0]
 
     # -- helpers ----------------------------------------------------------------
     def _reduced(self, batch):
@@ -461,16 +590,98 @@ class BatchedGpuExecutor:
             if not qids:
                 continue
             self.calls += 1
+            with_dv = [q for q in qids if len(pending[q]) > 4]          # requests that carry their planner
+            bad = self._sync_tables([(q, pending[q][4]) for q in with_dv]) if with_dv else {}
             seeds = np.array([pending[q][1] for q in qids])
             batch = geo.build_sets_point(self.scene, seeds, self.ws_min, self.ws_max, fixed_mid=fixed_mid,
                                          optimize=optimize, row_cap=REFERENCE_MAX_ROWS,
                                          item_scene=np.asarray(qids, np.int32))
+            dv = None
+            if with_dv:
+                import torch
+
+                dv = self._dvertex(batch, torch.as_tensor(np.asarray(qids, np.int64)).cuda()).cpu().numpy()
             peak = batch.rows_peak.cpu().numpy()
             A, b, m, Q, P, st, Ar, br, mr = self._reduced(batch)
             for k, q in enumerate(qids):
+                err = bad.get(q) or _set_errors(int(st[k]), int(peak[k]) if optimize else None)
+                if err is not None:
+                    out[q] = err
+                    continue
+                out[q] = (A[k, : m[k]].copy(), b[k, : m[k]].copy(), Q[k].copy(), P[k].copy(),
+                          Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy())
+                if len(pending[q]) > 4:
+                    out[q] = out[q] + (float(dv[k]),)
+
+        # -- sampling round on the device: K11 (first accepted candidate) -> K5 at it -> K8 -> K12
+        for optimize in (True, False):
+            qids = [q for q in by_kind.get("sample_set", []) if bool(pending[q][2]) == optimize]
+            if not qids:
+                continue
+            import torch
+
+            self.calls += 1
+            bad = self._sync_tables([(q, pending[q][3]) for q in qids])
+            tab = self._tables()
+            counts = [np.asarray(pending[q][1]).reshape(-1, 3).shape[0] for q in qids]
+            C = max(counts)
+            cand = np.empty((len(qids), C, 3))
+            for k, q in enumerate(qids):
+                c = np.asarray(pending[q][1], float).reshape(-1, 3)
+                cand[k, : counts[k]] = c
+                cand[k, counts[k]:] = c[0]               # padding: copies of the first candidate never win
+            cand_d = torch.as_tensor(cand).cuda()
+            qi = torch.as_tensor(np.asarray(qids, np.int64)).cuda()
+            first_d = geo.sample_filter_tables(self.scene, cand_d, tab["A"], tab["b"], tab["m"], tab["begin"][qi],
+                                               tab["count"][qi], item_scene=qi.to(torch.int32))
+            pick = first_d.clamp(min=0).to(torch.int64)
+            seeds_d = cand_d[torch.arange(len(qids), device="cuda"), pick]
+            batch = geo.build_sets_point(self.scene, seeds_d, self.ws_min, self.ws_max, fixed_mid=True,
+                                         optimize=optimize, row_cap=REFERENCE_MAX_ROWS,
+                                         item_scene=qi.to(torch.int32))
+            dv = self._dvertex(batch, qi).cpu().numpy()
+            first = first_d.cpu().numpy()
+            peak = batch.rows_peak.cpu().numpy()
+            A, b, m, Q, P, st, Ar, br, mr = self._reduced(batch)
+            for k, q in enumerate(qids):
+                if q in bad:
+                    out[q] = bad[q]
+                    continue
+                f = int(first[k])
+                if f < 0 or f >= counts[k]:
+                    out[q] = (-1, None)
+                    continue
                 err = _set_errors(int(st[k]), int(peak[k]) if optimize else None)
-                out[q] = err if err is not None else (A[k, : m[k]].copy(), b[k, : m[k]].copy(), Q[k].copy(), P[k].copy(),
-                                                      Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy())
+                out[q] = (f, err if err is not None else
+                          (A[k, : m[k]].copy(), b[k, : m[k]].copy(), Q[k].copy(), P[k].copy(),
+                           Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy(), float(dv[k])))
+
+        # -- shortest paths through the intersection graphs (K13, one warp per graph)
+        qids = by_kind.get("shortest_path", [])
+        if qids:
+            self.calls += 1
+            node_off, edge_off, edge_dst, edge_w = [0], [], [], []
+            for q in qids:
+                g = pending[q][1]
+                n = g.number_of_nodes()                 # intersection ids are 0 .. n-1 in insertion order
+                adj = g._adj
+                for v in range(n):
+                    edge_off.append(len(edge_dst))
+                    for u, d in adj[v].items():
+                        edge_dst.append(u)
+                        edge_w.append(d["weight"])
+                node_off.append(node_off[-1] + n)
+            edge_off.append(len(edge_dst))
+            G = len(qids)
+            path, plen, _ = geo.shortest_paths(np.asarray(node_off, np.int32), np.asarray(edge_off, np.int32),
+                                               np.asarray(edge_dst, np.int32), np.asarray(edge_w, float),
+                                               np.zeros(G, np.int32), np.ones(G, np.int32), max_len=64)
+            path, plen = path.cpu().numpy(), plen.cpu().numpy()
+            for k, q in enumerate(qids):
+                if plen[k] <= 0:
+                    out[q] = nx.NetworkXNoPath("No path between 0 and 1.")
+                else:
+                    out[q] = [int(v) for v in path[k, : plen[k]]]
 
         qids = by_kind.get("set_line", [])
         if qids:
@@ -591,7 +802,8 @@ def plan_batch(queries, obs_size_increase=0.01, workspace_max=(1.0, 1.0, 1.2), w
     finish = [0.0] * len(queries)              # seconds after the start of the batch at which query i was answered
     for i, q in enumerate(queries):
         pl = SetSequencePlanner(q["obstacles"], obs_size_increase, workspace_max, workspace_min,
-                                rng=np.random.default_rng(rng_seeds[i] if rng_seeds is not None else None))
+                                rng=np.random.default_rng(rng_seeds[i] if rng_seeds is not None else None),
+                                device_loop=bool(getattr(executor, "device_loop", False)))
         planners.append(pl)
         gens[i] = pl.plan_gen(q["start"], q["end"], q["r0"], q["r1"], q.get("first_sample"))
         try:

@@ -243,6 +243,17 @@ int bp_sample_filter(const bp_scene* scene, const int* item_scene_dev, const dou
 int bp_dedupe_distance(const double* q_new_dev, const double* p_new_dev, int P, const double* q_nodes_dev,
                        const double* p_nodes_dev, const int* node_off_dev, double* dmin_dev, int* argmin_dev,
                        void* stream);
+
+/* The same two tests over per-query TABLES that stay resident on the device (the lock-step planner driver keeps
+ * every query's known sets and node ellipsoids in fixed-size blocks): the known sets of query q are rows
+ * set_begin[q] .. set_begin[q]+set_count[q]-1 of (A, b, m); the nodes of item i are node_begin[i] ..
+ * node_begin[i]+node_count[i]-1. */
+int bp_sample_filter_tables(const bp_scene* scene, const int* item_scene_dev, const double* cand_dev, int Q, int C,
+                            const double* A_dev, const double* b_dev, const int* m_dev, int m_max,
+                            const int* set_begin_dev, const int* set_count_dev, int* first_ok_dev, void* stream);
+int bp_dedupe_distance_tables(const double* q_new_dev, const double* p_new_dev, int P, const double* q_nodes_dev,
+                              const double* p_nodes_dev, const int* node_begin_dev, const int* node_count_dev,
+                              double* dmin_dev, int* argmin_dev, void* stream);
 int bp_shortest_paths(const int* node_off_dev, const int* edge_off_dev, const int* edge_dst_dev,
                       const double* edge_w_dev, const int* src_dev, const int* dst_dev, int G, int max_len,
                       int* path_dev, int* path_len_dev, double* cost_dev, void* stream);

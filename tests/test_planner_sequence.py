@@ -167,3 +167,39 @@ def test_lockstep_driver_equals_sequential_driver_on_cpu():
         else:
             assert res["path"] == want["path"] and res["set_ids"] == want["set_ids"]
             assert np.array_equal(res["p_via"], want["p_via"])
+
+
+def test_device_loop_protocol_equals_host_loop_on_cpu():
+    """The planner's device-loop requests (candidates drawn ahead + generator rewind, set built in the sampling
+    round, duplicate distance and shortest path from the backend) give the same plan -- and leave the generator in
+    the same state -- as the reference's one-at-a-time host loops.  Both sides use the oracle's primitives."""
+    from scipy.spatial.transform import Rotation as R
+
+    from boundplanner_b200 import scenes
+    from boundplanner_b200.planner import SetSequencePlanner
+    from tests.util import OracleBackend, OracleDeviceLoopBackend
+
+    r0 = R.from_euler("XYZ", [0, 90, 0], degrees=True).as_matrix()
+    cases = []
+    boxes, ws_min, ws_max, inflate = scenes.example_scene()
+    cases.append((boxes, inflate, np.array([0.3, 0.0, 0.7]), np.array([0.45, -0.5, 0.2]), ws_min, ws_max, 3))
+    for i in (7, 8):
+        ob, infl, st, en, wmin, wmax = scenes.config_c3_query(i)
+        cases.append((ob, infl, st, en, wmin, wmax, i))
+    for ob, infl, st, en, wmin, wmax, seed in cases:
+        outs = []
+        for cls in (OracleBackend, OracleDeviceLoopBackend):
+            backend = cls(ob, infl, list(wmax), list(wmin))
+            pl = SetSequencePlanner(ob, infl, list(wmax), list(wmin), backend=backend, rng=np.random.default_rng(seed))
+            pl.sample_chunk = 5                       # several chunks per sample: exercises the rewind
+            assert pl.device_loop == (cls is OracleDeviceLoopBackend)
+            try:
+                res = pl.plan_set_sequence(st.copy(), en.copy(), r0, r0)
+                outs.append((res["path"], res["set_ids"], res["p_via"], pl.rng.uniform(0, 1, 4)))
+            except (RuntimeError, ValueError) as e:
+                outs.append((type(e).__name__, str(e), None, pl.rng.uniform(0, 1, 4)))
+        a, b = outs
+        assert a[0] == b[0] and a[1] == b[1]
+        if a[2] is not None:
+            assert np.array_equal(a[2], b[2])
+        assert np.array_equal(a[3], b[3])             # same number of draws consumed

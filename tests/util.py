@@ -106,3 +106,33 @@ class OracleBackend:
         if kind == "project":
             return self.project(req[1], req[2], req[3])
         raise ValueError(kind)
+
+
+class OracleDeviceLoopBackend(OracleBackend):
+    """OracleBackend that also answers the device-loop requests of the planner (sample_set, shortest_path, set_point
+    with the planner attached) -- with the REFERENCE'S host loops, so that the planner-side protocol (candidates
+    drawn ahead in chunks, generator rewind) can be checked against the plain host loop without a GPU."""
+
+    device_loop = True
+
+    def execute(self, req):
+        import networkx as nx
+
+        kind = req[0]
+        if kind == "sample_set":
+            cand, optimize, pl = np.asarray(req[1], float).reshape(-1, 3), req[2], req[3]
+            for i, c in enumerate(cand):                      # BoundPlanner.py:459-478, one candidate at a time
+                if not pl._in_collision(c) and not pl._in_safe(c):
+                    try:
+                        A, b, Q, p = self.find_set_around_point(c, True, optimize)
+                    except (RuntimeError, ValueError) as e:
+                        return i, e
+                    Ar, br = self.reduce_ineqs(A, b)
+                    return i, (A, b, Q, p, Ar, br, pl._min_node_distance(Q, p))
+            return -1, None
+        if kind == "shortest_path":
+            return nx.shortest_path(req[1], 0, 1, weight="weight")
+        if kind == "set_point" and len(req) > 4:
+            out = super().execute(req[:4])
+            return out + (req[4]._min_node_distance(out[2], out[3]),)
+        return super().execute(req)
