@@ -27,6 +27,13 @@ _c = ctypes
 _vp, _i, _d, _sz = _c.c_void_p, _c.c_int, _c.c_double, _c.c_size_t
 _dp = _c.POINTER(_c.c_double)
 
+class BpTail(ctypes.Structure):
+    """bp_tail of include/bpgeo.h (pair tests in the tail of the set build)"""
+    _fields_ = [("S_glob", _c.c_int), ("words", _c.c_int), ("A", _vp), ("b", _vp), ("m", _vp), ("aabb", _vp),
+                ("flags", _vp), ("bits", _vp), ("epoch", _vp), ("off_flags", _sz), ("off_bits", _sz),
+                ("tol", _c.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/bpgeo.h declares
 SIGNATURES = {
     "bpgeo_abi_version": (_i, []),
@@ -51,6 +58,10 @@ SIGNATURES = {
                                     _vp, _i, _vp, _sz, _vp]),
     "bp_build_sets_point_x": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _i, _vp, _vp, _i, _i, _sz, _sz, _sz, _sz, _vp, _sz, _vp]),
+    "bp_step_begin": (_i, [_c.POINTER(BpTail), _i, _vp]),
+    "bp_build_sets_point_tail": (_i, [_vp, _vp, _vp, _i, _dp, _dp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _i, _vp, _vp, _i, _i, _sz, _sz, _sz, _sz, _c.POINTER(BpTail), _vp, _sz,
+                                      _vp]),
     "bp_build_sets_line_ms": (_i, [_vp, _vp, _vp, _vp, _i, _dp, _dp, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _sz, _vp]),
     "bp_pairs_feasible_list": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -1240,7 +1240,27 @@ struct PeerTables {
   size_t off_A, off_b, off_m, off_aabb;
 };
 
+// Pair tests in the tail of the set build ("finished CTAs become pair workers", section 7 of DESIGN.md): a CTA whose
+// set is finished publishes an arrival flag and then tests its set against every set that arrives AFTER it, so
+// that when the last set of the whole job arrives only its own pairs are left -- one per waiting CTA.
+struct TailParams {
+  int S;                     // number of sets in the (global) tables; 0: no tail work
+  int words;                 // adjacency words per row
+  const double* A;           // LOCAL copies of the tables [S,m_max,3] | [S,m_max] | [S] | [S,6]
+  const double* b;
+  const int* m;
+  const double* aabb;
+  int* flags;                // [S] arrival flags (epoch of the step in which the set was written)
+  unsigned int* bits;        // [2][S][words] adjacency, double-buffered by the parity of the epoch (multi-GPU)
+  const int* epoch;          // device int, bumped by bp_step_begin
+  size_t off_flags, off_bits;   // byte offsets of flags / bits in every rank's symmetric allocation
+  double tol;
+};
+#define BP_TAIL_WORK_DOUBLES (4 * (BP_LP_SCRATCH_DOUBLES + 2 * (BP_MAX_ROWS * 4 + 8)))
+__device__ void fused_tail_pairs(TailParams tp, PeerTables peers, int g, int m_max, const double* my_box, double* work);
+
 struct FusedParams {
+  TailParams tail;
   double* aabb;              // [S,6] or NULL: exact bounding box of every finished set (what k_set_aabb computes)
   PeerTables peers;          // peers.world > 0: finished sets and boxes are also stored into every rank's tables
   const double* seeds;       // [S,3] seeds (MODE 0) / segment starts p0 (MODE 1)
@@ -1488,7 +1508,7 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     if (pr.iters) pr.iters[s] = k;
     if (pr.rows_peak) pr.rows_peak[s] = rows_peak;
   }
-  if (MODE == 0 && (pr.aabb || pr.peers.world > 0)) {
+  if (MODE == 0 && (pr.aabb || pr.peers.world > 0 || pr.tail.S > 0)) {
     // Epilogue: the set's exact bounding box (the pair filter's input) while its rows are still in shared memory,
     // and -- multi-GPU -- the owner's stores of rows, row count and box straight into every rank's global tables
     // over NVLink: no separate box / scatter kernels, and a finished seed's stores overlap the seeds still running.
@@ -1509,6 +1529,10 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
       for (int e = tid; e < pr.m_max; e += blockDim.x) bd[e] = sb[e];
       if (tid < 6) ((double*)(base + pr.peers.off_aabb))[(size_t)g * 6 + tid] = e_box[tid];
       if (tid == 6) ((int*)(base + pr.peers.off_m))[g] = m_out;
+    }
+    if (pr.tail.S > 0) {
+      __syncthreads();                    // shared-memory rows are no longer needed: the dynamic area becomes scratch
+      fused_tail_pairs(pr.tail, pr.peers, g, pr.m_max, e_box, s_dist);
     }
   }
 #ifdef BPGEO_PROFILE
@@ -2033,29 +2057,32 @@ __global__ void __launch_bounds__(256) k_pair_filter(const double* __restrict__ 
 //   * for some row r of set i the smallest a_r.x over the eroded box of j already exceeds b_r - tol
 //     (the oriented test the box-box test misses), or the same with i and j exchanged.
 // Only "disjoint" is ever concluded here; every "intersects" still comes from the LP.
-__device__ __forceinline__ bool bp_pair_margin_reject(const double* __restrict__ Ai, const double* __restrict__ bi,
-                                                      int mi, const double* __restrict__ boxi,
-                                                      const double* __restrict__ Aj, const double* __restrict__ bj,
-                                                      int mj, const double* __restrict__ boxj, double tol) {
+template <bool G>
+__device__ __forceinline__ double bp_ldv(const double* p) { return G ? __ldg(p) : *p; }
+// G: the operands are read-only global memory (ld.global.nc); else plain loads (shared-memory staging of the tail)
+template <bool G = true>
+__device__ __forceinline__ bool bp_pair_margin_reject(const double* Ai, const double* bi, int mi, const double* boxi,
+                                                      const double* Aj, const double* bj, int mj, const double* boxj,
+                                                      double tol) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double lo_i[3], hi_i[3], lo_j[3], hi_j[3];
   bool finite = true;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    lo_i[k] = __ldg(boxi + k); hi_i[k] = __ldg(boxi + 3 + k);
-    lo_j[k] = __ldg(boxj + k); hi_j[k] = __ldg(boxj + 3 + k);
+    lo_i[k] = bp_ldv<G>(boxi + k); hi_i[k] = bp_ldv<G>(boxi + 3 + k);
+    lo_j[k] = bp_ldv<G>(boxj + k); hi_j[k] = bp_ldv<G>(boxj + 3 + k);
     finite = finite && fabs(lo_i[k]) < 1e6 && fabs(hi_i[k]) < 1e6 && fabs(lo_j[k]) < 1e6 && fabs(hi_j[k]) < 1e6;
   }
   if (!finite) return false;                       // no bounding box (unbounded / degenerate description)
   // largest row norm of each set
   double ni = 0.0, nj = 0.0;
   for (int r = lane; r < mi; r += 32) {
-    const double a0 = __ldg(Ai + 3 * r), a1 = __ldg(Ai + 3 * r + 1), a2 = __ldg(Ai + 3 * r + 2);
+    const double a0 = bp_ldv<G>(Ai + 3 * r), a1 = bp_ldv<G>(Ai + 3 * r + 1), a2 = bp_ldv<G>(Ai + 3 * r + 2);
     ni = fmax(ni, a0 * a0 + a1 * a1 + a2 * a2);
   }
   for (int r = lane; r < mj; r += 32) {
-    const double a0 = __ldg(Aj + 3 * r), a1 = __ldg(Aj + 3 * r + 1), a2 = __ldg(Aj + 3 * r + 2);
+    const double a0 = bp_ldv<G>(Aj + 3 * r), a1 = bp_ldv<G>(Aj + 3 * r + 1), a2 = bp_ldv<G>(Aj + 3 * r + 2);
     nj = fmax(nj, a0 * a0 + a1 * a1 + a2 * a2);
   }
   ni = sqrt(-bp_warp_min(-ni));
@@ -2072,15 +2099,15 @@ __device__ __forceinline__ bool bp_pair_margin_reject(const double* __restrict__
   }
   if (!apart) {
     for (int r = lane; r < mi; r += 32) {           // rows of i against the eroded box of j
-      const double a0 = __ldg(Ai + 3 * r), a1 = __ldg(Ai + 3 * r + 1), a2 = __ldg(Ai + 3 * r + 2);
+      const double a0 = bp_ldv<G>(Ai + 3 * r), a1 = bp_ldv<G>(Ai + 3 * r + 1), a2 = bp_ldv<G>(Ai + 3 * r + 2);
       const double mu = (fmin(a0 * lo_j[0], a0 * hi_j[0]) + fmin(a1 * lo_j[1], a1 * hi_j[1])) + fmin(a2 * lo_j[2], a2 * hi_j[2]);
-      const double rhs = __ldg(bi + r) - tol;
+      const double rhs = bp_ldv<G>(bi + r) - tol;
       if (mu - rhs > 1e-9 * (1.0 + fabs(rhs))) apart = true;
     }
     for (int r = lane; r < mj; r += 32) {           // rows of j against the eroded box of i
-      const double a0 = __ldg(Aj + 3 * r), a1 = __ldg(Aj + 3 * r + 1), a2 = __ldg(Aj + 3 * r + 2);
+      const double a0 = bp_ldv<G>(Aj + 3 * r), a1 = bp_ldv<G>(Aj + 3 * r + 1), a2 = bp_ldv<G>(Aj + 3 * r + 2);
       const double mu = (fmin(a0 * lo_i[0], a0 * hi_i[0]) + fmin(a1 * lo_i[1], a1 * hi_i[1])) + fmin(a2 * lo_i[2], a2 * hi_i[2]);
-      const double rhs = __ldg(bj + r) - tol;
+      const double rhs = bp_ldv<G>(bj + r) - tol;
       if (mu - rhs > 1e-9 * (1.0 + fabs(rhs))) apart = true;
     }
   }
@@ -2154,6 +2181,142 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
     __syncwarp();
   }
 }
+
+// ---------------------------------------------------------------------------
+// Tail of the fused set build: pair tests by the CTAs whose set is finished (TailParams above).
+//   1. snapshot the arrival flags: the sets already there are NOT this CTA's business -- their CTAs are waiting
+//      for us and will test the pair (snapshot BEFORE publishing: of two sets each pair is then tested by at least
+//      one of them, by both only when they finish within a memory round trip of each other; the results are
+//      idempotent atomicOr's);
+//   2. publish: fence, then the arrival flag of this set in every rank's table (release, system scope);
+//   3. until every other set has arrived: sets that arrive are box-tested against this one (the k_pair_filter
+//      test), survivors go through the margin pre-test and the LP of k_pair_lp, one warp per pair, on rows staged in
+//      shared memory with coherent loads; a 1 is OR-ed into row min(g,h) of every rank's adjacency.
+// All CTAs of the launch must be resident at once (a waiting CTA never yields its SM): the host checks that.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int bp_ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bp_st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __noinline__ void fused_tail_pairs(TailParams tp, PeerTables peers, int g, int m_max, const double* my_box,
+                                              double* work) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int t_list[128];
+  __shared__ int t_n;
+  const int epoch = *tp.epoch;
+  double bx[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) bx[k] = my_box[k];
+  // 1. snapshot: bit k of `pend` <-> set h = tid + 128 k has not arrived yet
+  unsigned long long pend = 0ull;
+  {
+    int k = 0;
+    for (int h = tid; h < tp.S; h += 128, ++k)
+      if (h != g && bp_ld_acquire_sys(tp.flags + h) != epoch) pend |= 1ull << k;
+  }
+  __syncthreads();
+  // 2. publish
+  __threadfence_system();
+  __syncthreads();
+  if (peers.world > 0) {
+    if (tid < peers.world) bp_st_release_sys((int*)((char*)peers.base[tid] + tp.off_flags) + g, epoch);
+  } else if (tid == 0) {
+    bp_st_release_sys(tp.flags + g, epoch);
+  }
+  const size_t par_off = peers.world > 0 ? (size_t)(epoch & 1) * tp.S * tp.words : 0;
+  constexpr int SET_D = BP_MAX_ROWS * 4 + 8;            // rows [48*3] | b [48] | box [6] (+2)
+  double* lp_scr = work + warp * (BP_LP_SCRATCH_DOUBLES + 2 * SET_D);
+  double* set_lo = lp_scr + BP_LP_SCRATCH_DOUBLES;
+  double* set_hi = set_lo + SET_D;
+  // 3. pairs with the sets that arrive later
+  for (;;) {
+    if (tid == 0) t_n = 0;
+    __syncthreads();
+    for (unsigned long long mk = pend; mk; mk &= mk - 1) {
+      const int kk = __ffsll((long long)mk) - 1;
+      const int h = tid + 128 * kk;
+      if (bp_ld_acquire_sys(tp.flags + h) != epoch) continue;
+      const volatile double* bh = tp.aabb + (size_t)h * 6;
+      bool keep = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double loj = bh[k], hij = bh[3 + k];
+        if (bx[k] > hij + BP_AABB_EPS || loj > bx[3 + k] + BP_AABB_EPS) keep = false;
+      }
+      if (keep) {
+        const int slot = atomicAdd(&t_n, 1);
+        if (slot >= 128) continue;                       // list full: stays pending for the next sweep
+        t_list[slot] = h;
+      }
+      pend &= ~(1ull << kk);
+    }
+    __syncthreads();
+    const int n = t_n < 128 ? t_n : 128;
+    for (int e = warp; e < n; e += 4) {
+      const int h = t_list[e];
+      const int lo = g < h ? g : h, hi = g < h ? h : g;
+      const int mlo = *(const volatile int*)(tp.m + lo), mhi = *(const volatile int*)(tp.m + hi);
+      const volatile double* Al = tp.A + (size_t)lo * m_max * 3;
+      const volatile double* bl = tp.b + (size_t)lo * m_max;
+      const volatile double* Ah = tp.A + (size_t)hi * m_max * 3;
+      const volatile double* bhh = tp.b + (size_t)hi * m_max;
+      for (int x = lane; x < mlo * 3; x += 32) set_lo[x] = Al[x];
+      for (int x = lane; x < mlo; x += 32) set_lo[BP_MAX_ROWS * 3 + x] = bl[x];
+      for (int x = lane; x < mhi * 3; x += 32) set_hi[x] = Ah[x];
+      for (int x = lane; x < mhi; x += 32) set_hi[BP_MAX_ROWS * 3 + x] = bhh[x];
+      if (lane < 6) {
+        set_lo[BP_MAX_ROWS * 4 + lane] = ((const volatile double*)tp.aabb)[(size_t)lo * 6 + lane];
+        set_hi[BP_MAX_ROWS * 4 + lane] = ((const volatile double*)tp.aabb)[(size_t)hi * 6 + lane];
+      }
+      __syncwarp();
+      const double* boxl = set_lo + BP_MAX_ROWS * 4;
+      const double* boxh = set_hi + BP_MAX_ROWS * 4;
+      int res = 0;
+      if (!bp_pair_margin_reject<false>(set_lo, set_lo + BP_MAX_ROWS * 3, mlo, boxl, set_hi, set_hi + BP_MAX_ROWS * 3, mhi,
+                                        boxh, tp.tol)) {
+        double xi[3], x0[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                   // start at the middle of the overlap of the two boxes
+          const double lov = fmax(boxl[k], boxh[k]);
+          const double hiv = fmin(boxl[3 + k], boxh[3 + k]);
+          x0[k] = 0.5 * (lov + hiv);
+          if (!(fabs(x0[k]) < 1e6)) x0[k] = 0.0;
+        }
+        res = bp_pair_feasible_warp(set_lo, set_lo + BP_MAX_ROWS * 3, mlo, set_hi, set_hi + BP_MAX_ROWS * 3, mhi, tp.tol,
+                                    lp_scr, nullptr, xi, x0, BP_LP_T0_SCALE);
+      }
+      if (lane == 0 && res) {
+        const size_t word = par_off + (size_t)lo * tp.words + (hi >> 5);
+        const unsigned int bit = 1u << (hi & 31);
+        if (peers.world > 0) {
+          for (int r = 0; r < peers.world; ++r)
+            atomicOr((unsigned int*)((char*)peers.base[r] + tp.off_bits) + word, bit);
+        } else {
+          atomicOr(tp.bits + word, bit);
+        }
+      }
+      __syncwarp();
+    }
+    const int any = __syncthreads_or(pend != 0ull);
+    if (!any) break;
+    if (n == 0) __nanosleep(300);
+  }
+}
+
+// start of a step of the tail pipelines: next epoch; the adjacency buffer the NEXT step will use is cleared now
+// (it was last written two steps ago, and nobody writes it before every rank has passed this step's final barrier)
+__global__ void k_step_begin(const int* epoch, unsigned int* bits, size_t words_per_buffer, int double_buffered) {
+  const int ep = *epoch + 1;                       // (the increment itself is k_step_epoch, launched after this)
+  unsigned int* buf = bits + (double_buffered ? (size_t)((ep + 1) & 1) * words_per_buffer : 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_buffer; i += (size_t)gridDim.x * blockDim.x)
+    buf[i] = 0u;
+}
+__global__ void k_step_epoch(int* epoch) { *epoch += 1; }
 
 // K6 over an explicit pair list (batched planner rounds: the pairs "new set vs every existing set" of
 // many queries at once).  One warp per listed pair: box test, then the LP from the middle of the overlap.
@@ -3264,8 +3427,36 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
                           double* aabb_dev, const unsigned long long* peer_base_dev, int world, int slot0,
                           size_t off_A, size_t off_b, size_t off_m, size_t off_aabb, void* workspace_dev,
                           size_t workspace_bytes, void* stream_) {
+  return bp_build_sets_point_tail(scene, seed_scene_dev, seeds_dev, S, ws_min_host, ws_max_host, fixed_mid, optimize,
+                                  max_iter, m_max, A_dev, b_dev, m_dev, q_ellipse_dev, p_mid_dev, status_dev, iters_dev,
+                                  rows_peak_dev, row_cap, aabb_dev, peer_base_dev, world, slot0, off_A, off_b, off_m,
+                                  off_aabb, nullptr, workspace_dev, workspace_bytes, stream_);
+}
+
+int bp_step_begin(const bp_tail* tail, int double_buffered, void* stream_) {
+  if (!tail || !tail->epoch || !tail->bits || tail->S_glob < 1 || tail->words < 1) return bp_fail("bp_step_begin: bad arguments");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t n = (size_t)tail->S_glob * tail->words;
+  int ctas = (int)((n + 255) / 256);
+  if (ctas > 296) ctas = 296;
+  k_step_begin<<<ctas, 256, 0, stream>>>(tail->epoch, tail->bits, n, double_buffered);
+  k_step_epoch<<<1, 1, 0, stream>>>(tail->epoch);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, const double* seeds_dev, int S,
+                             const double* ws_min_host, const double* ws_max_host, int fixed_mid, int optimize,
+                             int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                             double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                             double* aabb_dev, const unsigned long long* peer_base_dev, int world, int slot0,
+                             size_t off_A, size_t off_b, size_t off_m, size_t off_aabb, const bp_tail* tail,
+                             void* workspace_dev, size_t workspace_bytes, void* stream_) {
   if (world < 0 || slot0 < 0 || (world > 0 && !peer_base_dev))
     return bp_fail("bp_build_sets_point_x: bad peer arguments");
+  if (tail && (tail->S_glob < S || tail->S_glob > 128 * 64 || tail->words < (tail->S_glob + 31) / 32 || !tail->A ||
+               !tail->b || !tail->m || !tail->aabb || !tail->flags || !tail->bits || !tail->epoch || !aabb_dev))
+    return bp_fail("bp_build_sets_point_tail: bad tail arguments");
   if (scene && ((scene->seg_off != nullptr) != (seed_scene_dev != nullptr)))
     return bp_fail("bp_build_sets_point: a scene batch needs seed_scene, a single scene must not have it");
   if (!scene || S < 0 || m_max < 6 || m_max > BP_MAX_ROWS || max_iter < 1 || !ws_min_host || !ws_max_host)
@@ -3285,6 +3476,12 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
     fp.aabb = aabb_dev;
     fp.peers.base = peer_base_dev; fp.peers.world = world; fp.peers.slot0 = slot0;
     fp.peers.off_A = off_A; fp.peers.off_b = off_b; fp.peers.off_m = off_m; fp.peers.off_aabb = off_aabb;
+    if (tail) {
+      fp.tail.S = tail->S_glob; fp.tail.words = tail->words;
+      fp.tail.A = tail->A; fp.tail.b = tail->b; fp.tail.m = tail->m; fp.tail.aabb = tail->aabb;
+      fp.tail.flags = tail->flags; fp.tail.bits = tail->bits; fp.tail.epoch = tail->epoch;
+      fp.tail.off_flags = tail->off_flags; fp.tail.off_bits = tail->off_bits; fp.tail.tol = tail->tol;
+    }
     size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
     // box scenes small enough for two CTAs per SM: the scene columns are staged in shared memory by TMA
     // (BPGEO_STAGE=0 keeps the global / L1 loads: the A/B switch of profiles/r02_stage_ab.txt)
@@ -3294,20 +3491,31 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
       const size_t staged = 16 * ((sizeof(ShellMem) + 15) / 16) + sizeof(double) * (size_t)((scene->n + 1) & ~1) * 7;
       if (env && !scene->rows && staged + 20 * 1024 <= 110 * 1024) { fp.stage = 1; fsmem = staged; }
     }
-    if (scene->rows) {
-      if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
-      if (set_dyn_smem((const void*)k_iris_fused<0, true>, fsmem)) return 1;
-      k_iris_fused<0, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
-    } else if (scene->n <= 64 * 128) {
-      if (set_dyn_smem((const void*)k_iris_fused<0, false>, fsmem)) return 1;
-      k_iris_fused<0, false><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
-    } else {                                   // two words of alive bits per thread: N <= 16384
-      if (set_dyn_smem((const void*)k_iris_fused<0, false, 2>, fsmem)) return 1;
-      k_iris_fused<0, false, 2><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    const void* kfn = scene->rows ? (const void*)k_iris_fused<0, true>
+                      : (scene->n <= 64 * 128 ? (const void*)k_iris_fused<0, false>
+                                              : (const void*)k_iris_fused<0, false, 2>);   // (2 words of alive bits)
+    if (scene->rows && !fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    if (tail && fsmem < sizeof(double) * BP_TAIL_WORK_DOUBLES) fsmem = sizeof(double) * BP_TAIL_WORK_DOUBLES;
+    if (set_dyn_smem(kfn, fsmem)) return 1;
+    if (tail) {
+      // the pair workers of the tail wait inside the kernel for the other sets: every CTA has to be resident
+      int nb = 0, dev = 0, nsm = 0;
+      BP_CUDA(cudaGetDevice(&dev));
+      BP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      BP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 128, fsmem));
+      if ((long long)S > (long long)nb * nsm) {
+        snprintf(g_err, sizeof(g_err), "bp_build_sets_point_tail: %d seeds exceed the %d CTAs that are resident at once", S,
+                 nb * nsm);
+        return 1;
+      }
     }
+    if (scene->rows) k_iris_fused<0, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    else if (scene->n <= 64 * 128) k_iris_fused<0, false><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    else k_iris_fused<0, false, 2><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     BP_CUDA(cudaGetLastError());
     return 0;
   }
+  if (tail) return bp_fail("bp_build_sets_point_tail: the launch-sequence path (N > 16384 or BPGEO_FUSED=0) has no tail");
   SeedState* st = (SeedState*)workspace_dev;
   k_state_init<<<(S + 127) / 128, 128, 0, stream>>>(st, seeds_dev, S);
   PolyParams pp;

@@ -196,13 +196,14 @@ def alloc_set_batch(S, m_max=BP_MAX_ROWS):
 
 
 def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=True, max_iter=5, m_max=BP_MAX_ROWS,
-                     row_cap=0, out=None, item_scene=None, aabb=None, peers=None):
+                     row_cap=0, out=None, item_scene=None, aabb=None, peers=None, tail=None):
     """ConvexSetFinder.find_set_around_point (ConvexSetFinder.py:190-240) for S seeds.
     row_cap=20 reproduces the reference's failure on passes with more than 20 rows (status 5).
     out: a batch from alloc_set_batch to write into (no allocation, CUDA-graph capturable).
     aabb: [S,6] tensor that receives every set's exact bounding box from the kernel's epilogue.
     peers: dict(base=int64 tensor [world] of mapped base addresses, world, slot0, off_A, off_b, off_m, off_aabb):
-    the sets are also stored into every rank's global tables (multi-GPU exchange by peer stores)."""
+    the sets are also stored into every rank's global tables (multi-GPU exchange by peer stores).
+    tail: a BpTail from make_tail(): the finished CTAs also do the pair tests (see bp_build_sets_point_tail)."""
     lib = _lib.load()
     seeds = _dev(seeds).reshape(-1, 3)
     S = seeds.shape[0]
@@ -217,12 +218,13 @@ def build_sets_point(scene, seeds, ws_min, ws_max, fixed_mid=False, optimize=Tru
     if item_scene is not None:
         item_scene = _dev(item_scene, torch.int32).reshape(S)
     pk = peers or {}
-    check(lib.bp_build_sets_point_x(scene._h, _ptr(item_scene), _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)),
-                                    int(bool(optimize)), int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m),
-                                    _ptr(q), _ptr(p), _ptr(status), _ptr(iters), _ptr(peak), int(row_cap),
-                                    _ptr(aabb), _ptr(pk.get("base")), int(pk.get("world", 0)), int(pk.get("slot0", 0)),
-                                    int(pk.get("off_A", 0)), int(pk.get("off_b", 0)), int(pk.get("off_m", 0)),
-                                    int(pk.get("off_aabb", 0)), _ptr(work), wbytes, _stream()))
+    check(lib.bp_build_sets_point_tail(scene._h, _ptr(item_scene), _ptr(seeds), S, pmin, pmax, int(bool(fixed_mid)),
+                                       int(bool(optimize)), int(max_iter), int(m_max), _ptr(A), _ptr(b), _ptr(m),
+                                       _ptr(q), _ptr(p), _ptr(status), _ptr(iters), _ptr(peak), int(row_cap),
+                                       _ptr(aabb), _ptr(pk.get("base")), int(pk.get("world", 0)),
+                                       int(pk.get("slot0", 0)), int(pk.get("off_A", 0)), int(pk.get("off_b", 0)),
+                                       int(pk.get("off_m", 0)), int(pk.get("off_aabb", 0)),
+                                       ctypes.byref(tail) if tail is not None else None, _ptr(work), wbytes, _stream()))
     del amin, amax
     return out
 
@@ -637,3 +639,21 @@ def dedupe_distance_tables(q_new, p_new, q_nodes, p_nodes, node_begin, node_coun
     check(lib.bp_dedupe_distance_tables(_ptr(q_new), _ptr(p_new), P, _ptr(q_nodes), _ptr(p_nodes), _ptr(node_begin),
                                         _ptr(node_count), _ptr(dmin), _ptr(arg), _stream()))
     return dmin, arg
+
+
+def make_tail(A, b, m, aabb, flags, bits, epoch, tol, off_flags=0, off_bits=0):
+    """bp_tail descriptor over device tensors: tables A [S,m_max,3], b, m, aabb [S,6]; flags [S] int32; bits
+    [S,words] or [2,S,words] int32; epoch: int32 tensor of one element (0 at allocation)."""
+    S = A.shape[0]
+    t = _lib.BpTail()
+    t.S_glob, t.words = int(S), int(bits.shape[-1])
+    t.A, t.b, t.m, t.aabb = A.data_ptr(), b.data_ptr(), m.data_ptr(), aabb.data_ptr()
+    t.flags, t.bits, t.epoch = flags.data_ptr(), bits.data_ptr(), epoch.data_ptr()
+    t.off_flags, t.off_bits, t.tol = int(off_flags), int(off_bits), float(tol)
+    return t
+
+
+def step_begin(tail, double_buffered):
+    """Start a step of a tail pipeline: clear the adjacency buffer (of the next step when double-buffered) and
+    bump the epoch."""
+    check(_lib.load().bp_step_begin(ctypes.byref(tail), int(bool(double_buffered)), _stream()))

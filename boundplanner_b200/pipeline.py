@@ -20,7 +20,16 @@ from . import geometry as geo
 
 class SetGraphPipeline:
     def __init__(self, scene, n_seeds, ws_min, ws_max, fixed_mid=True, optimize=True, max_iter=5, tol=0.01,
-                 m_max=geo.BP_MAX_ROWS, use_cuda_graph=True):
+                 m_max=geo.BP_MAX_ROWS, use_cuda_graph=True, tail=None):
+        import os
+
+        # tail: the pair tests run in the tail of the set-build kernel (finished CTAs test their set against the
+        # sets that arrive later) instead of as k_pair_filter / k_pair_lp launches; needs every CTA resident
+        # (n_seeds <= 2 per SM); BPGEO_TAIL=0 forces the separate pair stage
+        if tail is None:
+            tail = os.environ.get("BPGEO_TAIL", "1") != "0" and int(n_seeds) <= 2 * torch.cuda.get_device_properties(
+                torch.cuda.current_device()).multi_processor_count
+        self.tail = bool(tail)
         self.scene, self.S = scene, int(n_seeds)
         self.ws_min, self.ws_max = ws_min, ws_max
         self.kw = dict(fixed_mid=fixed_mid, optimize=optimize, max_iter=max_iter)
@@ -47,6 +56,11 @@ class SetGraphPipeline:
         self.batch = geo.SetBatch(A, b, m, q, p, status, iters=own.iters, rows_peak=own.rows_peak, work=own.work)
         self.pair_buf = (self.bits, geo.alloc_pair_buffers(self.S)[1])
         self.aabb = torch.empty((self.S, 6), dtype=torch.float64, device="cuda")   # written by the build's epilogue
+        self._tail = None
+        if self.tail:
+            self._flags = torch.zeros((self.S,), dtype=torch.int32, device="cuda")
+            self._epoch = torch.zeros((1,), dtype=torch.int32, device="cuda")
+            self._tail = geo.make_tail(A, b, m, self.aabb, self._flags, self.bits, self._epoch, tol)
         self._views = (A, b, m, q, p, status, self.bits)
         self._host = None
         self._graph = None
@@ -55,6 +69,11 @@ class SetGraphPipeline:
             self._capture()
 
     def _enqueue(self):
+        if self._tail is not None:
+            geo.step_begin(self._tail, False)
+            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb,
+                                 tail=self._tail, **self.kw)
+            return
         geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb,
                              **self.kw)
         geo.pair_feasible(self.batch.A, self.batch.b, self.batch.m, self.tol, out=self.pair_buf, aabb=self.aabb)
@@ -76,6 +95,16 @@ class SetGraphPipeline:
         k_pair_filter | k_pair_lp."""
         import statistics
 
+        if self._tail is not None:
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self._enqueue()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return {"build_and_pairs": statistics.median(ts), "aabb": 0.0, "filter": 0.0, "lp": 0.0}
         acc = {"build": [], "aabb": [], "filter": [], "lp": []}
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,10 +325,19 @@ class PeerSetGraphPipeline:
     has finished reading.  Same results as ShardedSetGraphPipeline (tools/check_sharded.py --peer)."""
 
     def __init__(self, scene, n_seeds_local, ws_min, ws_max, fixed_mid=True, optimize=True, max_iter=5, tol=0.01,
-                 m_max=geo.BP_MAX_ROWS, group=None):
+                 m_max=geo.BP_MAX_ROWS, group=None, tail=None):
+        import os
+
         import numpy as np
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
+
+        # tail: pair tests in the tail of the set-build kernel, driven by per-set arrival flags in every rank's
+        # tables (no barrier between build and pairs, no pair kernels); needs every CTA resident
+        if tail is None:
+            tail = os.environ.get("BPGEO_TAIL", "1") != "0" and int(n_seeds_local) <= 2 * torch.cuda.get_device_properties(
+                torch.cuda.current_device()).multi_processor_count and int(n_seeds_local) * dist.get_world_size(group) <= 8192
+        self.tail = bool(tail)
 
         from . import _lib
         from . import distributed as bpd
@@ -315,12 +353,12 @@ class PeerSetGraphPipeline:
         S, words = self.S, (self.S + 31) // 32
         self.words = words
         # layout of the symmetric allocation (bytes, 256-aligned regions)
-        sizes = [S * m_max * 3 * 8, S * m_max * 8, S * 6 * 8, S * 4, S * words * 4]
+        sizes = [S * m_max * 3 * 8, S * m_max * 8, S * 6 * 8, S * 4, 2 * S * words * 4, S * 4]
         offs, o = [], 0
         for sz in sizes:
             offs.append(o)
             o += (sz + 255) // 256 * 256
-        self.off_A, self.off_b, self.off_aabb, self.off_m, self.off_bits = offs
+        self.off_A, self.off_b, self.off_aabb, self.off_m, self.off_bits, self.off_flags = offs
         dev = torch.device("cuda", torch.cuda.current_device())
         self.symm = symm_mem.empty((o,), dtype=torch.uint8, device=dev)
         self.symm.zero_()
@@ -334,7 +372,12 @@ class PeerSetGraphPipeline:
         self.bg = view(self.off_b, sizes[1], torch.float64, (S, m_max))
         self.aabb_g = view(self.off_aabb, sizes[2], torch.float64, (S, 6))
         self.mg = view(self.off_m, sizes[3], torch.int32, (S,))
-        self.bits_g = view(self.off_bits, sizes[4], torch.int32, (S, words))
+        self.bits2_g = view(self.off_bits, sizes[4], torch.int32, (2, S, words))     # tail mode: alternate by epoch
+        self.bits_g = self.bits2_g[0]                                                # classic mode: buffer 0
+        self.flags_g = view(self.off_flags, sizes[5], torch.int32, (S,))
+        self._epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._tail = geo.make_tail(self.Ag, self.bg, self.mg, self.aabb_g, self.flags_g, self.bits2_g, self._epoch, tol,
+                                   off_flags=self.off_flags, off_bits=self.off_bits) if self.tail else None
         self.seeds_dev = torch.zeros((self.S_loc, 3), dtype=torch.float64, device=dev)
         self.batch = geo.alloc_set_batch(self.S_loc, m_max)
         self.aabb_loc = torch.empty((self.S_loc, 6), dtype=torch.float64, device=dev)
@@ -343,7 +386,9 @@ class PeerSetGraphPipeline:
         self.pair_buf = geo.alloc_pair_buffers(S, max(self.r1 - self.r0, 1))
         self._stream = torch.cuda.Stream()
         self._graph = None
+        self._steps = 0
         self._capture()
+        self._steps = int(self._epoch.item())            # warm-up + capture runs have advanced the epoch
 
     def _peers(self):
         return dict(base=self.peer_base, world=self.world, slot0=self.rank * self.S_loc, off_A=self.off_A,
@@ -351,6 +396,14 @@ class PeerSetGraphPipeline:
 
     def _enqueue(self):
         lib, st = self._lib, geo._stream()
+        if self._tail is not None:
+            # one kernel per step and rank: set build, exchange (peer stores + arrival flags) and pair tests; the
+            # only rank synchronisation is the barrier at the end of the step
+            geo.step_begin(self._tail, True)
+            geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb_loc,
+                                 peers=self._peers(), tail=self._tail, **self.kw)
+            self.hdl.barrier(channel=1)
+            return
         # the owner's stores of every finished set (rows, row count, bounding box) into all ranks' tables happen in
         # the epilogue of the set-build kernel: no separate box / scatter launches
         geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch, aabb=self.aabb_loc,
@@ -373,6 +426,22 @@ class PeerSetGraphPipeline:
         names = ["build", "aabb", "scatter_sets", "barrier0", "filter", "lp", "scatter_rows", "barrier1"]
         acc = {k: [] for k in names}
         lib, st = self._lib, geo._stream()
+        if self._tail is not None:
+            for _ in range(reps):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                self.hdl.barrier(channel=0)
+                ev[0].record()
+                geo.step_begin(self._tail, True)
+                geo.build_sets_point(self.scene, self.seeds_dev, self.ws_min, self.ws_max, out=self.batch,
+                                     aabb=self.aabb_loc, peers=self._peers(), tail=self._tail, **self.kw)
+                ev[1].record()
+                self.hdl.barrier(channel=1)
+                ev[2].record()
+                torch.cuda.synchronize()
+                acc["build"].append(ev[0].elapsed_time(ev[1]))
+                acc["barrier1"].append(ev[1].elapsed_time(ev[2]))
+            self._steps = int(self._epoch.item())
+            return {"build_exchange_pairs": statistics.median(acc["build"]), "barrier1": statistics.median(acc["barrier1"])}
         for _ in range(reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             self.hdl.barrier(channel=0)                  # start the ranks together, like back-to-back steps do
@@ -430,8 +499,11 @@ class PeerSetGraphPipeline:
             self._graph.replay()
         else:
             self._enqueue()
-        return self.batch, self.bits_g
+        self._steps += 1                                 # (== the device epoch: every step bumps it once)
+        return self.batch, (self.bits2_g[self._steps & 1] if self._tail is not None else self.bits_g)
 
     def adjacency_bits(self):
-        """Global bit matrix [S, words]: already complete on every rank."""
+        """Global bit matrix [S, words]: already complete on every rank (tail mode: the buffer of the last epoch)."""
+        if self._tail is not None:
+            return self.bits2_g[self._steps & 1]
         return self.bits_g

@@ -141,6 +141,40 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
                           size_t off_A, size_t off_b, size_t off_m, size_t off_aabb, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* ---- pair tests in the tail of the set build -------------------------------------------------------------
+ * With a bp_tail the CTAs of the fused set build do not exit when their set is finished: each publishes an arrival
+ * flag (to every rank when world > 0) and tests its set against every set that arrives after it -- bounding-box
+ * test, margin pre-test and LP of bp_pair_feasible, results OR-ed into row min(i,j) of the adjacency of every rank.
+ * When the kernel ends on every rank the adjacency is complete: no pair kernels, no barrier between build and
+ * pairs; what is left after the last set of the job arrives is one pair per waiting CTA.  Needs aabb_dev, the
+ * fused path, and S <= the CTAs resident at once (checked).  bp_step_begin starts a step: it clears the adjacency
+ * buffer and bumps *epoch (multi-GPU: two buffers [2][S_glob][words] alternate by the parity of the epoch and the
+ * buffer of the NEXT step is the one cleared, so that no rank can clear bits a faster rank has already written;
+ * the ranks synchronise once per step, after the kernel).  Tables: this rank's copies of A[S_glob,m_max,3] |
+ * b | m | aabb (single GPU: the set build's own outputs); off_*: offsets of flags / bits in the symmetric
+ * allocation of every rank (multi-GPU).  Replaces BoundPlanner.set_intersection over all pairs
+ * (BoundPlanner.py:774-798) as a stage of its own. */
+typedef struct {
+  int S_glob, words;
+  const double* A;
+  const double* b;
+  const int* m;
+  const double* aabb;
+  int* flags;              /* [S_glob] */
+  unsigned int* bits;      /* [S_glob, words] (single GPU) or [2, S_glob, words] */
+  int* epoch;              /* device int, 0 at allocation */
+  size_t off_flags, off_bits;
+  double tol;
+} bp_tail;
+int bp_step_begin(const bp_tail* tail, int double_buffered, void* stream);
+int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, const double* seeds_dev, int S,
+                             const double* ws_min_host, const double* ws_max_host, int fixed_mid, int optimize,
+                             int max_iter, int m_max, double* A_dev, double* b_dev, int* m_dev, double* q_ellipse_dev,
+                             double* p_mid_dev, int* status_dev, int* iters_dev, int* rows_peak_dev, int row_cap,
+                             double* aabb_dev, const unsigned long long* peer_base_dev, int world, int slot0,
+                             size_t off_A, size_t off_b, size_t off_m, size_t off_aabb, const bp_tail* tail,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Replaces ConvexSetFinder.find_set_around_line (:242-307) for S segments p0 .. p0 + dp1: the IRIS loop around
  * the segment midpoint with the fixed-rotation MVIE (not called by the reference planner on main,
  * BoundPlanner.py:378-380, but part of ConvexSetFinder's surface).  optimize == 0: one pass + one free-centre
