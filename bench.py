@@ -443,6 +443,9 @@ def run_gpu(args):
     launches_per_step = (1 + 2) if fused else (1 + 5 * 2 + 1 + 1 + 3)
     if is_peer:
         launches_per_step += 1 if fused else 2      # the adjacency-row scatter (+ the set scatter when not fused)
+    tail_mode = bool(getattr(pipe if pipe is not None else spipe, "tail", False))
+    if tail_mode:
+        launches_per_step = 3                       # k_step_begin, k_step_epoch, k_iris_fused (build + exchange + pairs)
     if rank == 0:
         peaks = {}
         try:
@@ -451,7 +454,12 @@ def run_gpu(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         which = "measured" if "hbm_gbs" in peaks else "fallback"
-        launch = ("one CUDA graph per step" if pipe is not None else
+        launch = (("one CUDA graph per step; pair tests in the tail of the set-build kernel" if tail_mode else
+                   "one CUDA graph per step") if pipe is not None else
+                  ("one CUDA graph per step and rank: set build, exchange by peer stores + per-set arrival flags over "
+                   "NVLink and pair tests in ONE kernel, one signal-pad barrier per step (no NCCL on the data path)"
+                   + ("" if getattr(spipe, "_graph", None) is not None else " [eager: capture refused]"))
+                  if is_peer and tail_mode else
                   ("one CUDA graph per step; sets and adjacency rows exchanged by peer stores over NVLink + two "
                    "signal-pad barriers (no NCCL on the data path)"
                    + ("" if getattr(spipe, "_graph", None) is not None else " [eager: capture refused]"))

@@ -30,8 +30,8 @@ _dp = _c.POINTER(_c.c_double)
 class BpTail(ctypes.Structure):
     """bp_tail of include/bpgeo.h (pair tests in the tail of the set build)"""
     _fields_ = [("S_glob", _c.c_int), ("words", _c.c_int), ("A", _vp), ("b", _vp), ("m", _vp), ("aabb", _vp),
-                ("flags", _vp), ("bits", _vp), ("epoch", _vp), ("off_flags", _sz), ("off_bits", _sz),
-                ("tol", _c.c_double)]
+                ("count", _vp), ("log", _vp), ("bits", _vp), ("epoch", _vp), ("off_count", _sz), ("off_log", _sz),
+                ("off_bits", _sz), ("tol", _c.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/bpgeo.h declares

@@ -1250,10 +1250,11 @@ struct TailParams {
   const double* b;
   const int* m;
   const double* aabb;
-  int* flags;                // [S] arrival flags (epoch of the step in which the set was written)
+  unsigned int* count;       // arrival counter of this rank's log (S per step, never reset)
+  unsigned long long* log;   // [S] ring of (epoch << 32 | set id)
   unsigned int* bits;        // [2][S][words] adjacency, double-buffered by the parity of the epoch (multi-GPU)
   const int* epoch;          // device int, bumped by bp_step_begin
-  size_t off_flags, off_bits;   // byte offsets of flags / bits in every rank's symmetric allocation
+  size_t off_count, off_log, off_bits;   // byte offsets in every rank's symmetric allocation
   double tol;
 };
 #define BP_TAIL_WORK_DOUBLES (4 * (BP_LP_SCRATCH_DOUBLES + 2 * (BP_MAX_ROWS * 4 + 8)))
@@ -2184,23 +2185,30 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
 
 // ---------------------------------------------------------------------------
 // Tail of the fused set build: pair tests by the CTAs whose set is finished (TailParams above).
-//   1. snapshot the arrival flags: the sets already there are NOT this CTA's business -- their CTAs are waiting
-//      for us and will test the pair (snapshot BEFORE publishing: of two sets each pair is then tested by at least
-//      one of them, by both only when they finish within a memory round trip of each other; the results are
-//      idempotent atomicOr's);
-//   2. publish: fence, then the arrival flag of this set in every rank's table (release, system scope);
-//   3. until every other set has arrived: sets that arrive are box-tested against this one (the k_pair_filter
-//      test), survivors go through the margin pre-test and the LP of k_pair_lp, one warp per pair, on rows staged in
-//      shared memory with coherent loads; a 1 is OR-ed into row min(g,h) of every rank's adjacency.
+// Every rank's tables hold an ARRIVAL LOG: a counter that grows by one per arrived set (S per step, never reset)
+// and a ring of S entries (epoch, set id).  A CTA whose set is finished
+//   1. snapshots the counter: the sets logged before are NOT its business -- their CTAs are waiting and will see
+//      this set arrive (snapshot BEFORE publishing: of two sets each pair is then tested by at least one of them,
+//      by both only when they finish within a memory round trip of each other; results are idempotent atomicOr's);
+//   2. publishes: fence, then in every rank's log a slot (atomicAdd on the counter) and the entry (release);
+//   3. follows its own rank's log from the snapshot on until all S sets of the step are there: an arriving set is
+//      box-tested against this one (the k_pair_filter test), survivors go through the margin pre-test and the LP of
+//      k_pair_lp, one warp per pair, on rows staged in shared memory with coherent loads; a 1 is OR-ed into row
+//      min(g,h) of every rank's adjacency.  One polled word per waiting CTA, O(1) work per arrival.
 // All CTAs of the launch must be resident at once (a waiting CTA never yields its SM): the host checks that.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int bp_ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long bp_ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void bp_st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void bp_st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int bp_ld_relaxed_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 __device__ __noinline__ void fused_tail_pairs(TailParams tp, PeerTables peers, int g, int m_max, const double* my_box,
@@ -2208,55 +2216,59 @@ __device__ __noinline__ void fused_tail_pairs(TailParams tp, PeerTables peers, i
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int t_list[128];
   __shared__ int t_n;
+  __shared__ unsigned int t_cnt;
   const int epoch = *tp.epoch;
+  const unsigned int S = (unsigned int)tp.S;
+  const unsigned int base = (unsigned int)(epoch - 1) * S;        // counter value at the start of this step
   double bx[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) bx[k] = my_box[k];
-  // 1. snapshot: bit k of `pend` <-> set h = tid + 128 k has not arrived yet
-  unsigned long long pend = 0ull;
-  {
-    int k = 0;
-    for (int h = tid; h < tp.S; h += 128, ++k)
-      if (h != g && bp_ld_acquire_sys(tp.flags + h) != epoch) pend |= 1ull << k;
-  }
+  // 1. snapshot
+  if (tid == 0) t_cnt = bp_ld_relaxed_sys_u32(tp.count) - base;
   __syncthreads();
-  // 2. publish
+  unsigned int seen = t_cnt;
+  // 2. publish (the table stores of the epilogue first)
   __threadfence_system();
   __syncthreads();
-  if (peers.world > 0) {
-    if (tid < peers.world) bp_st_release_sys((int*)((char*)peers.base[tid] + tp.off_flags) + g, epoch);
-  } else if (tid == 0) {
-    bp_st_release_sys(tp.flags + g, epoch);
+  if (tid < (peers.world > 0 ? peers.world : 1)) {
+    unsigned int* cnt = peers.world > 0 ? (unsigned int*)((char*)peers.base[tid] + tp.off_count) : tp.count;
+    unsigned long long* lg = peers.world > 0 ? (unsigned long long*)((char*)peers.base[tid] + tp.off_log) : tp.log;
+    const unsigned int slot = atomicAdd(cnt, 1u) - base;
+    bp_st_release_sys_u64(lg + (slot % S), ((unsigned long long)(unsigned int)epoch << 32) | (unsigned int)g);
   }
   const size_t par_off = peers.world > 0 ? (size_t)(epoch & 1) * tp.S * tp.words : 0;
   constexpr int SET_D = BP_MAX_ROWS * 4 + 8;            // rows [48*3] | b [48] | box [6] (+2)
   double* lp_scr = work + warp * (BP_LP_SCRATCH_DOUBLES + 2 * SET_D);
   double* set_lo = lp_scr + BP_LP_SCRATCH_DOUBLES;
   double* set_hi = set_lo + SET_D;
-  // 3. pairs with the sets that arrive later
-  for (;;) {
-    if (tid == 0) t_n = 0;
+  // 3. the sets that arrive from the snapshot on
+  while (seen < S) {
+    __syncthreads();                                   // t_cnt / t_list of the previous trip consumed
+    if (tid == 0) { t_cnt = bp_ld_relaxed_sys_u32(tp.count) - base; t_n = 0; }
     __syncthreads();
-    for (unsigned long long mk = pend; mk; mk &= mk - 1) {
-      const int kk = __ffsll((long long)mk) - 1;
-      const int h = tid + 128 * kk;
-      if (bp_ld_acquire_sys(tp.flags + h) != epoch) continue;
-      const volatile double* bh = tp.aabb + (size_t)h * 6;
-      bool keep = true;
+    unsigned int n_new = t_cnt - seen;
+    if (n_new == 0) { __nanosleep(400); continue; }
+    if (n_new > 128) n_new = 128;
+    if ((unsigned int)tid < n_new) {
+      unsigned long long e;
+      do {                                             // the entry follows its counter increment within a round trip
+        e = bp_ld_acquire_sys_u64(tp.log + ((seen + tid) % S));
+      } while ((int)(e >> 32) != epoch);
+      const int h = (int)(unsigned int)e;
+      if (h != g) {
+        const volatile double* bh = tp.aabb + (size_t)h * 6;
+        bool keep = true;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double loj = bh[k], hij = bh[3 + k];
-        if (bx[k] > hij + BP_AABB_EPS || loj > bx[3 + k] + BP_AABB_EPS) keep = false;
+        for (int k = 0; k < 3; ++k) {
+          const double loj = bh[k], hij = bh[3 + k];
+          if (bx[k] > hij + BP_AABB_EPS || loj > bx[3 + k] + BP_AABB_EPS) keep = false;
+        }
+        if (keep) t_list[atomicAdd(&t_n, 1)] = h;
       }
-      if (keep) {
-        const int slot = atomicAdd(&t_n, 1);
-        if (slot >= 128) continue;                       // list full: stays pending for the next sweep
-        t_list[slot] = h;
-      }
-      pend &= ~(1ull << kk);
     }
     __syncthreads();
-    const int n = t_n < 128 ? t_n : 128;
+    seen += n_new;
+    const int n = t_n;
     for (int e = warp; e < n; e += 4) {
       const int h = t_list[e];
       const int lo = g < h ? g : h, hi = g < h ? h : g;
@@ -2302,9 +2314,6 @@ __device__ __noinline__ void fused_tail_pairs(TailParams tp, PeerTables peers, i
       }
       __syncwarp();
     }
-    const int any = __syncthreads_or(pend != 0ull);
-    if (!any) break;
-    if (n == 0) __nanosleep(300);
   }
 }
 
@@ -3455,7 +3464,8 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
   if (world < 0 || slot0 < 0 || (world > 0 && !peer_base_dev))
     return bp_fail("bp_build_sets_point_x: bad peer arguments");
   if (tail && (tail->S_glob < S || tail->S_glob > 128 * 64 || tail->words < (tail->S_glob + 31) / 32 || !tail->A ||
-               !tail->b || !tail->m || !tail->aabb || !tail->flags || !tail->bits || !tail->epoch || !aabb_dev))
+               !tail->b || !tail->m || !tail->aabb || !tail->count || !tail->log || !tail->bits || !tail->epoch ||
+               !aabb_dev))
     return bp_fail("bp_build_sets_point_tail: bad tail arguments");
   if (scene && ((scene->seg_off != nullptr) != (seed_scene_dev != nullptr)))
     return bp_fail("bp_build_sets_point: a scene batch needs seed_scene, a single scene must not have it");
@@ -3479,8 +3489,9 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
     if (tail) {
       fp.tail.S = tail->S_glob; fp.tail.words = tail->words;
       fp.tail.A = tail->A; fp.tail.b = tail->b; fp.tail.m = tail->m; fp.tail.aabb = tail->aabb;
-      fp.tail.flags = tail->flags; fp.tail.bits = tail->bits; fp.tail.epoch = tail->epoch;
-      fp.tail.off_flags = tail->off_flags; fp.tail.off_bits = tail->off_bits; fp.tail.tol = tail->tol;
+      fp.tail.count = tail->count; fp.tail.log = tail->log; fp.tail.bits = tail->bits; fp.tail.epoch = tail->epoch;
+      fp.tail.off_count = tail->off_count; fp.tail.off_log = tail->off_log; fp.tail.off_bits = tail->off_bits;
+      fp.tail.tol = tail->tol;
     }
     size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
     // box scenes small enough for two CTAs per SM: the scene columns are staged in shared memory by TMA

@@ -641,15 +641,16 @@ def dedupe_distance_tables(q_new, p_new, q_nodes, p_nodes, node_begin, node_coun
     return dmin, arg
 
 
-def make_tail(A, b, m, aabb, flags, bits, epoch, tol, off_flags=0, off_bits=0):
-    """bp_tail descriptor over device tensors: tables A [S,m_max,3], b, m, aabb [S,6]; flags [S] int32; bits
-    [S,words] or [2,S,words] int32; epoch: int32 tensor of one element (0 at allocation)."""
+def make_tail(A, b, m, aabb, count, log, bits, epoch, tol, off_count=0, off_log=0, off_bits=0):
+    """bp_tail descriptor over device tensors: tables A [S,m_max,3], b, m, aabb [S,6]; arrival log: count (int32,
+    one element) + log [S] int64; bits [S,words] or [2,S,words] int32; epoch: int32 tensor of one element.
+    count, log, epoch must be 0 at allocation."""
     S = A.shape[0]
     t = _lib.BpTail()
     t.S_glob, t.words = int(S), int(bits.shape[-1])
     t.A, t.b, t.m, t.aabb = A.data_ptr(), b.data_ptr(), m.data_ptr(), aabb.data_ptr()
-    t.flags, t.bits, t.epoch = flags.data_ptr(), bits.data_ptr(), epoch.data_ptr()
-    t.off_flags, t.off_bits, t.tol = int(off_flags), int(off_bits), float(tol)
+    t.count, t.log, t.bits, t.epoch = count.data_ptr(), log.data_ptr(), bits.data_ptr(), epoch.data_ptr()
+    t.off_count, t.off_log, t.off_bits, t.tol = int(off_count), int(off_log), int(off_bits), float(tol)
     return t
 
 

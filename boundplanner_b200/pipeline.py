@@ -58,9 +58,10 @@ class SetGraphPipeline:
         self.aabb = torch.empty((self.S, 6), dtype=torch.float64, device="cuda")   # written by the build's epilogue
         self._tail = None
         if self.tail:
-            self._flags = torch.zeros((self.S,), dtype=torch.int32, device="cuda")
+            self._count = torch.zeros((1,), dtype=torch.int32, device="cuda")
+            self._log = torch.zeros((self.S,), dtype=torch.int64, device="cuda")
             self._epoch = torch.zeros((1,), dtype=torch.int32, device="cuda")
-            self._tail = geo.make_tail(A, b, m, self.aabb, self._flags, self.bits, self._epoch, tol)
+            self._tail = geo.make_tail(A, b, m, self.aabb, self._count, self._log, self.bits, self._epoch, tol)
         self._views = (A, b, m, q, p, status, self.bits)
         self._host = None
         self._graph = None
@@ -353,12 +354,12 @@ class PeerSetGraphPipeline:
         S, words = self.S, (self.S + 31) // 32
         self.words = words
         # layout of the symmetric allocation (bytes, 256-aligned regions)
-        sizes = [S * m_max * 3 * 8, S * m_max * 8, S * 6 * 8, S * 4, 2 * S * words * 4, S * 4]
+        sizes = [S * m_max * 3 * 8, S * m_max * 8, S * 6 * 8, S * 4, 2 * S * words * 4, S * 8, 256]
         offs, o = [], 0
         for sz in sizes:
             offs.append(o)
             o += (sz + 255) // 256 * 256
-        self.off_A, self.off_b, self.off_aabb, self.off_m, self.off_bits, self.off_flags = offs
+        self.off_A, self.off_b, self.off_aabb, self.off_m, self.off_bits, self.off_log, self.off_count = offs
         dev = torch.device("cuda", torch.cuda.current_device())
         self.symm = symm_mem.empty((o,), dtype=torch.uint8, device=dev)
         self.symm.zero_()
@@ -374,10 +375,12 @@ class PeerSetGraphPipeline:
         self.mg = view(self.off_m, sizes[3], torch.int32, (S,))
         self.bits2_g = view(self.off_bits, sizes[4], torch.int32, (2, S, words))     # tail mode: alternate by epoch
         self.bits_g = self.bits2_g[0]                                                # classic mode: buffer 0
-        self.flags_g = view(self.off_flags, sizes[5], torch.int32, (S,))
+        self.log_g = view(self.off_log, sizes[5], torch.int64, (S,))
+        self.count_g = view(self.off_count, 4, torch.int32, (1,))
         self._epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self._tail = geo.make_tail(self.Ag, self.bg, self.mg, self.aabb_g, self.flags_g, self.bits2_g, self._epoch, tol,
-                                   off_flags=self.off_flags, off_bits=self.off_bits) if self.tail else None
+        self._tail = geo.make_tail(self.Ag, self.bg, self.mg, self.aabb_g, self.count_g, self.log_g, self.bits2_g,
+                                   self._epoch, tol, off_count=self.off_count, off_log=self.off_log,
+                                   off_bits=self.off_bits) if self.tail else None
         self.seeds_dev = torch.zeros((self.S_loc, 3), dtype=torch.float64, device=dev)
         self.batch = geo.alloc_set_batch(self.S_loc, m_max)
         self.aabb_loc = torch.empty((self.S_loc, 6), dtype=torch.float64, device=dev)

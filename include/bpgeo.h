@@ -142,8 +142,9 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
                           size_t workspace_bytes, void* stream);
 
 /* ---- pair tests in the tail of the set build -------------------------------------------------------------
- * With a bp_tail the CTAs of the fused set build do not exit when their set is finished: each publishes an arrival
- * flag (to every rank when world > 0) and tests its set against every set that arrives after it -- bounding-box
+ * With a bp_tail the CTAs of the fused set build do not exit when their set is finished: each appends its set to
+ * the arrival log of every rank (a counter + a ring of set ids in the tables) and tests its set against every set
+ * that is logged after it -- bounding-box
  * test, margin pre-test and LP of bp_pair_feasible, results OR-ed into row min(i,j) of the adjacency of every rank.
  * When the kernel ends on every rank the adjacency is complete: no pair kernels, no barrier between build and
  * pairs; what is left after the last set of the job arrives is one pair per waiting CTA.  Needs aabb_dev, the
@@ -151,7 +152,7 @@ int bp_build_sets_point_x(const bp_scene* scene, const int* seed_scene_dev, cons
  * buffer and bumps *epoch (multi-GPU: two buffers [2][S_glob][words] alternate by the parity of the epoch and the
  * buffer of the NEXT step is the one cleared, so that no rank can clear bits a faster rank has already written;
  * the ranks synchronise once per step, after the kernel).  Tables: this rank's copies of A[S_glob,m_max,3] |
- * b | m | aabb (single GPU: the set build's own outputs); off_*: offsets of flags / bits in the symmetric
+ * b | m | aabb (single GPU: the set build's own outputs); off_*: offsets of counter / log / bits in the symmetric
  * allocation of every rank (multi-GPU).  Replaces BoundPlanner.set_intersection over all pairs
  * (BoundPlanner.py:774-798) as a stage of its own. */
 typedef struct {
@@ -160,10 +161,11 @@ typedef struct {
   const double* b;
   const int* m;
   const double* aabb;
-  int* flags;              /* [S_glob] */
+  unsigned int* count;     /* arrival counter of this rank's log, 0 at allocation (grows by S_glob per step) */
+  unsigned long long* log; /* [S_glob] ring of (epoch << 32 | set id), 0 at allocation */
   unsigned int* bits;      /* [S_glob, words] (single GPU) or [2, S_glob, words] */
   int* epoch;              /* device int, 0 at allocation */
-  size_t off_flags, off_bits;
+  size_t off_count, off_log, off_bits;
   double tol;
 } bp_tail;
 int bp_step_begin(const bp_tail* tail, int double_buffered, void* stream);
