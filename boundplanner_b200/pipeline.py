@@ -25,9 +25,11 @@ class SetGraphPipeline:
 
         # tail: the pair tests run in the tail of the set-build kernel (finished CTAs test their set against the
         # sets that arrive later) instead of as k_pair_filter / k_pair_lp launches; needs every CTA resident
-        # (n_seeds <= 2 per SM); BPGEO_TAIL=0 forces the separate pair stage
+        # (n_seeds <= 2 per SM).  Opt-in (BPGEO_TAIL=1): measured SLOWER than the separate pair stage on C2 (one B200:
+        # 0.567 vs 0.525 ms per step; two: 0.730 vs 0.653 ms -- the sets of the slowest seed chains arrive together at
+        # the very end, so most pair work cannot start early, and the tail runs it on 8 warps per SM instead of 16)
         if tail is None:
-            tail = os.environ.get("BPGEO_TAIL", "1") != "0" and int(n_seeds) <= 2 * torch.cuda.get_device_properties(
+            tail = os.environ.get("BPGEO_TAIL", "0") == "1" and int(n_seeds) <= 2 * torch.cuda.get_device_properties(
                 torch.cuda.current_device()).multi_processor_count
         self.tail = bool(tail)
         self.scene, self.S = scene, int(n_seeds)
@@ -334,9 +336,10 @@ class PeerSetGraphPipeline:
         import torch.distributed._symmetric_memory as symm_mem
 
         # tail: pair tests in the tail of the set-build kernel, driven by per-set arrival flags in every rank's
-        # tables (no barrier between build and pairs, no pair kernels); needs every CTA resident
+        # tables (no barrier between build and pairs, no pair kernels); needs every CTA resident.  Opt-in
+        # (BPGEO_TAIL=1), see SetGraphPipeline
         if tail is None:
-            tail = os.environ.get("BPGEO_TAIL", "1") != "0" and int(n_seeds_local) <= 2 * torch.cuda.get_device_properties(
+            tail = os.environ.get("BPGEO_TAIL", "0") == "1" and int(n_seeds_local) <= 2 * torch.cuda.get_device_properties(
                 torch.cuda.current_device()).multi_processor_count and int(n_seeds_local) * dist.get_world_size(group) <= 8192
         self.tail = bool(tail)
 
