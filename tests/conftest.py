@@ -23,7 +23,8 @@ def host_harness():
     so = os.path.join(build, "libbp_host_harness.so")
     src = os.path.join(ROOT, "tests", "host_harness.cpp")
     deps = [src] + [os.path.join(ROOT, "boundplanner_b200", "csrc", f)
-                    for f in ("bp_math.cuh", "bp_mvie.cuh", "bp_lp.cuh", "bp_fk.cuh")]
+                    for f in ("bp_math.cuh", "bp_mvie.cuh", "bp_lp.cuh", "bp_fk.cuh", "bp_mvie_fixed_r.cuh",
+                              "bp_mvie_pd.cuh", "bp_planner.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     lib = ctypes.CDLL(so)

@@ -9,6 +9,7 @@
 #include "../boundplanner_b200/csrc/bp_mvie_pd.cuh"
 #include "../boundplanner_b200/csrc/bp_lp.cuh"
 #include "../boundplanner_b200/csrc/bp_fk.cuh"
+#include "../boundplanner_b200/csrc/bp_planner.h"
 
 struct HostRows {
   const double* A;   // [m,3]
@@ -166,5 +167,73 @@ void hh_fk_kin(const double* q, const double* dq, int n, double* T_ee, double* j
 }
 
 double hh_min_eig(const double* A) { return bp_sym3_min_eig(A); }
+
+
+// ---- the native lock-step planner driver (csrc/bp_planner.h) with its requests answered by callbacks: the CPU
+// test plugs the oracle in and compares with the Python planner (tests/test_planner_native.py) ----
+typedef int (*hh_cb_set)(int qid, const bpplan::SetReq* req, int n_nodes, const bpplan::Node* nodes, bpplan::SetAns* out);
+typedef int (*hh_cb_edges)(int qid, int id_new, int n_nodes, const bpplan::Node* nodes, bpplan::EdgeAns* out);
+typedef int (*hh_cb_project)(int qid, int id0, int id1, const double* xd, int n_nodes, const bpplan::Node* nodes,
+                             bpplan::ProjAns* out);
+typedef int (*hh_cb_path)(int qid, int n_nodes, const int* edge_off, const int* edge_dst, const double* edge_w,
+                          int* path_out, int* path_len);
+
+struct HhCallbackExecutor : bpplan::Executor {
+  hh_cb_set cb_set; hh_cb_edges cb_edges; hh_cb_project cb_project; hh_cb_path cb_path;
+  int commits = 0;
+  void commit_node(int, int, const bpplan::Node&) override { ++commits; }
+  int execute(bpplan::Round& r, const std::vector<bpplan::Query>& qs) override {
+    for (size_t k = 0; k < r.sets.size(); ++k) {
+      const bpplan::Query& q = qs[r.set_owner[k]];
+      if (int rc = cb_set(q.qid, &r.sets[k], (int)q.nodes.size(), q.nodes.data(), &r.set_ans[k])) return rc;
+    }
+    for (size_t k = 0; k < r.edges.size(); ++k) {
+      const bpplan::Query& q = qs[r.edge_owner[k]];
+      if (int rc = cb_edges(q.qid, r.edges[k].id_new, (int)q.nodes.size(), q.nodes.data(),
+                            r.edge_ans.data() + r.edges[k].first_pair)) return rc;
+    }
+    size_t po = 0;
+    for (size_t k = 0; k < r.proj_owner.size(); ++k) {
+      const bpplan::Query& q = qs[r.proj_owner[k]];
+      for (int e = 0; e < r.proj_count[k]; ++e, ++po)
+        if (int rc = cb_project(q.qid, r.projs[po].id0, r.projs[po].id1, r.projs[po].xd, (int)q.nodes.size(),
+                                q.nodes.data(), &r.proj_ans[po])) return rc;
+    }
+    for (size_t k = 0; k < r.paths.size(); ++k) {
+      const int n0 = r.node_off[k];
+      if (int rc = cb_path(r.paths[k].qid, r.paths[k].n_nodes, r.edge_off.data() + n0, r.edge_dst.data(), r.edge_w.data(),
+                           r.path_out.data() + k * (size_t)bpplan::MAX_PATH, &r.path_len[k])) return rc;
+    }
+    return 0;
+  }
+};
+
+int hh_plan_batch(const bp_plan_in* in, bp_plan_out* out, hh_cb_set cb_set, hh_cb_edges cb_edges,
+                  hh_cb_project cb_project, hh_cb_path cb_path) {
+  bpplan::Params par;
+  std::vector<bpplan::Query> qs;
+  bpplan::load_queries(*in, par, qs);
+  HhCallbackExecutor ex;
+  ex.cb_set = cb_set; ex.cb_edges = cb_edges; ex.cb_project = cb_project; ex.cb_path = cb_path;
+  bpplan::RunStats st;
+  std::vector<int> fin(qs.size(), -1);
+  const int rc = bpplan::run_lockstep(qs, ex, par, &st, fin.data());
+  if (rc) return rc;
+  bpplan::store_results(qs, st, fin.data(), *out);
+  return 0;
+}
+
+// numpy's PCG64 stream: n draws of rng.uniform(lo, hi, (n, 3)) from the given state
+void hh_pcg64_uniform3(unsigned long long* state4, const double* lo, const double* hi, int n, double* out) {
+  bpplan::Pcg64 g;
+  g.set((const uint64_t*)state4);
+  double range[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+  g.uniform3(lo, range, n, out);
+  g.get((uint64_t*)state4);
+}
+int hh_sizeof(int what) {
+  return what == 0 ? (int)sizeof(bpplan::SetReq) : what == 1 ? (int)sizeof(bpplan::SetAns) : what == 2 ? (int)sizeof(bpplan::Node)
+       : what == 3 ? (int)sizeof(bpplan::EdgeAns) : what == 4 ? (int)sizeof(bpplan::ProjAns) : -1;
+}
 
 }  // extern "C"

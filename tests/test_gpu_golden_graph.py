@@ -101,6 +101,11 @@ def test_c2_whole_graph_bit_exact(geo):
     A, b, m, q, p, status, pbits = pipe.run(torch.as_tensor(seeds).pin_memory())
     assert np.array_equal(A.numpy(), out.A.cpu().numpy()) and np.array_equal(b.numpy(), out.b.cpu().numpy())
     assert np.array_equal(pbits.numpy(), bits.cpu().numpy())
+    # ... and so does the opt-in variant with the pair tests in the tail of the set-build kernel
+    tpipe = SetGraphPipeline(sc, 256, ws_min, ws_max, fixed_mid=True, optimize=True, tol=0.01, tail=True)
+    for _ in range(2):
+        At, bt, mt, _, _, _, tbits = tpipe.run(torch.as_tensor(seeds).pin_memory())
+        assert np.array_equal(At.numpy(), out.A.cpu().numpy()) and np.array_equal(tbits.numpy(), bits.cpu().numpy())
 
 
 def test_c4_golden_subset_sets_and_pairs(geo):
