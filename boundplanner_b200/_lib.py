@@ -87,6 +87,10 @@ SIGNATURES = {
     "bp_debug_counters": (_i, [_c.POINTER(_c.c_ulonglong), _i, _i]),
     "bp_fk_iiwa14_kin": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_probe_fp64": (_i, [_i, _i, _i, _i, _vp, _vp]),
+    # native lock-step planner driver: (scene batch, Q, &handle) / (handle, &bp_plan_in, &bp_plan_out, stream)
+    "bp_plan_create": (_i, [_vp, _i, _c.POINTER(_vp)]),
+    "bp_plan_run": (_i, [_vp, _vp, _vp, _vp]),
+    "bp_plan_destroy": (_i, [_vp]),
 }
 
 _lib = None

@@ -20,6 +20,8 @@
 #include <string>
 #include <vector>
 
+#include "../../include/bpgeo.h"
+
 namespace bpplan {
 
 constexpr int MAX_NODES = 64;     // graph nodes per query (2 + 20 samples + via-point re-samples)
@@ -346,7 +348,13 @@ struct Query {
     seq_via.clear();
     for (int i = 0; i + 2 < n; ++i) {
       const Inter& nd = inter[pth[1 + i]];
-      if (!nd.has_proj) { fail(ERR_RUNTIME, "intersection node on the path without projection point"); return false; }
+      if (!nd.has_proj) {
+        // an intersection node without edges at its creation never got a projection point; on a path the
+        // reference's x0 = np.concatenate((x0, None, [0.5])) (:595) raises this ValueError
+        fail(ERR_VALUE, "all the input arrays must have same number of dimensions, but the array at index 0 has 1 "
+                        "dimension(s) and the array at index 1 has 0 dimension(s)");
+        return false;
+      }
       const double* last = &pv[pv.size() - 3];
       const double d0 = nd.p_proj[0] - last[0], d1 = nd.p_proj[1] - last[1], d2 = nd.p_proj[2] - last[2];
       if (std::sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 1e-4) {
@@ -762,47 +770,7 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
 
 }  // namespace bpplan
 
-// ---- flat C views of a batch (shared by the library entry point and the test harness) ----
-extern "C" {
-typedef struct {
-  int Q;
-  const double* boxes;        // all scenes back to back [sum n_obs, 6]
-  const int* box_off;         // [Q+1]
-  double inflate;             // obs_size_increase
-  const double* ws_min;       // [3]
-  const double* ws_max;       // [3]
-  const double* starts;       // [Q,3]
-  const double* ends;         // [Q,3]
-  const double* l_ee;         // [Q,3]   r0 @ (-length_ee, 0, 0)
-  const double* l_ee_end;     // [Q,3]   r1 @ (-length_ee, 0, 0)
-  const double* ee_samples;   // [Q,20,3] Rodrigues(omega_hat, |omega| k/19) l_ee
-  const unsigned long long* rng;   // [Q,4]  PCG64 (state_hi, state_lo, inc_hi, inc_lo) of every query's generator
-  const int* has_first;       // [Q] or NULL
-  const double* first_sample; // [Q,3] or NULL
-  int sample_chunk;           // candidates drawn ahead per sampling request (<= 0: 32)
-  int max_rounds;             // <= 0: default
-} bp_plan_in;
-
-typedef struct {
-  int* err_kind;              // [Q] 0 planned, 1 RuntimeError, 2 ValueError
-  char* err_msg;              // [Q,160]
-  int* path;                  // [Q,64] intersection-graph node ids of the shortest path
-  int* path_len;              // [Q]
-  int* set_ids;               // [Q,64] planned set sequence (graph node ids)
-  int* n_ids;                 // [Q]
-  double* p_via;              // [Q,66,3] via points (start, projections, end)
-  int* n_via;                 // [Q]
-  unsigned long long* rng_out;   // [Q,4] generator state after the query (or NULL)
-  int* n_nodes;               // [Q] graph nodes
-  int* n_inter;               // [Q] intersection-graph nodes
-  int* n_edges;               // [Q] intersection-graph edges
-  int* finish_round;          // [Q] lock-step round in which the query was answered
-  double* node_A;             // [Q,64,24,3] or NULL: every graph node's reduced set
-  double* node_b;             // [Q,64,24]   or NULL
-  int* node_m;                // [Q,64]      or NULL
-  long long* stats;           // [8] or NULL: rounds, set requests, pair tests, projections, shortest paths
-} bp_plan_out;
-}
+// (the flat C views of a batch, bp_plan_in / bp_plan_out, are declared in include/bpgeo.h)
 
 namespace bpplan {
 

@@ -3901,6 +3901,9 @@ int bp_fk_iiwa14_kin(const double* q_dev, const double* dq_dev, int B, double* T
 
 }  // extern "C"
 
+// Native lock-step planner driver (bp_plan_create / bp_plan_run / bp_plan_destroy).
+#include "bp_plan_gpu.cuh"
+
 // ---------------------------------------------------------------------------
 // Diagnostics: FP64 pipe probe used by bench.py for the roofline denominator.
 // chains independent DFMA chains per thread, iters steps each.

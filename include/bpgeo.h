@@ -294,6 +294,61 @@ int bp_shortest_paths(const int* node_off_dev, const int* edge_off_dev, const in
                       const double* edge_w_dev, const int* src_dev, const int* dst_dev, int G, int max_len,
                       int* path_dev, int* path_len_dev, double* cost_dev, void* stream);
 
+/* ---- native lock-step planner driver (BASELINE config C3) ---------------------------------------
+ * bp_plan_run plans Q independent queries, one scene each (a scene batch), in lock step: the per-query loop of
+ * BoundPlanner.plan_convex_set_path (BoundPlanner.py:174-584, non-replanning branch) up to the planned set
+ * sequence, add_edges (:789-896) and compute_via_points (:586-743, no rotations) run as C++ state machines on the
+ * host (csrc/bp_planner.h); every round, the pending requests of all queries are answered by ONE chain of the
+ * kernels above (K11 -> K5 -> K12 -> K8 for sampling rounds, K6 + K9 for add_edges, K10, K13) against per-query
+ * node tables resident on the device, with one H2D and one D2H copy per round.  Each query consumes its own
+ * numpy-compatible PCG64 stream exactly as the reference's rng.uniform calls would.
+ * The caller provides what involves rotations (scipy's as_rotvec in the reference, :207-219): l_ee, l_ee_end and
+ * the 20 rotated offsets of check_intersection (:745-772) per query. */
+typedef struct {
+  int Q;
+  const double* boxes;        /* all scenes back to back [sum n_obs, 6] (lb, ub), as given to bp_scene_create_batch */
+  const int* box_off;         /* [Q+1] */
+  double inflate;             /* obs_size_increase */
+  const double* ws_min;       /* [3] */
+  const double* ws_max;       /* [3] */
+  const double* starts;       /* [Q,3] */
+  const double* ends;         /* [Q,3] */
+  const double* l_ee;         /* [Q,3]   r0 @ (-length_ee, 0, 0) */
+  const double* l_ee_end;     /* [Q,3]   r1 @ (-length_ee, 0, 0) */
+  const double* ee_samples;   /* [Q,20,3] Rodrigues(omega_hat, |omega| k/19) l_ee */
+  const unsigned long long* rng; /* [Q,4] PCG64 (state_hi, state_lo, inc_hi, inc_lo) of every query's generator */
+  const int* has_first;       /* [Q] or NULL */
+  const double* first_sample; /* [Q,3] or NULL */
+  int sample_chunk;           /* candidates drawn ahead per sampling request (<= 0: 32; at most 64) */
+  int max_rounds;             /* <= 0: default (4000) */
+} bp_plan_in;
+
+typedef struct {
+  int* err_kind;              /* [Q] 0 planned, 1 RuntimeError, 2 ValueError (the reference's exits) */
+  char* err_msg;              /* [Q,160] */
+  int* path;                  /* [Q,64] intersection-graph node ids of the shortest path */
+  int* path_len;              /* [Q] */
+  int* set_ids;               /* [Q,64] planned set sequence (graph node ids) */
+  int* n_ids;                 /* [Q] */
+  double* p_via;              /* [Q,66,3] via points (start, projections, end) */
+  int* n_via;                 /* [Q] */
+  unsigned long long* rng_out; /* [Q,4] generator state after the query (or NULL) */
+  int* n_nodes;               /* [Q] graph nodes */
+  int* n_inter;               /* [Q] intersection-graph nodes */
+  int* n_edges;               /* [Q] intersection-graph edges */
+  int* finish_round;          /* [Q] lock-step round in which the query was answered */
+  double* node_A;             /* [Q,64,24,3] or NULL: every graph node's reduced set */
+  double* node_b;             /* [Q,64,24]   or NULL */
+  int* node_m;                /* [Q,64]      or NULL */
+  long long* stats;           /* [8] or NULL: rounds, set requests, pair tests, projections, shortest paths,
+                                 kernel chains launched, microseconds spent waiting for the device */
+} bp_plan_out;
+
+typedef struct bp_plan bp_plan;
+int bp_plan_create(const bp_scene* scene_batch, int Q, bp_plan** out);
+int bp_plan_run(bp_plan* plan, const bp_plan_in* in, bp_plan_out* out, void* stream);
+int bp_plan_destroy(bp_plan* plan);
+
 /* ---- multi-GPU exchange by peer stores -------------------------------------------------------
  * The owner of S_loc sets writes them into the global tables A[S,m_max,3] | b[S,m_max] | m[S] | aabb[S,6] of EVERY
  * rank at rows slot0 .. slot0+S_loc-1, through the peers' mapped addresses: peer_base_dev[world] holds the base
