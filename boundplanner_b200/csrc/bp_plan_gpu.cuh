@@ -48,6 +48,8 @@ struct bp_plan : bpplan::Executor {
   const bp_scene* scene = nullptr;
   int Q = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;           // add_edges / projection / shortest-path chain, concurrent with the set builds
+  cudaEvent_t ev_in = nullptr, ev_side = nullptr;
   // device tables of the queries' graph nodes
   double *tabA = nullptr, *tabb = nullptr, *tabq = nullptr, *tabp = nullptr, *tabaabb = nullptr;
   int* tabm = nullptr;
@@ -64,6 +66,7 @@ struct bp_plan : bpplan::Executor {
   std::vector<const double*> ee_group_samples;
   double ws_min[3], ws_max[3];
   long long chains = 0, wait_us = 0;
+  bool trace = getenv("BPGEO_PLAN_TRACE") != nullptr;
   std::string error;
 
   int fail(const char* what, cudaError_t e = cudaSuccess) {
@@ -242,6 +245,15 @@ struct bp_plan : bpplan::Executor {
       new_slots.clear();
       new_nodes.clear();
     }
+    // the requests of a round belong to different queries: the set builds (main stream) and the add_edges /
+    // projection / shortest-path chain (side stream) run concurrently between the two copies
+    const bool fork = nS && (nPairs || nProj || nG);
+    cudaStream_t st2 = fork ? side : stream;
+    if (fork) {
+      e = cudaEventRecord(ev_in, stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev_in, 0);
+      if (e != cudaSuccess) return fail("bp_plan: fork", e);
+    }
     if (nS) {
       // the seeds of the point groups: given points are copied, sampled ones gathered from the candidates
       e = cudaMemcpyAsync(OUT_D(double, o_seed), IN_D(double, i_p0), sizeof(double) * 3 * nS, cudaMemcpyDeviceToDevice, stream);
@@ -276,22 +288,27 @@ struct bp_plan : bpplan::Executor {
         return fail(bp_last_error_string());
     }
     if (nPairs) {
-      k_pair_list<<<(nPairs + 7) / 8, 256, 0, stream>>>(tabA, tabb, tabm, R, 0.01, tabaabb, (const int2*)IN_D(int, i_pairs), nPairs,
+      k_pair_list<<<(nPairs + 7) / 8, 256, 0, st2>>>(tabA, tabb, tabm, R, 0.01, tabaabb, (const int2*)IN_D(int, i_pairs), nPairs,
                                                         OUT_D(int, o_res), OUT_D(double, o_x));
       for (size_t g = 0; g < grp_range.size(); ++g) {
         const int f = grp_range[g].first, n = grp_range[g].second;
         if (n && bp_check_fit(tabA, tabb, tabm, S_tab, R, IN_D(int, i_pairs) + 2 * (size_t)f, n, OUT_D(double, o_x) + 3 * (size_t)f,
                               OUT_D(int, o_res) + f, ee_group_samples[g], FIT_SAMPLES, 0.001, OUT_D(int, o_fits) + f,
-                              OUT_D(int, o_fk) + f, stream))
+                              OUT_D(int, o_fk) + f, st2))
           return fail(bp_last_error_string());
       }
     }
     if (nProj && bp_project_points(tabA, tabb, tabm, S_tab, R, IN_D(int, i_ppairs), nProj, IN_D(double, i_xd), OUT_D(double, o_px),
-                                   OUT_D(int, o_pst), stream))
+                                   OUT_D(int, o_pst), st2))
       return fail(bp_last_error_string());
     if (nG && bp_shortest_paths(IN_D(int, i_noff), IN_D(int, i_eoff), IN_D(int, i_edst), IN_D(double, i_ew), IN_D(int, i_src),
-                                IN_D(int, i_dst), nG, MAX_PATH, OUT_D(int, o_path), OUT_D(int, o_plen), OUT_D(double, o_cost), stream))
+                                IN_D(int, i_dst), nG, MAX_PATH, OUT_D(int, o_path), OUT_D(int, o_plen), OUT_D(double, o_cost), st2))
       return fail(bp_last_error_string());
+    if (fork) {
+      e = cudaEventRecord(ev_side, side);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ev_side, 0);
+      if (e != cudaSuccess) return fail("bp_plan: join", e);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail("bp_plan: kernel launch", e);
     if (out_used) e = cudaMemcpyAsync(h_out, d_out, out_used, cudaMemcpyDeviceToHost, stream);
@@ -301,6 +318,10 @@ struct bp_plan : bpplan::Executor {
     wait_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     if (e != cudaSuccess) return fail("bp_plan: round", e);
     ++chains;
+    if (trace)
+      fprintf(stderr, "bp_plan round %lld: sets %d (opt %d, single %d, line %d; sampled %d) pairs %d proj %d paths %d new %d  wait %lld us\n",
+              chains, nS, n_grp[0], n_grp[1], n_grp[2], nSmp, nPairs, nProj, nG, nNew,
+              (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
 
     // ---- answers
     for (int j = 0; j < nS; ++j) {
@@ -355,6 +376,9 @@ struct bp_plan : bpplan::Executor {
     if (d_in) cudaFree(d_in);
     if (h_out) cudaFreeHost(h_out);
     if (d_out) cudaFree(d_out);
+    if (side) cudaStreamDestroy(side);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_side) cudaEventDestroy(ev_side);
   }
 };
 
@@ -377,8 +401,12 @@ int bp_plan_create(const bp_scene* scene_batch, int Q, bp_plan** out) {
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabp, sizeof(double) * n * 3);
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabaabb, sizeof(double) * n * 6);
   if (e == cudaSuccess) e = cudaMalloc(&pl->work, pl->work_bytes);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_side, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMemset(pl->tabm, 0, sizeof(int) * n);
   if (e == cudaSuccess) e = cudaMemset(pl->tabA, 0, sizeof(double) * n * R * 3);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();        // (the side stream does not order with the memsets)
   if (e != cudaSuccess) {
     pl->release();
     delete pl;

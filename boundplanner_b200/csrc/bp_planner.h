@@ -13,6 +13,7 @@
 // What is NOT here (as in planner.py): the final via-point NLP with rotations (Ipopt, :540-555).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -677,13 +678,18 @@ struct Executor {
   virtual int execute(Round& r, const std::vector<Query>& queries) = 0;
 };
 
-struct RunStats { int rounds = 0; long long set_requests = 0, edge_pairs = 0, projections = 0, paths = 0; };
+struct RunStats {
+  int rounds = 0;
+  long long set_requests = 0, edge_pairs = 0, projections = 0, paths = 0;
+  std::vector<double> round_end_ms;   // wall time since the start of the run at the end of every round
+};
 
 // Advance all queries in lock step until every one is finished.  finish_round[q] (or null) receives the round in
 // which query q finished.
 inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par, RunStats* stats, int* finish_round) {
   Round r;
   std::vector<size_t> committed(qs.size(), 0);
+  const auto t_start = std::chrono::steady_clock::now();
   for (auto& q : qs) q.resume(nullptr, nullptr, nullptr, nullptr, 0);
   int rounds = 0;
   for (;;) {
@@ -763,6 +769,8 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
       qs[r.path_owner[k]].resume(nullptr, nullptr, nullptr, r.path_out.data() + k * (size_t)MAX_PATH, r.path_len[k]);
     for (auto& q : qs)
       if (!q.finished) q.rounds = rounds;
+    if (stats)
+      stats->round_end_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
   }
   if (stats) stats->rounds = rounds;
   return 0;
@@ -818,6 +826,10 @@ inline void store_results(const std::vector<Query>& qs, const RunStats& st, cons
     for (const Inter& it : Qy.inter) ne += (int)it.adj.size();
     out.n_edges[q] = ne / 2;
     out.finish_round[q] = finish_round[q];
+    if (out.finish_ms) {
+      const int fr = finish_round[q];
+      out.finish_ms[q] = (fr >= 1 && (size_t)fr <= st.round_end_ms.size()) ? st.round_end_ms[(size_t)fr - 1] : 0.0;
+    }
     if (out.node_A && out.node_b && out.node_m) {
       for (size_t n = 0; n < (size_t)MAX_NODES; ++n) {
         const size_t slot = q * MAX_NODES + n;

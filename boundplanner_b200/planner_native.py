@@ -32,7 +32,7 @@ class BpPlanIn(ctypes.Structure):
 class BpPlanOut(ctypes.Structure):
     _fields_ = [("err_kind", _ip), ("err_msg", ctypes.c_char_p), ("path", _ip), ("path_len", _ip), ("set_ids", _ip),
                 ("n_ids", _ip), ("p_via", _dp), ("n_via", _ip), ("rng_out", _up), ("n_nodes", _ip), ("n_inter", _ip),
-                ("n_edges", _ip), ("finish_round", _ip), ("node_A", _dp), ("node_b", _dp), ("node_m", _ip),
+                ("n_edges", _ip), ("finish_round", _ip), ("finish_ms", _dp), ("node_A", _dp), ("node_b", _dp), ("node_m", _ip),
                 ("stats", ctypes.POINTER(ctypes.c_longlong))]
 
 
@@ -121,6 +121,7 @@ class PackedQueries:
         self.n_inter = np.zeros(Q, np.int32)
         self.n_edges = np.zeros(Q, np.int32)
         self.finish_round = np.full(Q, -1, np.int32)
+        self.finish_ms = np.zeros(Q)
         self.node_A = np.zeros((Q, MAX_NODES, NODE_ROWS, 3)) if want_nodes else None
         self.node_b = np.zeros((Q, MAX_NODES, NODE_ROWS)) if want_nodes else None
         self.node_m = np.zeros((Q, MAX_NODES), np.int32) if want_nodes else None
@@ -131,7 +132,7 @@ class PackedQueries:
                              self.p_via.ctypes.data_as(_dp), self.n_via.ctypes.data_as(_ip),
                              self.rng_out.ctypes.data_as(_up), self.n_nodes.ctypes.data_as(_ip),
                              self.n_inter.ctypes.data_as(_ip), self.n_edges.ctypes.data_as(_ip),
-                             self.finish_round.ctypes.data_as(_ip),
+                             self.finish_round.ctypes.data_as(_ip), self.finish_ms.ctypes.data_as(_dp),
                              self.node_A.ctypes.data_as(_dp) if want_nodes else None,
                              self.node_b.ctypes.data_as(_dp) if want_nodes else None,
                              self.node_m.ctypes.data_as(_ip) if want_nodes else None,
@@ -161,7 +162,7 @@ class PackedQueries:
         return dict(rounds=int(self.stats[0]), set_requests=int(self.stats[1]), pair_tests=int(self.stats[2]),
                     projections=int(self.stats[3]), shortest_paths=int(self.stats[4]),
                     kernel_chains=int(self.stats[5]), device_wait_ms=self.stats[6] / 1e3,
-                    finish_round=self.finish_round.copy())
+                    finish_round=self.finish_round.copy(), finish_ms=self.finish_ms.copy())
 
 
 class NativePlanner:

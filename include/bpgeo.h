@@ -337,6 +337,7 @@ typedef struct {
   int* n_inter;               /* [Q] intersection-graph nodes */
   int* n_edges;               /* [Q] intersection-graph edges */
   int* finish_round;          /* [Q] lock-step round in which the query was answered */
+  double* finish_ms;          /* [Q] or NULL: wall time since the start of the run at the end of that round */
   double* node_A;             /* [Q,64,24,3] or NULL: every graph node's reduced set */
   double* node_b;             /* [Q,64,24]   or NULL */
   int* node_m;                /* [Q,64]      or NULL */
