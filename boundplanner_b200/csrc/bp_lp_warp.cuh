@@ -12,13 +12,15 @@
 #include "bp_lp.cuh"
 #include "bp_mvie_warp.cuh"   // bp_warp_min / bp_warp_prod
 
-#define BP_LP_SLOTS 3                                   // rows per lane: m1 + m2 <= 96
 #define BP_LP_SCRATCH_DOUBLES (96 * 5 + 16)
 
-// ROWFN(i, a[3], c): row i of the system a.x <= c, i in [0, m), m <= 96.
-template <class ROWFN>
-__device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, int* iters_out, double* xout = nullptr,
-                                   const double* x0 = nullptr, double t0_scale = 0.0) {
+// ROWFN(i, a[3], c): row i of the system a.x <= c, i in [0, m), m <= 32 * BP_LP_SLOTS <= 96.
+// BP_LP_SLOTS = rows per lane: the solver is instantiated for 1, 2 and 3 (a pair of the reference's sets has at
+// most 40 rows, typically 26: one row per lane, a third of the row work of the 96-row form; same arithmetic per
+// row, same reduction trees, so the results are bit-identical).
+template <int BP_LP_SLOTS, class ROWFN>
+__device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int m, double* scratch, int* iters_out,
+                                                        double* xout, const double* x0, double t0_scale) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double* F = scratch;              // [m][5]: v0 v1 v2 v3 (stride 5: conflict-free row writes)
@@ -183,6 +185,14 @@ done:
   if (iters_out) *iters_out = iters;
   if (xout) { xout[0] = x[0]; xout[1] = x[1]; xout[2] = x[2]; }   // last iterate: strictly inside when result == 1
   return result;
+}
+
+template <class ROWFN>
+__device__ int bp_lp_feasible_warp(const ROWFN& rowfn, int m, double* scratch, int* iters_out, double* xout = nullptr,
+                                   const double* x0 = nullptr, double t0_scale = 0.0) {
+  if (m <= 32) return bp_lp_feasible_warp_impl<1>(rowfn, m, scratch, iters_out, xout, x0, t0_scale);
+  if (m <= 64) return bp_lp_feasible_warp_impl<2>(rowfn, m, scratch, iters_out, xout, x0, t0_scale);
+  return bp_lp_feasible_warp_impl<3>(rowfn, m, scratch, iters_out, xout, x0, t0_scale);
 }
 
 // rows of set 1 then set 2, every offset shrunk by tol (BoundPlanner.set_intersection, :774-787)

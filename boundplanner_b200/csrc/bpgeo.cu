@@ -2657,7 +2657,7 @@ __global__ void __launch_bounds__(256) k_fit_check(const double* __restrict__ A,
   const int m1 = m[pr.x], m2 = (pr.y == pr.x) ? 0 : m[pr.y];     // i == j: a single set
   const int mtot = m1 + m2;
   int found = -1;
-  if (2 * mtot <= 32 * BP_LP_SLOTS) {
+  if (2 * mtot <= 96) {                          // (bp_lp_feasible_warp takes at most 96 rows)
     double x0[3] = {0.0, 0.0, 0.0};
     if (x0s) { x0[0] = x0s[3 * p]; x0[1] = x0s[3 * p + 1]; x0[2] = x0s[3 * p + 2]; }
     for (int k = 0; k < fp.n_samples && found < 0; ++k) {
