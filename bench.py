@@ -688,9 +688,34 @@ def bench_c5(torch, geo, scenes):
         mpc_geometry.collision_sets(scene, q0, qf, ws_min, ws_max)
     torch.cuda.synchronize()
     batched_us = (time.perf_counter() - t0) / 5 / n * 1e6
-    return {"what": "C5: geometry of one MPC step through the drop-in API from host arrays -- forward_kinematics(q, dq) "
+    # the replanning call of the receding-horizon loop (plan_convex_set_path(replanning=True, p_horizon=...),
+    # BoundPlanner.py:231-276) up to the planned set sequence, from points along the first plan
+    from scipy.spatial.transform import Rotation as R
+
+    from boundplanner_b200.planner import GpuBackend, SetSequencePlanner
+
+    boxes_p, wmin_p, wmax_p, infl_p = scenes.example_scene()
+    r0 = R.from_euler("XYZ", [0, 90, 0], degrees=True).as_matrix()
+    p0, p1 = np.array([0.3, 0.0, 0.7]), np.array([0.45, -0.5, 0.2])
+    pl = SetSequencePlanner(boxes_p, infl_p, list(wmax_p), list(wmin_p), rng=np.random.default_rng(0),
+                            backend=GpuBackend(boxes_p, infl_p, list(wmax_p), list(wmin_p)))
+    first = pl.plan_set_sequence(p0.copy(), p1.copy(), r0, r0)
+    pv = first["p_via"]
+    replan_ms = []
+    for frac in (0.02, 0.1, 0.2, 0.3, 0.4, 0.5):
+        start = pv[0] + frac * (pv[1] - pv[0])
+        horizon = np.array([start + ti * (pv[1] - start) for ti in np.linspace(0.05, 0.6, 8)])
+        t0 = time.perf_counter()
+        try:
+            pl.plan_set_sequence(start.copy(), p1.copy(), r0, r0, replanning=True, p_horizon=horizon)
+        except (RuntimeError, ValueError):
+            pass
+        replan_ms.append((time.perf_counter() - t0) * 1e3)
+    return {"replan_ms_p50": float(np.percentile(replan_ms, 50)), "replans": len(replan_ms),
+            "what": "C5: geometry of one MPC step through the drop-in API from host arrays -- forward_kinematics(q, dq) "
                     "+ 12 FK evaluations + 6 find_set_collision_avoidance(limit_space=True, e_max=0.7) over the 12 "
-                    "example obstacles, results back on the host",
+                    "example obstacles, results back on the host; replan_ms = plan_set_sequence(replanning=True, p_horizon) on "
+                    "the C1 scene from points along the first plan",
             "steps": n, "us_per_mpc_step_p50": float(np.percentile(lat, 50)),
             "us_per_mpc_step_p95": float(np.percentile(lat, 95)),
             "us_per_mpc_step_batched_200": batched_us}

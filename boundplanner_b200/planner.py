@@ -1,17 +1,18 @@
 """Set-sequence planner: the reference's ``plan_convex_set_path`` up to the planned
 set sequence, with every geometric primitive served by the GPU kernels.
 
-Restates the control flow of bound_planner/BoundPlanner/BoundPlanner.py
-(non-replanning branch):
+Restates the control flow of bound_planner/BoundPlanner/BoundPlanner.py:
 
-  plan_convex_set_path  :174-584   start / end sets, sampling loop, dedupe, convergence test
+  plan_convex_set_path  :174-584   start / end sets (incl. the replanning branch :231-276 and the
+                                   start-in-collision fallbacks :296-324), sampling loop, dedupe, convergence test
   compute_via_points    :586-743   with_rot=False branch (the via points are the p_proj's)
   add_edges             :789-896   intersection nodes, projection points, edge costs (quirk Q6)
 
-What is NOT here: the final via-point NLP with rotations (Ipopt, :540-555) and the
-replanning branch (:231-276) -- both stay with the reference.  The output is what
-precedes them: the shortest path through the intersection graph, the sets it
-visits ("planned set sequence") and the position via points.
+What is NOT here: the final via-point NLP with rotations (Ipopt, :540-555) and, with it, the backwards
+extension of the first segment when replanning (:706-729) -- they stay with the reference.  The output is what
+precedes them: the shortest path through the intersection graph, the sets it visits ("planned set sequence") and
+the position via points; ``sets_via_prev`` is kept for the next (re)planning call like the reference does
+(:372, :556).
 
 The loop is written ONCE, as a generator that yields *requests* for geometric
 primitives and receives their results:
@@ -22,6 +23,7 @@ primitives and receives their results:
                                            every existing set + check_intersection of every hit (one device round:
                                            the fit check starts from the LP's point and never leaves the GPU)
   ("project", A, b, x_d)                -> x                                         projection QP of add_edges
+  ("reduce", A, b)                      -> (A_red, b_red)                            reduce_ineqs of a given set
   with ``device_loop`` (backends that keep every query's known sets and node ellipsoids in device tables):
   ("sample_set", cand[C,3], optimize, planner) -> (first, (A, b, q, p, A_red, b_red, dvertex) | Exception)
                                            the rejection loop of :459-478 over C pre-drawn candidates (first accepted
@@ -118,6 +120,7 @@ class SetSequencePlanner:
         self.nr_optimized = 10
         self.nr_free_mid = 5
         self.max_samples = 500
+        self.sets_via_prev = []              # :37; set by every successful plan (:372, :556)
         self.rng = rng if rng is not None else np.random.default_rng()      # unseeded in the reference (quirk Q4)
         self.backend = backend
         if obs_sets is not None:
@@ -296,7 +299,28 @@ class SetSequencePlanner:
         return np.array(p_via), p_via, sets_via, seq_via
 
     # ---- :174-534 -------------------------------------------------------------
-    def plan_gen(self, start, end, r0, r1, first_sample=None):
+    def replanning_horizon_index(self, start, p_horizon, new_obs=False):
+        """:231-266: how far along the MPC horizon the previous plan's sets still hold.  Walks ``sets_via_prev`` in
+        order; a set that contains ``start`` extends the index to the last horizon point before the first one
+        outside it (the whole horizon: stop); ``new_obs`` resets it to 1."""
+        p_horizon = np.asarray(p_horizon, float).reshape(-1, 3)
+        max_horizon_idx = 1
+        for s in self.sets_via_prev:
+            dist_start = s[0] @ start - s[1]
+            dist_horizon = s[0] @ p_horizon.T - np.expand_dims(s[1], 1)
+            start_in = np.max(dist_start) < 1e-8
+            horizon_idx = np.where(np.logical_not(np.max(dist_horizon, axis=0) < 1e-8))[0]
+            if horizon_idx.shape[0] > 0:
+                if horizon_idx[0] != 0 and start_in:
+                    max_horizon_idx = int(np.max((max_horizon_idx, horizon_idx[0] - 1)))
+            elif start_in:
+                max_horizon_idx = len(p_horizon) - 1
+                break
+        if new_obs:
+            max_horizon_idx = 1
+        return max_horizon_idx
+
+    def plan_gen(self, start, end, r0, r1, first_sample=None, replanning=False, p_horizon=(), new_obs=False):
         """Generator form of the planner loop (see the module docstring for the request protocol)."""
         start = np.array(start, float)
         end = np.array(end, float)
@@ -324,12 +348,32 @@ class SetSequencePlanner:
         self._nodes_reset()
         self._inter_by_node = {}
 
-        a_set, b_set, q_start, p_mid_start, a_red, b_red = yield ("set_point", start, True, True)     # :278-283
-        collision = False
-        if np.max(a_set @ (start + self.l_ee) - b_set) > 1e-8:
-            a_set, b_set, q_start, p_mid_start, collision, a_red, b_red = yield ("set_line", start, start + self.l_ee)
-        if collision:
-            raise RuntimeError("start point in collision (the replanning fallbacks of :296-324 are not restated)")
+        self.replanning = bool(replanning)
+        if replanning:                                            # :231-276
+            self.p_horizon = np.asarray(p_horizon, float).reshape(-1, 3)
+            self.p_horizon_max = self.p_horizon[self.replanning_horizon_index(start, self.p_horizon, new_obs)]
+            a_set, b_set, q_start, p_mid_start, collision, a_red, b_red = yield ("set_line", start, self.p_horizon_max)
+        else:
+            a_set, b_set, q_start, p_mid_start, a_red, b_red = yield ("set_point", start, True, True)     # :278-283
+            collision = False
+            if np.max(a_set @ (start + self.l_ee) - b_set) > 1e-8:
+                a_set, b_set, q_start, p_mid_start, collision, a_red, b_red = yield ("set_line", start, start + self.l_ee)
+        if collision:                                             # :296-324
+            if new_obs:
+                # the reference pushes `start` out of every inflated obstacle that contains it -- through
+                # `ob.A()[idx, :]` on a list (:311), i.e. it raises AttributeError as soon as one does (quirk Q12);
+                # without such an obstacle the loop does nothing and the start set is built around `start`
+                for k in range(len(self.obs_sets)):
+                    if not np.any(np.concatenate((start, -start)) - self._b6[k] > 0):
+                        raise AttributeError("'list' object has no attribute 'A'")
+                a_set, b_set, q_start, p_mid_start, a_red, b_red = yield ("set_point", start, True, True)
+            else:
+                # "Could not find start set, reusing old end set": IndexError on a first plan, like the reference
+                prev = self.sets_via_prev[-1]
+                a_prev, b_prev = np.array(prev[0], float), np.array(prev[1], float)
+                a_red, b_red = yield ("reduce", a_prev, b_prev)
+                p_mid_start = start
+                q_start = np.eye(3)
         a_set, b_set = a_red, b_red                               # reduce_ineqs (:327)
         set_start = [a_set, b_set]
         self.id_inter = 0
@@ -343,6 +387,9 @@ class SetSequencePlanner:
         self.nr_sets += 1
         connected = yield from self._add_edges(0, graph, inter_graph, end, start)
         if np.max(a_set @ end - b_set) < 1e-8 and np.max(a_set @ (end + self.l_ee_end) - b_set) < 1e-8:   # :361-375
+            from .utils import normalize_set_size
+
+            self.sets_via_prev = normalize_set_size([[set_start[0], set_start[1]]], 15).copy()                          # :371-372
             return dict(path=[0], set_ids=[0], sets_via=[set_start], p_via=np.array([start, end]), graph=graph,
                         inter_graph=inter_graph)
         _, _, q_end, p_mid_end, collision, a_set, b_set = yield ("set_line", end, end + self.l_ee_end)  # :381-390
@@ -423,14 +470,17 @@ class SetSequencePlanner:
                     conn = yield from self._add_edges(self.id_graph, graph, inter_graph, end, start)
                     connected = conn or connected
         self.graph, self.inter_graph = graph, inter_graph
+        self.sets_via_prev = list(sets_via)                                                          # :556
         return dict(path=path, set_ids=seq_via, sets_via=sets_via, p_via=p_via, graph=graph, inter_graph=inter_graph)
 
-    def plan_set_sequence(self, start, end, r0, r1, first_sample=None):
+    def plan_set_sequence(self, start, end, r0, r1, first_sample=None, replanning=False, p_horizon=(), new_obs=False):
         """Sequential driver: every request is answered at once by ``self.backend.execute``.
-        Returns dict(path, set_ids, sets_via, p_via, graph, inter_graph)."""
+        Returns dict(path, set_ids, sets_via, p_via, graph, inter_graph).  replanning / p_horizon / new_obs as in
+        plan_convex_set_path (:180-183): the start set then comes from the segment start .. horizon point that the
+        previous plan's sets (``sets_via_prev``) still cover."""
         if self.backend is None:
             self.backend = GpuBackend(self._obstacles, self.obs_size_increase, self.workspace_max, self.workspace_min)
-        gen = self.plan_gen(start, end, r0, r1, first_sample)
+        gen = self.plan_gen(start, end, r0, r1, first_sample, replanning, p_horizon, new_obs)
         try:
             req = next(gen)
             while True:
@@ -563,7 +613,7 @@ class BatchedGpuExecutor:
             worst = max((s[0].shape[0] + req[2][0].shape[0] for s in req[1]), default=0)
         elif kind == "fit_many":
             worst = max((a.shape[0] for a, _, _ in req[1]), default=0)
-        elif kind == "project":
+        elif kind in ("project", "reduce"):
             worst = np.asarray(req[1]).shape[0]
         if worst > BP_MAX_ROWS:
             return ValueError(f"'{kind}' request with {worst} rows exceeds the kernels' {BP_MAX_ROWS}-row sets")
@@ -772,6 +822,15 @@ class BatchedGpuExecutor:
                     out[q] = [(bool(fits[o + k]), np.concatenate((items[k][2], [omega[o + k] if fits[o + k] else 0.0])))
                               for k in range(n)]
                     o += n
+
+        qids = by_kind.get("reduce", [])                   # reduce_ineqs of a given set (start-set fallback, :321-327)
+        if qids:
+            self.calls += 1
+            A, b, m = self._pack([[pending[q][1], pending[q][2]] for q in qids])
+            Ar, br, mr, _, _ = geo.reduce_ineqs(A, b, m)
+            Ar, br, mr = Ar.cpu().numpy(), br.cpu().numpy(), mr.cpu().numpy()
+            for k, q in enumerate(qids):
+                out[q] = (Ar[k, : mr[k]].copy(), br[k, : mr[k]].copy())
 
         qids = by_kind.get("project", [])
         if qids:

@@ -203,3 +203,76 @@ def test_device_loop_protocol_equals_host_loop_on_cpu():
         if a[2] is not None:
             assert np.array_equal(a[2], b[2])
         assert np.array_equal(a[3], b[3])             # same number of draws consumed
+
+
+def test_replanning_branch_and_start_fallbacks_with_oracle_backend():
+    """BoundPlanner.py:231-276 / :296-324: after a first plan, replanning from a point on the first segment builds
+    the start set around the segment start .. horizon point that the previous sets still cover; the fallbacks for a
+    start segment in collision reuse the previous end set (IndexError on a first plan) or rebuild around `start`."""
+    boxes, ws_min, ws_max, inflate = scenes.example_scene()
+    backend = OracleBackend(boxes, inflate, list(ws_max), list(ws_min))
+    pl = SetSequencePlanner(boxes, inflate, list(ws_max), list(ws_min), backend=backend, rng=np.random.default_rng(0))
+    first = pl.plan_set_sequence(P0.copy(), P1.copy(), R0, R0)
+    assert len(pl.sets_via_prev) == len(first["sets_via"]) >= 1
+    p_via = first["p_via"]
+    # MPC horizon: points along the first segment(s) of the planned path
+    t = np.linspace(0.05, 0.6, 8)
+    horizon = np.array([p_via[0] + ti * (p_via[1] - p_via[0]) for ti in t])
+    start = p_via[0] + 0.02 * (p_via[1] - p_via[0])
+    idx = pl.replanning_horizon_index(start, horizon)
+    s0 = pl.sets_via_prev[0]
+    assert np.max(s0[0] @ start - s0[1]) < 1e-8
+    inside = np.max(s0[0] @ horizon.T - s0[1][:, None], axis=0) < 1e-8
+    assert idx == (len(horizon) - 1 if inside.all() else max(1, int(np.argmin(inside)) - 1))
+    assert pl.replanning_horizon_index(start, horizon, new_obs=True) == 1
+    prev_sets = [[a.copy(), b.copy()] for a, b in pl.sets_via_prev]
+    res = pl.plan_set_sequence(start.copy(), P1.copy(), R0, R0, replanning=True, p_horizon=horizon)
+    a0, b0 = res["graph"].nodes[0]["cset"]
+    assert np.max(a0 @ start - b0) < 1e-6 and np.max(a0 @ pl.p_horizon_max - b0) < 1e-6      # segment inside its set
+    assert res["path"][0] == 0 and res["path"][-1] == 1 and np.allclose(res["p_via"][-1], P1)
+    # fallbacks: a start segment that runs through an obstacle
+    lo, hi = boxes[0][:3], boxes[0][3:]
+    through = 0.5 * (lo + hi)
+    pl2 = SetSequencePlanner(boxes, inflate, list(ws_max), list(ws_min), backend=backend, rng=np.random.default_rng(0))
+    with pytest.raises(IndexError):                       # first plan: no previous end set to reuse
+        pl2.plan_set_sequence(P0.copy(), P1.copy(), R0, R0, replanning=True, p_horizon=np.array([P0, through]))
+    pl2.sets_via_prev = prev_sets
+    res2 = pl2.plan_set_sequence(P0.copy(), P1.copy(), R0, R0, replanning=True, p_horizon=np.array([P0, through]))
+    a0, b0 = res2["graph"].nodes[0]["cset"]
+    want_a, want_b = backend.reduce_ineqs(np.array(prev_sets[-1][0]), np.array(prev_sets[-1][1]))
+    assert np.array_equal(a0, want_a) and np.array_equal(b0, want_b)                          # old end set reused
+    assert np.array_equal(res2["graph"].nodes[0]["q_ellipse"], np.eye(3))
+    pl3 = SetSequencePlanner(boxes, inflate, list(ws_max), list(ws_min), backend=backend, rng=np.random.default_rng(0))
+    res3 = pl3.plan_set_sequence(P0.copy(), P1.copy(), R0, R0, replanning=True, p_horizon=np.array([P0, through]),
+                                 new_obs=True)                                                # rebuilt around start
+    a0, b0 = res3["graph"].nodes[0]["cset"]
+    assert np.max(a0 @ P0 - b0) < 1e-6
+    with pytest.raises(AttributeError):                   # quirk Q12: start inside an inflated obstacle + new_obs
+        pl3.plan_set_sequence(through.copy(), P1.copy(), R0, R0, replanning=True, p_horizon=np.array([through, P0]),
+                              new_obs=True)
+
+
+@pytest.mark.gpu
+def test_replanning_gpu_matches_oracle_sequence():
+    """The replanning call (:231-276) through the kernels == through the oracle: same start set, path and sequence."""
+    from boundplanner_b200.planner import GpuBackend
+
+    outs = []
+    for cls in (OracleBackend, GpuBackend):
+        boxes, ws_min, ws_max, inflate = scenes.example_scene()
+        backend = cls(boxes, inflate, list(ws_max), list(ws_min))
+        pl = SetSequencePlanner(boxes, inflate, list(ws_max), list(ws_min), backend=backend, rng=np.random.default_rng(0))
+        first = pl.plan_set_sequence(P0.copy(), P1.copy(), R0, R0)
+        p_via = first["p_via"]
+        horizon = np.array([p_via[0] + ti * (p_via[1] - p_via[0]) for ti in np.linspace(0.05, 0.6, 8)])
+        start = p_via[0] + 0.02 * (p_via[1] - p_via[0])
+        res = pl.plan_set_sequence(start.copy(), P1.copy(), R0, R0, replanning=True, p_horizon=horizon)
+        outs.append((first, res, pl.p_horizon_max.copy()))
+    (f0, r0_, h0), (f1, r1_, h1) = outs
+    assert f0["path"] == f1["path"] and f0["set_ids"] == f1["set_ids"]
+    assert np.abs(h0 - h1).max() < 1e-6
+    assert r0_["path"] == r1_["path"] and r0_["set_ids"] == r1_["set_ids"]
+    assert np.abs(r0_["p_via"] - r1_["p_via"]).max() < 1e-6
+    a0, b0 = r0_["graph"].nodes[0]["cset"]
+    a1, b1 = r1_["graph"].nodes[0]["cset"]
+    assert a0.shape == a1.shape and np.abs(a0 - a1).max() < 1e-6 and np.abs(b0 - b1).max() < 1e-6

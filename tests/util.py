@@ -105,6 +105,8 @@ class OracleBackend:
             return [self.check_intersection(a, b, l_ee, s, omega_normed, omega_norm) for a, b, s in req[1]]
         if kind == "project":
             return self.project(req[1], req[2], req[3])
+        if kind == "reduce":
+            return self.reduce_ineqs(req[1], req[2])
         raise ValueError(kind)
 
 
