@@ -41,6 +41,8 @@ SIGNATURES = {
     "bp_scene_create": (_i, [_dp, _i, _d, _c.POINTER(_vp)]),
     "bp_scene_create_batch": (_i, [_dp, _c.POINTER(_c.c_int), _i, _d, _c.POINTER(_vp)]),
     "bp_scene_create_polytopes": (_i, [_dp, _c.POINTER(_c.c_int), _dp, _c.POINTER(_c.c_int), _i, _i, _c.POINTER(_vp)]),
+    "bp_scene_create_polytopes_batch": (_i, [_dp, _c.POINTER(_c.c_int), _dp, _c.POINTER(_c.c_int),
+                                             _c.POINTER(_c.c_int), _i, _i, _c.POINTER(_vp)]),
     "bp_scene_update": (_i, [_vp, _dp, _i, _d, _vp]),
     "bp_scene_destroy": (_i, [_vp]),
     "bp_scene_size": (_i, [_vp]),

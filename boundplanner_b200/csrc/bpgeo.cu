@@ -105,7 +105,12 @@ __device__ __forceinline__ SceneView scene_of_item(const SceneView& sc, int item
 #pragma unroll
   for (int a = 0; a < 3; ++a) { v.lb[a] = sc.lb[a] + o; v.ub[a] = sc.ub[a] + o; }
   v.n = sc.seg_off[k + 1] - o;
-  v.rows = nullptr; v.nrows = nullptr; v.verts = nullptr; v.nverts = nullptr; v.vmax = 0;   // batches hold boxes
+  // polytope batches: the obstacles' rows / vertex lists are stored back to back like the bounding boxes
+  v.rows = sc.rows ? sc.rows + (size_t)o * BP_OBS_ROWS * 4 : nullptr;
+  v.nrows = sc.rows ? sc.nrows + o : nullptr;
+  v.verts = sc.rows ? sc.verts + (size_t)o * sc.vmax * 3 : nullptr;
+  v.nverts = sc.rows ? sc.nverts + o : nullptr;
+  v.vmax = sc.vmax;
   v.seg_off = nullptr;
   v.item_seg = nullptr;
   v.staged = 0;
@@ -537,8 +542,7 @@ __device__ __forceinline__ double poly_min_halfspace(const SceneView& sc, int j,
 // values once no bound is smaller or equal -- the same obstacle, the same bits as solving all N QPs (the QP of
 // an entry is the same code on the same inputs whenever it runs).
 // POLY: the obstacles are general polytopes (sc.rows != NULL): the bounds come from their bounding boxes, the exact
-// closest points from warp-cooperative QPs over a shared work list, the vertex test walks their vertex lists;
-// needs cache_y.
+// closest points from warp-cooperative QPs over a shared work list, the vertex test walks their vertex lists.
 template <bool POLY, int AW = 1>
 __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassMetric& pm, const double* p,
                                                 double* s_dist, int cache_y, double (*red_val)[32],
@@ -646,7 +650,7 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
               d = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
             }
             s_dist[j] = d;
-            s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2];
+            if (cache_y) { s_y[j] = y[0]; s_y[sc.n + j] = y[1]; s_y[2 * sc.n + j] = y[2]; }
           }
           __syncwarp();
         }
@@ -683,6 +687,19 @@ __device__ __forceinline__ void poly_pass_point(const SceneView& sc, const PassM
     double y[3];
     if (cache_y) {
       y[0] = s_y[idx]; y[1] = s_y[sc.n + idx]; y[2] = s_y[2 * sc.n + idx];
+    } else if (POLY) {                         // large polytope scenes: warp 0 re-solves the winner's QP (same
+      __shared__ double s_ywin[3];             // inputs, same candidate order, same bits) and hands it round
+      if (tid < 32) {
+        const int R = sc.nrows[idx];
+        for (int e = tid; e < R * 4; e += 32) s_prow[0][e] = __ldg(sc.rows + (size_t)idx * BP_OBS_ROWS * 4 + e);
+        __syncwarp();
+        double yw[3] = {0.0, 0.0, 0.0};
+        polytope_qp_warp(pmq, s_prow[0], R, p, yw);
+        if (tid == 0) { s_ywin[0] = yw[0]; s_ywin[1] = yw[1]; s_ywin[2] = yw[2]; }
+      }
+      __syncthreads();
+      y[0] = s_ywin[0]; y[1] = s_ywin[1]; y[2] = s_ywin[2];
+      __syncthreads();                         // (s_prow[0] / s_ywin are reused by the next refinement round / pick)
     } else {                                   // large scenes: re-solve the winner's QP (same inputs, same bits)
       double lb[3], ub[3];
       load_box(sc, idx, lb, ub);
@@ -1556,6 +1573,7 @@ struct LineParams {
   int* status;
   int* collision;
   int m_max;
+  int cache_x;               // polytope scenes: closest points kept in shared memory (x[3][N] | p_closest[3][N])
 };
 
 __device__ __forceinline__ double seg_closest(const double* p0, const double* d, const double* lb,
@@ -1702,7 +1720,9 @@ __device__ __forceinline__ bool seg_polytope_qp_warp(const double* rows4, int R,
   return true;
 }
 
-__global__ void __launch_bounds__(512) k_poly_line_p(SceneView sc, LineParams pr) {
+__global__ void __launch_bounds__(512) k_poly_line_p(SceneView sc_all, LineParams pr) {
+  const SceneView sc = scene_of_item(sc_all, blockIdx.x);
+  const int cache_x = pr.cache_x, n_tab = sc_all.n;     // n_tab: the table stride (largest scene of a batch)
   extern __shared__ double s_dist[];
   __shared__ double red_val[2][32];
   __shared__ int red_idx[2][32];
@@ -1711,8 +1731,9 @@ __global__ void __launch_bounds__(512) k_poly_line_p(SceneView sc, LineParams pr
   __shared__ double s_prow[16][BP_OBS_ROWS * 4];
   const int s = blockIdx.x;
   const int tid = threadIdx.x, T = blockDim.x;
-  double* s_x = s_dist + sc.n;                 // [3][N]
-  double* s_pc = s_dist + 4 * (size_t)sc.n;    // [3][N]
+  double* s_x = s_dist + n_tab;                // [3][N] when cache_x
+  double* s_pc = s_dist + 4 * (size_t)n_tab;   // [3][N] when cache_x
+  __shared__ double s_win[6];
   double p0[3], d[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -1780,8 +1801,10 @@ __global__ void __launch_bounds__(512) k_poly_line_p(SceneView sc, LineParams pr
         const bool okq = seg_polytope_qp_warp(s_prow[warp], R, 0.001, p0, d, x, &phi, &d2);   // b - 0.001 (:496)
         if (lane == 0) {
           s_dist[j] = okq ? sqrt(d2) : BP_INF;               // :327
-          s_x[j] = x[0]; s_x[sc.n + j] = x[1]; s_x[2 * sc.n + j] = x[2];
-          s_pc[j] = p0[0] + phi * d[0]; s_pc[sc.n + j] = p0[1] + phi * d[1]; s_pc[2 * sc.n + j] = p0[2] + phi * d[2];
+          if (cache_x) {
+            s_x[j] = x[0]; s_x[n_tab + j] = x[1]; s_x[2 * n_tab + j] = x[2];
+            s_pc[j] = p0[0] + phi * d[0]; s_pc[n_tab + j] = p0[1] + phi * d[1]; s_pc[2 * n_tab + j] = p0[2] + phi * d[2];
+          }
         }
         __syncwarp();
       }
@@ -1799,8 +1822,26 @@ __global__ void __launch_bounds__(512) k_poly_line_p(SceneView sc, LineParams pr
       }
       continue;
     }
-    double x[3] = {s_x[idx], s_x[sc.n + idx], s_x[2 * sc.n + idx]};
-    double pc[3] = {s_pc[idx], s_pc[sc.n + idx], s_pc[2 * sc.n + idx]};
+    double x[3], pc[3];
+    if (cache_x) {
+      x[0] = s_x[idx]; x[1] = s_x[n_tab + idx]; x[2] = s_x[2 * n_tab + idx];
+      pc[0] = s_pc[idx]; pc[1] = s_pc[n_tab + idx]; pc[2] = s_pc[2 * n_tab + idx];
+    } else {                                     // large scenes: warp 0 re-solves the winner's QP (same bits)
+      if (tid < 32) {
+        const int R = sc.nrows[idx];
+        for (int e = tid; e < R * 4; e += 32) s_prow[0][e] = __ldg(sc.rows + (size_t)idx * BP_OBS_ROWS * 4 + e);
+        __syncwarp();
+        double xw[3] = {0.0, 0.0, 0.0}, phiw = 0.0, d2w = 0.0;
+        seg_polytope_qp_warp(s_prow[0], R, 0.001, p0, d, xw, &phiw, &d2w);
+        if (tid == 0) {
+          s_win[0] = xw[0]; s_win[1] = xw[1]; s_win[2] = xw[2];
+          s_win[3] = p0[0] + phiw * d[0]; s_win[4] = p0[1] + phiw * d[1]; s_win[5] = p0[2] + phiw * d[2];
+        }
+      }
+      __syncthreads();
+      x[0] = s_win[0]; x[1] = s_win[1]; x[2] = s_win[2]; pc[0] = s_win[3]; pc[1] = s_win[4]; pc[2] = s_win[5];
+      __syncthreads();
+    }
     double a[3] = {x[0] - pc[0], x[1] - pc[1], x[2] - pc[2]};
     double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
     if (nrm < 1e-6) {                                  // line touches an obstacle (:336-345)
@@ -3101,6 +3142,7 @@ static size_t poly_point_smem_bytes(int n, bool polytopes) {
   return sizeof(double) * (size_t)n;
 }
 // fused per-seed kernel for small / medium scenes; BPGEO_FUSED=0 forces the launch sequence
+#define BP_POLY_SCENE_MAX 16384               // polytope scenes: obstacles per scene (one alive bit per thread and entry)
 static bool use_fused_iris(int n) {
   static int env = -1;
   if (env < 0) {
@@ -3276,6 +3318,30 @@ int bp_scene_create_polytopes(const double* rows_host, const int* nrows_host, co
   return 0;
 }
 
+int bp_scene_create_polytopes_batch(const double* rows_host, const int* nrows_host, const double* verts_host,
+                                    const int* nverts_host, const int* offsets_host, int n_scenes, int vmax,
+                                    bp_scene** out) {
+  if (!out || n_scenes < 1 || !offsets_host || offsets_host[0] != 0)
+    return bp_fail("bp_scene_create_polytopes_batch: bad arguments");
+  int n_max = 0;
+  for (int k = 0; k < n_scenes; ++k) {
+    const int nk = offsets_host[k + 1] - offsets_host[k];
+    if (nk < 0) return bp_fail("bp_scene_create_polytopes_batch: offsets must be non-decreasing");
+    n_max = nk > n_max ? nk : n_max;
+  }
+  bp_scene* sc = nullptr;
+  int rc = bp_scene_create_polytopes(rows_host, nrows_host, verts_host, nverts_host, offsets_host[n_scenes], vmax, &sc);
+  if (rc) return rc;
+  sc->n = n_max;                                  // sizes shared memory / picks the kernel variant
+  sc->n_seg = n_scenes;
+  cudaError_t e = cudaMalloc(&sc->seg_off, sizeof(int) * (size_t)(n_scenes + 1));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(sc->seg_off, offsets_host, sizeof(int) * (size_t)(n_scenes + 1), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { bp_scene_destroy(sc); return bp_fail("bp_scene_create_polytopes_batch", e); }
+  *out = sc;
+  return 0;
+}
+
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream) {
   if (scene && scene->seg_off) return bp_fail("bp_scene_update: not supported for scene batches");
   if (scene && scene->rows) return bp_fail("bp_scene_update: not supported for polytope scenes (create a new one)");
@@ -3332,7 +3398,7 @@ int bp_polyhedron(const bp_scene* scene, const double* seeds_dev, const double* 
   pr.shell = !scene->rows && poly_point_shell(scene->n);
   size_t smem = poly_point_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows) {
-    if (!pr.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    if (scene->n > BP_POLY_SCENE_MAX) return bp_fail("polytope scenes hold at most 16384 obstacles");
     if (set_dyn_smem((const void*)k_poly_point<true>, smem)) return 1;
     k_poly_point<true><<<S, poly_threads(scene->n), smem, (cudaStream_t)stream>>>(view_of(scene), pr);
   } else {
@@ -3395,7 +3461,7 @@ int bp_build_sets_around_line(const bp_scene* scene, const double* p0_dev, const
   fp.row_cap = row_cap; fp.cache_y = poly_cache_y(scene->n);
   const size_t fsmem = poly_smem_bytes(scene->n, scene->rows != nullptr);
   if (scene->rows) {
-    if (!fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    if (scene->n > 64 * 128) return bp_fail("bp_build_sets_around_line: polytope scenes of at most 8192 obstacles");
     if (set_dyn_smem((const void*)k_iris_fused<1, true>, fsmem)) return 1;
     k_iris_fused<1, true><<<S, 128, fsmem, (cudaStream_t)stream>>>(view_of(scene), fp);
   } else {
@@ -3474,7 +3540,7 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
   if (S == 0) return 0;
   if (workspace_bytes < bp_build_sets_workspace_bytes(S)) return bp_fail("bp_build_sets_point: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (use_fused_iris(scene->n)) {
+  if (use_fused_iris(scene->n) && !(scene->rows && scene->n > 64 * 128)) {   // (polytope kernels: one word of alive bits)
     FusedParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.seeds = seeds_dev;
@@ -3505,7 +3571,6 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
     const void* kfn = scene->rows ? (const void*)k_iris_fused<0, true>
                       : (scene->n <= 64 * 128 ? (const void*)k_iris_fused<0, false>
                                               : (const void*)k_iris_fused<0, false, 2>);   // (2 words of alive bits)
-    if (scene->rows && !fp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
     if (tail && fsmem < sizeof(double) * BP_TAIL_WORK_DOUBLES) fsmem = sizeof(double) * BP_TAIL_WORK_DOUBLES;
     if (set_dyn_smem(kfn, fsmem)) return 1;
     if (tail) {
@@ -3541,7 +3606,7 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
   pp.cache_y = poly_cache_y(scene->n);
   pp.shell = !scene->rows && poly_point_shell(scene->n);
   size_t smem = poly_point_smem_bytes(scene->n, scene->rows != nullptr);
-  if (scene->rows && !pp.cache_y) return bp_fail("polytope scenes hold at most 3072 obstacles");
+  if (scene->rows && scene->n > BP_POLY_SCENE_MAX) return bp_fail("polytope scenes hold at most 16384 obstacles");
   if (set_dyn_smem(scene->rows ? (const void*)k_poly_point<true> : (const void*)k_poly_point<false>, smem)) return 1;
   const int T = poly_threads(scene->n);
   const int passes = optimize ? max_iter : 1;
@@ -3597,10 +3662,11 @@ int bp_build_sets_line_ms(const bp_scene* scene, const int* seg_scene_dev, const
   for (int i = 0; i < 3; ++i) { lp.ws_rows[2 * i] = ws_max_host[i]; lp.ws_rows[2 * i + 1] = -ws_min_host[i]; }
   lp.A = A_dev; lp.b = b_dev; lp.m = m_dev; lp.status = status_dev; lp.collision = collision_dev; lp.m_max = m_max;
   if (scene->rows) {                                     // general polytopes: dist | x[3] | p_closest[3] per obstacle
-    const size_t psmem = sizeof(double) * 7 * (size_t)scene->n;
-    if (scene->n > 3072) return bp_fail("polytope scenes hold at most 3072 obstacles");
+    lp.cache_x = scene->n <= 3072;
+    const size_t psmem = sizeof(double) * (lp.cache_x ? 7 : 1) * (size_t)scene->n;
+    if (scene->n > BP_POLY_SCENE_MAX) return bp_fail("polytope scenes hold at most 16384 obstacles");
     if (set_dyn_smem((const void*)k_poly_line_p, psmem)) return 1;
-    k_poly_line_p<<<S, poly_threads(scene->n), psmem, stream>>>(view_of(scene), lp);
+    k_poly_line_p<<<S, poly_threads(scene->n), psmem, stream>>>(view_of(scene, seg_scene_dev), lp);
   } else {
     size_t smem = sizeof(double) * (size_t)(scene->n > 0 ? scene->n : 1);
     if (set_dyn_smem((const void*)k_poly_line, smem)) return 1;

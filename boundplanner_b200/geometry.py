@@ -83,11 +83,12 @@ class Scene:
 class PolytopeScene(Scene):
     """General convex polytope obstacles resident in HBM: what ConvexSetFinder is handed when the obstacles are not
     boxes -- obs_sets = [[A (<= 15 rows, zero-padded), b], ...] (already inflated) and obs_points_sets = [vertices
-    (V x 3), ...] (the reference enumerates them with cddlib, util_functions.py:66-79).  At most 3072 obstacles."""
+    (V x 3), ...] (the reference enumerates them with cddlib, util_functions.py:66-79).  At most 16384 obstacles
+    (their closest points are cached in shared memory up to 3072; beyond that the winner of every pick is re-solved)."""
 
     MAX_ROWS = 15
 
-    def __init__(self, obs_sets, obs_points_sets=None):
+    def __init__(self, obs_sets, obs_points_sets=None, _offsets=None):
         _require_cuda()
         self._lib = _lib.load()
         self._h = ctypes.c_void_p(0)
@@ -119,14 +120,41 @@ class PolytopeScene(Scene):
             nverts[j] = v.shape[0]
         ip = ctypes.POINTER(ctypes.c_int)
         torch.cuda.current_device()
-        check(self._lib.bp_scene_create_polytopes(rows.ctypes.data_as(_dp), nrows.ctypes.data_as(ip),
-                                                  verts.ctypes.data_as(_dp), nverts.ctypes.data_as(ip), n, vmax,
-                                                  ctypes.byref(self._h)))
-        self.n = n
+        if _offsets is None:
+            check(self._lib.bp_scene_create_polytopes(rows.ctypes.data_as(_dp), nrows.ctypes.data_as(ip),
+                                                      verts.ctypes.data_as(_dp), nverts.ctypes.data_as(ip), n, vmax,
+                                                      ctypes.byref(self._h)))
+            self.n = n
+        else:
+            offs = np.ascontiguousarray(_offsets, dtype=np.int32)
+            check(self._lib.bp_scene_create_polytopes_batch(rows.ctypes.data_as(_dp), nrows.ctypes.data_as(ip),
+                                                            verts.ctypes.data_as(_dp), nverts.ctypes.data_as(ip),
+                                                            offs.ctypes.data_as(ip), len(offs) - 1, vmax,
+                                                            ctypes.byref(self._h)))
+            self.n = int(np.diff(offs).max())
+            self.n_scenes = len(offs) - 1
         self.inflate = 0.0
 
     def update(self, boxes, inflate=None):
         raise _lib.BpGeoError("PolytopeScene is immutable: create a new one")
+
+
+class PolytopeSceneBatch(PolytopeScene):
+    """Several polytope scenes stored back to back in HBM (one per planning query): ``scenes`` is a list of
+    (obs_sets, obs_points_sets | None) pairs.  Use with build_sets_point / build_sets_line / sample_filter and
+    ``item_scene`` = scene index of every seed / segment."""
+
+    def __init__(self, scenes_list):
+        from .utils import obstacle_points_sets
+
+        sets, pts, offs = [], [], [0]
+        for obs_sets, obs_points in scenes_list:
+            if obs_points is None:
+                obs_points = obstacle_points_sets(obs_sets)
+            sets.extend(obs_sets)
+            pts.extend(obs_points)
+            offs.append(len(sets))
+        super().__init__(sets, pts, _offsets=offs)
 
 
 class SceneBatch(Scene):

@@ -56,10 +56,17 @@ int bp_scene_create_batch(const double* boxes_host, const int* offsets_host /*[n
  * a caller hands to ConvexSetFinder): rows_host [n,15,4] = (a0,a1,a2,b) per row, real rows first, then zero rows
  * with b = 10 (normalize_set_size padding, util_functions.py:119-133); nrows_host [n]; verts_host [n,vmax,3] with
  * nverts_host [n] vertices each.  Rows are taken as given (already inflated).  Supported by bp_closest_points(_line),
- * bp_polyhedron, bp_build_sets_point, bp_build_sets_around_line and bp_build_sets_line (at most 3072 obstacles);
- * scene batches take boxes only. */
+ * bp_polyhedron, bp_build_sets_point, bp_build_sets_around_line, bp_build_sets_line and bp_sample_filter; at most
+ * 16384 obstacles per scene (bp_build_sets_around_line: 8192).  While
+ * the closest points of all obstacles fit in shared memory (3072 obstacles) they are cached there; beyond that the
+ * winner of every pick is re-solved (same bits). */
 int bp_scene_create_polytopes(const double* rows_host, const int* nrows_host, const double* verts_host,
                               const int* nverts_host, int n, int vmax, bp_scene** out);
+/* A batch of polytope scenes stored back to back (scene k owns obstacles [offsets[k], offsets[k+1]) of the four
+ * arrays); use with the *_ms entry points like bp_scene_create_batch. */
+int bp_scene_create_polytopes_batch(const double* rows_host, const int* nrows_host, const double* verts_host,
+                                    const int* nverts_host, const int* offsets_host /*[n_scenes+1]*/, int n_scenes,
+                                    int vmax, bp_scene** out);
 int bp_scene_update(bp_scene* scene, const double* boxes_host, int n, double inflate, void* stream);
 int bp_scene_destroy(bp_scene* scene);
 int bp_scene_size(const bp_scene* scene);

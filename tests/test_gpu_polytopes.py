@@ -220,3 +220,85 @@ def test_compute_polytope_vertices_on_device(poly_scene):
     w = geo.build_sets_point(scene, seeds[:6], ws_min, ws_max, fixed_mid=True)
     assert np.array_equal(a.m.cpu().numpy(), w.m.cpu().numpy())
     assert np.abs(a.A.cpu().numpy() - w.A.cpu().numpy()).max() < 1e-9
+
+
+def test_large_polytope_scene_without_the_shared_memory_cache(poly_scene):
+    """More than 3072 polytope obstacles: the closest points no longer fit in shared memory and the winner of every
+    pick is re-solved.  4000 boxes handed over as polytopes (rows + 8 corners) must give the box path's sets, for
+    the IRIS loop (fused kernel), one polyhedron pass and the segment sets."""
+    geo, *_ = poly_scene
+    import torch
+
+    from boundplanner_b200 import scenes
+    from oracle.obstacles import obstacle_reps
+
+    boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(4000, 12, seed=5)
+    obs_sets, pts, _ = obstacle_reps(boxes, inflate)
+    sp = geo.PolytopeScene(obs_sets, pts)
+    sb = geo.Scene(boxes, inflate)
+    assert sp.n == 4000
+    for optimize in (True, False):
+        op = geo.build_sets_point(sp, seeds, ws_min, ws_max, fixed_mid=True, optimize=optimize)
+        ob = geo.build_sets_point(sb, seeds, ws_min, ws_max, fixed_mid=True, optimize=optimize)
+        assert np.array_equal(op.status.cpu().numpy(), ob.status.cpu().numpy())
+        assert np.array_equal(op.m.cpu().numpy(), ob.m.cpu().numpy())
+        assert np.array_equal(op.iters.cpu().numpy(), ob.iters.cpu().numpy())
+        assert np.abs(op.A.cpu().numpy() - ob.A.cpu().numpy()).max() < 1e-9
+        assert np.abs(op.b.cpu().numpy() - ob.b.cpu().numpy()).max() < 1e-9
+    rng = np.random.default_rng(2)
+    d = rng.normal(size=seeds.shape)
+    d *= 0.04 / np.linalg.norm(d, axis=1)[:, None]
+    lp = geo.build_sets_line(sp, seeds, seeds + d, ws_min, ws_max, compute_ellipsoid=True)
+    lb = geo.build_sets_line(sb, seeds, seeds + d, ws_min, ws_max, compute_ellipsoid=True)
+    assert np.array_equal(lp.m.cpu().numpy(), lb.m.cpu().numpy())
+    assert np.array_equal(lp.collision.cpu().numpy(), lb.collision.cpu().numpy())
+    assert np.abs(lp.A.cpu().numpy() - lb.A.cpu().numpy()).max() < 1e-9
+    assert np.abs(lp.b.cpu().numpy() - lb.b.cpu().numpy()).max() < 1e-9
+    # the cached and the re-solving form agree bit for bit: the first 3000 obstacles alone vs the same 3000 plus
+    # 1000 far-away ones that never matter
+    far = boxes[:1000].copy()
+    far[:, :3] += 50.0
+    far[:, 3:] += 50.0
+    os_small, pts_small, _ = obstacle_reps(boxes[:3000], inflate)
+    os_big, pts_big, _ = obstacle_reps(np.vstack((boxes[:3000], far)), inflate)
+    a = geo.build_sets_point(geo.PolytopeScene(os_small, pts_small), seeds, ws_min, ws_max, fixed_mid=True)
+    b = geo.build_sets_point(geo.PolytopeScene(os_big, pts_big), seeds, ws_min, ws_max, fixed_mid=True)
+    assert torch.equal(a.A, b.A) and torch.equal(a.b, b.b) and torch.equal(a.q_ellipse, b.q_ellipse)
+
+
+def test_polytope_scene_batch_equals_single_scenes(poly_scene):
+    """A batch of polytope scenes (one per planning query) gives, seed by seed, the sets of the single scenes."""
+    geo, scene, ora, obs_sets, obs_points, seeds, ws_min, ws_max = poly_scene
+    import torch
+
+    from boundplanner_b200 import scenes
+
+    parts = [(obs_sets, obs_points)]
+    for k, n in ((1, 120), (2, 57)):
+        parts.append(scenes.random_polytope_scene(n, np.random.default_rng(40 + k), 0.04, 0.16))
+    batch = geo.PolytopeSceneBatch(parts)
+    sd, item = [], []
+    for k, (os_k, _) in enumerate(parts):
+        pts = seeds[:5] if k == 0 else scenes.polytope_free_points(5, os_k, 0.03, np.random.default_rng(50 + k))
+        sd.append(pts)
+        item += [k] * len(pts)
+    sd = np.vstack(sd)
+    order = np.random.default_rng(0).permutation(len(item))          # seeds of different scenes interleaved
+    sd, item = sd[order], np.asarray(item, np.int32)[order]
+    got = geo.build_sets_point(batch, sd, ws_min, ws_max, fixed_mid=True, optimize=True, item_scene=item)
+    d = np.tile(np.array([0.03, -0.02, 0.04]), (len(item), 1))
+    got_l = geo.build_sets_line(batch, sd, sd + d, ws_min, ws_max, compute_ellipsoid=True, item_scene=item)
+    cand = np.random.default_rng(3).uniform(ws_min, ws_max, (len(item), 16, 3))
+    got_f = geo.sample_filter(batch, cand, item_scene=item)
+    for k, (os_k, op_k) in enumerate(parts):
+        single = geo.PolytopeScene(os_k, op_k)
+        sel = np.flatnonzero(item == k)
+        want = geo.build_sets_point(single, sd[sel], ws_min, ws_max, fixed_mid=True, optimize=True)
+        t = torch.as_tensor(sel, device="cuda")
+        assert torch.equal(got.A[t], want.A) and torch.equal(got.b[t], want.b) and torch.equal(got.m[t], want.m)
+        assert torch.equal(got.q_ellipse[t], want.q_ellipse) and torch.equal(got.status[t], want.status)
+        want_l = geo.build_sets_line(single, sd[sel], sd[sel] + d[sel], ws_min, ws_max, compute_ellipsoid=True)
+        assert torch.equal(got_l.A[t], want_l.A) and torch.equal(got_l.b[t], want_l.b)
+        assert torch.equal(got_l.collision[t], want_l.collision)
+        want_f = geo.sample_filter(single, cand[sel])
+        assert torch.equal(got_f[t], want_f)
