@@ -140,13 +140,14 @@ struct bp_plan : bpplan::Executor {
                            al(sizeof(int) * nNew) + al(sizeof(double) * nNew * 9) + al(sizeof(double) * nNew * 3) +
                            2 * al(sizeof(double) * nS * 3) + 3 * al(sizeof(int) * nS) +
                            al(sizeof(double) * (size_t)nSmp * C * 3) + 4 * al(sizeof(int) * nSmp) +
-                           al(sizeof(int) * 2 * nPairs) + al(sizeof(int) * 2 * nProj) + al(sizeof(double) * 3 * nProj) +
+                           al(sizeof(int) * 2 * nPairs) + al(sizeof(int) * nPairs) + al(sizeof(double) * 3 * nPairs) +
+                           al(sizeof(int) * 2 * nProj) + al(sizeof(double) * 3 * nProj) +
                            al(sizeof(int) * (nG + 1)) + 2 * al(sizeof(int) * nG) + al(sizeof(int) * (nNodesCsr + 1)) +
                            al(sizeof(int) * nEdgesCsr) + al(sizeof(double) * nEdgesCsr);
     const size_t need_out = 64 * 16 + al(sizeof(double) * nNew * 6) + 2 * al(sizeof(double) * nS * M * 3) +
                             2 * al(sizeof(double) * nS * M) + al(sizeof(double) * nS * 9) + al(sizeof(double) * nS * 3) +
                             8 * al(sizeof(int) * nS) + al(sizeof(double) * nS) + al(sizeof(double) * nS * 3) + al(sizeof(int) * nSmp) +
-                            3 * al(sizeof(int) * nPairs) + al(sizeof(double) * 3 * nPairs) + al(sizeof(double) * 3 * nProj) +
+                            4 * al(sizeof(int) * nPairs) + 2 * al(sizeof(double) * 3 * nPairs) + al(sizeof(double) * 3 * nProj) +
                             al(sizeof(int) * nProj) + al(sizeof(int) * nG * MAX_PATH) + al(sizeof(int) * nG) + al(sizeof(double) * nG);
     if (int rc = reserve(need_in, need_out)) return rc;
 #define IN_H(T, off) ((T*)(h_in + (off)))
@@ -193,12 +194,16 @@ struct bp_plan : bpplan::Executor {
       }
     }
     // edges / projections / paths
-    const size_t i_pairs = take_in(sizeof(int) * 2 * nPairs), i_ppairs = take_in(sizeof(int) * 2 * nProj),
+    const size_t i_pairs = take_in(sizeof(int) * 2 * nPairs), i_ehas = take_in(sizeof(int) * nPairs),
+                 i_exd = take_in(sizeof(double) * 3 * nPairs), i_ppairs = take_in(sizeof(int) * 2 * nProj),
                  i_xd = take_in(sizeof(double) * 3 * nProj);
     for (int k = 0; k < nE; ++k) {
       const EdgeReq& e = r.edges[k];
       int* pp = IN_H(int, i_pairs) + 2 * (size_t)e_off[k];
       for (int v = 0; v < e.n_others; ++v) { pp[2 * v] = e.qid * MAX_NODES + v; pp[2 * v + 1] = e.qid * MAX_NODES + e.id_new; }
+      // the point every hit of this request is projected from, when it is known already (see Query::spec_target)
+      memcpy(IN_H(int, i_ehas) + e_off[k], r.edge_has_target.data() + e.first_pair, sizeof(int) * e.n_others);
+      memcpy(IN_H(double, i_exd) + 3 * (size_t)e_off[k], r.edge_xd.data() + 3 * (size_t)e.first_pair, sizeof(double) * 3 * e.n_others);
     }
     for (int k = 0; k < nProj; ++k) {
       const ProjReq& p = r.projs[k];
@@ -229,6 +234,7 @@ struct bp_plan : bpplan::Executor {
                  o_seed = take_out(sizeof(double) * nS * 3), o_first = take_out(sizeof(int) * nSmp);
     const size_t o_res = take_out(sizeof(int) * nPairs), o_x = take_out(sizeof(double) * 3 * nPairs),
                  o_fits = take_out(sizeof(int) * nPairs), o_fk = take_out(sizeof(int) * nPairs),
+                 o_epx = take_out(sizeof(double) * 3 * nPairs), o_epst = take_out(sizeof(int) * nPairs),
                  o_px = take_out(sizeof(double) * 3 * nProj), o_pst = take_out(sizeof(int) * nProj),
                  o_path = take_out(sizeof(int) * nG * MAX_PATH), o_plen = take_out(sizeof(int) * nG), o_cost = take_out(sizeof(double) * nG);
     if (out_used > out_cap) return fail("bp_plan: output arena overflow");
@@ -298,6 +304,9 @@ struct bp_plan : bpplan::Executor {
           return fail(bp_last_error_string());
       }
     }
+    if (nPairs)       // the hits' projections from their known targets, gated by the intersection result (K10)
+      k_project<<<(nPairs + 7) / 8, 256, 0, st2>>>(tabA, tabb, tabm, R, (const int2*)IN_D(int, i_pairs), nPairs, IN_D(double, i_exd),
+                                                   OUT_D(double, o_epx), OUT_D(int, o_epst), OUT_D(int, o_res), IN_D(int, i_ehas));
     if (nProj && bp_project_points(tabA, tabb, tabm, S_tab, R, IN_D(int, i_ppairs), nProj, IN_D(double, i_xd), OUT_D(double, o_px),
                                    OUT_D(int, o_pst), st2))
       return fail(bp_last_error_string());
@@ -353,6 +362,8 @@ struct bp_plan : bpplan::Executor {
         for (int c = 0; c < 3; ++c) ea.x[c] = OUT_H(double, o_x)[3 * p + c];
         const int fk = OUT_H(int, o_fk)[p];
         ea.omega = fk >= 0 ? (double)fk / (FIT_SAMPLES - 1) : -1.0;
+        ea.proj_ok = ea.ok && r.edge_has_target[er.first_pair + v] && OUT_H(int, o_epst)[p] >= 0;
+        for (int c = 0; c < 3; ++c) ea.proj[c] = OUT_H(double, o_epx)[3 * p + c];
       }
     }
     for (int k = 0; k < nProj; ++k) {

@@ -78,7 +78,12 @@ struct SetAns {
 struct EdgeReq {          // set_intersection + check_intersection of node id_new against nodes 0 .. id_new-1
   int qid, id_new, n_others, first_pair;   // answers: pair first_pair + k  <->  (node k, id_new)
 };
-struct EdgeAns { int ok, fits; double x[3], omega; };
+struct EdgeAns {          // proj: projection of the pair's target point onto the intersection (when ok and asked for)
+  int ok, fits;
+  double x[3], omega;
+  int proj_ok;
+  double proj[3];
+};
 struct ProjReq { int qid, id0, id1; double xd[3]; };     // projection onto rows(node id0) + rows(node id1)
 struct ProjAns { double x[3]; int status; };
 struct PathReq { int qid, n_nodes, edge_begin; };        // CSR of the query's intersection graph (see Round)
@@ -154,6 +159,11 @@ struct Query {
   SetReq set_req;
   EdgeReq edge_req;
   std::vector<ProjReq> proj_reqs;          // the projections of one add_edges call that are ready together
+  // an "edges" request also carries, per other node v, the point that a hit (v, id_new) will be projected from:
+  // it is known before the answers when v (or id_new) already has intersection nodes -- the first candidate of the
+  // hit is then the oldest of those -- so that projection is computed in the same device round, gated by the hit
+  std::vector<int> spec_target;            // [n_others] intersection node whose p_proj is the target, -1: none yet
+  std::vector<double> spec_xd;             // [n_others,3]
   PathReq path_req;
   std::vector<double> cand;                // candidates of the pending sampling request
 
@@ -180,7 +190,7 @@ struct Query {
   Pcg64 rng_chunk_start;
   // add_edges in flight
   int e_id_new = 0;
-  struct Hit { int vid, inter_id; bool fits; int target; bool pending; };
+  struct Hit { int vid, inter_id; bool fits; int target; bool pending; bool have_spec = false; double spec[3] = {0, 0, 0}; };
   std::vector<Hit> hits;
   size_t hit_next = 0;                     // first hit whose bookkeeping has not run yet
   size_t proj_first = 0, proj_end = 0;     // hits [proj_first, proj_end) have their projection in flight
@@ -440,6 +450,18 @@ struct Query {
           if (e_id_new == 0) { pc = PC_EDGES_DONE; continue; }       // no other node yet
           req_kind = REQ_EDGES;
           edge_req.qid = qid; edge_req.id_new = e_id_new; edge_req.n_others = e_id_new; edge_req.first_pair = 0;
+          spec_target.assign((size_t)e_id_new, -1);
+          spec_xd.assign(3 * (size_t)e_id_new, 0.0);
+          for (int v = 0; v < e_id_new; ++v) {
+            int t = -1;
+            if (!by_node[v].empty()) t = by_node[v][0];
+            if (!by_node[e_id_new].empty() && (t < 0 || by_node[e_id_new][0] < t)) t = by_node[e_id_new][0];
+            spec_target[(size_t)v] = t;
+            if (t >= 0) {
+              const double* xd = inter[t].has_proj ? inter[t].p_proj : end;
+              for (int c = 0; c < 3; ++c) spec_xd[3 * (size_t)v + c] = xd[c];
+            }
+          }
           pc = PC_WAIT_EDGES;
           return;
         }
@@ -451,6 +473,11 @@ struct Query {
             const int id = add_inter(v, e_id_new, false, false, nullptr, via, ea.fits != 0);
             nr_inter_set += 2;
             hits.push_back(Hit{v, id, ea.fits != 0, -2, false});
+            if (spec_target[(size_t)v] >= 0 && ea.proj_ok) {          // projected in this very round
+              Hit& h = hits.back();
+              h.have_spec = true;
+              for (int c = 0; c < 3; ++c) h.spec[c] = ea.proj[c];
+            }
           }
           // the reference registers a hit in the node index when it is created, hit by hit; the candidates of hit
           // k therefore never contain the hits after it: by_node is filled as the hits are processed
@@ -480,6 +507,12 @@ struct Query {
               break;
             }
             h.pending = h.target != -2;
+            if (h.pending && h.have_spec && h.target == spec_target[(size_t)h.vid]) {
+              Inter& me = inter[h.inter_id];                        // already projected with the edges request
+              for (int c = 0; c < 3; ++c) me.p_proj[c] = h.spec[c];
+              me.has_proj = true;
+              h.pending = false;
+            }
             if (h.pending) {
               ProjReq pr;
               pr.qid = qid; pr.id0 = h.vid; pr.id1 = e_id_new;
@@ -492,9 +525,9 @@ struct Query {
           }
           proj_end = k;
           if (proj_end == proj_first) { pc = PC_EDGES_DONE; continue; }      // no hits (left)
-          if (proj_reqs.empty()) {                                           // hits without candidates: nothing to do
-            hit_next = proj_end;
-            pc = hit_next < hits.size() ? PC_PROJECT_NEXT : PC_EDGES_DONE;
+          if (proj_reqs.empty()) {                  // nothing left to ask for: the bookkeeping of these hits runs now
+            proj_ans = nullptr;
+            pc = PC_WAIT_PROJECT;
             continue;
           }
           req_kind = REQ_PROJECT;
@@ -657,6 +690,7 @@ struct Query {
 struct Round {
   std::vector<SetReq> sets;          std::vector<SetAns> set_ans;
   std::vector<EdgeReq> edges;        std::vector<EdgeAns> edge_ans;      // flat, EdgeReq::first_pair indexes it
+  std::vector<int> edge_has_target;  std::vector<double> edge_xd;        // per pair: project this point when it hits
   std::vector<ProjReq> projs;        std::vector<ProjAns> proj_ans;
   std::vector<PathReq> paths;                                            // CSR over all graphs of the round:
   std::vector<int> node_off, edge_off, edge_dst;                         //   node_off[g], edge_off[node], edge_dst
@@ -665,6 +699,7 @@ struct Round {
   std::vector<int> set_owner, edge_owner, proj_owner, proj_count, path_owner;   // index into the query array
   void clear() {
     sets.clear(); edges.clear(); projs.clear(); paths.clear(); node_off.clear(); edge_off.clear(); edge_dst.clear();
+    edge_has_target.clear(); edge_xd.clear();
     edge_w.clear(); set_owner.clear(); edge_owner.clear(); proj_owner.clear(); proj_count.clear(); path_owner.clear();
   }
 };
@@ -711,6 +746,8 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
           e.first_pair = 0;
           for (const EdgeReq& p : r.edges) e.first_pair += p.n_others;
           r.edges.push_back(e); r.edge_owner.push_back((int)i);
+          for (int v = 0; v < e.n_others; ++v) r.edge_has_target.push_back(q.spec_target[(size_t)v] >= 0 ? 1 : 0);
+          r.edge_xd.insert(r.edge_xd.end(), q.spec_xd.begin(), q.spec_xd.end());
           break;
         }
         case REQ_PROJECT:

@@ -2724,11 +2724,16 @@ __global__ void __launch_bounds__(256) k_fit_check(const double* __restrict__ A,
 __global__ void __launch_bounds__(256) k_project(const double* __restrict__ A, const double* __restrict__ b,
                                                  const int* __restrict__ m, int m_max, const int2* __restrict__ pairs,
                                                  int P, const double* __restrict__ xd, double* __restrict__ xout,
-                                                 int* __restrict__ status) {
+                                                 int* __restrict__ status, const int* __restrict__ act_a = nullptr,
+                                                 const int* __restrict__ act_b = nullptr) {
   __shared__ double sA[8][2 * BP_MAX_ROWS * 3], sb[8][2 * BP_MAX_ROWS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int p = blockIdx.x * 8 + wib;
   if (p >= P) return;
+  if ((act_a && !act_a[p]) || (act_b && !act_b[p])) {       // gated off (e.g. the pair does not intersect)
+    if (lane == 0 && status) status[p] = -1;
+    return;
+  }
   const int2 pr = pairs[p];
   const int m1 = m[pr.x], m2 = (pr.y == pr.x) ? 0 : m[pr.y];
   const int mt = m1 + m2;

@@ -172,7 +172,8 @@ double hh_min_eig(const double* A) { return bp_sym3_min_eig(A); }
 // ---- the native lock-step planner driver (csrc/bp_planner.h) with its requests answered by callbacks: the CPU
 // test plugs the oracle in and compares with the Python planner (tests/test_planner_native.py) ----
 typedef int (*hh_cb_set)(int qid, const bpplan::SetReq* req, int n_nodes, const bpplan::Node* nodes, bpplan::SetAns* out);
-typedef int (*hh_cb_edges)(int qid, int id_new, int n_nodes, const bpplan::Node* nodes, bpplan::EdgeAns* out);
+typedef int (*hh_cb_edges)(int qid, int id_new, int n_nodes, const bpplan::Node* nodes, const int* has_target,
+                           const double* xd, bpplan::EdgeAns* out);
 typedef int (*hh_cb_project)(int qid, int id0, int id1, const double* xd, int n_nodes, const bpplan::Node* nodes,
                              bpplan::ProjAns* out);
 typedef int (*hh_cb_path)(int qid, int n_nodes, const int* edge_off, const int* edge_dst, const double* edge_w,
@@ -190,6 +191,7 @@ struct HhCallbackExecutor : bpplan::Executor {
     for (size_t k = 0; k < r.edges.size(); ++k) {
       const bpplan::Query& q = qs[r.edge_owner[k]];
       if (int rc = cb_edges(q.qid, r.edges[k].id_new, (int)q.nodes.size(), q.nodes.data(),
+                            r.edge_has_target.data() + r.edges[k].first_pair, r.edge_xd.data() + 3 * (size_t)r.edges[k].first_pair,
                             r.edge_ans.data() + r.edges[k].first_pair)) return rc;
     }
     size_t po = 0;

@@ -42,7 +42,8 @@ class Node(ctypes.Structure):
 
 
 class EdgeAns(ctypes.Structure):
-    _fields_ = [("ok", ctypes.c_int), ("fits", ctypes.c_int), ("x", ctypes.c_double * 3), ("omega", ctypes.c_double)]
+    _fields_ = [("ok", ctypes.c_int), ("fits", ctypes.c_int), ("x", ctypes.c_double * 3), ("omega", ctypes.c_double),
+                ("proj_ok", ctypes.c_int), ("proj", ctypes.c_double * 3)]
 
 
 class ProjAns(ctypes.Structure):
@@ -51,7 +52,7 @@ class ProjAns(ctypes.Structure):
 
 CB_SET = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.POINTER(SetReq), ctypes.c_int, ctypes.POINTER(Node),
                           ctypes.POINTER(SetAns))
-CB_EDGES = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Node),
+CB_EDGES = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Node), _ip, _dp,
                             ctypes.POINTER(EdgeAns))
 CB_PROJECT = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, ctypes.c_int,
                               ctypes.POINTER(Node), ctypes.POINTER(ProjAns))
@@ -175,15 +176,22 @@ def run_native_with_oracle(host_harness, queries, inflate, ws_max, ws_min, seeds
             errors.append(e)
             return 7
 
-    def cb_edges(qid, id_new, n_nodes, nodes, out):
+    def cb_edges(qid, id_new, n_nodes, nodes, has_target, xd, out):
         try:
             others = [_node_set(nodes[k]) for k in range(id_new)]
-            res = backends[qid].execute(("edges", others, _node_set(nodes[id_new]), 0.01, ee[qid]))
+            new = _node_set(nodes[id_new])
+            res = backends[qid].execute(("edges", others, new, 0.01, ee[qid]))
             for k, (x, ok, fits, via) in enumerate(res):
-                out[k].ok, out[k].fits = int(bool(ok)), int(bool(fits))
+                out[k].ok, out[k].fits, out[k].proj_ok = int(bool(ok)), int(bool(fits)), 0
                 if ok:
                     out[k].x[:] = np.asarray(x).tolist()
                     out[k].omega = float(via[3]) if fits else -1.0
+                    if has_target[k]:                         # the hit's projection, asked for with the edges
+                        pr = backends[qid].execute(("project", np.concatenate((others[k][0], new[0])),
+                                                    np.concatenate((others[k][1], new[1])),
+                                                    np.array([xd[3 * k], xd[3 * k + 1], xd[3 * k + 2]])))
+                        out[k].proj[:] = np.asarray(pr).tolist()
+                        out[k].proj_ok = 1
             return 0
         except Exception as e:                               # noqa: BLE001
             errors.append(e)
