@@ -711,7 +711,34 @@ def bench_c5(torch, geo, scenes):
         except (RuntimeError, ValueError):
             pass
         replan_ms.append((time.perf_counter() - t0) * 1e3)
+    # per-call latency of the drop-ins an UNCHANGED planner would hit one call at a time (host arrays in, host
+    # arrays out): ConvexSetFinder.find_set_around_point / find_set_collision_avoidance, set_intersection, fk_pos_col
+    from boundplanner_b200.planner import obstacle_sets
+    from boundplanner_b200.utils import obstacle_points_sets
+
+    obs_sets = obstacle_sets(boxes_p, infl_p)
+    finder = bp.ConvexSetFinder(obs_sets, obstacle_points_sets(obs_sets), list(wmax_p), list(wmin_p))
+    pts = scenes.free_points(24, boxes_p, infl_p, np.random.default_rng(3), wmin_p + 0.05, wmax_p - 0.05)
+
+    def p50_us(fn, n):
+        fn(0)
+        ts = []
+        for k in range(n):
+            t0 = time.perf_counter()
+            fn(k)
+            ts.append((time.perf_counter() - t0) * 1e6)
+        return float(np.percentile(ts, 50))
+
+    sets_h = [finder.find_set_around_point(pts[k], fixed_mid=True)[:2] for k in range(8)]
+    dropin = {
+        "find_set_around_point": p50_us(lambda k: finder.find_set_around_point(pts[k % 24], fixed_mid=True), 24),
+        "find_set_collision_avoidance": p50_us(lambda k: finder.find_set_collision_avoidance(
+            pts[k % 24], pts[k % 24] + np.array([0.03, -0.02, 0.02]), True), 24),
+        "set_intersection": p50_us(lambda k: bp.set_intersection(sets_h[k % 8], sets_h[(k + 3) % 8], 0.01), 24),
+        "fk_pos_col": p50_us(lambda k: model.fk_pos_col(traj[k % n], k % 6), 24),
+    }
     return {"replan_ms_p50": float(np.percentile(replan_ms, 50)), "replans": len(replan_ms),
+            "dropin_call_us_p50": dropin,
             "what": "C5: geometry of one MPC step through the drop-in API from host arrays -- forward_kinematics(q, dq) "
                     "+ 12 FK evaluations + 6 find_set_collision_avoidance(limit_space=True, e_max=0.7) over the 12 "
                     "example obstacles, results back on the host; replan_ms = plan_set_sequence(replanning=True, p_horizon) on "

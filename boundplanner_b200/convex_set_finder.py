@@ -229,13 +229,30 @@ class ConvexSetFinder:
         return q_new[0].cpu().numpy(), q_ell[0].cpu().numpy(), eigs[0].cpu().numpy()
 
     # ---- :190-240 ---------------------------------------------------------
+    @staticmethod
+    def _fetch_one(out, with_collision=False):
+        """Everything a batch-of-one call hands back, in ONE device-to-host copy: rows, offsets, ellipsoid, centre and
+        the integer outputs (as doubles) packed on the device first."""
+        ints = [out.m, out.status, out.rows_peak if out.rows_peak is not None else out.m]
+        if with_collision:
+            ints.append(out.collision)
+        flat = torch.cat([out.A[0].reshape(-1), out.b[0].reshape(-1), out.q_ellipse[0].reshape(-1),
+                          out.p_mid[0].reshape(-1)] + [t[:1].to(torch.float64) for t in ints]).cpu().numpy()
+        m_max = out.A.shape[1]
+        o = 0
+        A = flat[o: o + 3 * m_max].reshape(m_max, 3); o += 3 * m_max
+        b = flat[o: o + m_max]; o += m_max
+        q = flat[o: o + 9].reshape(3, 3).copy(); o += 9
+        p = flat[o: o + 3].copy(); o += 3
+        m, status, peak = int(flat[o]), int(flat[o + 1]), int(flat[o + 2])
+        coll = bool(flat[o + 3]) if with_collision else False
+        return A[:m].copy(), b[:m].copy(), q, p, m, status, peak, coll
+
     def find_set_around_point(self, p_seed, fixed_mid=False, optimize=True):
         out = self.find_sets_around_points(np.asarray(p_seed, float)[None], fixed_mid=fixed_mid, optimize=optimize)
-        status = int(out.status.item())
-        m = int(out.m.item())
-        self._raise_for_status(status, int(out.rows_peak.item()) if optimize else None)
-        return (out.A[0, :m].cpu().numpy(), out.b[0, :m].cpu().numpy(), out.q_ellipse[0].cpu().numpy(),
-                out.p_mid[0].cpu().numpy())
+        A, b, q, p, m, status, peak, _ = self._fetch_one(out)
+        self._raise_for_status(status, peak if optimize else None)
+        return A, b, q, p
 
     def find_sets_around_points(self, seeds, fixed_mid=False, optimize=True, m_max=BP_MAX_ROWS):
         """Batched form: S seeds -> geometry.SetBatch (device tensors)."""
@@ -275,15 +292,12 @@ class ConvexSetFinder:
     def find_set_collision_avoidance(self, p0, p1, compute_ellipsoid=False, limit_space=False, e_max=0.3):
         out = self.find_sets_collision_avoidance(np.asarray(p0, float)[None], np.asarray(p1, float)[None],
                                                  compute_ellipsoid, limit_space, e_max)
-        m = int(out.m.item())
-        collision = bool(out.collision.item())
+        A, b, q, p, m, status, _, collision = self._fetch_one(out, with_collision=True)
         if collision:
             print("(LineSet) [WARNING] Line is touching an obstacle")       # :337
-        status = int(out.status.item())
         self._raise_for_status(status, m if compute_ellipsoid else None)
-        A, b = out.A[0, :m].cpu().numpy(), out.b[0, :m].cpu().numpy()
         if compute_ellipsoid:
-            return A, b, out.q_ellipse[0].cpu().numpy(), out.p_mid[0].cpu().numpy(), collision
+            return A, b, q, p, collision
         return A, b, collision
 
     def find_sets_collision_avoidance(self, p0, p1, compute_ellipsoid=False, limit_space=False, e_max=0.3,

@@ -138,6 +138,7 @@ class SetSequencePlanner:
 
     # ---- known sets, stacked (vectorised forms of the per-node loops of :472-476 and :505-512) ----
     def _nodes_reset(self):
+        self._plan_epoch = getattr(self, "_plan_epoch", 0) + 1     # a new plan: device tables of the old one are stale
         self._rows_a = np.empty((0, 3))
         self._rows_b = np.empty(0)
         self._row_start = []                 # first stacked row of every node
@@ -545,9 +546,10 @@ class BatchedGpuExecutor:
         tab = self._tables()
         slots, rows_a, rows_b, ms, qs, ps, bad = [], [], [], [], [], [], {}
         for q, pl in items:
-            if tab["owner"][q] is not pl:                 # a new planner object on this slot: its table starts empty
-                tab["owner"][q] = pl
-                tab["count_host"][q] = 0
+            key = (pl, getattr(pl, "_plan_epoch", 0))
+            if tab["owner"][q] is None or tab["owner"][q][0] is not pl or tab["owner"][q][1] != key[1]:
+                tab["owner"][q] = key                     # a new planner (or a new plan of the same one) on this slot:
+                tab["count_host"][q] = 0                  # its table starts empty
             have, n = int(tab["count_host"][q]), len(pl._row_start)
             if n > self.MAX_NODES:
                 bad[q] = ValueError(f"more than {self.MAX_NODES} graph nodes in one query")

@@ -39,10 +39,16 @@ def set_intersection(set1, set2, tol=0.0):
         np.concatenate((set1[1], set2[1])),
     ]
     A, b, m = pack_sets([set1, set2])
-    bits, x = geo.pair_feasible(torch.as_tensor(A).cuda(), torch.as_tensor(b).cuda(), torch.as_tensor(m).cuda(),
-                                tol=tol, want_points=True)
-    success = bool(bits[0, 0].item() & 2)
-    point = x[0, 1].cpu().numpy().copy() if success else None
+    # one host-to-device copy (rows, offsets and row counts packed), one kernel chain, one copy back
+    m_max = A.shape[1]
+    packed = torch.as_tensor(np.concatenate((A.reshape(-1), b.reshape(-1), m.astype(np.float64)))).cuda()
+    A_d = packed[: 6 * m_max].view(2, m_max, 3)
+    b_d = packed[6 * m_max: 8 * m_max].view(2, m_max)
+    m_d = packed[8 * m_max:].to(torch.int32)
+    ok, x = geo.pairs_feasible_list(A_d, b_d, m_d, np.array([[0, 1]], np.int32), tol)
+    res = torch.cat((ok.to(torch.float64), x.reshape(-1))).cpu().numpy()
+    success = bool(res[0])
+    point = res[1:4].copy() if success else None
     return point, set_inter, success
 
 
