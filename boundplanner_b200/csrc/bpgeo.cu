@@ -3053,6 +3053,7 @@ __global__ void __launch_bounds__(32) k_shortest_path(const int* __restrict__ no
         if (ov < best || (ov == best && ou < u)) { best = ov; u = ou; }
       }
       if (!(best < BP_INF)) break;                              // the rest is unreachable
+      __syncwarp();                                             // every lane's scan of s_done precedes the write
       if (lane == 0) s_done[u] = 1;
       if (u == z) break;
       __syncwarp();
