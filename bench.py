@@ -784,15 +784,40 @@ def plan_latency(with_cpu):
                 lat[name] = ((time.perf_counter() - t0) * 1e3,) + info
         return lat
 
+    def run_native(reps=2):
+        """The same queries one at a time through the native driver (bp_plan_run with a batch of one): the planner
+        object (scene upload, device tables) is set up once per query, like the reference's BoundPlanner(...)."""
+        from boundplanner_b200.planner_native import NativePlanner
+
+        lat = {}
+        for name, ob, infl, st, en, wmin, wmax, seed in cases():
+            pl = NativePlanner([dict(obstacles=ob, start=st, end=en, r0=r0, r1=r0)], infl, list(wmax), list(wmin))
+            for rep in range(reps):
+                t0 = time.perf_counter()
+                res, _ = pl.run([seed])
+                ok = not isinstance(res[0], Exception)
+                lat[name] = ((time.perf_counter() - t0) * 1e3, len(res[0]["set_ids"]) if ok else 0, 0, ok)
+            pl.close()
+        return lat
+
     gpu = run(GpuBackend)
-    vals = sorted(v[0] for v in gpu.values())
-    vals_ok = sorted(v[0] for v in gpu.values() if v[3])
+    nat = run_native()
+    vals = sorted(v[0] for v in nat.values())
+    vals_ok = sorted(v[0] for v in nat.values() if v[3])
+    pvals = sorted(v[0] for v in gpu.values())
+    pvals_ok = sorted(v[0] for v in gpu.values() if v[3])
+    same = sum(1 for k in gpu if gpu[k][3] == nat[k][3] and gpu[k][1] == nat[k][1])
     out = {"unit": "ms", "p50": statistics.median(vals), "p95": float(np.percentile(vals, 95)), "max": vals[-1],
            "p50_successful": statistics.median(vals_ok) if vals_ok else None,
            "queries": len(vals), "success_fraction": len(vals_ok) / len(vals),
-           "c1_ms": gpu["C1"][0],
-           "what": "plan_convex_set_path up to the planned set sequence (no final Ipopt NLP), host loop + "
-                   "batch-of-one kernel calls; C1 + the first 24 C3 queries, the reference's error exits included"}
+           "c1_ms": nat["C1"][0],
+           "what": "plan_convex_set_path up to the planned set sequence (no final Ipopt NLP), one query at a time "
+                   "through the native driver (bp_plan_run, batch of one: one kernel chain per round); C1 + the "
+                   "first 24 C3 queries, the reference's error exits included",
+           "python_driver": {"p50": statistics.median(pvals), "p95": float(np.percentile(pvals, 95)),
+                             "p50_successful": statistics.median(pvals_ok) if pvals_ok else None, "c1_ms": gpu["C1"][0],
+                             "what": "the same queries through SetSequencePlanner.plan_set_sequence (Python generator, "
+                                     "batch-of-one kernel calls)", "same_outcome_and_sequence_length": f"{same} of {len(gpu)}"}}
     if with_cpu:
         from tests.util import OracleBackend
 
