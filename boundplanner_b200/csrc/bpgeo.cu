@@ -2186,20 +2186,24 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
 #endif
       continue;
     }
-    double xi[3], x0[3];
+    double xi[3], x0[3], region[6];
+    bool have_region = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {                       // start at the middle of the overlap of the two boxes
       const double lo = fmax(__ldg(aabb + (size_t)pr.x * 6 + k), __ldg(aabb + (size_t)pr.y * 6 + k));
       const double hi = fmin(__ldg(aabb + (size_t)pr.x * 6 + 3 + k), __ldg(aabb + (size_t)pr.y * 6 + 3 + k));
       x0[k] = 0.5 * (lo + hi);
       if (!(fabs(x0[k]) < 1e6)) x0[k] = 0.0;            // unbounded description: no box
+      region[k] = lo - BP_AABB_EPS; region[3 + k] = hi + BP_AABB_EPS;     // every common point lies in this box
+      have_region = have_region && fabs(lo) < 1e6 && fabs(hi) < 1e6;
     }
+    const double* reg = have_region ? region : nullptr;
 #ifdef BPGEO_PROFILE
     int lp_iters = 0;
     const long long lp_t0 = clock64();
     const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                           A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
-                                          scratch[wib], &lp_iters, xi, x0, BP_LP_T0_SCALE);
+                                          scratch[wib], &lp_iters, xi, x0, BP_LP_T0_SCALE, reg);
     if (lane == 0) {
       int bk = lp_iters / 2; if (bk > 63) bk = 63;
       atomicAdd((unsigned long long*)&g_prof_pair[bk], 1ull);
@@ -2211,7 +2215,7 @@ __global__ void __launch_bounds__(256) k_pair_lp(const double* __restrict__ A, c
 #else
     const int res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                           A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol,
-                                          scratch[wib], nullptr, xi, x0, BP_LP_T0_SCALE);
+                                          scratch[wib], nullptr, xi, x0, BP_LP_T0_SCALE, reg);
 #endif
     if (lane == 0 && res) {
       atomicOr(adj + (size_t)(pr.x - row_begin) * words + (pr.y >> 5), 1u << (pr.y & 31));
@@ -2379,8 +2383,8 @@ __global__ void __launch_bounds__(256) k_pair_list(const double* __restrict__ A,
   const int p = blockIdx.x * 8 + wib;
   if (p >= P) return;
   const int2 pr = pairs[p];
-  bool apart = false;
-  double x0[3];
+  bool apart = false, have_region = true;
+  double x0[3], region[6];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const double loi = __ldg(aabb + (size_t)pr.x * 6 + k), hii = __ldg(aabb + (size_t)pr.x * 6 + 3 + k);
@@ -2388,6 +2392,8 @@ __global__ void __launch_bounds__(256) k_pair_list(const double* __restrict__ A,
     if (loi > hij + BP_AABB_EPS || loj > hii + BP_AABB_EPS) apart = true;
     x0[k] = 0.5 * (fmax(loi, loj) + fmin(hii, hij));
     if (!(fabs(x0[k]) < 1e6)) x0[k] = 0.0;
+    region[k] = fmax(loi, loj) - BP_AABB_EPS; region[3 + k] = fmin(hii, hij) + BP_AABB_EPS;
+    have_region = have_region && fabs(region[k]) < 1e6 && fabs(region[3 + k]) < 1e6;
   }
   int res = 0;
   double xi[3] = {0.0, 0.0, 0.0};
@@ -2398,7 +2404,7 @@ __global__ void __launch_bounds__(256) k_pair_list(const double* __restrict__ A,
   if (!apart)
     res = bp_pair_feasible_warp(A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, m[pr.x],
                                 A + (size_t)pr.y * m_max * 3, b + (size_t)pr.y * m_max, m[pr.y], tol, scratch[wib],
-                                nullptr, xi, x0, BP_LP_T0_SCALE);
+                                nullptr, xi, x0, BP_LP_T0_SCALE, have_region ? region : nullptr);
   if (lane == 0) {
     result[p] = res;
     if (x_feas) { x_feas[3 * (size_t)p] = xi[0]; x_feas[3 * (size_t)p + 1] = xi[1]; x_feas[3 * (size_t)p + 2] = xi[2]; }
