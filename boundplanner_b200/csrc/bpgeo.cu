@@ -2672,6 +2672,8 @@ struct FitParams {
   double l[BP_FIT_SAMPLES][3];    // rotated end-effector offsets
   double margin;                  // 0.001 (:746)
   int n_samples;
+  int nu;                         // number of distinct offsets
+  int uidx[BP_FIT_SAMPLES];       // first sample index of every distinct offset, ascending
 };
 
 struct BpFitRows {
@@ -2687,36 +2689,50 @@ struct BpFitRows {
   }
 };
 
+// One warp per (pair, DISTINCT end-effector offset): the reference walks its 20 rotations one after the other and
+// stops at the first that fits (:745-772); here they are tested side by side and the smallest fitting index wins
+// (atomicMin), so a pair that does not fit costs one LP latency instead of twenty.  Offsets that repeat (no
+// rotation between start and end: all 20 are the same vector) are tested once: fp.uidx lists the first index of
+// every distinct offset.  first_sample must be preset to 0x7f7f7f7f; k_fit_finish turns it into the outputs.
 __global__ void __launch_bounds__(256) k_fit_check(const double* __restrict__ A, const double* __restrict__ b,
                                                    const int* __restrict__ m, int m_max, const int2* __restrict__ pairs,
                                                    int P, const double* __restrict__ x0s,
                                                    const int* __restrict__ active, FitParams fp,
-                                                   int* __restrict__ fits, int* __restrict__ first_sample) {
+                                                   int* __restrict__ first_sample) {
   __shared__ double scratch[8][BP_LP_SCRATCH_DOUBLES];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int p = blockIdx.x * 8 + wib;
+  const int w = blockIdx.x * 8 + wib;
+  const int p = w / fp.nu;
   if (p >= P) return;
-  if (active && !active[p]) {                 // e.g. the pair does not intersect: no fit check (fits = 0)
-    if (lane == 0) { fits[p] = 0; first_sample[p] = -1; }
-    return;
-  }
+  if (active && !active[p]) return;            // e.g. the pair does not intersect: no fit check
+  const int k = fp.uidx[w - p * fp.nu];
   const int2 pr = pairs[p];
   const int m1 = m[pr.x], m2 = (pr.y == pr.x) ? 0 : m[pr.y];     // i == j: a single set
   const int mtot = m1 + m2;
-  int found = -1;
-  if (2 * mtot <= 96) {                          // (bp_lp_feasible_warp takes at most 96 rows)
-    double x0[3] = {0.0, 0.0, 0.0};
-    if (x0s) { x0[0] = x0s[3 * p]; x0[1] = x0s[3 * p + 1]; x0[2] = x0s[3 * p + 2]; }
-    for (int k = 0; k < fp.n_samples && found < 0; ++k) {
-      BpFitRows rows{A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, A + (size_t)pr.y * m_max * 3,
-                     b + (size_t)pr.y * m_max, m1, mtot, fp.l[k][0], fp.l[k][1], fp.l[k][2], fp.margin};
-      if (bp_lp_feasible_warp(rows, 2 * mtot, scratch[wib], nullptr, nullptr, x0, BP_LP_T0_SCALE)) found = k;
-      __syncwarp();
-    }
-  } else {
-    found = -2;                                                   // too many rows for one warp
+  if (2 * mtot > 96) return;                   // (bp_lp_feasible_warp takes at most 96 rows; k_fit_finish flags it)
+  double x0[3] = {0.0, 0.0, 0.0};
+  if (x0s) { x0[0] = x0s[3 * p]; x0[1] = x0s[3 * p + 1]; x0[2] = x0s[3 * p + 2]; }
+  BpFitRows rows{A + (size_t)pr.x * m_max * 3, b + (size_t)pr.x * m_max, A + (size_t)pr.y * m_max * 3,
+                 b + (size_t)pr.y * m_max, m1, mtot, fp.l[k][0], fp.l[k][1], fp.l[k][2], fp.margin};
+  const int ok = bp_lp_feasible_warp(rows, 2 * mtot, scratch[wib], nullptr, nullptr, x0, BP_LP_T0_SCALE);
+  if (ok && lane == 0) atomicMin(first_sample + p, k);
+}
+
+__global__ void k_fit_finish(const int* __restrict__ m, const int2* __restrict__ pairs, int P,
+                             const int* __restrict__ active, int n_samples, int* __restrict__ fits,
+                             int* __restrict__ first_sample) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int found = first_sample[p];
+  if (found < 0 || found >= n_samples) found = -1;
+  if (active && !active[p]) found = -1;
+  else {
+    const int2 pr = pairs[p];
+    const int mtot = m[pr.x] + ((pr.y == pr.x) ? 0 : m[pr.y]);
+    if (2 * mtot > 96) found = -2;                              // too many rows for one warp
   }
-  if (lane == 0) { fits[p] = found >= 0 ? 1 : (found == -2 ? -1 : 0); first_sample[p] = found; }
+  fits[p] = found >= 0 ? 1 : (found == -2 ? -1 : 0);
+  first_sample[p] = found;
 }
 
 // ---------------------------------------------------------------------------
@@ -3832,8 +3848,19 @@ int bp_check_fit(const double* A_dev, const double* b_dev, const int* m_dev, int
     for (int c = 0; c < 3; ++c) fp.l[k][c] = l_ee_samples_host[3 * k + c];
   fp.margin = margin;
   fp.n_samples = n_samples;
-  k_fit_check<<<(P + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max, (const int2*)pairs_dev, P,
-                                                             x0_dev, active_dev, fp, fits_dev, first_sample_dev);
+  for (int k = 0; k < n_samples; ++k) {           // distinct offsets (bitwise), first occurrence each
+    bool seen = false;
+    for (int q = 0; q < fp.nu && !seen; ++q)
+      seen = memcmp(fp.l[fp.uidx[q]], fp.l[k], sizeof(double) * 3) == 0;
+    if (!seen) fp.uidx[fp.nu++] = k;
+  }
+  BP_CUDA(cudaMemsetAsync(first_sample_dev, 0x7f, sizeof(int) * (size_t)P, (cudaStream_t)stream));
+  const long long warps = (long long)P * fp.nu;
+  k_fit_check<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(A_dev, b_dev, m_dev, m_max,
+                                                                             (const int2*)pairs_dev, P, x0_dev, active_dev,
+                                                                             fp, first_sample_dev);
+  k_fit_finish<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m_dev, (const int2*)pairs_dev, P, active_dev, n_samples,
+                                                                   fits_dev, first_sample_dev);
   BP_CUDA(cudaGetLastError());
   return 0;
 }
