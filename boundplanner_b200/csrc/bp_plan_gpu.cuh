@@ -65,7 +65,7 @@ struct bp_plan : bpplan::Executor {
   std::vector<int> ee_group;                     // [Q]
   std::vector<const double*> ee_group_samples;
   double ws_min[3], ws_max[3];
-  long long chains = 0, wait_us = 0;
+  long long chains = 0, wait_us = 0, pack_us = 0, launch_us = 0, unpack_us = 0;
   bool trace = getenv("BPGEO_PLAN_TRACE") != nullptr;
   std::string error;
 
@@ -101,6 +101,7 @@ struct bp_plan : bpplan::Executor {
 
   int execute(bpplan::Round& r, const std::vector<bpplan::Query>& qs) override {
     using namespace bpplan;
+    const auto t_pack = std::chrono::steady_clock::now();
     constexpr int R = NODE_ROWS, M = SET_ROWS;
     const int S_tab = Q * MAX_NODES;
     // ---- order the set requests: optimised point sets | single-pass point sets | segment sets
@@ -240,6 +241,8 @@ struct bp_plan : bpplan::Executor {
     if (out_used > out_cap) return fail("bp_plan: output arena overflow");
 
     // ---- the kernel chain
+    const auto t_launch = std::chrono::steady_clock::now();
+    pack_us += std::chrono::duration_cast<std::chrono::microseconds>(t_launch - t_pack).count();
     cudaError_t e = cudaSuccess;
     if (in_used) e = cudaMemcpyAsync(d_in, h_in, in_used, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return fail("bp_plan: H2D", e);
@@ -323,8 +326,10 @@ struct bp_plan : bpplan::Executor {
     if (out_used) e = cudaMemcpyAsync(h_out, d_out, out_used, cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) return fail("bp_plan: D2H", e);
     const auto t0 = std::chrono::steady_clock::now();
+    launch_us += std::chrono::duration_cast<std::chrono::microseconds>(t0 - t_launch).count();
     e = cudaStreamSynchronize(stream);
-    wait_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    const auto t_unpack = std::chrono::steady_clock::now();
+    wait_us += std::chrono::duration_cast<std::chrono::microseconds>(t_unpack - t0).count();
     if (e != cudaSuccess) return fail("bp_plan: round", e);
     ++chains;
     if (trace)
@@ -378,6 +383,7 @@ struct bp_plan : bpplan::Executor {
 #undef IN_D
 #undef OUT_H
 #undef OUT_D
+    unpack_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_unpack).count();
     return 0;
   }
 
@@ -441,7 +447,7 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
   for (int k = 0; k < 3; ++k) { pl->ws_min[k] = in->ws_min[k]; pl->ws_max[k] = in->ws_max[k]; }
   pl->new_slots.clear();
   pl->new_nodes.clear();
-  pl->chains = pl->wait_us = 0;
+  pl->chains = pl->wait_us = pl->pack_us = pl->launch_us = pl->unpack_us = 0;
   pl->ee_group.assign((size_t)pl->Q, 0);
   pl->ee_group_samples.clear();
   for (int q = 0; q < pl->Q; ++q) {
@@ -458,6 +464,9 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
   if (rc) return bp_fail(pl->error.empty() ? "bp_plan_run: executor failed" : pl->error.c_str());
   bpplan::store_results(qs, st, fin.data(), *out);
   if (out->stats) { out->stats[5] = pl->chains; out->stats[6] = pl->wait_us; }
+  if (pl->trace)
+    fprintf(stderr, "bp_plan host phases: pack %lld us, launch %lld us, wait %lld us, unpack %lld us over %lld rounds\n", pl->pack_us,
+            pl->launch_us, pl->wait_us, pl->unpack_us, pl->chains);
   return 0;
 }
 

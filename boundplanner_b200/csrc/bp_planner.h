@@ -781,7 +781,7 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
         if (!q.finished) q.fail(ERR_RUNTIME, "lock-step round limit reached");
       break;
     }
-    r.set_ans.assign(r.sets.size(), SetAns());
+    if (r.set_ans.size() < r.sets.size()) r.set_ans.resize(r.sets.size());      // (records are fully written by the executor)
     size_t n_pairs = 0;
     for (const EdgeReq& e : r.edges) n_pairs += e.n_others;
     r.edge_ans.assign(n_pairs, EdgeAns());

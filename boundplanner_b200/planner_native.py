@@ -182,6 +182,7 @@ class NativePlanner:
         self.infl, self.ws_max, self.ws_min = float(obs_size_increase), list(workspace_max), list(workspace_min)
         self.scene = geo.SceneBatch([q["obstacles"] for q in queries], obs_size_increase)
         self._h = ctypes.c_void_p(0)
+        self._packed = {}
         _lib.check(self._lib.bp_plan_create(self.scene._h, len(queries), ctypes.byref(self._h)))
 
     def run(self, rng_seeds=None, sample_chunk=32, want_nodes=True):
@@ -189,7 +190,14 @@ class NativePlanner:
 
         from . import _lib
 
-        pk = PackedQueries(self.queries, self.infl, self.ws_max, self.ws_min, rng_seeds, sample_chunk, want_nodes)
+        # the packed host arrays of the batch (inputs incl. every query's generator state, output buffers) are kept
+        # per seed list: planning the same batch again only runs the driver
+        key = (None if rng_seeds is None else tuple(int(v) for v in rng_seeds), int(sample_chunk), bool(want_nodes))
+        pk = self._packed.get(key) if rng_seeds is not None else None
+        if pk is None:
+            pk = PackedQueries(self.queries, self.infl, self.ws_max, self.ws_min, rng_seeds, sample_chunk, want_nodes)
+            if rng_seeds is not None:
+                self._packed = {key: pk}
         _lib.check(self._lib.bp_plan_run(self._h, ctypes.byref(pk.inp), ctypes.byref(pk.out),
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return pk.results(), pk.stats_dict()
