@@ -44,15 +44,22 @@ __global__ void k_plan_gather_seeds(const double* __restrict__ cand, const int* 
   for (int k = 0; k < 3; ++k) seeds[3 * (size_t)slot[i] + k] = cand[((size_t)i * C + f) * 3 + k];
 }
 
-struct bp_plan : bpplan::Executor {
+// One lock-step lane: its own streams, arenas and build workspace; the node tables are shared (disjoint slots).
+struct PlanLane {
+  // shared with the other lanes (set by bp_plan_create / bp_plan_run)
   const bp_scene* scene = nullptr;
   int Q = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;           // add_edges / projection / shortest-path chain, concurrent with the set builds
-  cudaEvent_t ev_in = nullptr, ev_side = nullptr;
-  // device tables of the queries' graph nodes
   double *tabA = nullptr, *tabb = nullptr, *tabq = nullptr, *tabp = nullptr, *tabaabb = nullptr;
   int* tabm = nullptr;
+  const std::vector<int>* ee_group_p = nullptr;                  // [Q] end-effector group of every query
+  const std::vector<const double*>* ee_samples_p = nullptr;      // the groups' 20 offsets (host)
+  double ws_min[3], ws_max[3];
+  bool trace = false;
+  // per lane
+  cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;           // add_edges / projection / shortest-path chain, concurrent with the set builds
+  bool own_stream = false;
+  cudaEvent_t ev_in = nullptr, ev_side = nullptr;
   void* work = nullptr;
   size_t work_bytes = 0;
   // arenas (pinned host mirror + device), bump-allocated every round
@@ -61,13 +68,16 @@ struct bp_plan : bpplan::Executor {
   // nodes committed since the last round
   std::vector<int> new_slots;
   std::vector<bpplan::Node> new_nodes;
-  // end-effector groups (queries with identical check_intersection offsets share a k_fit_check launch)
-  std::vector<int> ee_group;                     // [Q]
-  std::vector<const double*> ee_group_samples;
-  double ws_min[3], ws_max[3];
   long long chains = 0, wait_us = 0, pack_us = 0, launch_us = 0, unpack_us = 0;
-  bool trace = getenv("BPGEO_PLAN_TRACE") != nullptr;
   std::string error;
+  // what collect() needs to know about the round submit() laid out
+  struct Layout {
+    int nS = 0, nE = 0, nProj = 0, nG = 0, nSmp = 0, nPairs = 0, nNew = 0;
+    int n_grp[3] = {0, 0, 0};
+    std::vector<int> order, smp_of, e_off;
+    size_t o_A, o_b, o_m, o_q, o_p, o_st, o_peak, o_coll, o_Ar, o_br, o_mr, o_dv, o_first, o_res, o_x, o_fits, o_fk, o_epx,
+        o_epst, o_px, o_pst, o_path, o_plen;
+  } lay;
 
   int fail(const char* what, cudaError_t e = cudaSuccess) {
     error = what;
@@ -94,12 +104,14 @@ struct bp_plan : bpplan::Executor {
   size_t take_in(size_t bytes) { const size_t o = in_used; in_used += al(bytes); return o; }
   size_t take_out(size_t bytes) { const size_t o = out_used; out_used += al(bytes); return o; }
 
-  void commit_node(int qid, int node_id, const bpplan::Node& n) override {
+  void commit_node(int qid, int node_id, const bpplan::Node& n) {
     new_slots.push_back(qid * bpplan::MAX_NODES + node_id);
     new_nodes.push_back(n);
   }
 
-  int execute(bpplan::Round& r, const std::vector<bpplan::Query>& qs) override {
+  int submit(bpplan::Round& r, const std::vector<bpplan::Query>& qs) {
+    const std::vector<int>& ee_group = *ee_group_p;
+    const std::vector<const double*>& ee_group_samples = *ee_samples_p;
     using namespace bpplan;
     const auto t_pack = std::chrono::steady_clock::now();
     constexpr int R = NODE_ROWS, M = SET_ROWS;
@@ -325,16 +337,41 @@ struct bp_plan : bpplan::Executor {
     if (e != cudaSuccess) return fail("bp_plan: kernel launch", e);
     if (out_used) e = cudaMemcpyAsync(h_out, d_out, out_used, cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) return fail("bp_plan: D2H", e);
+    launch_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_launch).count();
+    // what collect() needs
+    lay.nS = nS; lay.nE = nE; lay.nProj = nProj; lay.nG = nG; lay.nSmp = nSmp; lay.nPairs = nPairs; lay.nNew = nNew;
+    lay.n_grp[0] = n_grp[0]; lay.n_grp[1] = n_grp[1]; lay.n_grp[2] = n_grp[2];
+    lay.order.swap(order); lay.smp_of.swap(smp_of); lay.e_off.swap(e_off);
+    lay.o_A = o_A; lay.o_b = o_b; lay.o_m = o_m; lay.o_q = o_q; lay.o_p = o_p; lay.o_st = o_st; lay.o_peak = o_peak;
+    lay.o_coll = o_coll; lay.o_Ar = o_Ar; lay.o_br = o_br; lay.o_mr = o_mr; lay.o_dv = o_dv; lay.o_first = o_first;
+    lay.o_res = o_res; lay.o_x = o_x; lay.o_fits = o_fits; lay.o_fk = o_fk; lay.o_epx = o_epx; lay.o_epst = o_epst;
+    lay.o_px = o_px; lay.o_pst = o_pst; lay.o_path = o_path; lay.o_plen = o_plen;
+#undef IN_H
+#undef IN_D
+#undef OUT_H
+#undef OUT_D
+    return 0;
+  }
+
+  int collect(bpplan::Round& r) {
+    using namespace bpplan;
+    constexpr int M = SET_ROWS;
+#define OUT_H(T, off) ((T*)(h_out + (off)))
+    const int nS = lay.nS, nE = lay.nE, nProj = lay.nProj, nG = lay.nG;
+    const std::vector<int>&order = lay.order, &smp_of = lay.smp_of, &e_off = lay.e_off;
+    const size_t o_A = lay.o_A, o_b = lay.o_b, o_m = lay.o_m, o_q = lay.o_q, o_p = lay.o_p, o_st = lay.o_st, o_peak = lay.o_peak,
+                 o_coll = lay.o_coll, o_Ar = lay.o_Ar, o_br = lay.o_br, o_mr = lay.o_mr, o_dv = lay.o_dv, o_first = lay.o_first,
+                 o_res = lay.o_res, o_x = lay.o_x, o_fits = lay.o_fits, o_fk = lay.o_fk, o_epx = lay.o_epx, o_epst = lay.o_epst,
+                 o_px = lay.o_px, o_pst = lay.o_pst, o_path = lay.o_path, o_plen = lay.o_plen;
     const auto t0 = std::chrono::steady_clock::now();
-    launch_us += std::chrono::duration_cast<std::chrono::microseconds>(t0 - t_launch).count();
-    e = cudaStreamSynchronize(stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
     const auto t_unpack = std::chrono::steady_clock::now();
     wait_us += std::chrono::duration_cast<std::chrono::microseconds>(t_unpack - t0).count();
     if (e != cudaSuccess) return fail("bp_plan: round", e);
     ++chains;
     if (trace)
       fprintf(stderr, "bp_plan round %lld: sets %d (opt %d, single %d, line %d; sampled %d) pairs %d proj %d paths %d new %d  wait %lld us\n",
-              chains, nS, n_grp[0], n_grp[1], n_grp[2], nSmp, nPairs, nProj, nG, nNew,
+              chains, nS, lay.n_grp[0], lay.n_grp[1], lay.n_grp[2], lay.nSmp, lay.nPairs, nProj, nG, lay.nNew,
               (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
 
     // ---- answers
@@ -379,23 +416,54 @@ struct bp_plan : bpplan::Executor {
       r.path_len[g] = OUT_H(int, o_plen)[g];
       memcpy(r.path_out.data() + (size_t)g * MAX_PATH, OUT_H(int, o_path) + (size_t)g * MAX_PATH, sizeof(int) * MAX_PATH);
     }
-#undef IN_H
-#undef IN_D
 #undef OUT_H
-#undef OUT_D
     unpack_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_unpack).count();
     return 0;
   }
 
   void release() {
-    cudaFree(tabA); cudaFree(tabb); cudaFree(tabq); cudaFree(tabp); cudaFree(tabaabb); cudaFree(tabm); cudaFree(work);
+    cudaFree(work);
     if (h_in) cudaFreeHost(h_in);
     if (d_in) cudaFree(d_in);
     if (h_out) cudaFreeHost(h_out);
     if (d_out) cudaFree(d_out);
     if (side) cudaStreamDestroy(side);
+    if (own_stream && stream) cudaStreamDestroy(stream);
     if (ev_in) cudaEventDestroy(ev_in);
     if (ev_side) cudaEventDestroy(ev_side);
+  }
+};
+
+// The executor of bp_plan_run: up to BP_PLAN_LANES independent lock-step groups in flight (query i -> lane i mod L;
+// two by default, BPGEO_PLAN_LANES overrides):
+// while one lane's kernel chain runs, the host resumes the other lane's queries and packs its next round.
+#define BP_PLAN_LANES 4
+struct bp_plan : bpplan::Executor {
+  const bp_scene* scene = nullptr;
+  int Q = 0, L = 1;
+  double *tabA = nullptr, *tabb = nullptr, *tabq = nullptr, *tabp = nullptr, *tabaabb = nullptr;
+  int* tabm = nullptr;
+  PlanLane lane[BP_PLAN_LANES];
+  std::vector<int> ee_group;                     // [Q]
+  std::vector<const double*> ee_group_samples;
+  bool trace = getenv("BPGEO_PLAN_TRACE") != nullptr;
+  std::string error;
+
+  int lanes() const override { return L; }
+  void commit_node(int l, int qid, int node_id, const bpplan::Node& n) override { lane[l].commit_node(qid, node_id, n); }
+  int submit(int l, bpplan::Round& r, const std::vector<bpplan::Query>& qs) override {
+    const int rc = lane[l].submit(r, qs);
+    if (rc) error = lane[l].error;
+    return rc;
+  }
+  int collect(int l, bpplan::Round& r) override {
+    const int rc = lane[l].collect(r);
+    if (rc) error = lane[l].error;
+    return rc;
+  }
+  void release() {
+    cudaFree(tabA); cudaFree(tabb); cudaFree(tabq); cudaFree(tabp); cudaFree(tabaabb); cudaFree(tabm);
+    for (int l = 0; l < BP_PLAN_LANES; ++l) lane[l].release();
   }
 };
 
@@ -408,22 +476,38 @@ int bp_plan_create(const bp_scene* scene_batch, int Q, bp_plan** out) {
   bp_plan* pl = new bp_plan();
   pl->scene = scene_batch;
   pl->Q = Q;
+  // two lanes once there is enough work to split (BPGEO_PLAN_LANES=1 forces plain lock step)
+  pl->L = Q >= 32 ? 2 : 1;
+  if (const char* ev = getenv("BPGEO_PLAN_LANES")) pl->L = atoi(ev);
+  if (pl->L > BP_PLAN_LANES) pl->L = BP_PLAN_LANES;
+  if (pl->L < 1 || pl->L > Q) pl->L = 1;
   const size_t n = (size_t)Q * bpplan::MAX_NODES;
   constexpr int R = bpplan::NODE_ROWS;
-  pl->work_bytes = bp_build_sets_workspace_bytes(Q);
   cudaError_t e = cudaMalloc(&pl->tabA, sizeof(double) * n * R * 3);
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabb, sizeof(double) * n * R);
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabm, sizeof(int) * n);
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabq, sizeof(double) * n * 9);
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabp, sizeof(double) * n * 3);
   if (e == cudaSuccess) e = cudaMalloc(&pl->tabaabb, sizeof(double) * n * 6);
-  if (e == cudaSuccess) e = cudaMalloc(&pl->work, pl->work_bytes);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_side, cudaEventDisableTiming);
+  for (int l = 0; l < pl->L && e == cudaSuccess; ++l) {
+    PlanLane& ln = pl->lane[l];
+    ln.scene = scene_batch; ln.Q = Q;
+    ln.tabA = pl->tabA; ln.tabb = pl->tabb; ln.tabm = pl->tabm; ln.tabq = pl->tabq; ln.tabp = pl->tabp; ln.tabaabb = pl->tabaabb;
+    ln.ee_group_p = &pl->ee_group; ln.ee_samples_p = &pl->ee_group_samples;
+    ln.trace = pl->trace;
+    ln.work_bytes = bp_build_sets_workspace_bytes(Q);
+    e = cudaMalloc(&ln.work, ln.work_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking);
+    if (e == cudaSuccess && l > 0) {               // (lane 0 runs on the caller's stream)
+      e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
+      ln.own_stream = true;
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_side, cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaMemset(pl->tabm, 0, sizeof(int) * n);
   if (e == cudaSuccess) e = cudaMemset(pl->tabA, 0, sizeof(double) * n * R * 3);
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();        // (the side stream does not order with the memsets)
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();        // (the lanes' streams do not order with the memsets)
   if (e != cudaSuccess) {
     pl->release();
     delete pl;
@@ -443,11 +527,8 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
   bpplan::Params par;
   std::vector<bpplan::Query> qs;
   bpplan::load_queries(*in, par, qs);
-  pl->stream = (cudaStream_t)stream;
-  for (int k = 0; k < 3; ++k) { pl->ws_min[k] = in->ws_min[k]; pl->ws_max[k] = in->ws_max[k]; }
-  pl->new_slots.clear();
-  pl->new_nodes.clear();
-  pl->chains = pl->wait_us = pl->pack_us = pl->launch_us = pl->unpack_us = 0;
+  // the work queued on the caller's stream so far precedes the run on every lane
+  BP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   pl->ee_group.assign((size_t)pl->Q, 0);
   pl->ee_group_samples.clear();
   for (int q = 0; q < pl->Q; ++q) {
@@ -458,15 +539,32 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
     if (g == pl->ee_group_samples.size()) pl->ee_group_samples.push_back(s);
     pl->ee_group[(size_t)q] = (int)g;
   }
+  for (int l = 0; l < pl->L; ++l) {
+    PlanLane& ln = pl->lane[l];
+    if (l == 0) ln.stream = (cudaStream_t)stream;
+    for (int k = 0; k < 3; ++k) { ln.ws_min[k] = in->ws_min[k]; ln.ws_max[k] = in->ws_max[k]; }
+    ln.new_slots.clear();
+    ln.new_nodes.clear();
+    ln.chains = ln.wait_us = ln.pack_us = ln.launch_us = ln.unpack_us = 0;
+  }
   bpplan::RunStats st;
   std::vector<int> fin(qs.size(), -1);
-  const int rc = bpplan::run_lockstep(qs, *pl, par, &st, fin.data());
-  if (rc) return bp_fail(pl->error.empty() ? "bp_plan_run: executor failed" : pl->error.c_str());
-  bpplan::store_results(qs, st, fin.data(), *out);
-  if (out->stats) { out->stats[5] = pl->chains; out->stats[6] = pl->wait_us; }
+  std::vector<double> fin_ms(qs.size(), -1.0);
+  const int rc = bpplan::run_lockstep(qs, *pl, par, &st, fin.data(), fin_ms.data());
+  if (rc) {
+    for (int l = 0; l < pl->L; ++l) cudaStreamSynchronize(pl->lane[l].stream);       // nothing of the run stays in flight
+    return bp_fail(pl->error.empty() ? "bp_plan_run: executor failed" : pl->error.c_str());
+  }
+  bpplan::store_results(qs, st, fin.data(), fin_ms.data(), *out);
+  long long chains = 0, wait = 0, pack = 0, launch = 0, unpack = 0;
+  for (int l = 0; l < pl->L; ++l) {
+    const PlanLane& ln = pl->lane[l];
+    chains += ln.chains; wait += ln.wait_us; pack += ln.pack_us; launch += ln.launch_us; unpack += ln.unpack_us;
+  }
+  if (out->stats) { out->stats[5] = chains; out->stats[6] = wait; out->stats[7] = pl->L; }
   if (pl->trace)
-    fprintf(stderr, "bp_plan host phases: pack %lld us, launch %lld us, wait %lld us, unpack %lld us over %lld rounds\n", pl->pack_us,
-            pl->launch_us, pl->wait_us, pl->unpack_us, pl->chains);
+    fprintf(stderr, "bp_plan host phases (%d lanes): pack %lld us, launch %lld us, wait %lld us, unpack %lld us over %lld rounds\n",
+            pl->L, pack, launch, wait, unpack, chains);
   return 0;
 }
 

@@ -706,36 +706,51 @@ struct Round {
 
 struct Executor {
   virtual ~Executor() {}
+  // independent lock-step groups ("lanes") the executor can keep in flight at once: while one lane's round runs on
+  // the device the host resumes and packs another (1: plain lock step)
+  virtual int lanes() const { return 1; }
   // a node was added to query qid's graph (the executor keeps the tables the requests refer to)
-  virtual void commit_node(int qid, int node_id, const Node& n) = 0;
-  // answer every request of the round (fills set_ans / edge_ans / proj_ans / path_out / path_len); queries: for
-  // executors that look at the planners' state (the test harness).  Returns 0, or an error code that aborts the run.
-  virtual int execute(Round& r, const std::vector<Query>& queries) = 0;
+  virtual void commit_node(int lane, int qid, int node_id, const Node& n) = 0;
+  // start answering every request of the round (asynchronously, if the executor can) / wait for the answers
+  // (set_ans / edge_ans / proj_ans / path_out / path_len filled).  queries: for executors that look at the
+  // planners' state (the test harness).  Return 0, or an error code that aborts the run.
+  virtual int submit(int lane, Round& r, const std::vector<Query>& queries) = 0;
+  virtual int collect(int lane, Round& r) = 0;
 };
 
 struct RunStats {
-  int rounds = 0;
+  int rounds = 0;                     // lock-step rounds of the longest lane
   long long set_requests = 0, edge_pairs = 0, projections = 0, paths = 0;
-  std::vector<double> round_end_ms;   // wall time since the start of the run at the end of every round
 };
 
-// Advance all queries in lock step until every one is finished.  finish_round[q] (or null) receives the round in
-// which query q finished.
-inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par, RunStats* stats, int* finish_round) {
-  Round r;
+// Advance all queries until every one is finished.  The queries are dealt to the executor's lanes (query i -> lane
+// i mod L); every lane is a lock-step group of its own: each of its rounds collects the pending request of every
+// live query of the lane, hands them to the executor and resumes the queries with the answers.  finish_round[q]
+// (or null) receives the round of its lane in which query q finished, finish_ms[q] (or null) the wall time since
+// the start of the run at that moment.
+inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par, RunStats* stats, int* finish_round,
+                        double* finish_ms = nullptr) {
+  const int L = std::max(1, std::min(ex.lanes(), (int)qs.size()));
+  std::vector<Round> rounds_(L);
+  std::vector<int> n_rounds(L, 0);
+  std::vector<char> in_flight(L, 0);
   std::vector<size_t> committed(qs.size(), 0);
   const auto t_start = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   for (auto& q : qs) q.resume(nullptr, nullptr, nullptr, nullptr, 0);
-  int rounds = 0;
-  for (;;) {
+
+  // gather the pending requests of lane l into its round and submit it; returns the number of live queries (or < 0)
+  auto launch = [&](int l) -> int {
+    Round& r = rounds_[l];
     r.clear();
     size_t live = 0;
-    for (size_t i = 0; i < qs.size(); ++i) {
+    for (size_t i = (size_t)l; i < qs.size(); i += (size_t)L) {
       Query& q = qs[i];
       // nodes added since the last round go to the executor's tables first
-      for (; committed[i] < q.nodes.size(); ++committed[i]) ex.commit_node(q.qid, (int)committed[i], q.nodes[committed[i]]);
+      for (; committed[i] < q.nodes.size(); ++committed[i]) ex.commit_node(l, q.qid, (int)committed[i], q.nodes[committed[i]]);
       if (q.finished) {
-        if (finish_round && finish_round[i] < 0) finish_round[i] = rounds;
+        if (finish_round && finish_round[i] < 0) finish_round[i] = n_rounds[l];
+        if (finish_ms && finish_ms[i] < 0.0) finish_ms[i] = now_ms();
         continue;
       }
       ++live;
@@ -743,8 +758,7 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
         case REQ_SET: r.sets.push_back(q.set_req); r.set_owner.push_back((int)i); break;
         case REQ_EDGES: {
           EdgeReq e = q.edge_req;
-          e.first_pair = 0;
-          for (const EdgeReq& p : r.edges) e.first_pair += p.n_others;
+          e.first_pair = (int)r.edge_has_target.size();
           r.edges.push_back(e); r.edge_owner.push_back((int)i);
           for (int v = 0; v < e.n_others; ++v) r.edge_has_target.push_back(q.spec_target[(size_t)v] >= 0 ? 1 : 0);
           r.edge_xd.insert(r.edge_xd.end(), q.spec_xd.begin(), q.spec_xd.end());
@@ -767,33 +781,38 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
         }
         default:
           q.fail(ERR_RUNTIME, "planner state machine without a pending request");
+          --live;
           break;
       }
     }
-    if (live == 0) break;
+    if (live == 0) return 0;
     if (!r.paths.empty()) {
       r.node_off.push_back(r.node_off.back() + r.paths.back().n_nodes);
       r.edge_off.push_back((int)r.edge_dst.size());
     }
-    ++rounds;
-    if (rounds > par.max_rounds) {
-      for (auto& q : qs)
-        if (!q.finished) q.fail(ERR_RUNTIME, "lock-step round limit reached");
-      break;
+    ++n_rounds[l];
+    if (n_rounds[l] > par.max_rounds) {
+      for (size_t i = (size_t)l; i < qs.size(); i += (size_t)L)
+        if (!qs[i].finished) qs[i].fail(ERR_RUNTIME, "lock-step round limit reached");
+      return 0;
     }
     if (r.set_ans.size() < r.sets.size()) r.set_ans.resize(r.sets.size());      // (records are fully written by the executor)
-    size_t n_pairs = 0;
-    for (const EdgeReq& e : r.edges) n_pairs += e.n_others;
-    r.edge_ans.assign(n_pairs, EdgeAns());
-    r.proj_ans.assign(r.projs.size(), ProjAns());
+    const size_t n_pairs = r.edge_has_target.size();
+    if (r.edge_ans.size() < n_pairs) r.edge_ans.resize(n_pairs);
+    if (r.proj_ans.size() < r.projs.size()) r.proj_ans.resize(r.projs.size());
     r.path_out.assign(r.paths.size() * (size_t)MAX_PATH, -1);
     r.path_len.assign(r.paths.size(), -1);
-    const int rc = ex.execute(r, qs);
-    if (rc) return rc;
     if (stats) {
       stats->set_requests += (long long)r.sets.size(); stats->edge_pairs += (long long)n_pairs;
       stats->projections += (long long)r.projs.size(); stats->paths += (long long)r.paths.size();
     }
+    if (ex.submit(l, r, qs)) return -1;
+    in_flight[l] = 1;
+    return (int)live;
+  };
+  // resume the queries of lane l with the answers of its round
+  auto deliver = [&](int l) {
+    Round& r = rounds_[l];
     for (size_t k = 0; k < r.sets.size(); ++k) qs[r.set_owner[k]].resume(&r.set_ans[k], nullptr, nullptr, nullptr, 0);
     for (size_t k = 0; k < r.edges.size(); ++k)
       qs[r.edge_owner[k]].resume(nullptr, r.edge_ans.data() + r.edges[k].first_pair, nullptr, nullptr, 0);
@@ -804,12 +823,25 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
     }
     for (size_t k = 0; k < r.paths.size(); ++k)
       qs[r.path_owner[k]].resume(nullptr, nullptr, nullptr, r.path_out.data() + k * (size_t)MAX_PATH, r.path_len[k]);
-    for (auto& q : qs)
-      if (!q.finished) q.rounds = rounds;
-    if (stats)
-      stats->round_end_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    for (size_t i = (size_t)l; i < qs.size(); i += (size_t)L)
+      if (!qs[i].finished) qs[i].rounds = n_rounds[l];
+  };
+
+  for (int l = 0; l < L; ++l)
+    if (launch(l) < 0) return 9;
+  for (;;) {
+    bool any = false;
+    for (int l = 0; l < L; ++l) {
+      if (!in_flight[l]) continue;
+      any = true;
+      if (ex.collect(l, rounds_[l])) return 9;
+      in_flight[l] = 0;
+      deliver(l);
+      if (launch(l) < 0) return 9;           // (the other lanes' rounds run on the device meanwhile)
+    }
+    if (!any) break;
   }
-  if (stats) stats->rounds = rounds;
+  if (stats) stats->rounds = *std::max_element(n_rounds.begin(), n_rounds.end());
   return 0;
 }
 
@@ -842,7 +874,8 @@ inline void load_queries(const bp_plan_in& in, Params& par, std::vector<Query>& 
   }
 }
 
-inline void store_results(const std::vector<Query>& qs, const RunStats& st, const int* finish_round, bp_plan_out& out) {
+inline void store_results(const std::vector<Query>& qs, const RunStats& st, const int* finish_round, const double* finish_ms,
+                          bp_plan_out& out) {
   for (size_t q = 0; q < qs.size(); ++q) {
     const Query& Qy = qs[q];
     out.err_kind[q] = Qy.err_kind;
@@ -863,10 +896,7 @@ inline void store_results(const std::vector<Query>& qs, const RunStats& st, cons
     for (const Inter& it : Qy.inter) ne += (int)it.adj.size();
     out.n_edges[q] = ne / 2;
     out.finish_round[q] = finish_round[q];
-    if (out.finish_ms) {
-      const int fr = finish_round[q];
-      out.finish_ms[q] = (fr >= 1 && (size_t)fr <= st.round_end_ms.size()) ? st.round_end_ms[(size_t)fr - 1] : 0.0;
-    }
+    if (out.finish_ms) out.finish_ms[q] = finish_ms ? std::max(finish_ms[q], 0.0) : 0.0;
     if (out.node_A && out.node_b && out.node_m) {
       for (size_t n = 0; n < (size_t)MAX_NODES; ++n) {
         const size_t slot = q * MAX_NODES + n;

@@ -161,7 +161,7 @@ class PackedQueries:
     def stats_dict(self):
         return dict(rounds=int(self.stats[0]), set_requests=int(self.stats[1]), pair_tests=int(self.stats[2]),
                     projections=int(self.stats[3]), shortest_paths=int(self.stats[4]),
-                    kernel_chains=int(self.stats[5]), device_wait_ms=self.stats[6] / 1e3,
+                    kernel_chains=int(self.stats[5]), device_wait_ms=self.stats[6] / 1e3, lanes=int(self.stats[7]),
                     finish_round=self.finish_round.copy(), finish_ms=self.finish_ms.copy())
 
 

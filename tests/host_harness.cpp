@@ -182,8 +182,11 @@ typedef int (*hh_cb_path)(int qid, int n_nodes, const int* edge_off, const int* 
 struct HhCallbackExecutor : bpplan::Executor {
   hh_cb_set cb_set; hh_cb_edges cb_edges; hh_cb_project cb_project; hh_cb_path cb_path;
   int commits = 0;
-  void commit_node(int, int, const bpplan::Node&) override { ++commits; }
-  int execute(bpplan::Round& r, const std::vector<bpplan::Query>& qs) override {
+  int n_lanes = 1;
+  int lanes() const override { return n_lanes; }
+  void commit_node(int, int, int, const bpplan::Node&) override { ++commits; }
+  int collect(int, bpplan::Round&) override { return 0; }
+  int submit(int, bpplan::Round& r, const std::vector<bpplan::Query>& qs) override {
     for (size_t k = 0; k < r.sets.size(); ++k) {
       const bpplan::Query& q = qs[r.set_owner[k]];
       if (int rc = cb_set(q.qid, &r.sets[k], (int)q.nodes.size(), q.nodes.data(), &r.set_ans[k])) return rc;
@@ -211,17 +214,19 @@ struct HhCallbackExecutor : bpplan::Executor {
 };
 
 int hh_plan_batch(const bp_plan_in* in, bp_plan_out* out, hh_cb_set cb_set, hh_cb_edges cb_edges,
-                  hh_cb_project cb_project, hh_cb_path cb_path) {
+                  hh_cb_project cb_project, hh_cb_path cb_path, int lanes) {
   bpplan::Params par;
   std::vector<bpplan::Query> qs;
   bpplan::load_queries(*in, par, qs);
   HhCallbackExecutor ex;
   ex.cb_set = cb_set; ex.cb_edges = cb_edges; ex.cb_project = cb_project; ex.cb_path = cb_path;
+  ex.n_lanes = lanes > 0 ? lanes : 1;
   bpplan::RunStats st;
   std::vector<int> fin(qs.size(), -1);
-  const int rc = bpplan::run_lockstep(qs, ex, par, &st, fin.data());
+  std::vector<double> fin_ms(qs.size(), -1.0);
+  const int rc = bpplan::run_lockstep(qs, ex, par, &st, fin.data(), fin_ms.data());
   if (rc) return rc;
-  bpplan::store_results(qs, st, fin.data(), *out);
+  bpplan::store_results(qs, st, fin.data(), fin_ms.data(), *out);
   return 0;
 }
 

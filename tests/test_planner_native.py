@@ -123,7 +123,7 @@ def _error_status(e, out):
         raise e
 
 
-def run_native_with_oracle(host_harness, queries, inflate, ws_max, ws_min, seeds, backends, sample_chunk=32):
+def run_native_with_oracle(host_harness, queries, inflate, ws_max, ws_min, seeds, backends, sample_chunk=32, lanes=1):
     pk = pn.PackedQueries(queries, inflate, ws_max, ws_min, seeds, sample_chunk)
     helpers = [SetSequencePlanner(q["obstacles"], inflate, list(ws_max), list(ws_min), backend=backends[i],
                                   obs_sets=backends[i].obs_sets) for i, q in enumerate(queries)]
@@ -226,7 +226,7 @@ def run_native_with_oracle(host_harness, queries, inflate, ws_max, ws_min, seeds
 
     cbs = (CB_SET(cb_set), CB_EDGES(cb_edges), CB_PROJECT(cb_project), CB_PATH(cb_path))
     host_harness.hh_plan_batch.restype = ctypes.c_int
-    rc = host_harness.hh_plan_batch(ctypes.byref(pk.inp), ctypes.byref(pk.out), *cbs)
+    rc = host_harness.hh_plan_batch(ctypes.byref(pk.inp), ctypes.byref(pk.out), *cbs, int(lanes))
     assert not errors, errors[0]
     assert rc == 0
     return pk
@@ -282,12 +282,19 @@ def test_native_driver_equals_python_planner_on_cpu(host_harness):
         seeds.append(i)
     pk = _check(host_harness, queries, infl, list(wmax), list(wmin), seeds, chunk=32)
     assert (pk.err_kind != 0).sum() >= 1 and (pk.err_kind == 0).sum() >= 2
+    # two and three independent lock-step lanes (query i -> lane i mod L): the same answers per query
+    for lanes in (2, 3):
+        pk2 = _check(host_harness, queries, infl, list(wmax), list(wmin), seeds, chunk=32, lanes=lanes, backends=pk.backends)
+        assert np.array_equal(pk2.err_kind, pk.err_kind) and pk2.stats[0] <= pk.stats[0]
 
 
-def _check(host_harness, queries, inflate, ws_max, ws_min, seeds, chunk):
-    backends = [MemoBackend(q["obstacles"], inflate, ws_max, ws_min) for q in queries]
+def _check(host_harness, queries, inflate, ws_max, ws_min, seeds, chunk, lanes=1, backends=None):
+    if backends is None:
+        backends = [MemoBackend(q["obstacles"], inflate, ws_max, ws_min) for q in queries]
     want = [_python_plan(q, inflate, ws_max, ws_min, s, be) for q, s, be in zip(queries, seeds, backends)]
-    pk = run_native_with_oracle(host_harness, queries, inflate, ws_max, ws_min, seeds, backends, sample_chunk=chunk)
+    pk = run_native_with_oracle(host_harness, queries, inflate, ws_max, ws_min, seeds, backends, sample_chunk=chunk,
+                                lanes=lanes)
+    pk.backends = backends
     got = pk.results()
     for i, ((w, pl), g) in enumerate(zip(want, got)):
         if isinstance(w, Exception):
