@@ -935,9 +935,11 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
         bytes_alg = S * 24 + N * 48 + S * (m_mean * 32 + 12 * 8 + 12)
         return {"kernel": "k_iris_fused (set build: whole find_set_around_point loop, one CTA per seed)",
                 "bound": "fp64", "achieved": ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                "frac": ach / fp64_peak_tflops, "traffic": 191744,
-                "traffic_source": "ncu dram__bytes_read+write per launch (profiles/): compulsory bytes only "
-                                  f"(algorithmic bytes {int(bytes_alg)})",
+                "frac": ach / fp64_peak_tflops, "traffic": 388608,
+                "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r02b_ncu_iris.txt: 388.6 KB read, 0 "
+                                  f"written back before the kernel ends; algorithmic bytes {int(bytes_alg)}: scene + seeds "
+                                  "in, one padded set out -- the rest is the kernel's 380 KB of instructions and the "
+                                  "TMA-staged scene fetched once per SM instead of once per launch)",
                 "peak_source": "bp_probe_fp64: independent DFMA chains on all SMs, measured in this run",
                 "algorithmic_gflop_per_launch": flops / 1e9, "launch_ms": t_build,
                 "note": "latency-bound at 256 seeds (one CTA per seed, 256 CTAs on 148 SMs); `saturated` gives the "
@@ -946,7 +948,7 @@ def kernel_profile(geo, scene, seeds_dev, ws_min, ws_max, out, torch):
     def roofline_fk(hbm_peak, which):
         ach = fk_bytes / (t_fk * 1e-3) / 1e9
         return {"kernel": "k_fk<false,false> (B = 2^20 configurations, 248 B each)", "bound": "hbm", "achieved": ach,
-                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 201795328,
+                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 202077184,
                 "traffic_source": "ncu dram__bytes_read+write per launch (below the 260 MB algorithmic bytes: part "
                                   "of the output is still dirty in the 126 MB L2 at kernel end), profiles/",
                 "peak_source": which, "poses_per_sec": B / (t_fk * 1e-3)}
