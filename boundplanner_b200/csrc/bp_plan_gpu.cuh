@@ -526,7 +526,9 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
   if (in->sample_chunk > 64) return bp_fail("bp_plan_run: sample_chunk is at most 64");
   bpplan::Params par;
   std::vector<bpplan::Query> qs;
+  const auto t_run0 = std::chrono::steady_clock::now();
   bpplan::load_queries(*in, par, qs);
+  const auto t_run1 = std::chrono::steady_clock::now();
   // the work queued on the caller's stream so far precedes the run on every lane
   BP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   pl->ee_group.assign((size_t)pl->Q, 0);
@@ -555,7 +557,9 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
     for (int l = 0; l < pl->L; ++l) cudaStreamSynchronize(pl->lane[l].stream);       // nothing of the run stays in flight
     return bp_fail(pl->error.empty() ? "bp_plan_run: executor failed" : pl->error.c_str());
   }
+  const auto t_run2 = std::chrono::steady_clock::now();
   bpplan::store_results(qs, st, fin.data(), fin_ms.data(), *out);
+  const auto t_run3 = std::chrono::steady_clock::now();
   long long chains = 0, wait = 0, pack = 0, launch = 0, unpack = 0;
   for (int l = 0; l < pl->L; ++l) {
     const PlanLane& ln = pl->lane[l];
@@ -565,6 +569,11 @@ int bp_plan_run(bp_plan* pl, const bp_plan_in* in, bp_plan_out* out, void* strea
   if (pl->trace)
     fprintf(stderr, "bp_plan host phases (%d lanes): pack %lld us, launch %lld us, wait %lld us, unpack %lld us over %lld rounds\n",
             pl->L, pack, launch, wait, unpack, chains);
+  if (pl->trace)
+    fprintf(stderr, "bp_plan host phases: load %.1f ms, gather %.1f ms, resume %.1f ms, store %.1f ms, run total %.1f ms\n",
+            std::chrono::duration<double, std::milli>(t_run1 - t_run0).count(), st.gather_ms, st.resume_ms,
+            std::chrono::duration<double, std::milli>(t_run3 - t_run2).count(),
+            std::chrono::duration<double, std::milli>(t_run3 - t_run0).count());
   return 0;
 }
 

@@ -13,10 +13,16 @@
 // What is NOT here (as in planner.py): the final via-point NLP with rotations (Ipopt, :540-555).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -104,6 +110,8 @@ struct Params {           // BoundPlanner.__init__ (:47-58)
   double w_size = 0.1, c_fit = 1.0, w_bias = 0.01;
   int max_iters = 20, nr_optimized = 10, max_samples = 500, sample_chunk = 32;
   int max_rounds = 4000;  // safety net of the lock-step loop (the reference's loop has none)
+  int threads = 1;        // host threads that resume the state machines of a round (the queries are independent)
+  int pool_min = 64;      // rounds with fewer live queries are resumed by the calling thread alone
 };
 
 struct QueryInput {
@@ -227,6 +235,8 @@ struct Query {
 
   void init(int id, const Params* p, const QueryInput& qi) {
     qid = id; par = p; in = qi;
+    nodes.reserve(MAX_NODES); by_node.reserve(MAX_NODES); inter.reserve(128); hits.reserve(MAX_NODES);
+    cand.reserve(3 * 64); cand_tmp.reserve(128); spec_target.reserve(MAX_NODES); spec_xd.reserve(3 * MAX_NODES);
     rng.set(qi.rng);
     for (int k = 0; k < 3; ++k) { start[k] = qi.start[k]; end[k] = qi.end[k]; }
     // :199-204, obstacle by obstacle in order: an `end` inside an inflated obstacle is pushed out through the
@@ -704,6 +714,67 @@ struct Round {
   }
 };
 
+// A small pool of host threads for the one loop of the driver that is worth it: resuming the (independent) state
+// machines of a round.  parallel_for(n, fn) runs fn(i) for i in [0, n) on the pool and the calling thread.
+struct HostPool {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  const std::function<void(size_t)>* job = nullptr;
+  size_t n_items = 0;
+  std::atomic<size_t> next{0};
+  int generation = 0, busy = 0;
+  bool stop = false;
+
+  explicit HostPool(int threads) {
+    for (int t = 1; t < threads; ++t) workers.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_work.notify_all();
+    for (auto& w : workers) w.join();
+  }
+  void drain() {
+    for (;;) {
+      const size_t i = next.fetch_add(16);
+      if (i >= n_items) break;
+      const size_t e = std::min(n_items, i + 16);
+      for (size_t k = i; k < e; ++k) (*job)(k);
+    }
+  }
+  void loop() {
+    int seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return stop || generation != seen; });
+        if (stop) return;
+        seen = generation;
+      }
+      drain();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--busy == 0) cv_done.notify_one();
+      }
+    }
+  }
+  size_t min_items = 64;
+  void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+    if (workers.empty() || n < min_items) {
+      for (size_t i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = &fn; n_items = n; next.store(0); busy = (int)workers.size(); ++generation;
+    }
+    cv_work.notify_all();
+    drain();
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return busy == 0; });
+  }
+};
+
 struct Executor {
   virtual ~Executor() {}
   // independent lock-step groups ("lanes") the executor can keep in flight at once: while one lane's round runs on
@@ -721,6 +792,7 @@ struct Executor {
 struct RunStats {
   int rounds = 0;                     // lock-step rounds of the longest lane
   long long set_requests = 0, edge_pairs = 0, projections = 0, paths = 0;
+  double gather_ms = 0.0, resume_ms = 0.0;   // host time: building the rounds / resuming the state machines
 };
 
 // Advance all queries until every one is finished.  The queries are dealt to the executor's lanes (query i -> lane
@@ -741,6 +813,7 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
 
   // gather the pending requests of lane l into its round and submit it; returns the number of live queries (or < 0)
   auto launch = [&](int l) -> int {
+    const double t_g0 = now_ms();
     Round& r = rounds_[l];
     r.clear();
     size_t live = 0;
@@ -806,25 +879,39 @@ inline int run_lockstep(std::vector<Query>& qs, Executor& ex, const Params& par,
       stats->set_requests += (long long)r.sets.size(); stats->edge_pairs += (long long)n_pairs;
       stats->projections += (long long)r.projs.size(); stats->paths += (long long)r.paths.size();
     }
+    if (stats) stats->gather_ms += now_ms() - t_g0;
     if (ex.submit(l, r, qs)) return -1;
     in_flight[l] = 1;
     return (int)live;
   };
   // resume the queries of lane l with the answers of its round
+  HostPool pool(par.threads);
+  pool.min_items = (size_t)std::max(1, par.pool_min);
+  struct Task { int owner; const SetAns* sa; const EdgeAns* ea; const ProjAns* pa; const int* path; int path_len; };
+  std::vector<Task> tasks;
   auto deliver = [&](int l) {
+    const double t_d0 = now_ms();
     Round& r = rounds_[l];
-    for (size_t k = 0; k < r.sets.size(); ++k) qs[r.set_owner[k]].resume(&r.set_ans[k], nullptr, nullptr, nullptr, 0);
+    tasks.clear();
+    for (size_t k = 0; k < r.sets.size(); ++k) tasks.push_back(Task{r.set_owner[k], &r.set_ans[k], nullptr, nullptr, nullptr, 0});
     for (size_t k = 0; k < r.edges.size(); ++k)
-      qs[r.edge_owner[k]].resume(nullptr, r.edge_ans.data() + r.edges[k].first_pair, nullptr, nullptr, 0);
+      tasks.push_back(Task{r.edge_owner[k], nullptr, r.edge_ans.data() + r.edges[k].first_pair, nullptr, nullptr, 0});
     size_t po = 0;
     for (size_t k = 0; k < r.proj_owner.size(); ++k) {
-      qs[r.proj_owner[k]].resume(nullptr, nullptr, r.proj_ans.data() + po, nullptr, 0);
+      tasks.push_back(Task{r.proj_owner[k], nullptr, nullptr, r.proj_ans.data() + po, nullptr, 0});
       po += (size_t)r.proj_count[k];
     }
     for (size_t k = 0; k < r.paths.size(); ++k)
-      qs[r.path_owner[k]].resume(nullptr, nullptr, nullptr, r.path_out.data() + k * (size_t)MAX_PATH, r.path_len[k]);
+      tasks.push_back(Task{r.path_owner[k], nullptr, nullptr, nullptr, r.path_out.data() + k * (size_t)MAX_PATH, r.path_len[k]});
+    // one task per live query of the lane: the state machines are independent of each other
+    const std::function<void(size_t)> fn = [&](size_t k) {
+      const Task& t = tasks[k];
+      qs[(size_t)t.owner].resume(t.sa, t.ea, t.pa, t.path, t.path_len);
+    };
+    pool.parallel_for(tasks.size(), fn);
     for (size_t i = (size_t)l; i < qs.size(); i += (size_t)L)
       if (!qs[i].finished) qs[i].rounds = n_rounds[l];
+    if (stats) stats->resume_ms += now_ms() - t_d0;
   };
 
   for (int l = 0; l < L; ++l)
@@ -856,6 +943,14 @@ inline void load_queries(const bp_plan_in& in, Params& par, std::vector<Query>& 
   for (int k = 0; k < 3; ++k) { par.ws_min[k] = in.ws_min[k]; par.ws_max[k] = in.ws_max[k]; }
   if (in.sample_chunk > 0) par.sample_chunk = in.sample_chunk;
   if (in.max_rounds > 0) par.max_rounds = in.max_rounds;
+  {
+    // host threads for the resume loop: BPGEO_PLAN_THREADS, else up to four of the cores this process may use
+    int th = 0;
+    if (const char* ev = getenv("BPGEO_PLAN_THREADS")) th = atoi(ev);
+    if (th <= 0) th = (int)std::min(4u, std::max(1u, std::thread::hardware_concurrency()));
+    par.threads = std::min(th, 16);
+    if (const char* ev = getenv("BPGEO_PLAN_POOL_MIN")) par.pool_min = std::max(1, atoi(ev));
+  }
   qs.clear();
   qs.resize((size_t)in.Q);
   for (int q = 0; q < in.Q; ++q) {

@@ -26,7 +26,7 @@ def host_harness():
                     for f in ("bp_math.cuh", "bp_mvie.cuh", "bp_lp.cuh", "bp_fk.cuh", "bp_mvie_fixed_r.cuh",
                               "bp_mvie_pd.cuh", "bp_planner.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-o", so, src])
     lib = ctypes.CDLL(so)
     lib.hh_mvie.restype = ctypes.c_int
     lib.hh_pair_lp.restype = ctypes.c_int

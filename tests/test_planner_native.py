@@ -282,10 +282,15 @@ def test_native_driver_equals_python_planner_on_cpu(host_harness):
         seeds.append(i)
     pk = _check(host_harness, queries, infl, list(wmax), list(wmin), seeds, chunk=32)
     assert (pk.err_kind != 0).sum() >= 1 and (pk.err_kind == 0).sum() >= 2
-    # two and three independent lock-step lanes (query i -> lane i mod L): the same answers per query
+    # two and three independent lock-step lanes (query i -> lane i mod L), the state machines of a round resumed
+    # by a pool of three host threads: the same answers per query
+    import os
+
+    os.environ["BPGEO_PLAN_THREADS"], os.environ["BPGEO_PLAN_POOL_MIN"] = "3", "1"
     for lanes in (2, 3):
         pk2 = _check(host_harness, queries, infl, list(wmax), list(wmin), seeds, chunk=32, lanes=lanes, backends=pk.backends)
         assert np.array_equal(pk2.err_kind, pk.err_kind) and pk2.stats[0] <= pk.stats[0]
+    del os.environ["BPGEO_PLAN_THREADS"], os.environ["BPGEO_PLAN_POOL_MIN"]
 
 
 def _check(host_harness, queries, inflate, ws_max, ws_min, seeds, chunk, lanes=1, backends=None):
