@@ -97,6 +97,7 @@ struct PathReq { int qid, n_nodes, edge_begin; };        // CSR of the query's i
 struct Node {             // graph node: reduced set + ellipsoid
   int m;
   double A[NODE_ROWS * 3], b[NODE_ROWS], Q[9], P[3], size;
+  double c_size;          // tanh(0.25 - cbrt(size)): the node's factor in every edge cost (:876-878)
 };
 struct Inter {            // node of the intersection graph
   int id0, id1;
@@ -282,6 +283,7 @@ struct Query {
     std::memcpy(n.Q, Q, sizeof(n.Q));
     std::memcpy(n.P, P, sizeof(n.P));
     n.size = 1.0 / det3_lu(Q);
+    n.c_size = std::tanh(0.25 - std::cbrt(n.size));
     nodes.push_back(n);
     by_node.emplace_back();
     nr_sets += 1;
@@ -336,7 +338,7 @@ struct Query {
     for (int eid : cand_tmp) {
       Inter& ed = inter[eid];
       const bool cond1 = ed.id0 == h.vid || ed.id1 == h.vid;
-      const double size = cond1 ? nodes[h.vid].size : nodes[e_id_new].size;
+      const double c_size = cond1 ? nodes[h.vid].c_size : nodes[e_id_new].c_size;
       nr_edges += 2;
       const double* pp = ed.has_proj ? ed.p_proj : end;
       const double d0 = me.p_proj[0] - pp[0], d1 = me.p_proj[1] - pp[1], d2 = me.p_proj[2] - pp[2];
@@ -345,7 +347,6 @@ struct Query {
       me.conn_start = ed.conn_start = cs;
       me.conn_end = ed.conn_end = ce;
       edges_connected = cs && ce;                                 // last edge wins (quirk Q6)
-      const double c_size = std::tanh(0.25 - std::cbrt(size));
       double cost = dist * (1 + par->w_size * c_size) + par->w_bias;
       if (!h.fits) cost += par->c_fit;
       me.adj.emplace_back(eid, cost);

@@ -38,7 +38,8 @@ class SetAns(ctypes.Structure):
 
 class Node(ctypes.Structure):
     _fields_ = [("m", ctypes.c_int), ("A", ctypes.c_double * (pn.NODE_ROWS * 3)), ("b", ctypes.c_double * pn.NODE_ROWS),
-                ("Q", ctypes.c_double * 9), ("P", ctypes.c_double * 3), ("size", ctypes.c_double)]
+                ("Q", ctypes.c_double * 9), ("P", ctypes.c_double * 3), ("size", ctypes.c_double),
+                ("c_size", ctypes.c_double)]
 
 
 class EdgeAns(ctypes.Structure):
