@@ -69,7 +69,7 @@ BP_HD double bp_rcp(double x) {
 static int bp_mvie_count_armijo = 0;
 #endif
 template <int NV>
-BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx) {
+BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx, double* lam2_out = nullptr) {
   // right-looking (outer-product) LDL^T: after column j is scaled the trailing
   // updates are mutually independent, so the dependent chain per column is
   // reciprocal -> scale -> one update of the next pivot.
@@ -100,12 +100,21 @@ BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx) {
     for (int k = 0; k < i; ++k) v -= H[i * (i + 1) / 2 + k] * y[k];
     y[i] = v;
   }
-  // backward: L^T dx = D^-1 y
+  // Newton decrement^2 = g^T H^-1 g = sum y_i^2 / d_i: available before the back substitution, so that the
+  // caller's tests on it are off the dependent chain
+  if (lam2_out) {
+    double l2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) l2 += y[i] * y[i] * dinv[i];
+    *lam2_out = l2;
+  }
+  // backward: L^T dx = D^-1 y.  The terms are taken from the OLDEST dx to the newest, so that only the last
+  // multiply-add of a row waits for the entry computed just before (dependent chain: one FMA per row).
 #pragma unroll
   for (int i = NV - 1; i >= 0; --i) {
     double v = y[i] * dinv[i];
 #pragma unroll
-    for (int k = i + 1; k < NV; ++k) v -= H[k * (k + 1) / 2 + i] * dx[k];
+    for (int k = NV - 1; k > i; --k) v -= H[k * (k + 1) / 2 + i] * dx[k];
     dx[i] = v;
   }
   return true;
@@ -237,13 +246,11 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
         H[0] += t * i0 * i0; H[5] += 2.0 * t * i2 * i2; H[20] += t * i5 * i5;
       }
       double dx[NV];
-      if (!bp_ldl_solve<NV>(H, g, dx)) {
+      double lam2 = 0.0;                     // Newton decrement^2, from the factorisation (sum y_i^2 / d_i)
+      if (!bp_ldl_solve<NV>(H, g, dx, &lam2)) {
         status = (t > 1e8) ? BP_OK : BP_MVIE_NOT_CONVERGED;
         goto done;
       }
-      double lam2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) lam2 -= g[k] * dx[k];
       if (!(lam2 > 0.0)) { centred = true; break; }
       // backtracking: strict feasibility (+ Armijo on F_t while lambda >= 0.1; below
       // that the full Newton step of a self-concordant function is safe).

@@ -240,13 +240,11 @@ __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict_
       __syncwarp();                      // OUT is rewritten next iteration
       BP_MPROF_LAP(1);
       double dx[NV];
-      if (!bp_ldl_solve<NV>(H, g, dx)) {
+      double lam2 = 0.0;
+      if (!bp_ldl_solve<NV>(H, g, dx, &lam2)) {
         status = (t > 1e8) ? BP_OK : BP_MVIE_NOT_CONVERGED;
         goto done;
       }
-      double lam2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) lam2 -= g[k] * dx[k];
       if (!(lam2 > 0.0)) { centred = true; break; }
       BP_MPROF_LAP(2);
       // ---- line search: psi(x + alpha dx) = psi + alpha B1 + alpha^2 A2 per row
