@@ -65,6 +65,20 @@ BP_HD double bp_rcp(double x) {
 #endif
 }
 
+// 1/x for the pivots of the LDL^T factorisation only: one Newton step (relative error ~1e-12).  The pivots scale
+// the Newton DIRECTION; the point the iteration converges to is where the (accurately evaluated) gradient vanishes,
+// whatever the accuracy of the direction -- and every pivot's reciprocal sits on the solver's dependent chain.
+BP_HD double bp_rcp_pivot(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 #ifdef BP_MVIE_COUNT
 static int bp_mvie_count_armijo = 0;
 #endif
@@ -78,17 +92,19 @@ BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx, double* lam2_out
   for (int j = 0; j < NV; ++j) {
     const double dj = H[j * (j + 1) / 2 + j];
     if (!(dj > 0.0)) return false;
-    dinv[j] = bp_rcp(dj);
-    double col[NV];                       // unscaled column j below the diagonal: L_ij d_j
+    dinv[j] = bp_rcp_pivot(dj);
+    double col[NV], col2[NV];             // unscaled column j below the diagonal: L_ij d_j, and its squares
 #pragma unroll
     for (int i = j + 1; i < NV; ++i) {
       col[i] = H[i * (i + 1) / 2 + j];
+      col2[i] = col[i] * col[i];          // (independent of the reciprocal: the next pivot waits for one FMA only)
       H[i * (i + 1) / 2 + j] = col[i] * dinv[j];
     }
 #pragma unroll
     for (int i = j + 1; i < NV; ++i) {
 #pragma unroll
-      for (int k = j + 1; k <= i; ++k) H[i * (i + 1) / 2 + k] -= H[i * (i + 1) / 2 + j] * col[k];
+      for (int k = j + 1; k < i; ++k) H[i * (i + 1) / 2 + k] -= H[i * (i + 1) / 2 + j] * col[k];
+      H[i * (i + 1) / 2 + i] -= col2[i] * dinv[j];
     }
   }
   // forward: L y = -g
