@@ -88,10 +88,11 @@ BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx, double* lam2_out
   // updates are mutually independent, so the dependent chain per column is
   // reciprocal -> scale -> one update of the next pivot.
   double dinv[NV];
+  bool spd = true;                        // (one test at the end: no data-dependent branch per pivot on the chain)
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const double dj = H[j * (j + 1) / 2 + j];
-    if (!(dj > 0.0)) return false;
+    spd = spd && (dj > 0.0);
     dinv[j] = bp_rcp_pivot(dj);
     double col[NV], col2[NV];             // unscaled column j below the diagonal: L_ij d_j, and its squares
 #pragma unroll
@@ -107,6 +108,7 @@ BP_HD bool bp_ldl_solve(double* H, const double* g, double* dx, double* lam2_out
       H[i * (i + 1) / 2 + i] -= col2[i] * dinv[j];
     }
   }
+  if (!spd) return false;
   // forward: L y = -g
   double y[NV];
 #pragma unroll
