@@ -341,7 +341,7 @@ BP_HD int bp_mvie_solve(const ROWS& rows, int m, const double* c0, double* Lout,
     double t_next = t * (t >= BP_MVIE_T_LATE_FROM ? BP_MVIE_T_MULT_LATE : BP_MVIE_T_MULT);
     if (t_next > t_final) t_next = t_final;
     if (t_prev > 0.0 && t >= BP_MVIE_PRED_FROM) {
-      double w = (1.0 / t_next - 1.0 / t) / (1.0 / t - 1.0 / t_prev);
+      double w = ((t - t_next) * t_prev) / ((t_prev - t) * t_next);
       double xp[NV];
       bool ok = false;
       for (int tr = 0; tr < 4 && !ok; ++tr) {

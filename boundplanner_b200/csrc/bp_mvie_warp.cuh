@@ -316,7 +316,8 @@ __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict_
     double t_next = t * BP_MVIE_T_MULT;
     if (t_next > t_final) t_next = t_final;
     if (t_prev > 0.0 && t >= BP_MVIE_PRED_FROM) {
-      double w = (1.0 / t_next - 1.0 / t) / (1.0 / t - 1.0 / t_prev);
+      // (1/t_next - 1/t) / (1/t - 1/t_prev), with one division
+      double w = ((t - t_next) * t_prev) / ((t_prev - t) * t_next);
       double xp[NV];
       bool ok = false;
       for (int tr = 0; tr < 4 && !ok; ++tr) {
