@@ -134,24 +134,27 @@ __device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int 
       // exits
       if (x[3] - minq <= 0.0) { result = 1; goto done; }
       {
-        const double irn = 1.0 / rn;                    // (exact: this bound decides "disjoint")
-        const double rho0 = g[0] * irn, rho1 = g[1] * irn, rho2 = g[2] * irn;
-        // the dual residual is paid for over the distance to the farthest point that could still be feasible:
-        // BP_LP_DIAMETER, or -- when the caller knows a box that holds every feasible point (the overlap of the
-        // two sets' bounding boxes) -- the distance from the iterate to the farthest corner of that box: if the
-        // sets intersected, a point x' of the box would have max_i(a_i.x' - c_i) <= 0, but every x' of the box has
-        // max_i(.) >= sum lam_i (a_i.x' - c_i) >= lb.  Typically 0.3 m instead of 100 m: "disjoint" is proven
-        // without centring the iterate to 1e-4 of the margin first.
-        double diam = BP_LP_DIAMETER;
+        // weak-duality lower bound  lb = s - mm / rn - |sum lam_i a_i| * diam  with the barrier multipliers
+        // lam_i = r_i / rn (r_i = 1 / slack_i, rn = sum r_i): multiplied through by rn > 0 and squared,
+        //   lb > 0  <=>  A := s rn - mm > 0  and  A^2 > |sum r_i a_i|^2 diam^2
+        // -- no division and no square root on the solver's dependent chain.  The dual residual is paid for over
+        // the distance to the farthest point that could still be feasible: BP_LP_DIAMETER, or -- when the caller
+        // knows a box that holds every feasible point (the overlap of the two sets' bounding boxes) -- the distance
+        // from the iterate to the farthest corner of that box: if the sets intersected, a point x' of the box
+        // would have max_i(a_i.x' - c_i) <= 0, but every x' of the box has max_i(.) >= sum lam_i (a_i.x' - c_i)
+        // >= lb.  Typically 0.3 m instead of 100 m: "disjoint" is proven without centring the iterate to 1e-4 of
+        // the margin first.  (1 + 1e-9) and the relative 1e-12 below keep the test on the safe side of rounding.
+        double diam2 = BP_LP_DIAMETER * BP_LP_DIAMETER;
         if (region) {
           const double e0 = fmax(fabs(x[0] - region[0]), fabs(x[0] - region[3]));
           const double e1 = fmax(fabs(x[1] - region[1]), fabs(x[1] - region[4]));
           const double e2 = fmax(fabs(x[2] - region[2]), fabs(x[2] - region[5]));
-          const double dd = sqrt(e0 * e0 + e1 * e1 + e2 * e2) * (1.0 + 1e-9) + 1e-12;
-          if (dd < diam) diam = dd;
+          const double dd2 = (e0 * e0 + e1 * e1 + e2 * e2) * (1.0 + 1e-9) + 1e-24;
+          if (dd2 < diam2) diam2 = dd2;
         }
-        const double lb = x[3] - mm * irn - sqrt(rho0 * rho0 + rho1 * rho1 + rho2 * rho2) * diam;
-        if (lb > 0.0) { result = 0; goto done; }
+        const double Aq = x[3] * rn - mm;
+        const double g2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+        if (Aq > 0.0 && Aq * Aq * (1.0 - 1e-12) > g2 * diam2) { result = 0; goto done; }
       }
       double dx[4];
       if (!bp_ldl_solve<4>(H, g, dx)) { result = 0; goto done; }
