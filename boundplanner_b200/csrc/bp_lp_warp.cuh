@@ -87,7 +87,7 @@ __device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int 
     for (int inner = 0; inner < BP_LP_INNER_MAX; ++inner) {
       ++iters;
       double rslack[BP_LP_SLOTS], rinv[BP_LP_SLOTS];
-      double minq = BP_INF;
+      bool above = true;                                // every slack >= s: the iterate x is a common point
 #pragma unroll
       for (int q = 0; q < BP_LP_SLOTS; ++q) {
         const double slack = rc[q] - (ra[q][0] * x[0] + ra[q][1] * x[1] + ra[q][2] * x[2]) + x[3];
@@ -98,14 +98,16 @@ __device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int 
           if (rv[q]) {
             const double r = bp_rcp(slack);             // steers the Newton direction only
             rinv[q] = r;
-            minq = fmin(minq, slack);
+            above = above && (x[3] - slack <= 0.0);
             f[0] = ra[q][0] * r; f[1] = ra[q][1] * r; f[2] = ra[q][2] * r; f[3] = -r;
           } else {
             f[0] = 0.0; f[1] = 0.0; f[2] = 0.0; f[3] = 0.0;
           }
         }
       }
-      minq = bp_warp_min(minq);
+      // (a vote, not a five-stage shuffle reduction of the smallest slack: the warp is in-order, and everything
+      // below waits for what is issued here)
+      const bool common = __all_sync(full, above);
       __syncwarp();
       {
         // lanes 0-15 sum the even rows, lanes 16-31 the odd rows, four rows of a parity per trip (rows m .. m8-1 of
@@ -132,7 +134,7 @@ __device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int 
       const double rn = -g[3];                          // sum r_i
       g[3] += t;
       // exits
-      if (x[3] - minq <= 0.0) { result = 1; goto done; }
+      if (common) { result = 1; goto done; }            // s - min slack <= 0: max_i (a_i.x - c_i) <= 0, exactly
       {
         // weak-duality lower bound  lb = s - mm / rn - |sum lam_i a_i| * diam  with the barrier multipliers
         // lam_i = r_i / rn (r_i = 1 / slack_i, rn = sum r_i): multiplied through by rn > 0 and squared,
@@ -164,7 +166,9 @@ __device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int 
 #pragma unroll
       for (int q = 0; q < BP_LP_SLOTS; ++q)
         rdsl[q] = -(ra[q][0] * dx[0] + ra[q][1] * dx[1] + ra[q][2] * dx[2]) + dx[3];
-      const bool want_armijo = lam2 >= 0.01;
+      // full Newton step without the Armijo test while lambda^2 < 0.45: t s - sum log(slack_i) is self-concordant,
+      // the full step then is feasible and cannot increase it (see BP_MVIE_FULLSTEP_LAM2)
+      const bool want_armijo = lam2 >= 0.45;
       double alpha = 1.0;
       bool accepted = false;
       for (int bt = 0; bt < 60; ++bt) {
