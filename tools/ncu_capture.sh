@@ -7,6 +7,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${T}_launches_plan.csv python tools/bench_c3_native.py 64 --no-python --once > gpurun_out/${T}_launches_plan.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_iris_fused -s 2 -c 1 -f -o gpurun_out/${T}_prof_iris python tools/ncu_driver.py > gpurun_out/${T}_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_iris_fused -s 4 -c 1 -f -o gpurun_out/${T}_prof_iris_sat python tools/ncu_driver.py > gpurun_out/${T}_ncu2.log 2>&1
-ncu --set full --clock-control none -k regex:"k_pair_lp|k_pair_filter|k_fk" -s 6 -c 3 -f -o gpurun_out/${T}_prof_pair_fk python tools/ncu_driver.py > gpurun_out/${T}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pair_lp -s 1 -c 1 -f -o gpurun_out/${T}_prof_pair_lp python tools/ncu_driver.py > gpurun_out/${T}_ncu3.log 2>&1
+ncu --set full --clock-control none -k regex:k_pair_filter -s 1 -c 1 -f -o gpurun_out/${T}_prof_pair_filter python tools/ncu_driver.py > gpurun_out/${T}_ncu4.log 2>&1
+ncu --set full --clock-control none -k regex:k_fk -s 1 -c 1 -f -o gpurun_out/${T}_prof_fk python tools/ncu_driver.py > gpurun_out/${T}_ncu5.log 2>&1
 tail -3 gpurun_out/${T}_ncu1.log
 ls -la gpurun_out/${T}_*.ncu-rep
