@@ -185,7 +185,7 @@ __device__ __forceinline__ int bp_lp_feasible_warp_impl(const ROWFN& rowfn, int 
         if (ok) {
           if (!want_armijo) accepted = true;
           else {
-            const double dF = t * alpha * dx[3] - log(bp_warp_prod(prod));
+            const double dF = t * alpha * dx[3] - bp_log1p(bp_warp_prod(prod) - 1.0);
             if (dF <= -0.25 * alpha * lam2) accepted = true;
           }
           if (accepted) {

@@ -80,6 +80,36 @@ BP_HD double bp_rcp_pivot(double x) {
 #endif
 }
 
+// log(1 + x) for the Armijo tests of the warp solvers (x > -1): about 40 instructions instead of the ~125 of the
+// library's log1p, which sat on the dependent chain of every tested step (11 % of the MVIE's stall samples).
+// u = 1 + x = 2^e m with m in [sqrt(1/2), sqrt(2)), log m = 2 atanh z, z = (m - 1) / (m + 1) (|z| <= 0.172: ten
+// terms), plus the rounding of u repaired to first order: (x - (u - 1)) / u.  <= 4 ulp (checked against log1p on
+// 350 k arguments from -0.999 to 1000).  The tests it feeds compare a decrease with a quarter of the predicted one.
+BP_HD double bp_log1p(double x) {
+#ifdef __CUDA_ARCH__
+  const double u = 1.0 + x;
+  if (!(u > 1e-300) || !(u < 1e300)) return log1p(x);
+  const double c = x - (u - 1.0);
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  int e = ((hi >> 20) & 0x7ff) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, lo);
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double z = (m - 1.0) * bp_rcp(m + 1.0);
+  const double z2 = z * z;
+  double p = 1.0 / 21.0;
+  p = fma(p, z2, 1.0 / 19.0); p = fma(p, z2, 1.0 / 17.0); p = fma(p, z2, 1.0 / 15.0); p = fma(p, z2, 1.0 / 13.0);
+  p = fma(p, z2, 1.0 / 11.0); p = fma(p, z2, 1.0 / 9.0); p = fma(p, z2, 1.0 / 7.0); p = fma(p, z2, 1.0 / 5.0);
+  p = fma(p, z2, 1.0 / 3.0);
+  const double lm = 2.0 * z * fma(p, z2, 1.0);
+  const double ed = (double)e;
+  return fma(ed, 6.93147180369123816490e-01, lm + fma(ed, 1.90821492927058770002e-10, c * bp_rcp(u)));
+#else
+  return log1p(x);
+#endif
+}
+
 #ifdef BP_MVIE_COUNT
 static int bp_mvie_count_armijo = 0;
 #endif

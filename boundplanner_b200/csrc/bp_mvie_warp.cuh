@@ -288,7 +288,7 @@ __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict_
                              : lane == 1 ? alpha * dx[2] * i2
                              : lane == 2 ? alpha * dx[5] * i5
                              : ptot - 1.0;
-            const double lg = log1p(arg);
+            const double lg = bp_log1p(arg);
             const double l0 = __shfl_sync(full, lg, 0), l1 = __shfl_sync(full, lg, 1);
             const double l2 = __shfl_sync(full, lg, 2), l3 = __shfl_sync(full, lg, 3);
             const double dF = -t * (l0 + 2.0 * l1 + l2) - l3;
