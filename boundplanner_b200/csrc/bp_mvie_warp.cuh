@@ -84,9 +84,13 @@ struct BpMvieOut {
   int status, iters;
 };
 
-template <int NV, int RPL>
+#define BP_MVIE_ABORTED 99      // internal: a speculative solve was told to stop (never leaves the fused kernel)
+// ABORTABLE: abort_flag (shared memory) is polled once per Newton iteration; non-zero -> return BP_MVIE_ABORTED.
+// A template flag, not a run-time test: the poll costs the plain solver 1.7 % when it is compiled in.
+template <int NV, int RPL, bool ABORTABLE = false>
 __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict__ A, const double* __restrict__ b,
-                                                       int m, double c00, double c01, double c02, double* scratch) {
+                                                       int m, double c00, double c01, double c02, double* scratch,
+                                                       const volatile int* abort_flag) {
   const double c0[3] = {c00, c01, c02};
   BpMvieOut res;
   BP_MPROF_INIT();
@@ -160,6 +164,7 @@ __device__ __forceinline__ BpMvieOut bp_mvie_warp_impl(const double* __restrict_
     double lam2_prev = BP_INF;
     bool centred = false;
     for (int inner = 0; inner < BP_MVIE_INNER_MAX; ++inner) {
+      if (ABORTABLE && *abort_flag) { status = BP_MVIE_ABORTED; goto done; }
       ++iters;
       BP_MPROF_COUNT(5);
       BP_MPROF_MARK();
@@ -365,14 +370,24 @@ done:
 template <int NV>
 __device__ __noinline__ BpMvieOut bp_mvie_warp_fn(const double* A, const double* b, int m, double c00, double c01,
                                                   double c02, double* scratch) {
-  if (m <= 32) return bp_mvie_warp_impl<NV, 1>(A, b, m, c00, c01, c02, scratch);
-  return bp_mvie_warp_impl<NV, 2>(A, b, m, c00, c01, c02, scratch);
+  if (m <= 32) return bp_mvie_warp_impl<NV, 1>(A, b, m, c00, c01, c02, scratch, nullptr);
+  return bp_mvie_warp_impl<NV, 2>(A, b, m, c00, c01, c02, scratch, nullptr);
+}
+// the copy that a speculative solve runs (fused kernel, large scenes in waves): stops when *abort_flag != 0
+template <int NV>
+__device__ __noinline__ BpMvieOut bp_mvie_warp_abortable_fn(const double* A, const double* b, int m, double c00,
+                                                            double c01, double c02, double* scratch,
+                                                            const volatile int* abort_flag) {
+  if (m <= 32) return bp_mvie_warp_impl<NV, 1, true>(A, b, m, c00, c01, c02, scratch, abort_flag);
+  return bp_mvie_warp_impl<NV, 2, true>(A, b, m, c00, c01, c02, scratch, abort_flag);
 }
 
 template <int NV>
 __device__ __forceinline__ int bp_mvie_warp(const double* A, const double* b, int m, const double* c0, double* scratch,
-                                            double* Lout, double* dout, int* iters_out) {
-  const BpMvieOut o = bp_mvie_warp_fn<NV>(A, b, m, c0[0], c0[1], c0[2], scratch);
+                                            double* Lout, double* dout, int* iters_out,
+                                            const volatile int* abort_flag = nullptr) {
+  const BpMvieOut o = abort_flag ? bp_mvie_warp_abortable_fn<NV>(A, b, m, c0[0], c0[1], c0[2], scratch, abort_flag)
+                                 : bp_mvie_warp_fn<NV>(A, b, m, c0[0], c0[1], c0[2], scratch);
 #pragma unroll
   for (int k = 0; k < 6; ++k) Lout[k] = o.L[k];
   dout[0] = o.d[0]; dout[1] = o.d[1]; dout[2] = o.d[2];

@@ -1294,6 +1294,7 @@ struct FusedParams {
   int* rows_peak;
   int m_max, max_iter, fixed_mid, optimize, row_cap, cache_y;
   int stage;                 // box scene: stage the scene columns in shared memory (TMA) after key table + shell
+  int spec;                  // trailing free-centre solve speculatively next to EVERY pass's fixed-centre solve
 };
 
 struct GlobalRows {
@@ -1316,7 +1317,9 @@ struct SharedRows {
 // and with optimize == 0 one free-centre MVIE after the first pass (:278-282).
 __device__ unsigned g_sm_slot[256];     // CTAs started per SM (only its parity is used, never reset)
 
-template <int MODE, bool POLY, int AW = 1>
+// SPEC: the instantiation with the speculative trailing solve (and the second, abortable copy of the free-centre
+// solver); the plain one is what every launch without waves over a large scene runs.
+template <int MODE, bool POLY, int AW = 1, bool SPEC = false>
 __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParams pr) {
   SceneView sc = scene_of_item(sc_all, blockIdx.x);
   extern __shared__ __align__(16) double s_dist[];
@@ -1333,7 +1336,8 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
   }
   __shared__ double c_Q[9], c_p[3], c_det;
   __shared__ double f_Q[9], f_p[3];
-  __shared__ int c_status, c_small, f_status, c_mw;
+  __shared__ int c_status, c_small, f_status, c_mw, f_done;
+  __shared__ volatile int c_abort;
   const int s = blockIdx.x, tid = threadIdx.x;
 #ifdef BPGEO_PROFILE
   const long long prof_k0_ = clock64();
@@ -1435,11 +1439,16 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
       continue;
     }
     det_old = det;                                            // :217
-    __syncthreads();                                          // the picked rows are in shared memory
-    // Pass max_iter is the last one whatever its MVIE returns (:204-207), and the trailing free-centre solve
-    // (:235-238) depends only on this pass's rows and the seed: it runs NOW on a second warp, next to the
-    // fixed-centre solve, instead of after it.
+    // The trailing free-centre solve (:235-238) depends only on the rows of the pass the loop ends with and on the
+    // seed.  It runs SPECULATIVELY on a second warp next to every pass's fixed-centre solve (the two solver warps
+    // sit on different SM sub-partitions): if the loop ends with this pass the answer is (nearly) there, if the loop
+    // goes on the primary warp raises c_abort and the speculative solve stops at its next Newton iteration.  Pass
+    // max_iter is the last one whatever its MVIE returns (:204-207): no abort there.  BPGEO_SPEC=0 (pr.spec = 0)
+    // speculates on that last pass only.
     const bool spec_final = MODE == 0 && pr.fixed_mid && k == pr.max_iter;
+    const bool spec_any = MODE == 0 && pr.fixed_mid && pr.optimize && (spec_final || (SPEC && pr.spec));
+    if (tid == 0) { c_abort = 0; f_done = 0; }
+    __syncthreads();                                          // the picked rows are in shared memory
     if (warp_id == mw) {
       double L[6], d[3];
       BP_PROF_T0();
@@ -1454,24 +1463,32 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
         c_p[0] = d[0]; c_p[1] = d[1]; c_p[2] = d[2];
         c_det = dq;                                           // :229
         c_status = ms;
-        c_small = (ms == BP_OK && bp_sym3_min_eig(E) < 1e-3) ? 1 : 0;   // :232-233
+        const int small = (ms == BP_OK && bp_sym3_min_eig(E) < 1e-3) ? 1 : 0;   // :232-233
+        c_small = small;
+        // will the loop go on after this pass (:203-207, :232-233)?  Then (or on an error) nobody needs the
+        // speculative trailing solve: stop it
+        const bool goes_on = ms == BP_OK && !small && k < pr.max_iter && fabs(dq - det_old) / det_old > 0.01;
+        if (spec_any && !spec_final && (goes_on || ms != BP_OK)) c_abort = 1;
       }
-    } else if (spec_final && warp_id == mw2) {
+    } else if (spec_any && warp_id == mw2) {
       double L[6], d[3];
       BP_PROF_T0();
-      const int ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch2, L, d, nullptr);
+      int ms;
+      if (SPEC && !spec_final) ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch2, L, d, nullptr, &c_abort);
+      else ms = bp_mvie_warp<9>(sA, sb, m_cur, p, scratch2, L, d, nullptr);
       BP_PROF_ADD(2);
-      if ((tid & 31) == 0) {
+      if ((tid & 31) == 0 && ms != BP_MVIE_ABORTED) {
         double E[9], Qn[9], dq;
         bp_shape_from_L(L, E, Qn, &dq);
 #pragma unroll
         for (int q = 0; q < 9; ++q) f_Q[q] = Qn[q];
         f_p[0] = d[0]; f_p[1] = d[1]; f_p[2] = d[2];
         f_status = ms;
+        f_done = 1;
       }
     }
-    have_final = spec_final;
     __syncthreads();
+    have_final = f_done != 0;
     if (c_status != BP_OK) { status = c_status; break; }
 #pragma unroll
     for (int q = 0; q < 9; ++q) Q[q] = c_Q[q];
@@ -1480,8 +1497,6 @@ __global__ void __launch_bounds__(128) k_iris_fused(SceneView sc_all, FusedParam
     if (c_small) break;
   }
   if (MODE == 0 && pr.optimize && pr.fixed_mid && status == BP_OK) {       // :235-238
-    // (running this solve speculatively on an idle warp next to every pass's fixed-centre solve was measured
-    // slower: the two solves slow each other down by ~20 % and the pass then waits for the longer one)
     __syncthreads();
     if (!have_final && warp_id == mw) {
       double L[6], d[3];
@@ -3596,11 +3611,33 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
       const size_t staged = 16 * ((sizeof(ShellMem) + 15) / 16) + sizeof(double) * (size_t)((scene->n + 1) & ~1) * 7;
       if (env && !scene->rows && staged + 20 * 1024 <= 110 * 1024) { fp.stage = 1; fsmem = staged; }
     }
+    // (speculative trailing solve: decided below, box scenes only)
     const void* kfn = scene->rows ? (const void*)k_iris_fused<0, true>
                       : (scene->n <= 64 * 128 ? (const void*)k_iris_fused<0, false>
                                               : (const void*)k_iris_fused<0, false, 2>);   // (2 words of alive bits)
     if (tail && fsmem < sizeof(double) * BP_TAIL_WORK_DOUBLES) fsmem = sizeof(double) * BP_TAIL_WORK_DOUBLES;
     if (set_dyn_smem(kfn, fsmem)) return 1;
+    {
+      // speculative trailing solve on every pass: pays when the launch runs in waves (a seed that ends early hands
+      // its slot to the next one sooner) AND the polyhedron passes carry the seed's time: the two solver warps of a
+      // CTA slow each other down by ~15 % even on different sub-partitions.  Measured: C4 (10 k obstacles, 2048
+      // seeds) 2.24 -> 2.09 ms, the C2 scene with 2048 seeds 1.82 -> 1.98 ms, C2 itself 0.43 -> 0.46 ms.  Hence on
+      // for multi-wave launches over large scenes only; BPGEO_SPEC=0 / 1 forces it off / on.
+      static int env = -2, resident = 0;
+      if (env == -2) {
+        const char* e = getenv("BPGEO_SPEC");
+        env = e ? (e[0] == '0' ? 0 : 1) : -1;
+        int dev = 0, nsm = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        resident = 2 * nsm;
+      }
+      fp.spec = env >= 0 ? env : ((S > resident && scene->n >= 4096) ? 1 : 0);
+      if (scene->rows || tail) fp.spec = 0;
+      if (fp.spec) {
+        kfn = scene->n <= 64 * 128 ? (const void*)k_iris_fused<0, false, 1, true> : (const void*)k_iris_fused<0, false, 2, true>;
+        if (set_dyn_smem(kfn, fsmem)) return 1;
+      }
+    }
     if (tail) {
       // the pair workers of the tail wait inside the kernel for the other sets: every CTA has to be resident
       int nb = 0, dev = 0, nsm = 0;
@@ -3614,6 +3651,8 @@ int bp_build_sets_point_tail(const bp_scene* scene, const int* seed_scene_dev, c
       }
     }
     if (scene->rows) k_iris_fused<0, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    else if (fp.spec && scene->n <= 64 * 128) k_iris_fused<0, false, 1, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
+    else if (fp.spec) k_iris_fused<0, false, 2, true><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     else if (scene->n <= 64 * 128) k_iris_fused<0, false><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     else k_iris_fused<0, false, 2><<<S, 128, fsmem, stream>>>(view_of(scene, seed_scene_dev), fp);
     BP_CUDA(cudaGetLastError());
