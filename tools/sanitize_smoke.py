@@ -1,5 +1,5 @@
 """Small workloads for compute-sanitizer (memcheck / racecheck) on the GPU box: the fused set build on boxes and on
-polytopes (cached and re-solving form), the segment sets, the pair stage, and a short native planner run.
+polytopes (cached and re-solving form), the segment sets, the pair stage, a short native planner run, and (argument `spec`) the SPEC instantiation of the fused set build.
   compute-sanitizer --tool racecheck python tools/sanitize_smoke.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,6 +8,8 @@ from scipy.spatial.transform import Rotation as R
 from boundplanner_b200 import geometry as geo, scenes, planner_native as pn
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "spec":
+    os.environ["BPGEO_SPEC"] = "1"          # read once, at the library's first set build
 boxes, inflate, seeds, ws_min, ws_max = scenes.config_c2(300, 6)
 sc = geo.Scene(boxes, inflate)
 if which in ("all", "sets"):
@@ -17,6 +19,12 @@ if which in ("all", "sets"):
     geo.build_sets_line(sc, seeds, seeds + 0.03, ws_min, ws_max, compute_ellipsoid=True)
     geo.reduce_ineqs(out.A, out.b, out.m)
     print("sets ok", out.status.cpu().numpy())
+if which == "spec":
+    # SPEC instantiation of k_iris_fused (speculative free-centre solve on a second warp, shared abort flag):
+    # the same seeds must give the same sets as the plain kernel's golden rows, checked by the GPU tests; here
+    # the point is memcheck / racecheck over the two solver warps
+    out = geo.build_sets_point(sc, seeds, ws_min, ws_max, fixed_mid=True, optimize=True)
+    print("spec ok", out.status.cpu().numpy(), out.m.cpu().numpy())
 if which in ("all", "poly"):
     rng = np.random.default_rng(1)
     obs_sets, obs_points = scenes.random_polytope_scene(60, rng, 0.04, 0.16)
